@@ -1,0 +1,474 @@
+"""Host-side mirror of the reference's Lua API for the preload path, over libaukit_cuda.so.
+
+The reference is Lua (aukit.lua); no Lua interpreter exists in this image, so the host layer
+above the C ABI is Python with the reference's names, argument order, defaults and error
+strings ("A:n" = /root/reference/aukit.lua line n):
+
+    aukit.pcm(data, bitDepth=8, dataType="signed", channels=1, sampleRate=48000,
+              interleaved=True, bigEndian=False)                         A:1049
+    aukit.g711(data, ulaw, channels=1, sampleRate=8000)                  A:1361
+    aukit.adpcm(data, channels=1, sampleRate=48000, topFirst=True, interleaved=True,
+                predictor=None, step_index=None)                         A:1183
+    aukit.msadpcm(data, blockAlign, channels=1, sampleRate=48000, coefficients=None)  A:1283
+    aukit.wav(data, head=False)                                          A:1456
+    Audio.resample(sampleRate, interpolation=None)   (new object)        A:653
+    Audio.mono()                                     (new object)        A:677
+    Audio.len(), Audio.channels()                                        A:638-646
+    effects.amplify(audio, multiplier)               (in place, returns audio)  A:3356
+    effects.normalize(audio, peakAmplitude=1, independent=None)  (in place)     A:3431
+    aukit.defaultInterpolation = "linear"                                A:99
+
+Indices are Python's (0-based); everything else follows the reference.  The Lua facade with
+the identical surface is aukit_b200/lua/aukit.lua (bound through luaopen_aukit_cuda).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import AukitError, PipelineDesc, WavInfo
+
+_VERSION = "1.10.0-b200"
+defaultInterpolation = "linear"                                           # A:99
+
+_DATATYPES = {"signed": 0, "unsigned": 1, "float": 2}
+_INTERPS = {"none": 0, "linear": 1, "cubic": 2}
+DIALECT_LITERAL, DIALECT_GENERAL = 0, 1
+_WAV_TYPES = ["signed", "unsigned", "float", "alaw", "ulaw", "adpcm", "msadpcm", "dfpwm", None]
+
+# INFO tag names, A:198-220
+_WAV_METADATA = {
+    "IPRD": "album", "INAM": "title", "IART": "artist", "IWRI": "author", "IMUS": "composer",
+    "IPRO": "producer", "IPRT": "trackNumber", "ITRK": "trackNumber", "IFRM": "trackCount",
+    "PRT1": "partNumber", "PRT2": "partCount", "TLEN": "length", "IRTD": "rating", "ICRD": "date",
+    "ITCH": "encodedBy", "ISFT": "encoder", "ISRF": "media", "IGNR": "genre", "ICMT": "comment",
+    "ICOP": "copyright", "ILNG": "language",
+}
+
+
+# ------------------------------------------------------------------ context
+class Context:
+    """One aukit_ctx (device + stream).  Kernels are enqueued on its stream."""
+
+    def __init__(self, device: int = -1):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.aukit_cuda_init(device, C.byref(h)))
+        self.handle = h
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        _lib.check(self.lib.aukit_cuda_set_stream(self.handle, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        _lib.check(self.lib.aukit_cuda_synchronize(self.handle))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.aukit_cuda_launch_count(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.aukit_cuda_shutdown(self.handle)
+            self.handle = None
+
+
+_tls = threading.local()
+
+
+def context(device: Optional[int] = None) -> Context:
+    """The calling thread's default context (created on first use; no CPU fallback)."""
+    ctxs = getattr(_tls, "ctxs", None)
+    if ctxs is None:
+        ctxs = _tls.ctxs = {}
+    key = -1 if device is None else int(device)
+    if key not in ctxs:
+        ctxs[key] = Context(key)
+    return ctxs[key]
+
+
+def _expect(index, value, *types):
+    """cc.expect (A:84): type check with the reference's message."""
+    names = {str: "string", bytes: "string", bytearray: "string", memoryview: "string", int: "number",
+             float: "number", bool: "boolean", type(None): "nil", dict: "table", list: "table", tuple: "table"}
+    for t in types:
+        if t is float and isinstance(value, (int, float)) and not isinstance(value, bool):
+            return value
+        if t is bool and isinstance(value, bool):
+            return value
+        if t is not float and t is not bool and isinstance(value, t) and not (t is int and isinstance(value, bool)):
+            return value
+    want = sorted({names.get(t, t.__name__) for t in types})
+    got = names.get(type(value), type(value).__name__)
+    if isinstance(value, np.ndarray):
+        got = "table"
+    if len(want) > 1:
+        exp = ", ".join(want[:-1]) + " or " + want[-1]
+    else:
+        exp = want[0]
+    raise AukitError("bad argument #%d (expected %s, got %s)" % (index, exp, got))
+
+
+def _as_bytes(data):
+    if isinstance(data, (bytes, bytearray)):
+        return bytes(data) if isinstance(data, bytearray) else data
+    if isinstance(data, memoryview):
+        return data.tobytes()
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    raise AukitError("bad argument #1 (expected string, got %s)" % type(data).__name__)
+
+
+def _buf(b):
+    """(ctypes pointer, nbytes, keepalive) for bytes or a uint8 ndarray."""
+    if isinstance(b, np.ndarray):
+        return C.c_void_p(b.ctypes.data), b.size, b
+    return C.cast(C.c_char_p(b), C.c_void_p), len(b), b
+
+
+# ------------------------------------------------------------------ Audio
+class _ChannelData:
+    """audio.data: sequence of per-channel float32 arrays, downloaded lazily."""
+
+    def __init__(self, audio: "Audio"):
+        self._a = audio
+
+    def __len__(self):
+        return self._a.channels()
+
+    def __getitem__(self, c):
+        n = len(self)
+        if isinstance(c, slice):
+            return [self[i] for i in range(*c.indices(n))]
+        if c < 0:
+            c += n
+        if not 0 <= c < n:
+            raise IndexError(c)
+        return self._a._channel(c)
+
+    def __iter__(self):
+        return (self[c] for c in range(len(self)))
+
+
+class Audio:
+    """Device-resident aukit.Audio (A:116-123): planar float32 samples owned by the C library."""
+
+    def __init__(self, ctx: Context, handle, metadata=None, info=None):
+        self._ctx = ctx
+        self._h = handle
+        self.metadata = {} if metadata is None else metadata
+        self.info = {} if info is None else info
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and self._ctx.handle:
+            self._ctx.lib.aukit_cuda_audio_free(self._ctx.handle, h)
+
+    # --- reference surface
+    @property
+    def sampleRate(self):
+        r = self._ctx.lib.aukit_cuda_audio_sample_rate(self._h)
+        return int(r) if r == int(r) else r
+
+    @property
+    def data(self):
+        return _ChannelData(self)
+
+    def len(self) -> float:                                               # A:638
+        return self.frames / self._ctx.lib.aukit_cuda_audio_sample_rate(self._h)
+
+    def channels(self) -> int:                                            # A:644
+        return int(self._ctx.lib.aukit_cuda_audio_channels(self._h))
+
+    def resample(self, sampleRate, interpolation=None) -> "Audio":        # A:653
+        _expect(1, sampleRate, float)
+        interpolation = _expect(2, interpolation, str, type(None)) or defaultInterpolation
+        if interpolation not in _INTERPS:
+            # "sinc" is accepted by the reference (A:656) but is not part of the accelerated path
+            if interpolation == "sinc":
+                raise AukitError("aukit_b200: sinc interpolation is not implemented on the device")
+            raise AukitError("bad argument #2 (invalid interpolation type)")
+        out = C.c_void_p()
+        _lib.check(self._ctx.lib.aukit_cuda_resample(self._ctx.handle, self._h, float(sampleRate),
+                                                     _INTERPS[interpolation], C.byref(out)))
+        return Audio(self._ctx, out, dict(self.metadata), dict(self.info))   # copy(), A:657
+
+    def mono(self) -> "Audio":                                            # A:677
+        out = C.c_void_p()
+        _lib.check(self._ctx.lib.aukit_cuda_mono(self._ctx.handle, self._h, C.byref(out)))
+        return Audio(self._ctx, out, dict(self.metadata), dict(self.info))
+
+    def concat(self, *others: "Audio") -> "Audio":                        # A:696
+        parts = [self]
+        for i, o in enumerate(others):
+            if not isinstance(o, Audio):
+                raise AukitError("bad argument #%d (expected Audio, got %s)" % (i + 1, type(o).__name__))
+            if o.sampleRate != self.sampleRate:
+                o = o.resample(self.sampleRate)                           # A:702
+            parts.append(o)
+        arr = (C.c_void_p * len(parts))(*[p._h for p in parts])
+        out = C.c_void_p()
+        _lib.check(self._ctx.lib.aukit_cuda_concat(self._ctx.handle, arr, len(parts), C.byref(out)))
+        return Audio(self._ctx, out, dict(self.metadata), dict(self.info))
+
+    # --- Python-side conveniences
+    @property
+    def frames(self) -> int:
+        return int(self._ctx.lib.aukit_cuda_audio_frames(self._h))
+
+    @property
+    def stride(self) -> int:
+        return int(self._ctx.lib.aukit_cuda_audio_stride(self._h))
+
+    @property
+    def data_ptr(self) -> int:
+        return int(self._ctx.lib.aukit_cuda_audio_data(self._h) or 0)
+
+    def _channel(self, c: int) -> np.ndarray:
+        n = int(self._ctx.lib.aukit_cuda_audio_channel_frames(self._h, c))
+        out = np.empty(n, dtype=np.float32)
+        _lib.check(self._ctx.lib.aukit_cuda_audio_download(self._ctx.handle, self._h, c, 0, n,
+                                                           C.c_void_p(out.ctypes.data)))
+        return out
+
+    def numpy(self) -> np.ndarray:
+        """[channels, frames] float32 copy on the host (channel 1's length, like #data[1])."""
+        n = self.frames
+        out = np.zeros((self.channels(), n), dtype=np.float32)
+        for c in range(self.channels()):
+            ch = self._channel(c)
+            out[c, : ch.size] = ch[:n]
+        return out
+
+    @classmethod
+    def from_numpy(cls, x: np.ndarray, sampleRate=48000, ctx: Optional[Context] = None) -> "Audio":
+        ctx = ctx or context()
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float32)
+        h = C.c_void_p()
+        _lib.check(ctx.lib.aukit_cuda_audio_new(ctx.handle, x.shape[0], x.shape[1], float(sampleRate), C.byref(h)))
+        a = cls(ctx, h)
+        for c in range(x.shape[0]):
+            _lib.check(ctx.lib.aukit_cuda_audio_upload(ctx.handle, h, c, 0, x.shape[1], C.c_void_p(x[c].ctypes.data)))
+        return a
+
+    def __repr__(self):
+        return "<aukit_b200.Audio %d ch x %d frames @ %s Hz on device>" % (self.channels(), self.frames, self.sampleRate)
+
+
+def _expect_audio(n, v) -> Audio:
+    if isinstance(v, Audio):
+        return v
+    raise AukitError("bad argument #%d (expected Audio, got %s)" % (n, type(v).__name__))   # A:234-237
+
+
+# ------------------------------------------------------------------ loaders
+def new(duration, channels=None, sampleRate=None, ctx: Optional[Context] = None) -> Audio:   # A:1784
+    _expect(1, duration, float)
+    channels = _expect(2, channels, int, type(None)) or 1
+    sampleRate = _expect(3, sampleRate, float, type(None)) or 48000
+    ctx = ctx or context()
+    h = C.c_void_p()
+    frames = int(np.floor(duration * sampleRate)) if duration * sampleRate >= 1 else 0
+    _lib.check(ctx.lib.aukit_cuda_audio_new(ctx.handle, channels, frames, float(sampleRate), C.byref(h)))
+    return Audio(ctx, h, {}, {})
+
+
+def pcm(data, bitDepth=None, dataType=None, channels=None, sampleRate=None, interleaved=None, bigEndian=None,
+        ctx: Optional[Context] = None) -> Audio:                          # A:1049
+    if isinstance(data, (list, tuple)):
+        raise AukitError("aukit_b200: table (pre-unpacked) PCM input is host-side only; pass the packed string")
+    bitDepth = _expect(2, bitDepth, int, type(None)) or 8
+    dataType = _expect(3, dataType, str, type(None)) or "signed"
+    channels = _expect(4, channels, int, type(None)) or 1
+    sampleRate = _expect(5, sampleRate, float, type(None)) or 48000
+    _expect(6, interleaved, bool, type(None))
+    if interleaved is None:
+        interleaved = True
+    _expect(7, bigEndian, bool, type(None))
+    if bitDepth not in (8, 16, 24, 32):
+        raise AukitError("bad argument #2 (invalid bit depth)")
+    if dataType not in _DATATYPES:
+        raise AukitError("bad argument #3 (invalid data type)")
+    ctx = ctx or context()
+    p, n, keep = _buf(_as_bytes(data))
+    out = C.c_void_p()
+    _lib.check(ctx.lib.aukit_cuda_pcm(ctx.handle, p, n, bitDepth, _DATATYPES[dataType], channels, float(sampleRate),
+                                      int(interleaved), int(bool(bigEndian)), C.byref(out)))
+    return Audio(ctx, out, {}, {"bitDepth": bitDepth, "dataType": dataType})   # A:1072
+
+
+def g711(data, ulaw, channels=None, sampleRate=None, ctx: Optional[Context] = None) -> Audio:   # A:1361
+    _expect(2, ulaw, bool)
+    channels = _expect(3, channels, int, type(None)) or 1
+    sampleRate = _expect(4, sampleRate, float, type(None)) or 8000
+    ctx = ctx or context()
+    p, n, keep = _buf(_as_bytes(data))
+    out = C.c_void_p()
+    _lib.check(ctx.lib.aukit_cuda_g711(ctx.handle, p, n, int(ulaw), channels, float(sampleRate), C.byref(out)))
+    # A:1383 stores bitDepth/dataType in `metadata` and leaves `info` empty
+    return Audio(ctx, out, {"bitDepth": 14 if ulaw else 13, "dataType": "signed"}, {})
+
+
+def adpcm(data, channels=None, sampleRate=None, topFirst=None, interleaved=None, predictor=None, step_index=None,
+          ctx: Optional[Context] = None) -> Audio:                        # A:1183
+    channels = _expect(2, channels, int, type(None)) or 1
+    sampleRate = _expect(3, sampleRate, float, type(None)) or 48000
+    _expect(4, topFirst, bool, type(None))
+    if topFirst is None:
+        topFirst = True
+    _expect(5, interleaved, bool, type(None))
+    if interleaved is None:
+        interleaved = True
+
+    def _state(v, argn, lo, hi):
+        if v is None:
+            return None
+        if isinstance(v, (int, float)) and not isinstance(v, bool):
+            if channels != 1:
+                raise AukitError("bad argument #%d (table too short)" % argn)
+            v = [v]
+        if channels > len(v):
+            raise AukitError("bad argument #%d (table too short)" % argn)
+        for x in v[:channels]:
+            if not lo <= x <= hi:
+                raise AukitError("number outside of range (expected %s to be within %d and %d)" % (x, lo, hi))
+        return (C.c_int * channels)(*[int(x) for x in v[:channels]])
+
+    pr, si = _state(predictor, 6, -32768, 32767), _state(step_index, 7, 0, 88)
+    ctx = ctx or context()
+    p, n, keep = _buf(_as_bytes(data))
+    out = C.c_void_p()
+    _lib.check(ctx.lib.aukit_cuda_adpcm(ctx.handle, p, n, channels, float(sampleRate), int(topFirst), int(interleaved),
+                                        pr, si, C.byref(out)))
+    return Audio(ctx, out, {}, {"bitDepth": 16, "dataType": "signed"})
+
+
+def msadpcm(data, blockAlign, channels=None, sampleRate=None, coefficients=None, dialect=DIALECT_LITERAL,
+            ctx: Optional[Context] = None) -> Audio:                      # A:1283
+    _expect(2, blockAlign, int)
+    channels = _expect(3, channels, int, type(None)) or 1
+    sampleRate = _expect(4, sampleRate, float, type(None)) or 48000
+    c1 = c2 = None
+    nco = 0
+    if coefficients is not None:
+        if not isinstance(coefficients[0], (list, tuple)):
+            raise AukitError("bad argument #5 (first entry is not a table)")
+        if not isinstance(coefficients[1], (list, tuple)):
+            raise AukitError("bad argument #5 (second entry is not a table)")
+        if len(coefficients[0]) != len(coefficients[1]):
+            raise AukitError("bad argument #5 (lists are not the same length)")
+        nco = len(coefficients[0])
+        c1 = (C.c_int * nco)(*[int(v) for v in coefficients[0]])
+        c2 = (C.c_int * nco)(*[int(v) for v in coefficients[1]])
+    ctx = ctx or context()
+    p, n, keep = _buf(_as_bytes(data))
+    out = C.c_void_p()
+    _lib.check(ctx.lib.aukit_cuda_msadpcm(ctx.handle, p, n, blockAlign, channels, float(sampleRate), c1, c2, nco,
+                                          dialect, C.byref(out)))
+    return Audio(ctx, out, {}, {"bitDepth": 16, "dataType": "signed"})
+
+
+def _lua_tonumber(s: bytes):
+    """tonumber(str) for INFO tags (A:1566): decimal / hex numerals with surrounding whitespace."""
+    try:
+        t = s.decode("latin-1").strip(" \t\n\r\f\v")
+        if not t or "\0" in t or "_" in t:
+            return None
+        if t.lower().lstrip("+-").startswith("0x"):
+            return float(int(t, 16)) if "." not in t and "p" not in t.lower() else float.fromhex(t)
+        if t.lower().lstrip("+-") in ("inf", "infinity", "nan"):
+            return None
+        return float(t)
+    except ValueError:
+        return None
+
+
+def wav_info(data) -> dict:
+    """Host-only container walk of aukit.wav (A:1456-1574)."""
+    lib = _lib.load()
+    p, n, keep = _buf(_as_bytes(data))
+    info = WavInfo()
+    _lib.check(lib.aukit_cuda_wav_parse(p, n, C.byref(info)))
+    return _info_dict(info, keep)
+
+
+def _info_dict(info: WavInfo, raw) -> dict:
+    raw = raw.tobytes() if isinstance(raw, np.ndarray) else raw
+    meta = {}
+    for i in range(info.ntags):
+        t = info.tags[i]
+        key = _WAV_METADATA.get(t.id.decode("latin-1"))
+        if key:
+            s = raw[t.off: t.off + t.len]
+            num = _lua_tonumber(s)
+            meta[key] = num if num is not None else s                     # tonumber(str) or str
+    return {
+        "dataType": _WAV_TYPES[info.format], "channels": info.channels, "sampleRate": info.sampleRate,
+        "blockAlign": info.blockAlign, "bitDepth": info.bitDepth if info.have_fmt else None,
+        "coefficients": [list(info.coef1[: info.ncoef]), list(info.coef2[: info.ncoef])] if info.ncoef else None,
+        "data_off": info.data_off, "data_size": info.data_size, "metadata": meta,
+    }
+
+
+def wav(data, head=False, dialect=DIALECT_LITERAL, ctx: Optional[Context] = None) -> Audio:   # A:1456
+    ctx = ctx or context()
+    p, n, keep = _buf(_as_bytes(data))
+    info = WavInfo()
+    out = C.c_void_p()
+    _lib.check(ctx.lib.aukit_cuda_wav(ctx.handle, p, n, int(bool(head)), dialect, C.byref(info), C.byref(out)))
+    d = _info_dict(info, keep)
+    return Audio(ctx, out, d["metadata"], {"dataType": d["dataType"], "bitDepth": d["bitDepth"]})   # A:1553-1554
+
+
+# ------------------------------------------------------------------ effects (in place)
+class effects:
+    @staticmethod
+    def amplify(audio: Audio, multiplier) -> Audio:                        # A:3356
+        _expect_audio(1, audio)
+        _expect(2, multiplier, float)
+        _lib.check(audio._ctx.lib.aukit_cuda_amplify(audio._ctx.handle, audio._h, float(multiplier)))
+        return audio
+
+    @staticmethod
+    def normalize(audio: Audio, peakAmplitude=None, independent=None) -> Audio:   # A:3431
+        _expect_audio(1, audio)
+        peakAmplitude = _expect(2, peakAmplitude, float, type(None))
+        if peakAmplitude is None:
+            peakAmplitude = 1
+        _expect(3, independent, bool, type(None))
+        _lib.check(audio._ctx.lib.aukit_cuda_normalize(audio._ctx.handle, audio._h, float(peakAmplitude),
+                                                       int(bool(independent))))
+        return audio
+
+
+# ------------------------------------------------------------------ fused auplay chain
+def preload(data, bitDepth=16, dataType="signed", channels=2, sampleRate=44100, targetRate=48000,
+            interpolation=None, mono=True, peakAmplitude=0.8, bigEndian=False,
+            ctx: Optional[Context] = None) -> np.ndarray:
+    """auplay.lua:12-27 in one call on packed interleaved PCM held in HOST memory:
+    aukit.pcm -> :resample(targetRate) -> :mono() -> effects.normalize(peak).  H2D copy, the two
+    fused passes and the D2H copy all happen inside.  Returns [1 or channels, frames] float32."""
+    interpolation = interpolation or defaultInterpolation
+    if interpolation not in _INTERPS:
+        raise AukitError("bad argument #2 (invalid interpolation type)")
+    if dataType not in _DATATYPES:
+        raise AukitError("bad argument #3 (invalid data type)")
+    ctx = ctx or context()
+    b = _as_bytes(data)
+    p, n, keep = _buf(b)
+    B = bitDepth // 8
+    if bitDepth not in (8, 16, 24, 32):
+        raise AukitError("bad argument #2 (invalid bit depth)")
+    if n % (B * channels):
+        raise AukitError("bad argument #1 (uneven amount of data per channel)")
+    frames = n // (B * channels)
+    n_out = int(ctx.lib.aukit_resample_out_len(frames, float(sampleRate), float(targetRate)))
+    d = PipelineDesc(bitDepth, _DATATYPES[dataType], channels, int(bool(bigEndian)), float(sampleRate),
+                     float(targetRate), _INTERPS[interpolation], int(bool(mono)), frames, 0, frames, 0, n_out)
+    out = np.empty((1 if mono else channels, n_out), dtype=np.float32)
+    _lib.check(ctx.lib.aukit_cuda_pipeline_host(ctx.handle, C.byref(d), p, n, float(peakAmplitude),
+                                                C.c_void_p(out.ctypes.data)))
+    return out

@@ -1,0 +1,617 @@
+// capi.cu -- context, Audio handles, host-buffer loaders and the aukit.wav container walk.
+//
+// Host-side half of the C ABI in include/aukit_cuda.h.  Everything numeric happens in the
+// kernels of pcm.cu / adpcm.cu / resample.cu / effects.cu / pipeline*.cu; this file owns
+// device memory (stream-ordered allocations from the device's default pool), the H2D / D2H
+// copies of the end-to-end calls, and the integer-only parsing of RIFF headers (A:1456-1574).
+#include "common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+int aukit_launch_adpcm_stream(aukit_ctx *ctx, const uint8_t *d_in, size_t len, int channels, int topFirst,
+                              int interleaved, const int *d_pred, const int *d_idx, float *d_out, size_t stride);
+
+static thread_local char g_err[512];
+
+int aukit_fail(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+int aukit_cuda_check(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return 0;
+    return aukit_fail("CUDA error in %s: %s", what, cudaGetErrorString(e));
+}
+
+extern "C" const char *aukit_cuda_last_error(void) { return g_err; }
+extern "C" int aukit_cuda_abi_version(void) { return AUKIT_CUDA_ABI_VERSION; }
+
+// ------------------------------------------------------------------ context
+extern "C" int aukit_cuda_init(int device, aukit_ctx **out) {
+    g_err[0] = 0;
+    if (!out) return aukit_fail("aukit_cuda: null argument");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return aukit_fail("aukit_cuda: no CUDA device available (%s); there is no CPU fallback",
+                          e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0) AUKIT_CUDA_TRY(cudaGetDevice(&device));
+    if (device >= count) return aukit_fail("aukit_cuda: device %d out of range (%d devices)", device, count);
+    AUKIT_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    AUKIT_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return aukit_fail("aukit_cuda: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                          prop.major, prop.minor);
+    aukit_ctx *ctx = static_cast<aukit_ctx *>(calloc(1, sizeof(aukit_ctx)));
+    if (!ctx) return aukit_fail("aukit_cuda: out of host memory");
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    AUKIT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    AUKIT_CUDA_TRY(cudaMalloc(&ctx->d_status, sizeof(int)));
+    AUKIT_CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(int)));
+    AUKIT_CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(int)));
+    AUKIT_CUDA_TRY(cudaMalloc(&ctx->d_scratch, 1024 * sizeof(float)));
+    // keep freed blocks in the pool: the end-to-end calls allocate per call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void aukit_cuda_shutdown(aukit_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    cudaFree(ctx->d_status);
+    cudaFree(ctx->d_scratch);
+    cudaFreeHost(ctx->h_status);
+    cudaStreamDestroy(ctx->own_stream);
+    free(ctx);
+}
+
+extern "C" int aukit_cuda_set_stream(aukit_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return aukit_fail("aukit_cuda: null context");
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return 0;
+}
+
+extern "C" void *aukit_cuda_get_stream(aukit_ctx *ctx) { return ctx ? ctx->stream : nullptr; }
+extern "C" uint64_t aukit_cuda_launch_count(aukit_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int aukit_cuda_synchronize(aukit_ctx *ctx) {
+    if (!ctx) return aukit_fail("aukit_cuda: null context");
+    AUKIT_CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    AUKIT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const int st = *ctx->h_status;
+    if (st) {
+        cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream);
+        if (st & AUKIT_DEVERR_IMA_INDEX)
+            return aukit_fail("number outside of range (expected step index to be within 0 and 88)");   // A:1213
+        return aukit_fail("attempt to perform arithmetic on a nil value (MS-ADPCM predictor index has no coefficients)");
+    }
+    return 0;
+}
+
+int aukit_dev_alloc(aukit_ctx *ctx, size_t nbytes, void **d_out) {
+    return aukit_cuda_check(cudaMallocAsync(d_out, nbytes ? nbytes : 16, ctx->stream), "cudaMallocAsync");
+}
+
+void aukit_dev_free(aukit_ctx *ctx, void *d) {
+    if (d) cudaFreeAsync(d, ctx->stream);
+}
+
+// Lua strings / Python bytes are pageable: stage through a pinned buffer in slices so the
+// copy runs at PCIe rate and overlaps the next slice's memcpy.
+int aukit_upload_bytes(aukit_ctx *ctx, const void *h, size_t nbytes, void **d_out) {
+    void *d = nullptr;
+    if (aukit_dev_alloc(ctx, nbytes, &d)) return -1;
+    const size_t slice = (size_t)16 << 20;
+    if (nbytes > 0) {
+        cudaPointerAttributes at{};
+        const bool pinned = cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned || nbytes <= 4096) {
+            if (aukit_cuda_check(cudaMemcpyAsync(d, h, nbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D")) return -1;
+            if (!pinned) cudaStreamSynchronize(ctx->stream);   // small pageable copies are staged by the driver
+        } else {
+            if (!ctx->h_stage) {
+                if (aukit_cuda_check(cudaMallocHost(&ctx->h_stage, 2 * slice), "cudaMallocHost")) return -1;
+                ctx->h_stage_bytes = 2 * slice;
+            }
+            cudaEvent_t ev[2];
+            cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+            int k = 0;
+            for (size_t off = 0; off < nbytes; off += slice, k ^= 1) {
+                const size_t n = nbytes - off < slice ? nbytes - off : slice;
+                char *st = static_cast<char *>(ctx->h_stage) + (size_t)k * slice;
+                if (off >= 2 * slice) cudaEventSynchronize(ev[k]);
+                memcpy(st, static_cast<const char *>(h) + off, n);
+                cudaMemcpyAsync(static_cast<char *>(d) + off, st, n, cudaMemcpyHostToDevice, ctx->stream);
+                cudaEventRecord(ev[k], ctx->stream);
+            }
+            cudaEventSynchronize(ev[0]);
+            cudaEventSynchronize(ev[1]);
+            cudaEventDestroy(ev[0]);
+            cudaEventDestroy(ev[1]);
+            if (aukit_cuda_check(cudaGetLastError(), "staged H2D")) return -1;
+        }
+    }
+    *d_out = d;
+    return 0;
+}
+
+// ------------------------------------------------------------------ Audio handles
+int aukit_audio_alloc(aukit_ctx *ctx, int channels, size_t frames, double rate, aukit_audio **out) {
+    aukit_audio *a = static_cast<aukit_audio *>(calloc(1, sizeof(aukit_audio)));
+    if (!a) return aukit_fail("aukit_cuda: out of host memory");
+    a->channels = channels;
+    a->frames = frames;
+    a->stride = aukit_round_stride(frames ? frames : 1);
+    a->sampleRate = rate;
+    a->owned = true;
+    void *d = nullptr;
+    if (aukit_dev_alloc(ctx, a->stride * (size_t)(channels > 0 ? channels : 1) * sizeof(float), &d)) { free(a); return -1; }
+    a->data = static_cast<float *>(d);
+    *out = a;
+    return 0;
+}
+
+extern "C" int aukit_cuda_audio_new(aukit_ctx *ctx, int channels, size_t frames, double sampleRate, aukit_audio **out) {
+    if (!ctx || !out) return aukit_fail("aukit_cuda: null argument");
+    if (channels < 1) return aukit_fail("number outside of range (expected %d to be at least 1)", channels);
+    if (aukit_audio_alloc(ctx, channels, frames, sampleRate, out)) return -1;
+    return aukit_cuda_check(cudaMemsetAsync((*out)->data, 0, (*out)->stride * (size_t)channels * sizeof(float), ctx->stream),
+                            "cudaMemsetAsync");
+}
+
+extern "C" int aukit_cuda_audio_wrap(aukit_ctx *ctx, float *d_data, int channels, size_t frames, size_t stride,
+                                     double sampleRate, aukit_audio **out) {
+    if (!ctx || !out || !d_data) return aukit_fail("aukit_cuda: null argument");
+    if (channels < 1) return aukit_fail("aukit_cuda: channels < 1");
+    if (channels > 1 && stride < frames) return aukit_fail("aukit_cuda: stride < frames");
+    aukit_audio *a = static_cast<aukit_audio *>(calloc(1, sizeof(aukit_audio)));
+    if (!a) return aukit_fail("aukit_cuda: out of host memory");
+    a->data = d_data; a->channels = channels; a->frames = frames; a->stride = stride;
+    a->sampleRate = sampleRate; a->owned = false;
+    *out = a;
+    return 0;
+}
+
+extern "C" void aukit_cuda_audio_free(aukit_ctx *ctx, aukit_audio *a) {
+    if (!a) return;
+    if (a->owned && ctx) aukit_dev_free(ctx, a->data);
+    free(a->ch_frames);
+    free(a);
+}
+
+extern "C" int aukit_cuda_audio_channels(const aukit_audio *a) { return a ? a->channels : 0; }
+extern "C" size_t aukit_cuda_audio_frames(const aukit_audio *a) { return a ? a->frames : 0; }
+extern "C" size_t aukit_cuda_audio_stride(const aukit_audio *a) { return a ? a->stride : 0; }
+extern "C" double aukit_cuda_audio_sample_rate(const aukit_audio *a) { return a ? a->sampleRate : 0; }
+extern "C" float *aukit_cuda_audio_data(const aukit_audio *a) { return a ? a->data : nullptr; }
+extern "C" size_t aukit_cuda_audio_channel_frames(const aukit_audio *a, int channel) {
+    if (!a || channel < 0 || channel >= a->channels) return 0;
+    return a->ch_frames ? a->ch_frames[channel] : a->frames;
+}
+
+extern "C" int aukit_cuda_audio_download(aukit_ctx *ctx, const aukit_audio *a, int channel, size_t first, size_t count,
+                                         float *h_out) {
+    if (!ctx || !a || (!h_out && count)) return aukit_fail("aukit_cuda: null argument");
+    if (channel < 0 || channel >= a->channels) return aukit_fail("aukit_cuda: channel out of range");
+    if (first + count > aukit_cuda_audio_channel_frames(a, channel)) return aukit_fail("aukit_cuda: frame range out of bounds");
+    if (count)
+        AUKIT_CUDA_TRY(cudaMemcpyAsync(h_out, a->data + (size_t)channel * a->stride + first, count * sizeof(float),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    return aukit_cuda_synchronize(ctx);
+}
+
+extern "C" int aukit_cuda_audio_upload(aukit_ctx *ctx, aukit_audio *a, int channel, size_t first, size_t count,
+                                       const float *h_in) {
+    if (!ctx || !a || (!h_in && count)) return aukit_fail("aukit_cuda: null argument");
+    if (channel < 0 || channel >= a->channels) return aukit_fail("aukit_cuda: channel out of range");
+    if (first + count > a->frames) return aukit_fail("aukit_cuda: frame range out of bounds");
+    if (count) {
+        AUKIT_CUDA_TRY(cudaMemcpyAsync(a->data + (size_t)channel * a->stride + first, h_in, count * sizeof(float),
+                                       cudaMemcpyHostToDevice, ctx->stream));
+        AUKIT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ loaders
+extern "C" int aukit_cuda_pcm(aukit_ctx *ctx, const void *h_data, size_t nbytes, int bitDepth, int dataType,
+                              int channels, double sampleRate, int interleaved, int bigEndian, aukit_audio **out) {
+    if (!ctx || !out) return aukit_fail("aukit_cuda: null argument");
+    // argument validation in the reference's order (A:1058-1064) before any device work
+    if (bitDepth != 8 && bitDepth != 16 && bitDepth != 24 && bitDepth != 32)
+        return aukit_fail("bad argument #2 (invalid bit depth)");
+    if (dataType != AUKIT_SIGNED && dataType != AUKIT_UNSIGNED && dataType != AUKIT_FLOAT)
+        return aukit_fail("bad argument #3 (invalid data type)");
+    if (dataType == AUKIT_FLOAT && bitDepth != 32) return aukit_fail("bad argument #2 (float audio must have 32-bit depth)");
+    if (channels < 1) return aukit_fail("number outside of range (expected %d to be at least 1)", channels);
+    if (sampleRate < 1) return aukit_fail("number outside of range (expected %g to be at least 1)", sampleRate);
+    const size_t B = (size_t)bitDepth / 8;
+    if (nbytes % (B * (size_t)channels)) return aukit_fail("bad argument #1 (uneven amount of data per channel)");
+    const size_t frames = nbytes / B / (size_t)channels;
+    void *d_in = nullptr;
+    if (aukit_upload_bytes(ctx, h_data, nbytes, &d_in)) return -1;
+    aukit_audio *a = nullptr;
+    if (aukit_audio_alloc(ctx, channels, frames, sampleRate, &a)) { aukit_dev_free(ctx, d_in); return -1; }
+    int rc = aukit_cuda_dev_pcm(ctx, d_in, nbytes, bitDepth, dataType, channels, interleaved, bigEndian, a->data, a->stride);
+    aukit_dev_free(ctx, d_in);
+    if (rc) { aukit_cuda_audio_free(ctx, a); return -1; }
+    *out = a;
+    return 0;
+}
+
+extern "C" int aukit_cuda_g711(aukit_ctx *ctx, const void *h_data, size_t nbytes, int ulaw, int channels,
+                               double sampleRate, aukit_audio **out) {
+    if (!ctx || !out) return aukit_fail("aukit_cuda: null argument");
+    if (channels < 1) return aukit_fail("aukit_cuda: channels < 1");
+    const size_t C = (size_t)channels;
+    const size_t frames = (nbytes + C - 1) / C;                         // #data[1]
+    void *d_in = nullptr;
+    if (aukit_upload_bytes(ctx, h_data, nbytes, &d_in)) return -1;
+    aukit_audio *a = nullptr;
+    if (aukit_audio_alloc(ctx, channels, frames, sampleRate, &a)) { aukit_dev_free(ctx, d_in); return -1; }
+    if (nbytes % C) {                                                   // ragged: later channels are one short
+        a->ch_frames = static_cast<size_t *>(malloc(sizeof(size_t) * C));
+        for (size_t c = 0; c < C; c++) a->ch_frames[c] = nbytes > c ? (nbytes - c + C - 1) / C : 0;
+    }
+    int rc = aukit_cuda_dev_g711(ctx, d_in, nbytes, ulaw, channels, a->data, a->stride);
+    aukit_dev_free(ctx, d_in);
+    if (rc) { aukit_cuda_audio_free(ctx, a); return -1; }
+    *out = a;
+    return 0;
+}
+
+extern "C" int aukit_cuda_adpcm(aukit_ctx *ctx, const void *h_data, size_t nbytes, int channels, double sampleRate,
+                                int topFirst, int interleaved, const int *predictor, const int *step_index,
+                                aukit_audio **out) {
+    if (!ctx || !out) return aukit_fail("aukit_cuda: null argument");
+    if (channels < 1) return aukit_fail("number outside of range (expected %d to be at least 1)", channels);
+    for (int j = 0; j < channels; j++) {
+        if (predictor && (predictor[j] < -32768 || predictor[j] > 32767))
+            return aukit_fail("number outside of range (expected %d to be within -32768 and 32767)", predictor[j]);
+        if (step_index && (step_index[j] < 0 || step_index[j] > 88))
+            return aukit_fail("number outside of range (expected %d to be within 0 and 88)", step_index[j]);
+    }
+    const size_t len = nbytes * 2 / (size_t)channels;                   // A:1231
+    void *d_in = nullptr, *d_p = nullptr, *d_i = nullptr;
+    if (aukit_upload_bytes(ctx, h_data, nbytes, &d_in)) return -1;
+    if (predictor && aukit_upload_bytes(ctx, predictor, sizeof(int) * (size_t)channels, &d_p)) return -1;
+    if (step_index && aukit_upload_bytes(ctx, step_index, sizeof(int) * (size_t)channels, &d_i)) return -1;
+    aukit_audio *a = nullptr;
+    if (aukit_audio_alloc(ctx, channels, len, sampleRate, &a)) return -1;
+    int rc = len ? aukit_launch_adpcm_stream(ctx, static_cast<const uint8_t *>(d_in), len, channels, topFirst, interleaved,
+                                             static_cast<const int *>(d_p), static_cast<const int *>(d_i), a->data, a->stride)
+                 : 0;
+    aukit_dev_free(ctx, d_in); aukit_dev_free(ctx, d_p); aukit_dev_free(ctx, d_i);
+    if (rc) { aukit_cuda_audio_free(ctx, a); return -1; }
+    *out = a;
+    return 0;
+}
+
+extern "C" int aukit_cuda_ima_adpcm_wav(aukit_ctx *ctx, const void *h_data, size_t nbytes, int blockAlign, int channels,
+                                        double sampleRate, int dialect, aukit_audio **out) {
+    if (!ctx || !out) return aukit_fail("aukit_cuda: null argument");
+    if (blockAlign < 1) return aukit_fail("'for' step must be positive");
+    if (channels < 1) return aukit_fail("aukit_cuda: channels < 1");
+    if (nbytes == 0) return aukit_fail("attempt to index a nil value");
+    const size_t frames = aukit_ima_adpcm_wav_frames(nbytes, blockAlign, channels, dialect);
+    void *d_in = nullptr;
+    if (aukit_upload_bytes(ctx, h_data, nbytes, &d_in)) return -1;
+    aukit_audio *a = nullptr;
+    if (aukit_audio_alloc(ctx, channels, frames, sampleRate, &a)) { aukit_dev_free(ctx, d_in); return -1; }
+    int rc = aukit_cuda_dev_ima_adpcm_wav(ctx, d_in, nbytes, blockAlign, channels, dialect, a->data, a->stride);
+    aukit_dev_free(ctx, d_in);
+    if (rc) { aukit_cuda_audio_free(ctx, a); return -1; }
+    *out = a;
+    return 0;
+}
+
+extern "C" int aukit_cuda_msadpcm(aukit_ctx *ctx, const void *h_data, size_t nbytes, int blockAlign, int channels,
+                                  double sampleRate, const int *coef1, const int *coef2, int ncoef, int dialect,
+                                  aukit_audio **out) {
+    if (!ctx || !out) return aukit_fail("aukit_cuda: null argument");
+    if (blockAlign < 1) return aukit_fail("'for' step must be positive");
+    if (sampleRate < 1) return aukit_fail("number outside of range (expected %g to be at least 1)", sampleRate);
+    // the reference allocates data = {{}, channels == 2 and {} or nil} (A:1305): an empty string
+    // yields an empty Audio with 1 or 2 channels whatever `channels` says
+    const int out_ch = channels == 2 ? 2 : 1;
+    if (nbytes && dialect == AUKIT_DIALECT_LITERAL && channels != 1 && channels != 2)
+        return aukit_fail("Unsupported number of channels: %d", channels);
+    const int ch = nbytes ? channels : out_ch;
+    const size_t frames = nbytes ? aukit_msadpcm_frames(nbytes, blockAlign, channels) : 0;
+    void *d_in = nullptr;
+    if (aukit_upload_bytes(ctx, h_data, nbytes, &d_in)) return -1;
+    aukit_audio *a = nullptr;
+    if (aukit_audio_alloc(ctx, ch, frames, sampleRate, &a)) { aukit_dev_free(ctx, d_in); return -1; }
+    int rc = aukit_cuda_dev_msadpcm(ctx, d_in, nbytes, blockAlign, channels, coef1, coef2, ncoef, dialect, a->data, a->stride);
+    aukit_dev_free(ctx, d_in);
+    if (rc) { aukit_cuda_audio_free(ctx, a); return -1; }
+    *out = a;
+    return 0;
+}
+
+// ------------------------------------------------------------------ aukit.wav, A:1456-1574
+static uint32_t rd_u16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+static int rd_i16(const uint8_t *p) { return (int)(int16_t)rd_u16(p); }
+static uint32_t rd_u32(const uint8_t *p) { return rd_u16(p) | (rd_u16(p + 2) << 16); }
+
+extern "C" int aukit_cuda_wav_parse(const void *h_data, size_t nbytes, aukit_wav_info *info) {
+    g_err[0] = 0;
+    if (!h_data || !info) return aukit_fail("aukit_cuda: null argument");
+    const uint8_t *data = static_cast<const uint8_t *>(h_data);
+    memset(info, 0, sizeof *info);
+    info->format = AUKIT_WAV_NONE;
+    static const uint8_t ksTail[12] = {0x00, 0x00, 0x10, 0x00, 0x80, 0x00, 0x00, 0xaa, 0x00, 0x38, 0x9b, 0x71};
+    static const uint8_t dfpwm[16] = {0x3a, 0xc1, 0xfa, 0x38, 0x81, 0x1d, 0x43, 0x61,
+                                      0xa4, 0x0d, 0xce, 0x53, 0xca, 0x60, 0x7c, 0xd1};
+    if (nbytes < 4) return aukit_fail("data string too short");
+    if (memcmp(data, "RIFF", 4)) return aukit_fail("bad argument #1 (not a WAV file)");
+    if (nbytes < 12) return aukit_fail("data string too short");
+    if (memcmp(data + 8, "WAVE", 4)) return aukit_fail("bad argument #1 (not a WAV file)");
+    bool have_data = false;
+    size_t pos = 12;
+    while (pos < nbytes) {
+        if (nbytes - pos < 8) return aukit_fail("data string too short");
+        const uint8_t *id = data + pos;
+        const size_t size = rd_u32(data + pos + 4);
+        pos += 8;                                       // no pad byte after odd chunks (A:1471)
+        if (!memcmp(id, "fmt ", 4)) {
+            const size_t avail = pos < nbytes ? nbytes - pos : 0;
+            const size_t clen = size < avail ? size : avail;
+            const uint8_t *ch = data + pos;
+            pos += size;
+            if (clen < 16) return aukit_fail("data string too short");
+            const uint32_t format = rd_u16(ch);
+            info->channels = (int)rd_u16(ch + 2);
+            info->sampleRate = (int)rd_u32(ch + 4);
+            info->blockAlign = (int)rd_u16(ch + 12);
+            info->bitDepth = (int)rd_u16(ch + 14);
+            info->have_fmt = 1;
+            switch (format) {
+            case 1: info->format = info->bitDepth == 8 ? AUKIT_WAV_PCM_UNSIGNED : AUKIT_WAV_PCM_SIGNED; break;
+            case 2: {
+                info->format = AUKIT_WAV_MSADPCM;
+                if (clen < 22) return aukit_fail("data string too short");
+                const int numcoeff = (int)rd_u16(ch + 20);
+                if (numcoeff > 256) return aukit_fail("aukit_cuda: more than 256 coefficient pairs");
+                for (int i = 0; i < numcoeff; i++) {
+                    const size_t o = 22 + 4 * (size_t)i;
+                    if (o + 4 > clen) return aukit_fail("data string too short");
+                    info->coef1[i] = rd_i16(ch + o);
+                    info->coef2[i] = rd_i16(ch + o + 2);
+                }
+                if (numcoeff > 0) info->ncoef = numcoeff;
+                break;
+            }
+            case 3: info->format = AUKIT_WAV_FLOAT; break;
+            case 6: info->format = AUKIT_WAV_ALAW; break;
+            case 7: info->format = AUKIT_WAV_ULAW; break;
+            case 0x11: info->format = AUKIT_WAV_ADPCM; break;
+            case 0xFFFE: {
+                if (clen < 20) return aukit_fail("data string too short");
+                info->bitDepth = (int)rd_u16(ch + 18);
+                if (clen < 40) return aukit_fail("unsupported WAV file");
+                const uint8_t *u = ch + 24;
+                if (!memcmp(u, dfpwm, 16)) { info->format = AUKIT_WAV_DFPWM; break; }
+                if (memcmp(u + 4, ksTail, 12) || u[1] || u[2] || u[3]) return aukit_fail("unsupported WAV file");
+                switch (u[0]) {
+                case 0x01: info->format = info->bitDepth == 8 ? AUKIT_WAV_PCM_UNSIGNED : AUKIT_WAV_PCM_SIGNED; break;
+                case 0x02: info->format = AUKIT_WAV_MSADPCM; break;
+                case 0x03: info->format = AUKIT_WAV_FLOAT; break;
+                case 0x06: info->format = AUKIT_WAV_ALAW; break;
+                case 0x07: info->format = AUKIT_WAV_ULAW; break;
+                case 0x11: info->format = AUKIT_WAV_ADPCM; break;
+                default: return aukit_fail("unsupported WAV file");
+                }
+                break;
+            }
+            default: return aukit_fail("unsupported WAV file");
+            }
+        } else if (!memcmp(id, "data", 4)) {
+            if (size > nbytes - pos) return aukit_fail("invalid WAV file");
+            info->data_off = pos;
+            info->data_size = size;
+            have_data = true;
+            pos += size;
+        } else if (!memcmp(id, "LIST", 4)) {
+            if (nbytes - pos < 4) return aukit_fail("data string too short");
+            if (!memcmp(data + pos, "INFO", 4)) {
+                const size_t e = pos + size;
+                pos += 4;
+                while (pos < e) {                                       // "!2<c4s4Xh"
+                    if (pos > nbytes || nbytes - pos < 8) return aukit_fail("data string too short");
+                    const size_t len = rd_u32(data + pos + 4);
+                    if (len > nbytes - pos - 8) return aukit_fail("data string too short");
+                    if (info->ntags < 64) {
+                        memcpy(info->tags[info->ntags].id, data + pos, 4);
+                        info->tags[info->ntags].id[4] = 0;
+                        info->tags[info->ntags].off = pos + 8;
+                        info->tags[info->ntags].len = len;
+                        info->ntags++;
+                    }
+                    pos += 8 + len;
+                    if (pos & 1) {
+                        if (pos + 1 > nbytes) return aukit_fail("data string too short");
+                        pos++;
+                    }
+                }
+            } else pos += size;
+        } else pos += size;                                             // "fact" and unknown chunks
+    }
+    if (!have_data) return aukit_fail("invalid WAV file");
+    return 0;
+}
+
+extern "C" int aukit_cuda_wav(aukit_ctx *ctx, const void *h_data, size_t nbytes, int head_only, int dialect,
+                              aukit_wav_info *info_out, aukit_audio **out) {
+    if (!ctx || !out) return aukit_fail("aukit_cuda: null argument");
+    aukit_wav_info local;
+    aukit_wav_info *info = info_out ? info_out : &local;
+    if (aukit_cuda_wav_parse(h_data, nbytes, info)) return -1;
+    const uint8_t *payload = static_cast<const uint8_t *>(h_data) + info->data_off;
+    const size_t n = info->data_size;
+    // aukit.pcm defaults when a data chunk precedes any fmt chunk (channels/sampleRate nil)
+    const int ch = info->have_fmt ? info->channels : 1;
+    const double rate = info->have_fmt ? (double)info->sampleRate : 48000.0;
+    if (head_only) {                                                    // aukit.new(0, channels, sampleRate), A:1508
+        if (ch < 1) return aukit_fail("number outside of range (expected %d to be at least 1)", ch);
+        if (rate < 1) return aukit_fail("number outside of range (expected %g to be at least 1)", rate);
+        return aukit_cuda_audio_new(ctx, ch, 0, rate, out);
+    }
+    switch (info->format) {
+    case AUKIT_WAV_ADPCM: return aukit_cuda_ima_adpcm_wav(ctx, payload, n, info->blockAlign, ch, rate, dialect, out);
+    case AUKIT_WAV_MSADPCM:
+        return aukit_cuda_msadpcm(ctx, payload, n, info->blockAlign, ch, rate, info->ncoef ? info->coef1 : nullptr,
+                                  info->ncoef ? info->coef2 : nullptr, info->ncoef, dialect, out);
+    case AUKIT_WAV_ALAW: return aukit_cuda_g711(ctx, payload, n, 0, ch, rate, out);
+    case AUKIT_WAV_ULAW: return aukit_cuda_g711(ctx, payload, n, 1, ch, rate, out);
+    case AUKIT_WAV_DFPWM: return aukit_fail("aukit_cuda: DFPWM WAV data is outside the accelerated path");
+    case AUKIT_WAV_NONE: return aukit_cuda_pcm(ctx, payload, n, 8, AUKIT_SIGNED, 1, 48000.0, 1, 0, out);
+    case AUKIT_WAV_PCM_UNSIGNED: return aukit_cuda_pcm(ctx, payload, n, info->bitDepth, AUKIT_UNSIGNED, ch, rate, 1, 0, out);
+    case AUKIT_WAV_FLOAT: return aukit_cuda_pcm(ctx, payload, n, info->bitDepth, AUKIT_FLOAT, ch, rate, 1, 0, out);
+    default: return aukit_cuda_pcm(ctx, payload, n, info->bitDepth, AUKIT_SIGNED, ch, rate, 1, 0, out);
+    }
+}
+
+// ------------------------------------------------------------------ transforms
+static int ragged_error(const aukit_audio *a) {
+    if (a->ch_frames)
+        for (int c = 1; c < a->channels; c++)
+            if (a->ch_frames[c] != a->frames) return aukit_fail("attempt to perform arithmetic on a nil value");
+    return 0;
+}
+
+extern "C" int aukit_cuda_resample(aukit_ctx *ctx, const aukit_audio *in, double sampleRate, int interpolation,
+                                   aukit_audio **out) {
+    if (!ctx || !in || !out) return aukit_fail("aukit_cuda: null argument");
+    if (interpolation < 0 || interpolation > 2) return aukit_fail("bad argument #2 (invalid interpolation type)");
+    if (ragged_error(in)) return -1;
+    const uint64_t n_out = aukit_resample_out_len(in->frames, in->sampleRate, sampleRate);
+    aukit_audio *a = nullptr;
+    if (aukit_audio_alloc(ctx, in->channels, (size_t)n_out, sampleRate, &a)) return -1;
+    if (n_out && aukit_cuda_dev_resample(ctx, in->data, in->stride, in->channels, in->frames, 0, in->frames, in->sampleRate,
+                                         sampleRate, interpolation, 0, (size_t)n_out, a->data, a->stride)) {
+        aukit_cuda_audio_free(ctx, a);
+        return -1;
+    }
+    *out = a;
+    return 0;
+}
+
+extern "C" int aukit_cuda_mono(aukit_ctx *ctx, const aukit_audio *in, aukit_audio **out) {
+    if (!ctx || !in || !out) return aukit_fail("aukit_cuda: null argument");
+    if (ragged_error(in)) return -1;
+    aukit_audio *a = nullptr;
+    if (aukit_audio_alloc(ctx, 1, in->frames, in->sampleRate, &a)) return -1;
+    if (aukit_cuda_dev_mono(ctx, in->data, in->stride, in->channels, in->frames, a->data)) { aukit_cuda_audio_free(ctx, a); return -1; }
+    *out = a;
+    return 0;
+}
+
+extern "C" int aukit_cuda_concat(aukit_ctx *ctx, const aukit_audio *const *parts, int nparts, aukit_audio **out) {
+    if (!ctx || !parts || nparts < 1 || !out) return aukit_fail("aukit_cuda: null argument");
+    int cn = 0;
+    size_t total = 0;
+    for (int i = 0; i < nparts; i++) {
+        if (!parts[i]) return aukit_fail("bad argument #%d (expected Audio, got nil)", i);
+        if (parts[i]->sampleRate != parts[0]->sampleRate)
+            return aukit_fail("aukit_cuda: concat of different sample rates needs a resample first (A:702)");
+        cn = parts[i]->channels > cn ? parts[i]->channels : cn;
+        total += parts[i]->frames;
+    }
+    aukit_audio *a = nullptr;
+    if (aukit_cuda_audio_new(ctx, cn, total, parts[0]->sampleRate, &a)) return -1;   // missing channels stay 0 (A:713)
+    size_t pos = 0;
+    for (int i = 0; i < nparts; i++) {
+        if (parts[i]->frames)
+            AUKIT_CUDA_TRY(cudaMemcpy2DAsync(a->data + pos, a->stride * sizeof(float), parts[i]->data,
+                                             parts[i]->stride * sizeof(float), parts[i]->frames * sizeof(float),
+                                             (size_t)parts[i]->channels, cudaMemcpyDeviceToDevice, ctx->stream));
+        pos += parts[i]->frames;
+    }
+    *out = a;
+    return 0;
+}
+
+// ------------------------------------------------------------------ effects
+extern "C" int aukit_cuda_amplify(aukit_ctx *ctx, aukit_audio *a, double multiplier) {
+    if (!ctx || !a) return aukit_fail("aukit_cuda: null argument");
+    if (multiplier == 1.0) return 0;
+    if (!a->ch_frames) return aukit_cuda_dev_amplify(ctx, a->data, a->stride, a->channels, a->frames, multiplier);
+    for (int c = 0; c < a->channels; c++)
+        if (aukit_cuda_dev_amplify(ctx, a->data + (size_t)c * a->stride, a->stride, 1, a->ch_frames[c], multiplier)) return -1;
+    return 0;
+}
+
+extern "C" int aukit_cuda_absmax(aukit_ctx *ctx, const aukit_audio *a, int independent, float *d_max) {
+    if (!ctx || !a || !d_max) return aukit_fail("aukit_cuda: null argument");
+    if (!a->ch_frames) return aukit_cuda_dev_absmax(ctx, a->data, a->stride, a->channels, a->frames, independent, d_max);
+    for (int c = 0; c < a->channels; c++)
+        if (aukit_cuda_dev_absmax(ctx, a->data + (size_t)c * a->stride, a->stride, 1, a->ch_frames[c], 0,
+                                  d_max + (independent ? c : 0)))
+            return -1;
+    return 0;
+}
+
+extern "C" int aukit_cuda_scale_clamp(aukit_ctx *ctx, aukit_audio *a, double peakAmplitude, int independent,
+                                      const float *d_max) {
+    if (!ctx || !a || !d_max) return aukit_fail("aukit_cuda: null argument");
+    if (!a->ch_frames)
+        return aukit_cuda_dev_scale_clamp(ctx, a->data, a->stride, a->channels, a->frames, peakAmplitude, independent, d_max);
+    for (int c = 0; c < a->channels; c++)
+        if (aukit_cuda_dev_scale_clamp(ctx, a->data + (size_t)c * a->stride, a->stride, 1, a->ch_frames[c], peakAmplitude, 0,
+                                       d_max + (independent ? c : 0)))
+            return -1;
+    return 0;
+}
+
+extern "C" int aukit_cuda_normalize(aukit_ctx *ctx, aukit_audio *a, double peakAmplitude, int independent) {
+    if (!ctx || !a) return aukit_fail("aukit_cuda: null argument");
+    if (a->channels > 1024) return aukit_fail("aukit_cuda: more than 1024 channels");
+    const int nmax = independent ? a->channels : 1;
+    AUKIT_CUDA_TRY(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(float) * (size_t)nmax, ctx->stream));
+    if (aukit_cuda_absmax(ctx, a, independent, ctx->d_scratch)) return -1;
+    return aukit_cuda_scale_clamp(ctx, a, peakAmplitude, independent, ctx->d_scratch);
+}
+
+// ------------------------------------------------------------------ fused end-to-end call
+extern "C" int aukit_cuda_pipeline_host(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *h_in, size_t nbytes,
+                                        double peakAmplitude, float *h_out) {
+    if (!ctx || !p || !h_out) return aukit_fail("aukit_cuda: null argument");
+    const size_t need = p->in_avail * (size_t)p->channels * (size_t)(p->bitDepth / 8);
+    if (nbytes < need) return aukit_fail("aukit_cuda: host buffer smaller than in_avail frames");
+    void *d_in = nullptr, *d_out = nullptr;
+    if (aukit_upload_bytes(ctx, h_in, need, &d_in)) return -1;
+    const int out_ch = p->mono ? 1 : p->channels;
+    const size_t stride = aukit_round_stride(p->n_out ? p->n_out : 1);
+    if (aukit_dev_alloc(ctx, stride * (size_t)out_ch * sizeof(float), &d_out)) { aukit_dev_free(ctx, d_in); return -1; }
+    int rc = aukit_cuda_check(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(float), ctx->stream), "memset");
+    if (!rc) rc = aukit_cuda_dev_pipeline_peak(ctx, p, d_in, ctx->d_scratch);
+    if (!rc) rc = aukit_cuda_dev_pipeline_apply(ctx, p, d_in, peakAmplitude, ctx->d_scratch, static_cast<float *>(d_out), stride);
+    if (!rc && p->n_out)
+        rc = aukit_cuda_check(cudaMemcpy2DAsync(h_out, p->n_out * sizeof(float), d_out, stride * sizeof(float),
+                                                p->n_out * sizeof(float), (size_t)out_ch, cudaMemcpyDeviceToHost, ctx->stream),
+                              "D2H");
+    aukit_dev_free(ctx, d_in);
+    aukit_dev_free(ctx, d_out);
+    if (!rc) rc = aukit_cuda_synchronize(ctx);
+    return rc;
+}

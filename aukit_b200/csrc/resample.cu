@@ -1,0 +1,142 @@
+// resample.cu -- K5 resample (none / linear / cubic) on planar float32.
+//
+// Replaces Audio:resample (A:653-673) + interpolate.none/linear/cubic (A:253-266).
+// Positions are reproduced in fp64 exactly as the reference computes them,
+//     x = (i - 1) / ratio + 1,   ratio = newRate / oldRate            (A:658, A:666)
+// from the GLOBAL 1-based output index i with an IEEE round-to-nearest division, so
+// floor(x), the `x % 1 == 0` exact-hit test (A:667: copy, unclamped) and the fractional
+// part are bit-identical to Lua's -- on one GPU or on any time shard (SURVEY finding 5).
+// The blend itself runs in fp32: cubic as four bounded Catmull-Rom weights (sum |w| <= 1.25)
+// derived from the fp64 fraction, combined with FMAs; the result is clamped to [-1, 1]
+// exactly where the reference clamps (A:668).  Missing neighbours at the ends of the signal
+// follow the nil substitutions of A:259 and A:264.
+//
+// One thread per output frame: the position is computed once and shared by all channels.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace {
+
+struct resample_args {
+    const float *in;      // frames [in_first, in_first + in_avail) of each channel
+    size_t in_stride;
+    int channels;
+    unsigned long long n_total;   // frames of the whole signal (nil beyond)
+    unsigned long long in_first;
+    double ratio;
+    unsigned long long out_first;
+    size_t n_out;
+    float *out;
+    size_t out_stride;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) resample_kernel(resample_args a) {
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < a.n_out;
+         o += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long i0 = a.out_first + o;                 // = i - 1
+        const double x = __dadd_rn(__ddiv_rn((double)i0, a.ratio), 1.0);  // A:666
+        const double fl = floor(x);
+        const bool hit = (x == fl);                                    // x % 1 == 0, A:667
+        const long long f = (long long)fl;                             // 1-based index of p1
+        const double fxd = x - fl;                                     // exact
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+        const float fx = (float)fxd;
+        if (MODE == AUKIT_INTERP_CUBIC) {
+            // Catmull-Rom weights of A:265, evaluated in fp64 then narrowed
+            const double t = fxd, t2 = t * t, t3 = t2 * t;
+            w0 = (float)(-0.5 * t3 + t2 - 0.5 * t);
+            w1 = (float)(1.5 * t3 - 2.5 * t2 + 1.0);
+            w2 = (float)(-1.5 * t3 + 2.0 * t2 + 0.5 * t);
+            w3 = (float)(0.5 * t3 - 0.5 * t2);
+        }
+        const long long n = (long long)a.n_total;
+        const long long base = f - 1 - (long long)a.in_first;          // offset of p1 in `in`
+        for (int c = 0; c < a.channels; c++) {
+            const float *ch = a.in + (size_t)c * a.in_stride;
+            const float p1 = ch[base];
+            float v;
+            if (hit) {
+                v = p1;                                                // copied unclamped
+            } else if (MODE == AUKIT_INTERP_NONE) {
+                v = clamp_ref(p1);
+            } else if (MODE == AUKIT_INTERP_LINEAR) {
+                const float p2 = (f + 1 <= n) ? ch[base + 1] : p1;     // data[ffx+1] or data[ffx]
+                v = clamp_ref(__fmaf_rn(p2 - p1, fx, p1));
+            } else {
+                const float p0 = (f - 1 >= 1) ? ch[base - 1] : p1;     // A:264
+                const float p2 = (f + 1 <= n) ? ch[base + 1] : p1;
+                const float p3 = (f + 2 <= n) ? ch[base + 2] : p2;
+                v = clamp_ref(__fmaf_rn(w3, p3, __fmaf_rn(w2, p2, __fmaf_rn(w1, p1, w0 * p0))));
+            }
+            a.out[(size_t)c * a.out_stride + o] = v;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" uint64_t aukit_resample_out_len(uint64_t n_in, double srcRate, double dstRate) {
+    const double ratio = dstRate / srcRate;              // A:658
+    const double newlen = (double)n_in * ratio;          // A:659
+    if (!(newlen >= 1.0)) return 0;
+    return (uint64_t)floor(newlen);                      // for i = 1, newlen
+}
+
+extern "C" double aukit_resample_position(uint64_t i, double srcRate, double dstRate) {
+    const double ratio = dstRate / srcRate;
+    volatile double q = ((double)i - 1.0) / ratio;       // separately rounded, A:666
+    return q + 1.0;
+}
+
+extern "C" int aukit_resample_window(uint64_t n_in_total, double srcRate, double dstRate, int interpolation,
+                                     uint64_t out_first, uint64_t n_out, uint64_t *in_first,
+                                     uint64_t *in_count) {
+    if (interpolation < 0 || interpolation > 2) return aukit_fail("bad argument #2 (invalid interpolation type)");
+    if (n_out == 0 || n_in_total == 0) { *in_first = 0; *in_count = 0; return 0; }
+    const double xa = aukit_resample_position(out_first + 1, srcRate, dstRate);
+    const double xb = aukit_resample_position(out_first + n_out, srcRate, dstRate);
+    // positions are monotone in i; taps span floor(x) + [lo, hi] (1-based)
+    const int lo = interpolation == AUKIT_INTERP_CUBIC ? -1 : 0;
+    const int hi = interpolation == AUKIT_INTERP_CUBIC ? 2 : (interpolation == AUKIT_INTERP_LINEAR ? 1 : 0);
+    double fa = floor(xa) + lo, fb = floor(xb) + hi;
+    if (fa < 1) fa = 1;
+    if (fb > (double)n_in_total) fb = (double)n_in_total;
+    if (fb < fa) fb = fa;
+    *in_first = (uint64_t)fa - 1;
+    *in_count = (uint64_t)(fb - fa) + 1;
+    return 0;
+}
+
+extern "C" int aukit_cuda_dev_resample(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels,
+                                       uint64_t n_in_total, uint64_t in_first, size_t in_avail, double srcRate,
+                                       double dstRate, int interpolation, uint64_t out_first, size_t n_out,
+                                       float *d_out, size_t out_stride) {
+    if (!ctx) return aukit_fail("aukit_cuda: null context");
+    if (interpolation < 0 || interpolation > 2) return aukit_fail("bad argument #2 (invalid interpolation type)");  // A:656
+    if (channels < 1) return aukit_fail("aukit_cuda: channels < 1");
+    if (n_out == 0) return 0;
+    const uint64_t total_out = aukit_resample_out_len(n_in_total, srcRate, dstRate);
+    if (out_first + n_out > total_out) return aukit_fail("aukit_cuda: output range exceeds floor(n_in * ratio)");
+    uint64_t need_first = 0, need_count = 0;
+    if (aukit_resample_window(n_in_total, srcRate, dstRate, interpolation, out_first, n_out, &need_first, &need_count))
+        return -1;
+    // floor(x) can reach n_in_total + 1 only for absurd ratios (nil hole in the reference)
+    const double xlast = aukit_resample_position(out_first + n_out, srcRate, dstRate);
+    if (floor(xlast) > (double)n_in_total) return aukit_fail("aukit_cuda: position past the end of the input");
+    if (need_first < in_first || need_first + need_count > in_first + in_avail)
+        return aukit_fail("aukit_cuda: input window [%llu, %llu) does not cover the needed frames [%llu, %llu)",
+                          (unsigned long long)in_first, (unsigned long long)(in_first + in_avail),
+                          (unsigned long long)need_first, (unsigned long long)(need_first + need_count));
+    resample_args a{d_in, in_stride, channels, n_in_total, in_first, dstRate / srcRate, out_first, n_out, d_out, out_stride};
+    const int threads = 256;
+    const unsigned grid = aukit_grid(n_out, threads, (size_t)ctx->num_sms * 8 * 8);
+    switch (interpolation) {
+    case AUKIT_INTERP_NONE: resample_kernel<AUKIT_INTERP_NONE><<<grid, threads, 0, ctx->stream>>>(a); break;
+    case AUKIT_INTERP_LINEAR: resample_kernel<AUKIT_INTERP_LINEAR><<<grid, threads, 0, ctx->stream>>>(a); break;
+    default: resample_kernel<AUKIT_INTERP_CUBIC><<<grid, threads, 0, ctx->stream>>>(a); break;
+    }
+    ctx->launches++;
+    return aukit_cuda_check(cudaGetLastError(), "resample_kernel launch");
+}

@@ -1,0 +1,215 @@
+/*
+ * aukit_cuda.h -- C ABI of libaukit_cuda.so: AUKit's preload path on B200 (sm_100a).
+ *
+ * The reference (MCJack123/AUKit) is one interpreted Lua file with no FFI of its own; the
+ * drop-in boundary is therefore the Lua module table of aukit.lua and its Audio object.
+ * Each entry point below replaces one reference function ("A:n" = aukit.lua line n) and is
+ * what the thin Lua module (luaopen_aukit_cuda, csrc/lua_binding.c) and the Python host
+ * mirror (aukit_b200/) bind.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; aukit_cuda_last_error()
+ *     then returns a thread-local message that uses the reference's own error strings
+ *     where it has one (A:1058-1064, A:656, A:1460-1507, A:1349 ...).
+ *   - audio lives on the device as planar float32: sample (c, i) = data[c * stride + i],
+ *     stride % 4 == 0 and data 256-byte aligned (one cudaMalloc per Audio).
+ *   - all kernels are enqueued on the context's stream; host-visible results (download,
+ *     deferred decode errors) synchronise that stream.
+ *   - there is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef AUKIT_CUDA_H
+#define AUKIT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AUKIT_CUDA_ABI_VERSION 1
+
+typedef struct aukit_ctx aukit_ctx;     /* one per (host thread, device) */
+typedef struct aukit_audio aukit_audio; /* device-resident aukit.Audio (A:116-123) */
+
+enum { AUKIT_SIGNED = 0, AUKIT_UNSIGNED = 1, AUKIT_FLOAT = 2 };              /* dataType */
+enum { AUKIT_INTERP_NONE = 0, AUKIT_INTERP_LINEAR = 1, AUKIT_INTERP_CUBIC = 2 };
+/* ADPCM dialect: LITERAL reproduces aukit.wav / aukit.msadpcm for channels 1 and 2 exactly
+ * (A:1544 index mask, A:1331 first-header reuse); GENERAL is the standard N-channel block
+ * layout (IMA: aukit.stream.adpcm A:2798-2815), the only one defined for channels > 2. */
+enum { AUKIT_DIALECT_LITERAL = 0, AUKIT_DIALECT_GENERAL = 1 };
+enum {                                                                       /* aukit.wav dataType */
+    AUKIT_WAV_PCM_SIGNED = 0, AUKIT_WAV_PCM_UNSIGNED = 1, AUKIT_WAV_FLOAT = 2, AUKIT_WAV_ALAW = 3,
+    AUKIT_WAV_ULAW = 4, AUKIT_WAV_ADPCM = 5, AUKIT_WAV_MSADPCM = 6, AUKIT_WAV_DFPWM = 7,
+    AUKIT_WAV_NONE = 8
+};
+
+/* ------------------------------------------------------------------ context */
+int aukit_cuda_abi_version(void);
+const char *aukit_cuda_last_error(void);
+/* device < 0 => current device.  Fails (no fallback) when no CUDA device is usable. */
+int aukit_cuda_init(int device, aukit_ctx **ctx);
+void aukit_cuda_shutdown(aukit_ctx *ctx);
+/* Use an external cudaStream_t (e.g. torch's current stream); NULL => the ctx's own. */
+int aukit_cuda_set_stream(aukit_ctx *ctx, void *cuda_stream);
+void *aukit_cuda_get_stream(aukit_ctx *ctx);
+/* Waits for the stream and reports deferred device-side decode errors (bad IMA step index,
+ * A:1213; bad MS-ADPCM predictor index, A:1311). */
+int aukit_cuda_synchronize(aukit_ctx *ctx);
+/* Kernel launches issued by this context since init (bench.py's gpu_launches). */
+uint64_t aukit_cuda_launch_count(aukit_ctx *ctx);
+
+/* ------------------------------------------------------------------ Audio handle (A:116-123) */
+/* aukit.new-like: allocates zero-filled [channels][frames] (A:1784-1799 with duration*rate frames). */
+int aukit_cuda_audio_new(aukit_ctx *ctx, int channels, size_t frames, double sampleRate,
+                         aukit_audio **out);
+/* Wrap caller-owned device memory (not freed by audio_free). */
+int aukit_cuda_audio_wrap(aukit_ctx *ctx, float *d_data, int channels, size_t frames, size_t stride,
+                          double sampleRate, aukit_audio **out);
+void aukit_cuda_audio_free(aukit_ctx *ctx, aukit_audio *a);
+int aukit_cuda_audio_channels(const aukit_audio *a);                         /* Audio:channels A:644 */
+size_t aukit_cuda_audio_frames(const aukit_audio *a);                        /* #data[1] */
+size_t aukit_cuda_audio_stride(const aukit_audio *a);
+double aukit_cuda_audio_sample_rate(const aukit_audio *a);
+float *aukit_cuda_audio_data(const aukit_audio *a);                          /* device pointer */
+/* Per-channel length; differs from frames only for ragged G.711 input (A:1379). */
+size_t aukit_cuda_audio_channel_frames(const aukit_audio *a, int channel);
+/* Copy channel `channel` frames [first, first+count) to host floats (synchronises). */
+int aukit_cuda_audio_download(aukit_ctx *ctx, const aukit_audio *a, int channel, size_t first,
+                              size_t count, float *h_out);
+/* Copy host floats into channel `channel` (audio.data[c][i] = v writes). */
+int aukit_cuda_audio_upload(aukit_ctx *ctx, aukit_audio *a, int channel, size_t first, size_t count,
+                            const float *h_in);
+
+/* ------------------------------------------------------------------ loaders (host bytes in) */
+/* aukit.pcm(data, bitDepth, dataType, channels, sampleRate, interleaved, bigEndian) A:1049 */
+int aukit_cuda_pcm(aukit_ctx *ctx, const void *h_data, size_t nbytes, int bitDepth, int dataType,
+                   int channels, double sampleRate, int interleaved, int bigEndian,
+                   aukit_audio **out);
+/* aukit.g711(data, ulaw, channels, sampleRate) A:1361 */
+int aukit_cuda_g711(aukit_ctx *ctx, const void *h_data, size_t nbytes, int ulaw, int channels,
+                    double sampleRate, aukit_audio **out);
+/* aukit.adpcm(data, channels, sampleRate, topFirst, interleaved, predictor, step_index) A:1183
+ * for string input (one serial chain per channel; predictor/step_index NULL => zeros). */
+int aukit_cuda_adpcm(aukit_ctx *ctx, const void *h_data, size_t nbytes, int channels,
+                     double sampleRate, int topFirst, int interleaved, const int *predictor,
+                     const int *step_index, aukit_audio **out);
+/* aukit.wav's IMA ADPCM data path: block framing + aukit.adpcm + concat, A:1509-1548 */
+int aukit_cuda_ima_adpcm_wav(aukit_ctx *ctx, const void *h_data, size_t nbytes, int blockAlign,
+                             int channels, double sampleRate, int dialect, aukit_audio **out);
+/* aukit.msadpcm(data, blockAlign, channels, sampleRate, coefficients) A:1283 */
+int aukit_cuda_msadpcm(aukit_ctx *ctx, const void *h_data, size_t nbytes, int blockAlign,
+                       int channels, double sampleRate, const int *coef1, const int *coef2,
+                       int ncoef, int dialect, aukit_audio **out);
+
+/* aukit.wav(data, head) A:1456: container walk on the host, decode on the device. */
+typedef struct {
+    int format;                 /* AUKIT_WAV_* */
+    int channels, sampleRate, blockAlign, bitDepth, have_fmt;
+    int ncoef;                  /* msadpcm coefficient pairs from the fmt chunk; 0 => defaults */
+    int coef1[256], coef2[256];
+    size_t data_off, data_size; /* payload of the LAST data chunk (A:1505-1555) */
+    int ntags;                  /* LIST/INFO entries (A:1559-1568) */
+    struct { char id[5]; size_t off, len; } tags[64];
+} aukit_wav_info;
+int aukit_cuda_wav_parse(const void *h_data, size_t nbytes, aukit_wav_info *info); /* host only */
+int aukit_cuda_wav(aukit_ctx *ctx, const void *h_data, size_t nbytes, int head_only, int dialect,
+                   aukit_wav_info *info_out, aukit_audio **out);
+
+/* ------------------------------------------------------------------ transforms (new Audio) */
+/* Audio:resample(sampleRate, interpolation) A:653 */
+int aukit_cuda_resample(aukit_ctx *ctx, const aukit_audio *in, double sampleRate, int interpolation,
+                        aukit_audio **out);
+/* Audio:mono() A:677 */
+int aukit_cuda_mono(aukit_ctx *ctx, const aukit_audio *in, aukit_audio **out);
+/* Audio:concat(...) A:696 for same-rate inputs (the block join of A:1548). */
+int aukit_cuda_concat(aukit_ctx *ctx, const aukit_audio *const *parts, int nparts, aukit_audio **out);
+
+/* ------------------------------------------------------------------ effects (in place) */
+/* aukit.effects.amplify(audio, multiplier) A:3356 */
+int aukit_cuda_amplify(aukit_ctx *ctx, aukit_audio *a, double multiplier);
+/* aukit.effects.normalize(audio, peakAmplitude, independent) A:3431 (single device) */
+int aukit_cuda_normalize(aukit_ctx *ctx, aukit_audio *a, double peakAmplitude, int independent);
+/* The two halves of normalize, for time-sharded buffers: d_max is DEVICE memory holding 1
+ * float (global) or `channels` floats (independent).  absmax max-combines into whatever
+ * d_max already holds (zero it first); between the two calls the caller all-reduces d_max
+ * with MAX over the ranks (the path's only collective). */
+int aukit_cuda_absmax(aukit_ctx *ctx, const aukit_audio *a, int independent, float *d_max);
+int aukit_cuda_scale_clamp(aukit_ctx *ctx, aukit_audio *a, double peakAmplitude, int independent,
+                           const float *d_max);
+
+/* ------------------------------------------------------------------ device-pointer level */
+/* Same kernels on caller-owned DEVICE buffers (inputs already resident in HBM; what
+ * bench.py's `value` times).  Output layout: d_out[c * out_stride + i]. */
+int aukit_cuda_dev_pcm(aukit_ctx *ctx, const void *d_in, size_t nbytes, int bitDepth, int dataType,
+                       int channels, int interleaved, int bigEndian, float *d_out,
+                       size_t out_stride);
+int aukit_cuda_dev_g711(aukit_ctx *ctx, const void *d_in, size_t nbytes, int ulaw, int channels,
+                        float *d_out, size_t out_stride);
+int aukit_cuda_dev_ima_adpcm_wav(aukit_ctx *ctx, const void *d_in, size_t nbytes, int blockAlign,
+                                 int channels, int dialect, float *d_out, size_t out_stride);
+int aukit_cuda_dev_msadpcm(aukit_ctx *ctx, const void *d_in, size_t nbytes, int blockAlign,
+                           int channels, const int *coef1, const int *coef2, int ncoef,
+                           int dialect, float *d_out, size_t out_stride);
+/* Time-shardable resample: produces global output frames [out_first, out_first+n_out)
+ * (0-based) of a signal whose full length is n_in_total frames.  d_in holds input frames
+ * [in_first, in_first + in_avail) of every channel.  Positions are computed from the GLOBAL
+ * output index in fp64 exactly as A:666 does; use aukit_resample_window() to size the halo. */
+int aukit_cuda_dev_resample(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels,
+                            uint64_t n_in_total, uint64_t in_first, size_t in_avail,
+                            double srcRate, double dstRate, int interpolation,
+                            uint64_t out_first, size_t n_out, float *d_out, size_t out_stride);
+int aukit_cuda_dev_mono(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels, size_t n,
+                        float *d_out);
+int aukit_cuda_dev_amplify(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,
+                           double multiplier);
+int aukit_cuda_dev_absmax(aukit_ctx *ctx, const float *d, size_t stride, int channels, size_t n,
+                          int independent, float *d_max);
+int aukit_cuda_dev_scale_clamp(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,
+                               double peakAmplitude, int independent, const float *d_max);
+
+/* Fused auplay chain (auplay.lua:12-27) for integer/float PCM input resident on the device:
+ * unpack -> resample(dstRate, interpolation) -> [mono] -> normalize(peak), without
+ * materialising intermediates.  Two launches around the max barrier:
+ *   pass 1 (peak)  reads the packed bytes, max-combines |result| into d_max[0];
+ *   (caller all-reduces d_max with MAX when time-sharded)
+ *   pass 2 (apply) re-reads the packed bytes and writes clamp(result * peak/max).
+ * d_in holds interleaved frames [in_first, in_first + in_avail) of the full signal. */
+typedef struct {
+    int bitDepth, dataType, channels, bigEndian;  /* interleaved input only */
+    double srcRate, dstRate;
+    int interpolation;
+    int mono;                   /* 1 => Audio:mono() after resample */
+    uint64_t n_in_total;        /* frames of the whole (unsharded) signal */
+    uint64_t in_first;          /* global index of the first frame present in d_in */
+    size_t in_avail;            /* frames present in d_in */
+    uint64_t out_first;         /* first global output frame this call produces */
+    size_t n_out;               /* number of output frames this call produces */
+} aukit_pipeline_desc;
+int aukit_cuda_dev_pipeline_peak(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *d_in,
+                                 float *d_max);
+int aukit_cuda_dev_pipeline_apply(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *d_in,
+                                  double peakAmplitude, const float *d_max, float *d_out,
+                                  size_t out_stride);
+/* Host-buffer convenience = the end-to-end call (H2D + peak + apply + D2H), single device. */
+int aukit_cuda_pipeline_host(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *h_in,
+                             size_t nbytes, double peakAmplitude, float *h_out);
+
+/* ------------------------------------------------------------------ pure host helpers */
+/* floor(n_in * (dstRate/srcRate)) in double, the reference's loop bound (A:658-664). */
+uint64_t aukit_resample_out_len(uint64_t n_in, double srcRate, double dstRate);
+/* (i - 1)/ratio + 1 for the 1-based output index i, as A:666 computes it. */
+double aukit_resample_position(uint64_t i, double srcRate, double dstRate);
+/* Input frames (0-based, clipped to [0, n_in_total)) needed to produce global output frames
+ * [out_first, out_first + n_out): the shard plus its interpolation halo (-1/+2 cubic,
+ * 0/+1 linear, 0/0 none). */
+int aukit_resample_window(uint64_t n_in_total, double srcRate, double dstRate, int interpolation,
+                          uint64_t out_first, uint64_t n_out, uint64_t *in_first,
+                          uint64_t *in_count);
+size_t aukit_ima_adpcm_wav_frames(size_t nbytes, int blockAlign, int channels, int dialect);
+size_t aukit_msadpcm_frames(size_t nbytes, int blockAlign, int channels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,218 @@
+"""Parity of the float stages (resample / mono / amplify / normalize / fused chain) against the
+oracle.  Tolerance: |f32 - ref_double| <= 2^-20 (BASELINE.json:north_star); lengths exact;
++-1 LSB after the reference's 8/16-bit requantisation formula (A:874)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import TOL, f32_equal_bits, tone_s16
+
+pytestmark = pytest.mark.gpu
+
+RATES = [(44100, 48000), (22050, 48000), (96000, 48000), (11025, 48000), (48000, 44100), (8000, 48000),
+         (44100, 44100), (48000, 8000), (44056, 48000), (96000, 44100)]
+
+
+def _signal(n, ch, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-1, 1, (ch, n)).astype(np.float32)          # full-scale noise: cubic overshoots -> clamp path
+    x[:, : n // 2] *= np.float32(0.3)
+    return x
+
+
+def _requant_ok(got, ref, bits):
+    mx = 2.0 ** (bits - 1)
+    q = lambda d: np.where(d < 0, d * mx, d * (mx - 1))          # A:874, un-rounded
+    return np.nanmax(np.abs(np.round(q(got.astype(np.float64))) - np.round(q(ref)))) <= 1
+
+
+@pytest.mark.parametrize("src,dst", RATES)
+@pytest.mark.parametrize("interp", ["none", "linear", "cubic"])
+def test_resample_matches_oracle(ak, O, src, dst, interp):
+    x = _signal(20011, 2, src + dst)
+    a = ak.Audio.from_numpy(x, src)
+    r = a.resample(dst, interp)
+    ref = O.resample(x.astype(np.float64), src, dst, interp)
+    got = r.numpy()
+    assert got.shape == ref.shape and r.sampleRate == dst
+    if interp == "none":
+        assert f32_equal_bits(got, ref.astype(np.float32))       # selects samples: must be identical (finding 5)
+    else:
+        assert np.max(np.abs(got - ref)) <= TOL
+        assert _requant_ok(got, ref, 16) and _requant_ok(got, ref, 8)
+
+
+def test_resample_exact_hits_unclamped_and_edges(ak, O):
+    x = np.array([[2.0, -3.0, 0.5, 0.25, -0.75]], dtype=np.float32)   # out-of-range float PCM (A:667 vs A:668)
+    for interp in ("none", "linear", "cubic"):
+        for src, dst in ((1, 2), (1, 3), (2, 1), (3, 7)):
+            got = ak.Audio.from_numpy(x, src).resample(dst, interp).numpy()
+            ref = O.resample(x.astype(np.float64), src, dst, interp)
+            assert got.shape == ref.shape
+            assert np.max(np.abs(got - ref)) <= TOL, (interp, src, dst)
+    one = ak.Audio.from_numpy(np.array([[0.5]], dtype=np.float32), 8000).resample(48000, "cubic").numpy()
+    assert np.max(np.abs(one - O.resample(np.array([[0.5]]), 8000, 48000, "cubic"))) <= TOL
+    empty = ak.pcm(b"", 16).resample(48000)
+    assert empty.frames == 0
+    with pytest.raises(ak.AukitError, match="invalid interpolation type"):
+        ak.Audio.from_numpy(x, 1).resample(2, "bogus")
+
+
+def test_resample_default_interpolation_and_metadata_copy(ak, O):
+    x = _signal(1000, 1, 5)
+    a = ak.Audio.from_numpy(x, 44100)
+    a.metadata["title"] = "t"
+    r = a.resample(48000)                                        # aukit.defaultInterpolation = "linear" (A:99, A:655)
+    assert np.max(np.abs(r.numpy() - O.resample(x.astype(np.float64), 44100, 48000, "linear"))) <= TOL
+    assert r.metadata == {"title": "t"} and r.metadata is not a.metadata
+
+
+def test_resample_index_parity_none_mode_long(ak, O):
+    """floor(x) / exact-hit decisions over 2e6 outputs at 44.1k -> 48k: a ramp input makes the
+    selected index directly visible in 'none' mode (SURVEY finding 5: 2172 of 3000 rational
+    hits land one sample lower in the reference)."""
+    n = 1_900_000
+    ramp = (np.arange(n, dtype=np.float64) % 65521) / 65536.0
+    x = ramp.astype(np.float32)[None, :]
+    got = ak.Audio.from_numpy(x, 44100).resample(48000, "none").numpy()
+    ref = O.resample(x.astype(np.float64), 44100, 48000, "none")
+    assert f32_equal_bits(got, ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 8])
+def test_mono(ak, O, ch):
+    x = _signal(10007, ch, ch)
+    m = ak.Audio.from_numpy(x, 48000).mono()
+    ref = O.mono(x.astype(np.float64))
+    assert m.channels() == 1 and m.frames == 10007
+    assert f32_equal_bits(m.numpy(), ref.astype(np.float32))      # fp64 sum, one rounding
+
+
+def test_amplify_and_normalize_in_place(ak, O):
+    x = _signal(30011, 2, 9) * np.float32(0.6)
+    a = ak.Audio.from_numpy(x, 48000)
+    assert ak.effects.amplify(a, 1) is a and f32_equal_bits(a.numpy(), x)             # m == 1: untouched (A:3359)
+    assert ak.effects.amplify(a, 2.5) is a                                            # mutates and returns the argument
+    assert f32_equal_bits(a.numpy(), O.amplify(x.astype(np.float64), 2.5).astype(np.float32))
+    for peak, indep in ((1.0, False), (0.8, False), (0.8, True), (None, None)):
+        b = ak.Audio.from_numpy(x, 48000)
+        args = [] if peak is None else [peak, indep]
+        assert ak.effects.normalize(b, *args) is b
+        ref = O.normalize(x.astype(np.float64), 1.0 if peak is None else peak, bool(indep))
+        got = b.numpy()
+        assert np.max(np.abs(got - ref)) <= TOL
+        assert np.max(np.abs(got)) == pytest.approx(1.0 if peak is None else peak, abs=1e-6)
+
+
+def test_normalize_silence_nan_and_nan_input(ak, O):
+    z = ak.Audio.from_numpy(np.zeros((1, 100), dtype=np.float32), 48000)
+    assert np.isnan(ak.effects.normalize(z, 0.8).numpy()).all()                       # 0 * inf (A:3444, A:3455)
+    x = np.array([[np.nan, 0.5, -0.25]], dtype=np.float32)
+    got = ak.effects.normalize(ak.Audio.from_numpy(x, 48000)).numpy()
+    assert np.isnan(got[0, 0]) and got[0, 1] == 1.0 and got[0, 2] == -0.5             # math.max ignores NaN
+
+
+@pytest.mark.parametrize("interp", ["linear", "cubic", "none"])
+def test_auplay_chain_unfused_vs_oracle(ak, O, interp):
+    """BASELINE config 1: 10 s 44.1 kHz stereo s16 WAV -> aukit.wav -> :resample -> :mono -> normalize(0.8)."""
+    from util import wav_pcm
+    pcm = tone_s16(441000, 2, 44100, seed=1)
+    a = ak.wav(wav_pcm(pcm.tobytes(), 2, 44100, 16))
+    out = ak.effects.normalize(a.resample(48000, interp).mono(), 0.8)
+    ref = O.chain_s16(pcm.tobytes(), 2, 44100, 48000, interp, 0.8)
+    got = out.numpy()[0]
+    assert got.shape == ref.shape == (480000,)
+    assert np.max(np.abs(got - ref)) <= TOL
+    assert _requant_ok(got, ref, 16)
+
+
+@pytest.mark.parametrize("interp", ["linear", "cubic", "none"])
+@pytest.mark.parametrize("kind", ["tone", "noise"])
+def test_fused_pipeline_vs_oracle(ak, O, interp, kind):
+    n = 300007
+    pcm = tone_s16(n, 2, 44100, seed=2) if kind == "tone" else \
+        np.random.default_rng(2).integers(-32768, 32768, (n, 2)).astype(np.int16)
+    got = ak.preload(pcm.tobytes(), 16, "signed", 2, 44100, 48000, interp, True, 0.8)[0]
+    ref = O.chain_s16(pcm.tobytes(), 2, 44100, 48000, interp, 0.8)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= TOL
+    assert _requant_ok(got, ref, 16) and _requant_ok(got, ref, 8)
+
+
+@pytest.mark.parametrize("bits,dtype,be,ch,src", [(24, "signed", True, 2, 22050), (8, "unsigned", False, 1, 11025),
+                                                  (32, "float", False, 3, 96000), (16, "signed", True, 2, 48000),
+                                                  (32, "signed", False, 2, 44100)])
+def test_fused_pipeline_other_formats(ak, O, bits, dtype, be, ch, src):
+    rng = np.random.default_rng(bits + ch)
+    n = 50021
+    raw = rng.integers(0, 256, n * ch * bits // 8, dtype=np.uint8)
+    if dtype == "float":
+        raw = (rng.standard_normal(n * ch) * 0.4).astype("<f4").view(np.uint8)
+    for mono in (True, False):
+        got = ak.preload(raw, bits, dtype, ch, src, 48000, "cubic", mono, 1.0, be)
+        x = O.resample(O.pcm(raw, bits, dtype, ch, True, be), src, 48000, "cubic")
+        ref = O.normalize(O.mono(x) if mono else x, 1.0)
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= TOL
+
+
+def test_time_sharded_resample_is_bitwise_identical(ak, O):
+    """Sharding the OUTPUT range (each shard carrying its halo) reproduces the single-pass result
+    bit for bit, because positions come from the global index."""
+    lib = ak._lib.load()
+    ctx = ak.context()
+    x = _signal(100003, 2, 21)
+    for src, dst, interp in ((96000, 44100, "cubic"), (44100, 48000, "linear"), (96000, 48000, "cubic"), (44100, 48000, "none")):
+        mode = {"none": 0, "linear": 1, "cubic": 2}[interp]
+        whole = ak.Audio.from_numpy(x, src).resample(dst, interp).numpy()
+        n_out = whole.shape[1]
+        parts = []
+        for r in range(4):
+            o0, o1 = n_out * r // 4, n_out * (r + 1) // 4
+            f, c = C.c_uint64(), C.c_uint64()
+            assert lib.aukit_resample_window(x.shape[1], src, dst, mode, o0, o1 - o0, C.byref(f), C.byref(c)) == 0
+            shard_in = ak.Audio.from_numpy(x[:, f.value: f.value + c.value], src)      # shard + halo only
+            out = ak.Audio.from_numpy(np.zeros((2, o1 - o0), dtype=np.float32), dst)
+            ak._lib.check(lib.aukit_cuda_dev_resample(ctx.handle, shard_in.data_ptr, shard_in.stride, 2, x.shape[1], f.value,
+                                                      c.value, float(src), float(dst), mode, o0, o1 - o0, out.data_ptr, out.stride))
+            parts.append(out.numpy())
+        assert f32_equal_bits(np.concatenate(parts, axis=1), whole)
+
+
+def test_time_sharded_fused_pipeline_matches_single_pass(ak, O):
+    import torch
+    lib = ak._lib.load()
+    ctx = ak.context()
+    n = 200003
+    pcm = np.random.default_rng(5).integers(-20000, 20000, (n, 2)).astype(np.int16)
+    whole = ak.preload(pcm.tobytes(), 16, "signed", 2, 44100, 48000, "cubic", True, 0.8)
+    n_out = whole.shape[1]
+    dmax = torch.zeros(1, device="cuda")
+    descs, ins = [], []
+    for r in range(3):
+        o0, o1 = n_out * r // 3, n_out * (r + 1) // 3
+        f, c = C.c_uint64(), C.c_uint64()
+        lib.aukit_resample_window(n, 44100.0, 48000.0, 2, o0, o1 - o0, C.byref(f), C.byref(c))
+        t = torch.from_numpy(pcm[f.value: f.value + c.value].copy()).cuda()
+        d = ak.PipelineDesc(16, 0, 2, 0, 44100.0, 48000.0, 2, 1, n, f.value, c.value, o0, o1 - o0)
+        descs.append(d); ins.append(t)
+    torch.cuda.synchronize()
+    for d, t in zip(descs, ins):      # local peaks max-combine into one value (the allreduce-max on one GPU)
+        ak._lib.check(lib.aukit_cuda_dev_pipeline_peak(ctx.handle, C.byref(d), t.data_ptr(), dmax.data_ptr()))
+    ctx.synchronize()
+    outs = []
+    for d, t in zip(descs, ins):
+        o = torch.empty(d.n_out, device="cuda")
+        ak._lib.check(lib.aukit_cuda_dev_pipeline_apply(ctx.handle, C.byref(d), t.data_ptr(), 0.8, dmax.data_ptr(), o.data_ptr(), d.n_out))
+        ctx.synchronize()
+        outs.append(o.cpu().numpy())
+    assert f32_equal_bits(np.concatenate(outs)[None, :], whole)
+
+
+def test_concat_joins_blocks(ak):
+    a = ak.Audio.from_numpy(np.array([[1, 2, 3], [4, 5, 6]], dtype=np.float32) / 8, 8000)
+    b = ak.Audio.from_numpy(np.array([[7, 8]], dtype=np.float32) / 8, 8000)
+    c = a.concat(b)
+    assert (c.numpy() * 8).tolist() == [[1, 2, 3, 7, 8], [4, 5, 6, 0, 0]]       # missing channel -> silence (A:713)
+    assert a.len() == 3 / 8000 and c.channels() == 2
