@@ -61,7 +61,18 @@ class Context:
         self.handle = h
 
     def set_stream(self, cuda_stream: Optional[int]):
-        _lib.check(self.lib.aukit_cuda_set_stream(self.handle, C.c_void_p(cuda_stream or 0)))
+        """None -> the context's own stream.  A raw cudaStream_t handle otherwise; torch reports the
+        legacy default stream as handle 0, which is passed on as cudaStreamLegacy (1)."""
+        if cuda_stream is None:
+            h = 0
+        else:
+            h = int(cuda_stream) or 1
+        _lib.check(self.lib.aukit_cuda_set_stream(self.handle, C.c_void_p(h)))
+
+    def use_torch_stream(self):
+        """Enqueue on torch's current stream (ordering with torch ops and NCCL collectives)."""
+        import torch
+        self.set_stream(torch.cuda.current_stream().cuda_stream)
 
     def synchronize(self):
         _lib.check(self.lib.aukit_cuda_synchronize(self.handle))

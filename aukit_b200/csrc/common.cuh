@@ -69,17 +69,13 @@ static inline unsigned aukit_grid(size_t work_items, size_t per_cta, size_t cap)
 __device__ __forceinline__ float clamp_ref(float v) { return v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v); }
 __device__ __forceinline__ double clamp_ref(double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); }
 
-// 16-bit predictor -> sample, A:1255 / A:1312: p / (p < 0 and 32768 or 32767).
-// The non-negative branch is a reciprocal multiply plus one FMA residual correction; it is
-// bit-identical to (float)((double)p / 32767.0) for every p in [0, 32767] (checked
-// exhaustively on the host with exact rationals and on the device by tests/test_gpu_decode.py).
+// 16-bit predictor / sample -> float, A:1133 / A:1255 / A:1312: p / (p < 0 and 32768 or 32767).
+// Branch-free: p * 2^-15 is exact, and for p > 0 one FMA adds p / (32767 * 32768); the result is
+// bit-identical to (float)((double)p / 32767.0) for every p in [0, 32767] (checked exhaustively
+// on the host with exact rationals and on the device by tests/test_gpu_decode.py).
 __device__ __forceinline__ float s16_to_float(int p) {
     const float f = (float)p;
-    constexpr float r = 1.0f / 32767.0f;
-    const float q = __fmul_rn(f, r);
-    const float rem = __fmaf_rn(-q, 32767.0f, f);
-    const float pos = __fmaf_rn(rem, r, q);
-    return p < 0 ? __fmul_rn(f, 1.0f / 32768.0f) : pos;
+    return __fmaf_rn(fmaxf(f, 0.0f), 1.0f / (32767.0f * 32768.0f), __fmul_rn(f, 1.0f / 32768.0f));
 }
 
 // streaming 128-bit accesses: inputs are read once, outputs written once

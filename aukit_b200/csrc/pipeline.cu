@@ -145,6 +145,7 @@ static int validate(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *d_
     a->channels = p->channels;
     a->n_total = p->n_in_total;
     a->in_first = p->in_first;
+    a->in_avail = p->in_avail;
     a->ratio = p->dstRate / p->srcRate;
     a->out_first = p->out_first;
     a->n_out = p->n_out;

@@ -6,6 +6,7 @@ struct pipe_args {
     const uint8_t *in;            // interleaved frames [in_first, in_first + in_avail)
     int channels;
     unsigned long long n_total, in_first;
+    size_t in_avail;              // frames present in `in`
     double ratio;
     unsigned long long out_first;
     size_t n_out;

@@ -1,4 +1,363 @@
-// pipeline_poly.cu -- rational-ratio (polyphase) fast path of the fused pipeline.
+// pipeline_poly.cu -- rational-ratio (polyphase) fast path of the fused pipeline (K10).
+//
+// Audio:resample evaluates x = (i-1)/ratio + 1 in fp64 per output sample (A:666).  When both
+// rates are integers the positions are rational: with L = new/g, M = old/g (g = gcd), output n
+// (0-based) sits at input position n*M/L, i.e. floor F(n) = (n*M) div L and phase
+// j(n) = (n*M) mod L, periodic in n with period L.  The kernel exploits that:
+//
+//   * a CTA walks tiles of K iterations x Sp = L*m consecutive outputs; thread t owns outputs
+//     base + k*Sp + t, so its phase j_t = (t*M) mod L -- and therefore its interpolation weights --
+//     are loop invariants held in registers (computed once, in fp64, then narrowed);
+//   * phase A of a tile converts the K*m*M + 3 input frames the tile touches (its halo
+//     included) ONCE from packed bytes to float in shared memory (coalesced global loads);
+//   * phase B reads 4 (cubic) / 2 (linear) / 1 (none) taps per channel from shared memory,
+//     blends with FMAs, clamps (A:668), mixes to mono (A:686-687) and either max-reduces
+//     (peak pass) or scales by peak/max, clamps and stores coalesced float32 (apply pass).
+//
+// Bit-faithfulness of positions (SURVEY finding 5): for j != 0 the reference's floor(x) equals
+// F(n)+1 whenever |x_ref - x_true| < 1/L, and its fraction differs from j/L by at most
+// 1.5*x*2^-52, which is below 2^-24 for x < 2^28 -- the regime this path accepts (longer
+// buffers take the generic fp64 path unless the ratio is a power of two, where positions are
+// exact).  For j == 0 the reference either hits the integer exactly (sample copied UNCLAMPED,
+// A:667) or lands one ulp beside it (interpolated and clamped; `none` then selects the
+// PREVIOUS sample).  Those outputs -- one per period -- are decided exactly: one warp per tile
+// evaluates the reference's own fp64 expression for them (IEEE division) into a small shared
+// table before phase B.  That table is only needed when the decision can change the result:
+// interpolation `none`, or inputs that can exceed [-1, 1] (float, unsigned > 8 bit).
+#include "common.cuh"
 #include "pipeline.cuh"
+#include "sample_formats.cuh"
 
-int aukit_pipeline_poly_try(aukit_ctx *, const pipe_args &, const aukit_pipeline_desc *, bool) { return 0; }
+#include <math.h>
+#include <stdlib.h>
+
+using namespace aukit_fmt;
+
+namespace {
+
+struct poly_plan {
+    int L, M;                    // outputs / input frames per period (coprime)
+    int m;                       // periods per iteration
+    int Sp, Q;                   // outputs / input frames per iteration
+    int K;                       // iterations per tile
+    int nfr;                     // frames staged per tile = K*Q + 3
+    int fmt;                     // (B << 8) | (KIND << 4) | BE
+    unsigned long long tile0;    // first global tile index of this launch
+    unsigned long long ntiles;
+};
+
+enum { HIT = 0, NEAR_BELOW = 1, NEAR_ABOVE = 2 };
+
+template <int B, int KIND, bool BE>
+__device__ __forceinline__ float conv1(const uint8_t *p) {
+    if (B == 2 && KIND == K_SIGNED) {
+        const uint32_t v = load_raw_aligned<2, BE>(p);
+        return s16_to_float((int)(int16_t)v);
+    }
+    return convert<B, KIND>(load_raw_aligned<B, BE>(p), nullptr);
+}
+
+// phase A for one sample format: frames [0, nfr) of the tile -> shared floats.
+// CT == 2: float2 per frame; CT == 1: float per frame; CT == 0: planar [C][nfr].
+template <int B, int KIND, bool BE, int CT>
+__device__ __forceinline__ void stage_tile(const pipe_args &a, const poly_plan &pl, long long g0, float *sm, int plane) {
+    const int C = CT ? CT : a.channels;
+    const long long n_total = (long long)a.n_total;
+    const long long lo = (long long)a.in_first, hi = lo + (long long)a.in_avail;
+    for (int i = threadIdx.x; i < pl.nfr; i += blockDim.x) {
+        long long g = g0 + i;
+        g = g < 0 ? 0 : (g >= n_total ? n_total - 1 : g);      // nil neighbours == clamped index (A:259, A:264)
+        const bool ok = g >= lo && g < hi;                      // outside the shard: only masked outputs use it
+        const uint8_t *p = a.in + (size_t)(g - lo) * (size_t)(C * B);
+        if (CT == 2) {
+            float2 v = make_float2(0.f, 0.f);
+            if (ok) {
+                if (B == 2 && KIND == K_SIGNED && !BE) {        // one 32-bit load per stereo frame
+                    const uint32_t w = *reinterpret_cast<const uint32_t *>(p);
+                    v.x = s16_to_float((int)(int16_t)(w & 0xFFFFu));
+                    v.y = s16_to_float((int)(int16_t)(w >> 16));
+                } else {
+                    v.x = conv1<B, KIND, BE>(p);
+                    v.y = conv1<B, KIND, BE>(p + B);
+                }
+            }
+            reinterpret_cast<float2 *>(sm)[i] = v;
+        } else if (CT == 1) {
+            sm[i] = ok ? conv1<B, KIND, BE>(p) : 0.f;
+        } else {
+            for (int c = 0; c < C; c++) sm[(size_t)c * plane + i] = ok ? conv1<B, KIND, BE>(p + c * B) : 0.f;
+        }
+    }
+}
+
+template <int CT>
+__device__ __forceinline__ void stage_dispatch(const pipe_args &a, const poly_plan &pl, long long g0, float *sm, int plane) {
+    switch (pl.fmt) {
+#define AUKIT_STAGE(BB, KK, EE) case ((BB << 8) | (KK << 4) | EE): stage_tile<BB, KK, (EE != 0), CT>(a, pl, g0, sm, plane); break;
+        AUKIT_STAGE(1, K_SIGNED, 0) AUKIT_STAGE(1, K_UNSIGNED, 0)
+        AUKIT_STAGE(2, K_SIGNED, 0) AUKIT_STAGE(2, K_SIGNED, 1) AUKIT_STAGE(2, K_UNSIGNED, 0) AUKIT_STAGE(2, K_UNSIGNED, 1)
+        AUKIT_STAGE(3, K_SIGNED, 0) AUKIT_STAGE(3, K_SIGNED, 1) AUKIT_STAGE(3, K_UNSIGNED, 0) AUKIT_STAGE(3, K_UNSIGNED, 1)
+        AUKIT_STAGE(4, K_SIGNED, 0) AUKIT_STAGE(4, K_SIGNED, 1) AUKIT_STAGE(4, K_UNSIGNED, 0) AUKIT_STAGE(4, K_UNSIGNED, 1)
+        AUKIT_STAGE(4, K_FLOAT, 0) AUKIT_STAGE(4, K_FLOAT, 1)
+#undef AUKIT_STAGE
+    default: break;
+    }
+}
+
+// two s16 little-endian samples of one 32-bit word -> floats (A:1133 scaling, exact)
+__device__ __forceinline__ float2 s16x2_to_float2(uint32_t w) {
+    return make_float2(s16_to_float((int)(int16_t)(w & 0xFFFFu)), s16_to_float((int)w >> 16));
+}
+
+// CT: compile-time channel count (1, 2) or 0 = runtime.  EXACT: consult the j == 0 decision table
+// and keep the reference's NaN-transparent clamp (inputs may be non-finite / out of range).
+template <int CT, int MODE, bool MONO, bool APPLY, bool EXACT>
+__global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sm = reinterpret_cast<float *>(smem_raw);
+    const int C = CT ? CT : a.channels;
+    const int nfr_cap = pl.nfr + 16;                                    // room for the 16-byte alignment shift
+    unsigned char *hit_tab = smem_raw + (size_t)nfr_cap * C * sizeof(float);   // K*m entries
+    __shared__ float wm[32];
+
+    const int t = threadIdx.x;
+    const bool active = t < pl.Sp;
+    // loop-invariant phase of this thread: position of output (base + t) relative to the tile base
+    const long long tm = (long long)t * pl.M;
+    const int off_t = (int)(tm / pl.L), j_t = (int)(tm % pl.L);
+    const bool is_j0 = (j_t == 0);
+    float w0 = 0.f, w1 = 1.f, w2 = 0.f, w3 = 0.f, fx = 0.f;
+    {
+        const double x = (double)j_t / (double)pl.L;
+        fx = (float)x;
+        if (MODE == AUKIT_INTERP_CUBIC) {                               // Catmull-Rom weights of A:265
+            const double x2 = x * x, x3 = x2 * x;
+            w0 = (float)(-0.5 * x3 + x2 - 0.5 * x);
+            w1 = (float)(1.5 * x3 - 2.5 * x2 + 1.0);
+            w2 = (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x);
+            w3 = (float)(0.5 * x3 - 0.5 * x2);
+        }
+    }
+    float mult = 0.f;
+    if (APPLY) mult = (float)(a.peak / (double)a.d_max[0]);             // A:3444
+    const float inv_cn = a.inv_cn;                                      // s / cn (A:687) as a multiply
+    float mx = 0.f;
+    const unsigned long long out_lo = a.out_first, out_hi = a.out_first + a.n_out;
+    const unsigned long long tile_out = (unsigned long long)pl.Sp * pl.K;
+    const long long n_total = (long long)a.n_total;
+    const long long in_lo = (long long)a.in_first, in_hi = in_lo + (long long)a.in_avail;
+    const bool s16le = pl.fmt == ((2 << 8) | (K_SIGNED << 4) | 0);
+
+    auto clampv = [](float v) {
+        if (EXACT) return clamp_ref(v);                                 // NaN passes through like A:228-232
+        return fminf(fmaxf(v, -1.0f), 1.0f);                            // finite inputs: same result, 2 FMNMX
+    };
+
+    for (unsigned long long tile = pl.tile0 + blockIdx.x; tile < pl.tile0 + pl.ntiles; tile += gridDim.x) {
+        const unsigned long long base_out = tile * tile_out;
+        const long long F0 = (long long)(tile * (unsigned long long)pl.K * (unsigned long long)pl.Q);  // floor frame of base_out
+        const long long gA = F0 - 1;                                    // first frame the tile needs (p0 of output 0)
+        __syncthreads();                                                // previous tile fully consumed
+        // ---------------- phase A: packed frames -> shared floats (each frame converted once)
+        int sh = 0;                                                     // shared index of frame gA
+        bool fast = false;
+        if ((CT == 1 || CT == 2) && s16le && gA >= in_lo && gA >= 0 && ((uintptr_t)a.in & 15) == 0) {
+            // interior tile of 16-bit LE input: 128-bit streaming loads from a 16-byte aligned start
+            const size_t boff = (size_t)(gA - in_lo) * (size_t)(2 * CT);
+            const size_t a0 = boff & ~(size_t)15;
+            const int shf = (int)((boff - a0) / (size_t)(2 * CT));
+            constexpr int FPV = 16 / (2 * (CT ? CT : 1));               // frames per 16-byte vector
+            const int nvec = (pl.nfr + shf + FPV - 1) / FPV;
+            const long long last = (long long)(a0 / (size_t)(2 * CT)) + in_lo + (long long)nvec * FPV;   // one past the last frame read
+            if (last <= in_hi && last <= n_total) {
+                fast = true;
+                sh = shf;
+                const uint4 *src = reinterpret_cast<const uint4 *>(a.in + a0);
+                float4 *dst = reinterpret_cast<float4 *>(sm);
+                for (int v = t; v < nvec; v += blockDim.x) {
+                    const uint4 w = ldg_stream(src + v);
+                    const float2 f0 = s16x2_to_float2(w.x), f1 = s16x2_to_float2(w.y);
+                    const float2 f2 = s16x2_to_float2(w.z), f3 = s16x2_to_float2(w.w);
+                    dst[2 * v] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                    dst[2 * v + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+                }
+            }
+        }
+        if (!fast) stage_dispatch<CT>(a, pl, gA, sm, nfr_cap);
+        if (EXACT) {
+            // exact hit / near-hit decision for the tile's j == 0 outputs with the reference's own
+            // fp64 expression (A:666-667); entry e <-> iteration e / m, period e % m
+            for (int e = t; e < pl.K * pl.m; e += blockDim.x) {
+                const unsigned long long n = base_out + (unsigned long long)(e / pl.m) * pl.Sp + (unsigned long long)(e % pl.m) * pl.L;
+                const double xt = (double)(F0 + (long long)(e / pl.m) * pl.Q + (long long)(e % pl.m) * pl.M + 1);
+                const double x = __dadd_rn(__ddiv_rn((double)n, a.ratio), 1.0);
+                hit_tab[e] = (x == xt) ? HIT : (x < xt ? NEAR_BELOW : NEAR_ABOVE);
+            }
+        }
+        __syncthreads();
+        // ---------------- phase B: taps -> blend -> clamp -> mono -> peak / scale+store
+        if (!active) continue;
+        int k0 = 0, k1 = pl.K;
+        if (base_out < out_lo || base_out + tile_out > out_hi) {        // first / last tile of a shard: mask
+            const long long lo = (long long)out_lo - (long long)base_out - t;
+            const long long hi = (long long)out_hi - (long long)base_out - t;
+            k0 = lo <= 0 ? 0 : (int)((lo + pl.Sp - 1) / pl.Sp);
+            k1 = hi <= 0 ? 0 : (int)((hi + pl.Sp - 1) / pl.Sp);
+            if (k1 > pl.K) k1 = pl.K;
+        }
+        int s = k0 * pl.Q + off_t + sh;                                 // shared index of p0
+        float *outp = nullptr;
+        if (APPLY) outp = a.out + (size_t)((long long)base_out - (long long)out_lo + (long long)k0 * pl.Sp + t);
+#pragma unroll 4
+        for (int k = k0; k < k1; k++, s += pl.Q) {
+            int st = NEAR_ABOVE;
+            if (EXACT && is_j0) st = hit_tab[k * pl.m + t / pl.L];
+            // one channel: blend -> clamp (A:668) / exact-hit copy (A:667)
+            auto value = [&](float p0, float p1, float p2, float p3) {
+                float v;
+                if (MODE == AUKIT_INTERP_CUBIC) v = __fmaf_rn(w3, p3, __fmaf_rn(w2, p2, __fmaf_rn(w1, p1, w0 * p0)));
+                else if (MODE == AUKIT_INTERP_LINEAR) v = __fmaf_rn(p2 - p1, fx, p1);
+                else v = p1;
+                if (EXACT && is_j0) {
+                    // weights at j == 0 are (0, 1, 0, 0): the value is p1 itself
+                    if (st == HIT) return p1;                                              // copied unclamped
+                    if (MODE == AUKIT_INTERP_NONE && st == NEAR_BELOW) return clampv(p0);  // floor(x) is one lower
+                    return clampv(p1);
+                }
+                return clampv(v);
+            };
+            float acc = 0.f;
+            if (CT == 2) {
+                const float2 *f = reinterpret_cast<const float2 *>(sm) + s;
+                const float2 z = make_float2(0.f, 0.f);
+                const float2 f1 = f[1];
+                const float2 f0 = (MODE == AUKIT_INTERP_CUBIC || EXACT) ? f[0] : z;
+                const float2 f2 = (MODE != AUKIT_INTERP_NONE) ? f[2] : z;
+                const float2 f3 = (MODE == AUKIT_INTERP_CUBIC) ? f[3] : z;
+                const float vl = value(f0.x, f1.x, f2.x, f3.x), vr = value(f0.y, f1.y, f2.y, f3.y);
+                if (MONO) acc = vl + vr;                                // (0 + L) + R, A:686
+                else if (APPLY) { outp[0] = clampv(vl * mult); outp[a.out_stride] = clampv(vr * mult); }
+                else mx = fmaxf(mx, fmaxf(fabsf(vl), fabsf(vr)));
+            } else {
+                for (int c = 0; c < C; c++) {
+                    const float *f = sm + (CT == 1 ? 0 : (size_t)c * nfr_cap) + s;
+                    const float p1 = f[1];
+                    const float p0 = (MODE == AUKIT_INTERP_CUBIC || EXACT) ? f[0] : 0.f;
+                    const float p2 = (MODE != AUKIT_INTERP_NONE) ? f[2] : 0.f;
+                    const float p3 = (MODE == AUKIT_INTERP_CUBIC) ? f[3] : 0.f;
+                    const float v = value(p0, p1, p2, p3);
+                    if (MONO) acc += v;
+                    else if (APPLY) outp[(size_t)c * a.out_stride] = clampv(v * mult);
+                    else mx = fmaxf(mx, fabsf(v));
+                }
+            }
+            if (MONO) {
+                const float mv = acc * inv_cn;                          // s / cn, A:687
+                if (APPLY) outp[0] = clampv(mv * mult);                 // A:3455
+                else mx = fmaxf(mx, fabsf(mv));
+            }
+            if (APPLY) outp += pl.Sp;
+        }
+    }
+    if (!APPLY) {
+        mx = warp_max(mx);
+        if ((t & 31) == 0) wm[t >> 5] = mx;
+        __syncthreads();
+        if (t < 32) {
+            mx = t < ((blockDim.x + 31) >> 5) ? wm[t] : 0.0f;
+            mx = warp_max(mx);
+            if (t == 0) atomic_max_nonneg(a.d_max, mx);
+        }
+    }
+}
+
+long long gcd_ll(long long x, long long y) { while (y) { long long r = x % y; x = y; y = r; } return x; }
+
+template <int CT, int MODE, bool MONO, bool APPLY>
+int launch_exact(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, bool exact, int threads, size_t smem) {
+    auto go = [&](auto kern) -> int {
+        if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
+        int occ = 0;
+        if (aukit_cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem), "occupancy")) return -1;
+        if (occ < 1) return aukit_fail("aukit_cuda: polyphase kernel does not fit on an SM");
+        unsigned long long g = (unsigned long long)ctx->num_sms * occ;
+        if (g > pl.ntiles) g = pl.ntiles;
+        kern<<<(unsigned)g, threads, smem, ctx->stream>>>(a, pl);
+        ctx->launches++;
+        return aukit_cuda_check(cudaGetLastError(), "poly_kernel launch");
+    };
+    return exact ? go(poly_kernel<CT, MODE, MONO, APPLY, true>) : go(poly_kernel<CT, MODE, MONO, APPLY, false>);
+}
+
+template <int CT, int MODE>
+int launch_flags(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, bool exact, bool apply, int threads, size_t smem) {
+    if (a.mono) return apply ? launch_exact<CT, MODE, true, true>(ctx, a, pl, exact, threads, smem)
+                             : launch_exact<CT, MODE, true, false>(ctx, a, pl, exact, threads, smem);
+    return apply ? launch_exact<CT, MODE, false, true>(ctx, a, pl, exact, threads, smem)
+                 : launch_exact<CT, MODE, false, false>(ctx, a, pl, exact, threads, smem);
+}
+
+template <int CT>
+int launch_interp(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, int interp, bool exact, bool apply, int threads, size_t smem) {
+    switch (interp) {
+    case AUKIT_INTERP_NONE: return launch_flags<CT, AUKIT_INTERP_NONE>(ctx, a, pl, exact, apply, threads, smem);
+    case AUKIT_INTERP_LINEAR: return launch_flags<CT, AUKIT_INTERP_LINEAR>(ctx, a, pl, exact, apply, threads, smem);
+    default: return launch_flags<CT, AUKIT_INTERP_CUBIC>(ctx, a, pl, exact, apply, threads, smem);
+    }
+}
+
+}  // namespace
+
+int aukit_pipeline_poly_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p, bool apply) {
+    // AUKIT_DISABLE_POLY=1 forces the generic fp64-position kernels (used by the tests to cross-check)
+    static const bool disabled = getenv("AUKIT_DISABLE_POLY") && getenv("AUKIT_DISABLE_POLY")[0] == '1';
+    if (disabled) return 0;
+    // integer rates only
+    const double sr = p->srcRate, dr = p->dstRate;
+    if (!(sr >= 1 && dr >= 1 && sr < 2147483648.0 && dr < 2147483648.0) || sr != floor(sr) || dr != floor(dr)) return 0;
+    const long long g = gcd_ll((long long)sr, (long long)dr);
+    const long long L = (long long)dr / g, M = (long long)sr / g;
+    if (L > 512 || M > (1 << 20)) return 0;
+    // position regime: rational positions are within 2^-24 of the reference's below 2^28 frames;
+    // power-of-two ratios are exact at any length
+    int e2 = 0;
+    const bool pow2_ratio = frexp(a.ratio, &e2) == 0.5;
+    const double last_pos = (double)(a.out_first + a.n_out) * (double)M / (double)L;
+    if (!pow2_ratio && last_pos >= 268435456.0) return 0;
+    const int B = p->bitDepth / 8;
+    if ((B == 2 || B == 4) && ((uintptr_t)a.in % B)) return 0;
+    const int kind = p->dataType == AUKIT_FLOAT ? K_FLOAT : (p->dataType == AUKIT_UNSIGNED ? K_UNSIGNED : K_SIGNED);
+    const int be = (p->bigEndian && B > 1) ? 1 : 0;
+
+    poly_plan pl{};
+    pl.L = (int)L; pl.M = (int)M;
+    pl.m = (int)(L >= 512 ? 1 : 512 / L);
+    if ((long long)pl.m * M > 4096) pl.m = (int)(4096 / M) > 0 ? (int)(4096 / M) : 1;
+    pl.Sp = pl.L * pl.m;
+    pl.Q = pl.M * pl.m;
+    const int threads = (pl.Sp + 31) / 32 * 32;
+    if (threads > 512) return 0;
+    const int C = p->channels;
+    const size_t frame_bytes = sizeof(float) * (size_t)C;
+    const size_t budget = 40 * 1024;
+    long long K = ((long long)(budget / frame_bytes) - 3) / pl.Q;
+    if (K < 1) K = 1;
+    if (K > 64) K = 64;
+    pl.K = (int)K;
+    pl.nfr = pl.K * pl.Q + 3;
+    pl.fmt = (B << 8) | (kind << 4) | be;
+    size_t smem = (size_t)(pl.nfr + 16) * frame_bytes + (size_t)pl.K * pl.m + 16;
+    smem = (smem + 15) / 16 * 16;
+    if (smem > 200 * 1024) return 0;
+    const unsigned long long tile_out = (unsigned long long)pl.Sp * pl.K;
+    pl.tile0 = a.out_first / tile_out;
+    pl.ntiles = (a.out_first + a.n_out - 1) / tile_out - pl.tile0 + 1;
+    // exact j == 0 decisions matter when the hit/near-hit difference is visible
+    const bool unbounded = kind == K_FLOAT || (kind == K_UNSIGNED && B > 1);
+    const bool exact = unbounded || p->interpolation == AUKIT_INTERP_NONE;
+    int rc;
+    if (C == 1) rc = launch_interp<1>(ctx, a, pl, p->interpolation, exact, apply, threads, smem);
+    else if (C == 2) rc = launch_interp<2>(ctx, a, pl, p->interpolation, exact, apply, threads, smem);
+    else rc = launch_interp<0>(ctx, a, pl, p->interpolation, exact, apply, threads, smem);
+    return rc ? -1 : 1;
+}

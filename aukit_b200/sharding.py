@@ -89,7 +89,7 @@ class ShardedPreload:
         self.stride = (shard.n_out + 31) // 32 * 32
         self.d_max = torch.zeros(1, dtype=torch.float32, device="cuda")
         self.d_out = torch.empty((self.out_channels, self.stride), dtype=torch.float32, device="cuda")
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.use_torch_stream()
 
     @property
     def in_bytes(self) -> int:

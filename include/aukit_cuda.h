@@ -50,7 +50,8 @@ const char *aukit_cuda_last_error(void);
 /* device < 0 => current device.  Fails (no fallback) when no CUDA device is usable. */
 int aukit_cuda_init(int device, aukit_ctx **ctx);
 void aukit_cuda_shutdown(aukit_ctx *ctx);
-/* Use an external cudaStream_t (e.g. torch's current stream); NULL => the ctx's own. */
+/* Use an external cudaStream_t (e.g. torch's current stream); NULL => the ctx's own.  The legacy
+ * default stream is cudaStreamLegacy ((void *)1), not NULL. */
 int aukit_cuda_set_stream(aukit_ctx *ctx, void *cuda_stream);
 void *aukit_cuda_get_stream(aukit_ctx *ctx);
 /* Waits for the stream and reports deferred device-side decode errors (bad IMA step index,

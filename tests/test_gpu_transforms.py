@@ -188,6 +188,7 @@ def test_time_sharded_fused_pipeline_matches_single_pass(ak, O):
     pcm = np.random.default_rng(5).integers(-20000, 20000, (n, 2)).astype(np.int16)
     whole = ak.preload(pcm.tobytes(), 16, "signed", 2, 44100, 48000, "cubic", True, 0.8)
     n_out = whole.shape[1]
+    ctx.use_torch_stream()
     dmax = torch.zeros(1, device="cuda")
     descs, ins = [], []
     for r in range(3):
@@ -207,6 +208,7 @@ def test_time_sharded_fused_pipeline_matches_single_pass(ak, O):
         ak._lib.check(lib.aukit_cuda_dev_pipeline_apply(ctx.handle, C.byref(d), t.data_ptr(), 0.8, dmax.data_ptr(), o.data_ptr(), d.n_out))
         ctx.synchronize()
         outs.append(o.cpu().numpy())
+    ctx.set_stream(None)
     assert f32_equal_bits(np.concatenate(outs)[None, :], whole)
 
 
@@ -216,3 +218,38 @@ def test_concat_joins_blocks(ak):
     c = a.concat(b)
     assert (c.numpy() * 8).tolist() == [[1, 2, 3, 7, 8], [4, 5, 6, 0, 0]]       # missing channel -> silence (A:713)
     assert a.len() == 3 / 8000 and c.channels() == 2
+
+
+@pytest.mark.parametrize("src", [44100, 22050, 96000, 48000, 32000, 8000, 88200])
+@pytest.mark.parametrize("interp", ["none", "linear", "cubic"])
+def test_fused_polyphase_rates_and_exact_hits(ak, O, src, interp):
+    """The rational-ratio fast path against the oracle, with float input that exceeds [-1, 1] so the
+    exact-hit (copied unclamped, A:667) vs near-hit (clamped, A:668; `none` picks the previous
+    sample) decisions are visible in the output."""
+    rng = np.random.default_rng(src)
+    n = 40013
+    x = (rng.standard_normal((n, 2)) * 0.9).astype("<f4")
+    got = ak.preload(x.tobytes(), 32, "float", 2, src, 48000, interp, False, 1.0)
+    r = O.resample(O.pcm(x, 32, "float", 2), src, 48000, interp)
+    ref = O.normalize(r, 1.0)
+    assert got.shape == ref.shape
+    if interp == "none":
+        # same selected samples, same clamp decisions: only the final scale is rounded in f32
+        assert np.max(np.abs(got - ref)) <= 2.0 ** -22
+    else:
+        assert np.max(np.abs(got - ref)) <= TOL * 4      # |values| reach ~4: tolerance scales with magnitude
+    s16 = rng.integers(-32768, 32768, (n, 2)).astype("<i2")
+    got = ak.preload(s16.tobytes(), 16, "signed", 2, src, 48000, interp, True, 0.8)[0]
+    ref = O.chain_s16(s16.tobytes(), 2, src, 48000, interp, 0.8)
+    assert got.shape == ref.shape and np.max(np.abs(got - ref)) <= TOL
+
+
+def test_fused_polyphase_mono_input_and_8ch(ak, O):
+    rng = np.random.default_rng(77)
+    for ch, src in ((1, 44100), (8, 96000), (8, 44100), (4, 22050)):
+        x = rng.integers(-32768, 32768, (30011, ch)).astype("<i2")
+        for mono in (True, False):
+            got = ak.preload(x.tobytes(), 16, "signed", ch, src, 48000, "cubic", mono, 0.9)
+            r = O.resample(O.pcm(x, 16, "signed", ch), src, 48000, "cubic")
+            ref = O.normalize(O.mono(r) if mono else r, 0.9)
+            assert got.shape == ref.shape and np.max(np.abs(got - ref)) <= TOL
