@@ -44,7 +44,14 @@ struct poly_plan {
     int fmt;                     // (B << 8) | (KIND << 4) | BE
     unsigned long long tile0;    // first global tile index of this launch
     unsigned long long ntiles;
+    double y;                    // RN(1 / ratio), for the 3-operation exact quotient (PX_BIG)
+    int quotient_fma_ok;         // host-proved: fma(rem, y, q0) == RN(n / ratio) for every n in range
 };
+
+// how output positions are obtained
+enum { PX_RATIONAL = 0,   // n*M/L; hit / near-hit indistinguishable in the result (bounded input, interpolating)
+       PX_TABLE = 1,      // n*M/L plus an exact fp64 decision table for the one j == 0 output per period
+       PX_BIG = 2 };      // positions >= 2^28: every output evaluates the reference's fp64 x exactly
 
 enum { HIT = 0, NEAR_BELOW = 1, NEAR_ABOVE = 2 };
 
@@ -109,9 +116,9 @@ __device__ __forceinline__ float2 s16x2_to_float2(uint32_t w) {
     return make_float2(s16_to_float((int)(int16_t)(w & 0xFFFFu)), s16_to_float((int)w >> 16));
 }
 
-// CT: compile-time channel count (1, 2) or 0 = runtime.  EXACT: consult the j == 0 decision table
-// and keep the reference's NaN-transparent clamp (inputs may be non-finite / out of range).
-template <int CT, int MODE, bool MONO, bool APPLY, bool EXACT>
+// CT: compile-time channel count (1, 2) or 0 = runtime.  PX: position mode (above); PX != 0 also
+// keeps the reference's NaN-transparent clamp (inputs may be non-finite / out of range).
+template <int CT, int MODE, bool MONO, bool APPLY, int PX>
 __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sm = reinterpret_cast<float *>(smem_raw);
@@ -127,8 +134,10 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
     const int off_t = (int)(tm / pl.L), j_t = (int)(tm % pl.L);
     const bool is_j0 = (j_t == 0);
     float w0 = 0.f, w1 = 1.f, w2 = 0.f, w3 = 0.f, fx = 0.f;
+    float wd0 = 0.f, wd1 = 0.f, wd2 = 0.f, wd3 = 0.f;                   // d(weight)/d(fx), PX_BIG only
+    const double jL = (double)j_t / (double)pl.L;                       // rational fraction of this thread
     {
-        const double x = (double)j_t / (double)pl.L;
+        const double x = jL;
         fx = (float)x;
         if (MODE == AUKIT_INTERP_CUBIC) {                               // Catmull-Rom weights of A:265
             const double x2 = x * x, x3 = x2 * x;
@@ -136,6 +145,12 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
             w1 = (float)(1.5 * x3 - 2.5 * x2 + 1.0);
             w2 = (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x);
             w3 = (float)(0.5 * x3 - 0.5 * x2);
+            if (PX == PX_BIG) {
+                wd0 = (float)(-1.5 * x2 + 2.0 * x - 0.5);
+                wd1 = (float)(4.5 * x2 - 5.0 * x);
+                wd2 = (float)(-4.5 * x2 + 4.0 * x + 0.5);
+                wd3 = (float)(1.5 * x2 - x);
+            }
         }
     }
     float mult = 0.f;
@@ -149,7 +164,7 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
     const bool s16le = pl.fmt == ((2 << 8) | (K_SIGNED << 4) | 0);
 
     auto clampv = [](float v) {
-        if (EXACT) return clamp_ref(v);                                 // NaN passes through like A:228-232
+        if (PX != PX_RATIONAL) return clamp_ref(v);                     // NaN passes through like A:228-232
         return fminf(fmaxf(v, -1.0f), 1.0f);                            // finite inputs: same result, 2 FMNMX
     };
 
@@ -184,7 +199,7 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
             }
         }
         if (!fast) stage_dispatch<CT>(a, pl, gA, sm, nfr_cap);
-        if (EXACT) {
+        if (PX == PX_TABLE) {
             // exact hit / near-hit decision for the tile's j == 0 outputs with the reference's own
             // fp64 expression (A:666-667); entry e <-> iteration e / m, period e % m
             for (int e = t; e < pl.K * pl.m; e += blockDim.x) {
@@ -206,23 +221,55 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
             if (k1 > pl.K) k1 = pl.K;
         }
         int s = k0 * pl.Q + off_t + sh;                                 // shared index of p0
+        // PX_BIG: exact reference position of every output.  nd = global output index, xr = the
+        // integer part of the rational position (1-based) it should be near; both advance by exact steps.
+        double nd = 0.0, xr = 0.0;
+        if (PX == PX_BIG) {
+            nd = (double)(base_out + (unsigned long long)k0 * pl.Sp + t);
+            xr = (double)(F0 + (long long)k0 * pl.Q + off_t + 1);     // integer part only: exact in fp64
+        }
         float *outp = nullptr;
         if (APPLY) outp = a.out + (size_t)((long long)base_out - (long long)out_lo + (long long)k0 * pl.Sp + t);
 #pragma unroll 4
         for (int k = k0; k < k1; k++, s += pl.Q) {
             int st = NEAR_ABOVE;
-            if (EXACT && is_j0) st = hit_tab[k * pl.m + t / pl.L];
+            if (PX == PX_TABLE && is_j0) st = hit_tab[k * pl.m + t / pl.L];
+            float cw0 = w0, cw1 = w1, cw2 = w2, cw3 = w3, cfx = fx;
+            if (PX == PX_BIG) {
+                // x = (i - 1) / ratio + 1 exactly as A:666: correctly rounded quotient, then + 1
+                double q;
+                if (pl.quotient_fma_ok) {
+                    const double q0 = __dmul_rn(nd, pl.y);
+                    const double rem = __fma_rn(-q0, a.ratio, nd);
+                    q = __fma_rn(rem, pl.y, q0);
+                } else {
+                    q = __ddiv_rn(nd, a.ratio);
+                }
+                const double dev = (__dadd_rn(q, 1.0) - xr) - jL;       // reference - rational position; first difference is exact
+                const float dl = (float)dev;                            // |dev| <= ~x * 2^-51
+                if (is_j0) st = dev == 0.0 ? HIT : (dev < 0.0 ? NEAR_BELOW : NEAR_ABOVE);
+                if (MODE == AUKIT_INTERP_CUBIC) {                       // first-order update of the weights
+                    cw0 = __fmaf_rn(wd0, dl, w0); cw1 = __fmaf_rn(wd1, dl, w1);
+                    cw2 = __fmaf_rn(wd2, dl, w2); cw3 = __fmaf_rn(wd3, dl, w3);
+                } else {
+                    cfx = fx + dl;
+                }
+                nd += (double)pl.Sp;
+                xr += (double)pl.Q;
+            }
             // one channel: blend -> clamp (A:668) / exact-hit copy (A:667)
             auto value = [&](float p0, float p1, float p2, float p3) {
                 float v;
-                if (MODE == AUKIT_INTERP_CUBIC) v = __fmaf_rn(w3, p3, __fmaf_rn(w2, p2, __fmaf_rn(w1, p1, w0 * p0)));
-                else if (MODE == AUKIT_INTERP_LINEAR) v = __fmaf_rn(p2 - p1, fx, p1);
+                if (MODE == AUKIT_INTERP_CUBIC) v = __fmaf_rn(cw3, p3, __fmaf_rn(cw2, p2, __fmaf_rn(cw1, p1, cw0 * p0)));
+                else if (MODE == AUKIT_INTERP_LINEAR) v = __fmaf_rn(p2 - p1, cfx, p1);
                 else v = p1;
-                if (EXACT && is_j0) {
-                    // weights at j == 0 are (0, 1, 0, 0): the value is p1 itself
-                    if (st == HIT) return p1;                                              // copied unclamped
+                // PX_BIG, j == 0, x just BELOW the integer: the reference interpolates on the previous
+                // segment [p0, p1] at fx = 1 + dev.  Linear has a slope break at the knot (cubic is C1).
+                if (PX == PX_BIG && MODE == AUKIT_INTERP_LINEAR && is_j0 && st == NEAR_BELOW) v = __fmaf_rn(p1 - p0, cfx, p1);
+                if (PX != PX_RATIONAL && is_j0) {
+                    if (st == HIT) return p1;                                              // copied unclamped, A:667
                     if (MODE == AUKIT_INTERP_NONE && st == NEAR_BELOW) return clampv(p0);  // floor(x) is one lower
-                    return clampv(p1);
+                    if (PX == PX_TABLE) return clampv(p1);          // weights at j == 0 are (0, 1, 0, 0)
                 }
                 return clampv(v);
             };
@@ -231,7 +278,7 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
                 const float2 *f = reinterpret_cast<const float2 *>(sm) + s;
                 const float2 z = make_float2(0.f, 0.f);
                 const float2 f1 = f[1];
-                const float2 f0 = (MODE == AUKIT_INTERP_CUBIC || EXACT) ? f[0] : z;
+                const float2 f0 = (MODE == AUKIT_INTERP_CUBIC || PX != PX_RATIONAL) ? f[0] : z;
                 const float2 f2 = (MODE != AUKIT_INTERP_NONE) ? f[2] : z;
                 const float2 f3 = (MODE == AUKIT_INTERP_CUBIC) ? f[3] : z;
                 const float vl = value(f0.x, f1.x, f2.x, f3.x), vr = value(f0.y, f1.y, f2.y, f3.y);
@@ -242,7 +289,7 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
                 for (int c = 0; c < C; c++) {
                     const float *f = sm + (CT == 1 ? 0 : (size_t)c * nfr_cap) + s;
                     const float p1 = f[1];
-                    const float p0 = (MODE == AUKIT_INTERP_CUBIC || EXACT) ? f[0] : 0.f;
+                    const float p0 = (MODE == AUKIT_INTERP_CUBIC || PX != PX_RATIONAL) ? f[0] : 0.f;
                     const float p2 = (MODE != AUKIT_INTERP_NONE) ? f[2] : 0.f;
                     const float p3 = (MODE == AUKIT_INTERP_CUBIC) ? f[3] : 0.f;
                     const float v = value(p0, p1, p2, p3);
@@ -271,10 +318,45 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
     }
 }
 
+// Is q1 = fma(fma(-q0, r, n), y, q0) with q0 = RN(n * y), y = RN(1 / r) the correctly rounded n / r for
+// EVERY integer n with n / r < 2^max_k?  The value v = q0 + rem * y differs from n / r by at most
+// 1.5 * 2^(k-105) in binade k, so RN(v) can differ from RN(n / r) only if n / r lies that close to a
+// rounding midpoint mu = U * 2^(k-53) (U odd).  With r = R * 2^g (R odd) and s = 53 - g - k that means
+// |n * 2^s - R * U| < 3, i.e. R * U = n * 2^s -+ 1 (the left side is odd, the right side's first term
+// even).  For s >= 54 there is exactly one residue U mod 2^s that satisfies it, and it is a midpoint
+// only if it falls in [2^53, 2^54).  If no binade has such a U the three-operation quotient is exact
+// everywhere in range; otherwise (or when s < 54) the kernel uses the IEEE division instead.
+bool quotient_fma_is_exact(double r, int max_k) {
+    typedef unsigned __int128 u128;
+    if (!(r > 0) || !isfinite(r)) return false;
+    int e = 0;
+    const double fr = frexp(r, &e);                       // r = fr * 2^e, fr in [0.5, 1)
+    unsigned long long R = (unsigned long long)ldexp(fr, 53);
+    int g = e - 53;
+    while ((R & 1) == 0) { R >>= 1; g++; }
+    // inverse of R modulo 2^128 (Newton), R odd
+    u128 inv = R;
+    for (int i = 0; i < 8; i++) inv *= (u128)2 - (u128)R * inv;
+    int kmin = 0;
+    frexp(1.0 / r, &kmin);                                // smallest non-zero quotient is 1 / r
+    for (int k = kmin - 2; k <= max_k; k++) {
+        const int s = 53 - g - k;
+        if (s < 54) return false;                         // several candidates per binade: do not claim exactness
+        if (s > 127) return false;                        // residue not decidable in 128 bits
+        const u128 mask = (((u128)1) << s) - 1;
+        for (int sign = 0; sign < 2; sign++) {
+            // R * U == -+1 (mod 2^s)  =>  U == -+inv (mod 2^s)
+            u128 U = sign ? (inv & mask) : ((~inv + 1) & mask);
+            if (U >= (((u128)1) << 53) && U < (((u128)1) << 54)) return false;
+        }
+    }
+    return true;
+}
+
 long long gcd_ll(long long x, long long y) { while (y) { long long r = x % y; x = y; y = r; } return x; }
 
 template <int CT, int MODE, bool MONO, bool APPLY>
-int launch_exact(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, bool exact, int threads, size_t smem) {
+int launch_exact(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, int px, int threads, size_t smem) {
     auto go = [&](auto kern) -> int {
         if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
         int occ = 0;
@@ -286,11 +368,12 @@ int launch_exact(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, bool e
         ctx->launches++;
         return aukit_cuda_check(cudaGetLastError(), "poly_kernel launch");
     };
-    return exact ? go(poly_kernel<CT, MODE, MONO, APPLY, true>) : go(poly_kernel<CT, MODE, MONO, APPLY, false>);
+    if (px == PX_BIG) return go(poly_kernel<CT, MODE, MONO, APPLY, PX_BIG>);
+    return px == PX_TABLE ? go(poly_kernel<CT, MODE, MONO, APPLY, PX_TABLE>) : go(poly_kernel<CT, MODE, MONO, APPLY, PX_RATIONAL>);
 }
 
 template <int CT, int MODE>
-int launch_flags(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, bool exact, bool apply, int threads, size_t smem) {
+int launch_flags(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, int exact, bool apply, int threads, size_t smem) {
     if (a.mono) return apply ? launch_exact<CT, MODE, true, true>(ctx, a, pl, exact, threads, smem)
                              : launch_exact<CT, MODE, true, false>(ctx, a, pl, exact, threads, smem);
     return apply ? launch_exact<CT, MODE, false, true>(ctx, a, pl, exact, threads, smem)
@@ -298,7 +381,7 @@ int launch_flags(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, bool e
 }
 
 template <int CT>
-int launch_interp(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, int interp, bool exact, bool apply, int threads, size_t smem) {
+int launch_interp(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, int interp, int exact, bool apply, int threads, size_t smem) {
     switch (interp) {
     case AUKIT_INTERP_NONE: return launch_flags<CT, AUKIT_INTERP_NONE>(ctx, a, pl, exact, apply, threads, smem);
     case AUKIT_INTERP_LINEAR: return launch_flags<CT, AUKIT_INTERP_LINEAR>(ctx, a, pl, exact, apply, threads, smem);
@@ -323,7 +406,8 @@ int aukit_pipeline_poly_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipe
     int e2 = 0;
     const bool pow2_ratio = frexp(a.ratio, &e2) == 0.5;
     const double last_pos = (double)(a.out_first + a.n_out) * (double)M / (double)L;
-    if (!pow2_ratio && last_pos >= 268435456.0) return 0;
+    const bool big = !pow2_ratio && last_pos >= 268435456.0;
+    if (big && last_pos >= 1099511627776.0) return 0;                   // 2^40: beyond the proved range
     const int B = p->bitDepth / 8;
     if ((B == 2 || B == 4) && ((uintptr_t)a.in % B)) return 0;
     const int kind = p->dataType == AUKIT_FLOAT ? K_FLOAT : (p->dataType == AUKIT_UNSIGNED ? K_UNSIGNED : K_SIGNED);
@@ -354,7 +438,12 @@ int aukit_pipeline_poly_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipe
     pl.ntiles = (a.out_first + a.n_out - 1) / tile_out - pl.tile0 + 1;
     // exact j == 0 decisions matter when the hit/near-hit difference is visible
     const bool unbounded = kind == K_FLOAT || (kind == K_UNSIGNED && B > 1);
-    const bool exact = unbounded || p->interpolation == AUKIT_INTERP_NONE;
+    int exact = (unbounded || p->interpolation == AUKIT_INTERP_NONE) ? PX_TABLE : PX_RATIONAL;
+    if (big) {
+        exact = PX_BIG;
+        pl.y = 1.0 / a.ratio;
+        pl.quotient_fma_ok = quotient_fma_is_exact(a.ratio, 41) ? 1 : 0;
+    }
     int rc;
     if (C == 1) rc = launch_interp<1>(ctx, a, pl, p->interpolation, exact, apply, threads, smem);
     else if (C == 2) rc = launch_interp<2>(ctx, a, pl, p->interpolation, exact, apply, threads, smem);

@@ -253,3 +253,49 @@ def test_fused_polyphase_mono_input_and_8ch(ak, O):
             r = O.resample(O.pcm(x, 16, "signed", ch), src, 48000, "cubic")
             ref = O.normalize(O.mono(r) if mono else r, 0.9)
             assert got.shape == ref.shape and np.max(np.abs(got - ref)) <= TOL
+
+
+@pytest.mark.parametrize("src,dst", [(44100, 48000), (96000, 44100), (32000, 48000)])
+@pytest.mark.parametrize("interp", ["none", "linear", "cubic"])
+def test_huge_global_positions(ak, src, dst, interp):
+    """Shards near the END of a buffer of several 10^9 frames: positions are >= 2^28, where the
+    reference's fp64 rounding of x shows up in the interpolated value (x's ulp is ~2^-21).  Covers
+    the fused path's exact-position mode and the standalone resample kernel."""
+    import torch
+    from util import ref_resample_window
+    lib = ak._lib.load()
+    ctx = ak.context()
+    ctx.use_torch_stream()
+    n_total = 6_000_000_011
+    mode = {"none": 0, "linear": 1, "cubic": 2}[interp]
+    total_out = int(lib.aukit_resample_out_len(n_total, float(src), float(dst)))
+    rng = np.random.default_rng(src + mode)
+    for o0 in (total_out - 150_000, int(total_out * 0.37)):
+        cnt = 150_000 if o0 + 150_000 <= total_out else total_out - o0
+        f, c = C.c_uint64(), C.c_uint64()
+        assert lib.aukit_resample_window(n_total, float(src), float(dst), mode, o0, cnt, C.byref(f), C.byref(c)) == 0
+        pcm = rng.integers(-32768, 32768, (int(c.value), 2)).astype(np.int16)
+        dec = np.where(pcm < 0, pcm / 32768.0, pcm / 32767.0).T                    # A:1133
+        ref = ref_resample_window(dec, int(f.value), n_total, src, dst, o0, cnt, interp)
+        # fused pipeline (mono, normalize 0.8)
+        mono = (ref[0] + ref[1]) / 2
+        want = np.clip(mono * (0.8 / np.max(np.abs(mono))), -1, 1)
+        t = torch.from_numpy(pcm).cuda()
+        dmax = torch.zeros(1, device="cuda")
+        out = torch.empty(cnt, device="cuda")
+        d = ak.PipelineDesc(16, 0, 2, 0, float(src), float(dst), mode, 1, n_total, f.value, c.value, o0, cnt)
+        ak._lib.check(lib.aukit_cuda_dev_pipeline_peak(ctx.handle, C.byref(d), t.data_ptr(), dmax.data_ptr()))
+        ak._lib.check(lib.aukit_cuda_dev_pipeline_apply(ctx.handle, C.byref(d), t.data_ptr(), 0.8, dmax.data_ptr(), out.data_ptr(), cnt))
+        got = out.cpu().numpy()
+        assert np.max(np.abs(got - want)) <= TOL, (o0, float(np.max(np.abs(got - want))))
+        # standalone resample kernel on the decoded floats
+        fin = torch.from_numpy(dec.astype(np.float32)).cuda().contiguous()
+        fout = torch.empty((2, cnt), device="cuda")
+        ak._lib.check(lib.aukit_cuda_dev_resample(ctx.handle, fin.data_ptr(), fin.shape[1], 2, n_total, f.value, c.value,
+                                                  float(src), float(dst), mode, o0, cnt, fout.data_ptr(), cnt))
+        got2 = fout.cpu().numpy()
+        if interp == "none":
+            assert f32_equal_bits(got2, ref.astype(np.float32))
+        else:
+            assert np.max(np.abs(got2 - ref)) <= TOL
+    ctx.set_stream(None)

@@ -124,3 +124,17 @@ def test_argument_validation_strings(ak):
         ak.pcm(b"\0\0", "16")
     with pytest.raises(ak.AukitError, match=r"bad argument #1 \(expected Audio"):
         ak.effects.amplify("nope", 2)
+
+
+def test_numpy_window_reference(O):
+    """The numpy restatement used for sharded / huge-index GPU tests agrees with the C oracle."""
+    from util import ref_resample_window
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1.2, 1.2, (2, 5003))
+    for src, dst in ((44100, 48000), (96000, 44100), (8000, 48000), (48000, 48000)):
+        for interp in ("none", "linear", "cubic"):
+            ref = O.resample(x, src, dst, interp)
+            got = ref_resample_window(x, 0, x.shape[1], src, dst, 0, ref.shape[1], interp)
+            assert np.max(np.abs(got - ref)) <= 1e-15       # pow(fx, 3) vs fx**3: last-ulp differences only
+            if interp == "none":
+                assert np.array_equal(got, ref)

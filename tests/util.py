@@ -59,3 +59,32 @@ def f32_equal_bits(a, b):
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)
     return a.shape == b.shape and bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
+def ref_resample_window(window, in_first, n_total, src, dst, out_first, n_out, interp):
+    """numpy float64 restatement of Audio:resample (A:653-673) for global output frames
+    [out_first, out_first + n_out) when only input frames [in_first, in_first + window.shape[1])
+    are held.  Pinned to the C oracle by tests/test_host_logic.py::test_numpy_window_reference."""
+    w = np.asarray(window, dtype=np.float64)
+    ratio = np.float64(dst) / np.float64(src)                      # A:658
+    i0 = np.arange(out_first, out_first + n_out, dtype=np.float64)  # i - 1
+    x = i0 / ratio + 1.0                                           # A:666
+    fl = np.floor(x)
+    hit = x == fl
+    fx = x - fl
+    f = fl.astype(np.int64)                                        # 1-based index of p1
+
+    def tap(k):                                                    # data[f + k] with nil -> clamped index
+        idx = np.clip(f + k, 1, n_total) - 1 - in_first
+        return w[:, idx]
+
+    p1 = tap(0)
+    if interp == "none":
+        v = p1
+    elif interp == "linear":
+        v = p1 + (tap(1) - p1) * fx
+    else:
+        p0, p2, p3 = tap(-1), tap(1), tap(2)
+        v = (-0.5 * p0 + 1.5 * p1 - 1.5 * p2 + 0.5 * p3) * fx ** 3 + (p0 - 2.5 * p1 + 2 * p2 - 0.5 * p3) * fx ** 2 \
+            + (-0.5 * p0 + 0.5 * p2) * fx + p1
+    return np.where(hit, p1, np.clip(v, -1, 1))
