@@ -46,12 +46,15 @@ struct poly_plan {
     unsigned long long ntiles;
     double y;                    // RN(1 / ratio), for the 3-operation exact quotient (PX_BIG)
     int quotient_fma_ok;         // host-proved: fma(rem, y, q0) == RN(n / ratio) for every n in range
+    float eps_r;                 // (new/old) / RN(new/old) - 1: systematic drift of the reference's x (PX_MID)
 };
 
 // how output positions are obtained
 enum { PX_RATIONAL = 0,   // n*M/L; hit / near-hit indistinguishable in the result (bounded input, interpolating)
        PX_TABLE = 1,      // n*M/L plus an exact fp64 decision table for the one j == 0 output per period
-       PX_BIG = 2 };      // positions >= 2^28: every output evaluates the reference's fp64 x exactly
+       PX_BIG = 2,        // every output evaluates the reference's fp64 x exactly (positions >= 2^30.5, binade crossings)
+       PX_MID = 3 };      // 2^28 <= position < 2^30.5: PX_TABLE plus the systematic drift x*eps_r to first order;
+                          // what is left is the quotient's rounding, <= x * 2^-53 <= 2^-22.5
 
 enum { HIT = 0, NEAR_BELOW = 1, NEAR_ABOVE = 2 };
 
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
             w1 = (float)(1.5 * x3 - 2.5 * x2 + 1.0);
             w2 = (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x);
             w3 = (float)(0.5 * x3 - 0.5 * x2);
-            if (PX == PX_BIG) {
+            if (PX == PX_BIG || PX == PX_MID) {
                 wd0 = (float)(-1.5 * x2 + 2.0 * x - 0.5);
                 wd1 = (float)(4.5 * x2 - 5.0 * x);
                 wd2 = (float)(-4.5 * x2 + 4.0 * x + 0.5);
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
             }
         }
         if (!fast) stage_dispatch<CT>(a, pl, gA, sm, nfr_cap);
-        if (PX == PX_TABLE) {
+        if (PX == PX_TABLE || PX == PX_MID) {
             // exact hit / near-hit decision for the tile's j == 0 outputs with the reference's own
             // fp64 expression (A:666-667); entry e <-> iteration e / m, period e % m
             for (int e = t; e < pl.K * pl.m; e += blockDim.x) {
@@ -228,12 +231,15 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
             nd = (double)(base_out + (unsigned long long)k0 * pl.Sp + t);
             xr = (double)(F0 + (long long)k0 * pl.Q + off_t + 1);     // integer part only: exact in fp64
         }
+        float xf = 0.f;                                                 // PX_MID: rational position - 1, in fp32
+        if (PX == PX_MID) xf = (float)(F0 + (long long)k0 * pl.Q + off_t) + fx;
+        const float qf = (float)pl.Q;
         float *outp = nullptr;
         if (APPLY) outp = a.out + (size_t)((long long)base_out - (long long)out_lo + (long long)k0 * pl.Sp + t);
 #pragma unroll 4
         for (int k = k0; k < k1; k++, s += pl.Q) {
             int st = NEAR_ABOVE;
-            if (PX == PX_TABLE && is_j0) st = hit_tab[k * pl.m + t / pl.L];
+            if ((PX == PX_TABLE || PX == PX_MID) && is_j0) st = hit_tab[k * pl.m + t / pl.L];
             float cw0 = w0, cw1 = w1, cw2 = w2, cw3 = w3, cfx = fx;
             if (PX == PX_BIG) {
                 // x = (i - 1) / ratio + 1 exactly as A:666: correctly rounded quotient, then + 1
@@ -257,6 +263,16 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
                 nd += (double)pl.Sp;
                 xr += (double)pl.Q;
             }
+            if (PX == PX_MID) {
+                const float dl = xf * pl.eps_r;                         // x_ref - x_rational, systematic part
+                if (MODE == AUKIT_INTERP_CUBIC) {
+                    cw0 = __fmaf_rn(wd0, dl, w0); cw1 = __fmaf_rn(wd1, dl, w1);
+                    cw2 = __fmaf_rn(wd2, dl, w2); cw3 = __fmaf_rn(wd3, dl, w3);
+                } else {
+                    cfx = fx + dl;
+                }
+                xf += qf;
+            }
             // one channel: blend -> clamp (A:668) / exact-hit copy (A:667)
             auto value = [&](float p0, float p1, float p2, float p3) {
                 float v;
@@ -265,7 +281,7 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
                 else v = p1;
                 // PX_BIG, j == 0, x just BELOW the integer: the reference interpolates on the previous
                 // segment [p0, p1] at fx = 1 + dev.  Linear has a slope break at the knot (cubic is C1).
-                if (PX == PX_BIG && MODE == AUKIT_INTERP_LINEAR && is_j0 && st == NEAR_BELOW) v = __fmaf_rn(p1 - p0, cfx, p1);
+                if ((PX == PX_BIG || PX == PX_MID) && MODE == AUKIT_INTERP_LINEAR && is_j0 && st == NEAR_BELOW) v = __fmaf_rn(p1 - p0, cfx, p1);
                 if (PX != PX_RATIONAL && is_j0) {
                     if (st == HIT) return p1;                                              // copied unclamped, A:667
                     if (MODE == AUKIT_INTERP_NONE && st == NEAR_BELOW) return clampv(p0);  // floor(x) is one lower
@@ -369,6 +385,7 @@ int launch_exact(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, int px
         return aukit_cuda_check(cudaGetLastError(), "poly_kernel launch");
     };
     if (px == PX_BIG) return go(poly_kernel<CT, MODE, MONO, APPLY, PX_BIG>);
+    if (px == PX_MID) return go(poly_kernel<CT, MODE, MONO, APPLY, PX_MID>);
     return px == PX_TABLE ? go(poly_kernel<CT, MODE, MONO, APPLY, PX_TABLE>) : go(poly_kernel<CT, MODE, MONO, APPLY, PX_RATIONAL>);
 }
 
@@ -434,19 +451,58 @@ int aukit_pipeline_poly_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipe
     smem = (smem + 15) / 16 * 16;
     if (smem > 200 * 1024) return 0;
     const unsigned long long tile_out = (unsigned long long)pl.Sp * pl.K;
-    pl.tile0 = a.out_first / tile_out;
-    pl.ntiles = (a.out_first + a.n_out - 1) / tile_out - pl.tile0 + 1;
+    const unsigned long long tile_first = a.out_first / tile_out;
+    const unsigned long long tile_last = (a.out_first + a.n_out - 1) / tile_out;
     // exact j == 0 decisions matter when the hit/near-hit difference is visible
     const bool unbounded = kind == K_FLOAT || (kind == K_UNSIGNED && B > 1);
-    int exact = (unbounded || p->interpolation == AUKIT_INTERP_NONE) ? PX_TABLE : PX_RATIONAL;
-    if (big) {
-        exact = PX_BIG;
-        pl.y = 1.0 / a.ratio;
-        pl.quotient_fma_ok = quotient_fma_is_exact(a.ratio, 41) ? 1 : 0;
+    const int small_px = (unbounded || p->interpolation == AUKIT_INTERP_NONE) ? PX_TABLE : PX_RATIONAL;
+    pl.y = 1.0 / a.ratio;
+    pl.quotient_fma_ok = big ? (quotient_fma_is_exact(a.ratio, 41) ? 1 : 0) : 0;
+    pl.eps_r = (float)(fma(-(double)M, a.ratio, (double)L) / ((double)M * a.ratio));   // L/M / ratio_d - 1, numerator exact
+    // position mode of a tile = f(largest input position it touches); tiles in which x crosses a power of
+    // two >= 2^28 (the "+ 1" of A:666 rounds there) are evaluated exactly
+    const double frames_per_tile = (double)pl.K * (double)pl.Q;
+    auto tile_mode = [&](unsigned long long tile) -> int {
+        if (pow2_ratio) return small_px;
+        const double lo = (double)tile * frames_per_tile, hi = lo + frames_per_tile + 4.0;
+        if (hi < 268435456.0) return small_px;
+        if (hi >= 1518500249.0) return PX_BIG;                          // 2^30.5
+        int elo = 0, ehi = 0;
+        frexp(lo > 1.0 ? lo : 1.0, &elo);
+        frexp(hi, &ehi);
+        return elo != ehi ? PX_BIG : PX_MID;
+    };
+    // tile_mode() is piecewise constant and can only change next to a position threshold: collect
+    // those tile indices as breakpoints and launch one kernel per run of equal mode (usually one).
+    unsigned long long cuts[32];
+    int ncuts = 0;
+    cuts[ncuts++] = tile_first;
+    if (!pow2_ratio) {
+        const double thresholds[] = {268435456.0, 536870912.0, 1073741824.0, 1518500249.0};
+        for (double v : thresholds) {
+            const double b = floor(v / frames_per_tile);
+            for (int d = -2; d <= 2; d++) {
+                const double c = b + d;
+                if (c > (double)tile_first && c <= (double)tile_last) cuts[ncuts++] = (unsigned long long)c;
+            }
+        }
     }
-    int rc;
-    if (C == 1) rc = launch_interp<1>(ctx, a, pl, p->interpolation, exact, apply, threads, smem);
-    else if (C == 2) rc = launch_interp<2>(ctx, a, pl, p->interpolation, exact, apply, threads, smem);
-    else rc = launch_interp<0>(ctx, a, pl, p->interpolation, exact, apply, threads, smem);
+    for (int i = 1; i < ncuts; i++)                                      // insertion sort, <= 21 entries
+        for (int j = i; j > 0 && cuts[j] < cuts[j - 1]; j--) { unsigned long long tmp = cuts[j]; cuts[j] = cuts[j - 1]; cuts[j - 1] = tmp; }
+    int rc = 0;
+    int i = 0;
+    while (i < ncuts && !rc) {
+        const unsigned long long seg = cuts[i];
+        const int mode = tile_mode(seg);
+        int j = i + 1;
+        while (j < ncuts && (cuts[j] == seg || tile_mode(cuts[j]) == mode)) j++;   // merge runs of equal mode
+        const unsigned long long end = (j < ncuts ? cuts[j] : tile_last + 1) - 1;
+        pl.tile0 = seg;
+        pl.ntiles = end - seg + 1;
+        if (C == 1) rc = launch_interp<1>(ctx, a, pl, p->interpolation, mode, apply, threads, smem);
+        else if (C == 2) rc = launch_interp<2>(ctx, a, pl, p->interpolation, mode, apply, threads, smem);
+        else rc = launch_interp<0>(ctx, a, pl, p->interpolation, mode, apply, threads, smem);
+        i = j;
+    }
     return rc ? -1 : 1;
 }

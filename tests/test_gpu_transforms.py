@@ -257,7 +257,8 @@ def test_fused_polyphase_mono_input_and_8ch(ak, O):
 
 @pytest.mark.parametrize("src,dst", [(44100, 48000), (96000, 44100), (32000, 48000)])
 @pytest.mark.parametrize("interp", ["none", "linear", "cubic"])
-def test_huge_global_positions(ak, src, dst, interp):
+@pytest.mark.parametrize("n_total", [6_000_000_011, 1_400_000_003])
+def test_huge_global_positions(ak, src, dst, interp, n_total):
     """Shards near the END of a buffer of several 10^9 frames: positions are >= 2^28, where the
     reference's fp64 rounding of x shows up in the interpolated value (x's ulp is ~2^-21).  Covers
     the fused path's exact-position mode and the standalone resample kernel."""
@@ -266,11 +267,15 @@ def test_huge_global_positions(ak, src, dst, interp):
     lib = ak._lib.load()
     ctx = ak.context()
     ctx.use_torch_stream()
-    n_total = 6_000_000_011
     mode = {"none": 0, "linear": 1, "cubic": 2}[interp]
     total_out = int(lib.aukit_resample_out_len(n_total, float(src), float(dst)))
     rng = np.random.default_rng(src + mode)
-    for o0 in (total_out - 150_000, int(total_out * 0.37)):
+    starts = [total_out - 150_000, int(total_out * 0.37)]
+    for pos in (2 ** 28, 2 ** 29, 2 ** 30, 2 ** 30.5):                      # shards straddling every mode boundary
+        o = int(pos * dst / src) - 70_000
+        if 0 < o < total_out - 150_000:
+            starts.append(o)
+    for o0 in starts:
         cnt = 150_000 if o0 + 150_000 <= total_out else total_out - o0
         f, c = C.c_uint64(), C.c_uint64()
         assert lib.aukit_resample_window(n_total, float(src), float(dst), mode, o0, cnt, C.byref(f), C.byref(c)) == 0
