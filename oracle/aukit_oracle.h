@@ -7,12 +7,13 @@
  * cpu_baseline / --impl reference legs may load it. The product path (aukit_b200 ->
  * libaukit_cuda.so) never links, imports or calls anything in this directory.
  *
- * Pinning status: the reference ships no tests, fixtures or golden vectors (SURVEY.md
- * finding 2) and no Lua interpreter exists in this image.  The oracle is pinned against
- * (1) hand-derived known-answer anchors, and (2) golden vectors
- * produced by executing the UNMODIFIED /root/reference/aukit.lua under oracle/luavm (a
- * small Lua 5.2 interpreter written for this purpose; see tests/golden/README.md).
- * See DESIGN.md "Oracle" for what that does and does not prove.
+ * Pinning status: PINNED.  The reference ships no tests, fixtures or golden vectors (SURVEY.md
+ * finding 2) and no Lua interpreter exists in this image, so the reference itself is executed
+ * -- unmodified -- inside oracle/luavm (a small Lua 5.2 interpreter written for this purpose) to
+ * produce tests/golden/reference_vectors.npz (156 seeded calls over every function below);
+ * tests/test_golden_reference.py requires this oracle to reproduce every vector bit-exactly in
+ * float64, errors included.  The hand-derived anchors of SURVEY.md Appendix B are checked too
+ * (tests/test_oracle_anchors.py).  See tests/golden/README.md for what that does and does not prove.
  *
  * All sample outputs are doubles, planar: out[c * stride + i].
  */

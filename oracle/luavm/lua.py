@@ -314,9 +314,11 @@ ARITH = {b"__add": lambda x, y: x + y, b"__sub": lambda x, y: x - y, b"__mul": l
 
 
 def lua_eq(a, b):
+    ta, tb = type(a), type(b)
+    if ta is float and tb is float:
+        return a == b                      # NaN ~= NaN even for the same Python object
     if a is b:
         return True
-    ta, tb = type(a), type(b)
     if (ta is float or ta is int) and (tb is float or tb is int):
         return a == b
     if ta is not tb:

@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""Generates tests/golden/reference_vectors.npz by executing the UNMODIFIED reference
+/root/reference/aukit.lua (inside oracle/luavm, a Lua 5.2 interpreter written for this repo --
+no Lua binary exists in the image) on seeded inputs.
+
+    python tests/golden/generate.py          # only works where /root/reference exists
+
+The .npz holds, per case, the input bytes / arrays, the declarative description of the call
+(`op` + arguments, JSON) and the reference's outputs as float64 (or its error message).
+tests/test_golden_reference.py replays every case against the C oracle (bit-exact, CPU) and
+against the CUDA path (GPU).  Nothing reads /root/reference at test time.
+"""
+from __future__ import annotations
+
+import json
+import os
+import struct
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle.luavm.aukit_ref import Reference  # noqa: E402
+from oracle.luavm.lua import LuaError, LuaTable, call, index, to_lua  # noqa: E402
+from util import fmt_chunk, ima_blocks, ms_blocks, riff, tone_s16, wav_pcm  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.npz")
+
+
+def lua_table(values):
+    t = LuaTable()
+    t.arr = [float(v) for v in values]
+    return t
+
+
+def audio_from_numpy(R, x, rate):
+    """Builds an aukit.Audio from doubles by calling aukit.new and filling data (like a loader would)."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    a = R.call("new", 0, x.shape[0], rate)[0]
+    data = a.get(b"data")
+    for c in range(x.shape[0]):
+        data.arr[c].arr = [float(v) for v in x[c]]
+    return a
+
+
+def run_case(R, case, blobs):
+    op = case["op"]
+    A = case.get("args", {})
+    if op == "pcm":
+        a = R.call("pcm", blobs["in"], A["bitDepth"], A["dataType"], A["channels"], A["sampleRate"], A["interleaved"], A["bigEndian"])[0]
+    elif op == "g711":
+        a = R.call("g711", blobs["in"], A["ulaw"], A["channels"], A.get("sampleRate"))[0]
+    elif op == "adpcm":
+        args = [blobs["in"], A["channels"], A["sampleRate"], A["topFirst"], A["interleaved"]]
+        args.append(lua_table(A["predictor"]) if A.get("predictor") is not None else None)
+        args.append(lua_table(A["step_index"]) if A.get("step_index") is not None else None)
+        a = call(R.fn("adpcm"), [to_lua(v) if not isinstance(v, LuaTable) else v for v in args])[0]
+    elif op == "msadpcm":
+        co = A.get("coefficients")
+        cot = None
+        if co is not None:
+            cot = LuaTable()
+            cot.arr = [lua_table(co[0]), lua_table(co[1])]
+        a = call(R.fn("msadpcm"), [blobs["in"], float(A["blockAlign"]), float(A["channels"]), float(A["sampleRate"]), cot])[0]
+    elif op == "wav":
+        a = R.call("wav", blobs["in"], A.get("head", False))[0]
+    elif op in ("resample", "mono", "amplify", "normalize", "chain"):
+        if op == "chain":
+            a = R.call("wav", blobs["in"])[0]
+        else:
+            a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
+        if op in ("resample", "chain"):
+            a = R.method(a, "resample", A["targetRate"], A.get("interpolation"))[0]
+        if op in ("mono", "chain"):
+            a = R.method(a, "mono")[0]
+        if op == "amplify":
+            r = R.call(("effects", "amplify"), a, A["multiplier"])[0]
+            assert r is a                       # mutates and returns the argument (A:3368)
+        if op in ("normalize", "chain"):
+            r = call(R.fn("effects", "normalize"), [a, to_lua(A.get("peak")), to_lua(A.get("independent"))])[0]
+            assert r is a
+    else:
+        raise ValueError(op)
+    return a
+
+
+def main():
+    t0 = time.time()
+    R = Reference()
+    rng = np.random.default_rng(20260101)
+    cases, store = [], {}
+
+    def add(name, op, args=None, **blobs):
+        cases.append({"name": name, "op": op, "args": args or {}})
+        i = len(cases) - 1
+        for k, v in blobs.items():
+            store["c%d/%s" % (i, k)] = np.frombuffer(v, dtype=np.uint8).copy() if isinstance(v, (bytes, bytearray)) else np.asarray(v)
+
+    # ---- aukit.pcm: every depth / type / endianness / layout
+    for bits, dt in ((8, "signed"), (8, "unsigned"), (16, "signed"), (16, "unsigned"), (24, "signed"), (24, "unsigned"),
+                     (32, "signed"), (32, "unsigned"), (32, "float")):
+        for be in (False, True):
+            for ch, il in ((1, True), (2, True), (3, False)):
+                n = 96
+                raw = rng.integers(0, 256, n * ch * bits // 8, dtype=np.uint8)
+                raw[: bits // 8] = 0
+                raw[bits // 8: 2 * (bits // 8)] = 255
+                if dt == "float":
+                    f = (rng.standard_normal(n * ch) * 0.7).astype(">f4" if be else "<f4")
+                    f[:3] = [2.5, -0.0, 1e-30]
+                    raw = f.view(np.uint8)
+                add("pcm_%d%s_%s_c%d_%s" % (bits, dt[0], "be" if be else "le", ch, "il" if il else "pl"), "pcm",
+                    dict(bitDepth=bits, dataType=dt, channels=ch, sampleRate=44100, interleaved=il, bigEndian=be), **{"in": raw.tobytes()})
+    add("pcm_err_depth", "pcm", dict(bitDepth=12, dataType="signed", channels=1, sampleRate=48000, interleaved=True, bigEndian=False), **{"in": b"\0\0"})
+    add("pcm_err_uneven", "pcm", dict(bitDepth=16, dataType="signed", channels=2, sampleRate=48000, interleaved=True, bigEndian=False), **{"in": b"\0" * 6})
+    add("pcm_err_float16", "pcm", dict(bitDepth=16, dataType="float", channels=1, sampleRate=48000, interleaved=True, bigEndian=False), **{"in": b"\0" * 4})
+    # exhaustive 16-bit signed scaling (A:1133)
+    add("pcm_s16_all", "pcm", dict(bitDepth=16, dataType="signed", channels=1, sampleRate=48000, interleaved=True, bigEndian=False),
+        **{"in": np.arange(-32768, 32768, 17, dtype="<i2").tobytes()})
+
+    # ---- aukit.g711
+    allb = bytes(range(256))
+    for ulaw in (True, False):
+        add("g711_%s_all" % ("u" if ulaw else "a"), "g711", dict(ulaw=ulaw, channels=1, sampleRate=None), **{"in": allb})
+        add("g711_%s_ragged3" % ("u" if ulaw else "a"), "g711", dict(ulaw=ulaw, channels=3, sampleRate=8000), **{"in": allb[:200]})
+
+    # ---- aukit.adpcm (headerless nibble strings)
+    raw = rng.integers(0, 256, 150, dtype=np.uint8).tobytes()
+    for ch, top, il, pr, si in ((1, True, True, None, None), (2, False, True, [100, -200], [5, 60]), (3, True, False, [0, 1, 2], [88, 0, 44])):
+        add("adpcm_c%d_%s_%s" % (ch, "top" if top else "low", "il" if il else "pl"), "adpcm",
+            dict(channels=ch, sampleRate=48000, topFirst=top, interleaved=il, predictor=pr, step_index=si), **{"in": raw})
+
+    # ---- aukit.wav: IMA ADPCM (A:1509-1548), literal mono / stereo incl. the quirks
+    for ch, ba, nb, cut in ((1, 64, 5, 7), (1, 37, 3, 0), (2, 72, 4, 0), (2, 256, 2, 0)):
+        blocks = ima_blocks(nb, ba, ch, seed=ba + ch)
+        if ch == 1:
+            blocks[2] = 0x5B                            # header index 91 -> & 0x0F = 11 (A:1544)
+        payload = blocks.tobytes()[: nb * ba - cut]
+        add("wav_ima_c%d_ba%d" % (ch, ba), "wav", {}, **{"in": riff([(b"fmt ", fmt_chunk(0x11, ch, 22050, ba, 4)), (b"data", payload)])})
+    bad = ima_blocks(2, 72, 2, seed=9)
+    bad[72 + 6] = 120
+    add("wav_ima_err_index", "wav", {}, **{"in": riff([(b"fmt ", fmt_chunk(0x11, 2, 22050, 72, 4)), (b"data", bad.tobytes())])})
+    add("wav_ima_err_3ch", "wav", {}, **{"in": riff([(b"fmt ", fmt_chunk(0x11, 3, 22050, 96, 4)), (b"data", ima_blocks(2, 96, 3).tobytes())])})
+
+    # ---- aukit.msadpcm (A:1283-1353) mono (first-header bug) / stereo, tame + wild nibbles, custom coefficients
+    for ch, ba, nb, tame in ((1, 64, 4, True), (2, 64, 4, True), (2, 128, 3, False), (1, 256, 2, False)):
+        add("msadpcm_c%d_ba%d_%s" % (ch, ba, "tame" if tame else "wild"), "msadpcm",
+            dict(blockAlign=ba, channels=ch, sampleRate=44100, coefficients=None), **{"in": ms_blocks(nb, ba, ch, seed=ba + ch, tame=tame).tobytes()})
+    coefs = [[256, 512, 0, 192, 240, 460, 392, -300], [0, -256, 0, 64, 0, -208, -232, 77]]
+    blk = ms_blocks(3, 64, 2, seed=3)
+    blk.reshape(3, 64)[:, :2] = 7
+    extra = struct.pack("<HHH", 4 + 4 * 8, 100, 8) + b"".join(struct.pack("<hh", a, b) for a, b in zip(*coefs))
+    add("wav_msadpcm_coefs", "wav", {}, **{"in": riff([(b"fmt ", fmt_chunk(2, 2, 11025, 64, 4, extra)), (b"data", blk.tobytes())])})
+    add("msadpcm_err_3ch", "msadpcm", dict(blockAlign=64, channels=3, sampleRate=44100, coefficients=None), **{"in": ms_blocks(1, 64, 3).tobytes()})
+
+    # ---- aukit.wav containers: PCM / float / G.711 / extensible / INFO tags / errors
+    for bits, fmt, ch in ((8, 1, 2), (16, 1, 2), (24, 1, 1), (32, 1, 2), (32, 3, 2), (8, 6, 2), (8, 7, 1)):
+        payload = rng.integers(0, 256, 60 * ch * bits // 8, dtype=np.uint8)
+        if fmt == 3:
+            payload = rng.standard_normal(60 * ch).astype("<f4").view(np.uint8)
+        add("wav_fmt%d_%dbit_c%d" % (fmt, bits, ch), "wav", {}, **{"in": wav_pcm(payload.tobytes(), ch, 32000, bits, fmt)})
+    guid_tail = bytes.fromhex("000010008000" "00aa00389b71")
+    ext = struct.pack("<HHI", 22, 16, 3) + bytes([1, 0, 0, 0]) + guid_tail
+    add("wav_extensible_pcm", "wav", {}, **{"in": riff([(b"fmt ", fmt_chunk(0xFFFE, 2, 48000, 4, 16, ext)),
+                                                         (b"data", rng.integers(0, 256, 80, dtype=np.uint8).tobytes())])})
+    tags = b"INFO" + b"INAM" + struct.pack("<I", 5) + b"Song\0" + b"\0" + b"ITRK" + struct.pack("<I", 2) + b"7\0" + b"IART" + struct.pack("<I", 2) + b"12"
+    add("wav_info_tags", "wav", {}, **{"in": riff([(b"LIST", tags), (b"fmt ", fmt_chunk(1, 1, 8000, 2, 16)), (b"data", bytes(range(16)))])})
+    add("wav_two_data_chunks", "wav", {}, **{"in": riff([(b"fmt ", fmt_chunk(1, 1, 8000, 1, 8)), (b"data", b"\1\2\3"), (b"data", b"\4\5")])})
+    add("wav_head_only", "wav", dict(head=True), **{"in": wav_pcm(bytes(40), 2, 32000, 16)})
+    add("wav_err_riff", "wav", {}, **{"in": b"RIFX" + bytes(40)})
+    add("wav_err_unsupported", "wav", {}, **{"in": riff([(b"fmt ", fmt_chunk(85, 2, 44100, 4, 16)), (b"data", bytes(4))])})
+    add("wav_err_nodata", "wav", {}, **{"in": riff([(b"fmt ", fmt_chunk(1, 2, 44100, 4, 16))])})
+    add("wav_err_truncated", "wav", {}, **{"in": riff([(b"fmt ", fmt_chunk(1, 2, 44100, 4, 16)), (b"data", bytes(8))])[:-3]})
+
+    # ---- Audio:resample (A:653-673): every mode x rate pair; a signal that exceeds [-1, 1] (exact hits unclamped)
+    x = rng.uniform(-1, 1, (2, 400))
+    x[:, :200] *= 0.3
+    wild = rng.standard_normal((1, 300)) * 1.2
+    for src, dst in ((44100, 48000), (48000, 44100), (22050, 48000), (96000, 48000), (8000, 48000), (44100, 44100), (96000, 44100), (3, 7)):
+        for interp in ("none", "linear", "cubic"):
+            add("resample_%d_%d_%s" % (src, dst, interp), "resample", dict(sampleRate=src, targetRate=dst, interpolation=interp), x=x)
+            add("resample_wild_%d_%d_%s" % (src, dst, interp), "resample", dict(sampleRate=src, targetRate=dst, interpolation=interp), x=wild)
+    add("resample_default_interp", "resample", dict(sampleRate=44100, targetRate=48000, interpolation=None), x=x[:1])
+    add("resample_err_interp", "resample", dict(sampleRate=44100, targetRate=48000, interpolation="bogus"), x=x[:1])
+    add("resample_one_frame", "resample", dict(sampleRate=8000, targetRate=48000, interpolation="cubic"), x=np.array([[0.5]]))
+    # index quirk (SURVEY finding 5): a ramp through 'none' shows which sample floor(x) selects
+    ramp = (np.arange(14700) % 4093) / 4096.0
+    add("resample_index_quirk_none", "resample", dict(sampleRate=44100, targetRate=48000, interpolation="none"), x=ramp[None, :])
+
+    # ---- Audio:mono, effects.amplify, effects.normalize
+    y = rng.uniform(-0.9, 0.9, (3, 257))
+    add("mono_3ch", "mono", dict(sampleRate=48000), x=y)
+    add("mono_2ch", "mono", dict(sampleRate=48000), x=y[:2])
+    add("amplify_1", "amplify", dict(sampleRate=48000, multiplier=1), x=y)
+    add("amplify_2p5", "amplify", dict(sampleRate=48000, multiplier=2.5), x=y)
+    add("normalize_default", "normalize", dict(sampleRate=48000, peak=None, independent=None), x=y * 0.5)
+    add("normalize_0p8", "normalize", dict(sampleRate=48000, peak=0.8, independent=False), x=y * 0.5)
+    add("normalize_independent", "normalize", dict(sampleRate=48000, peak=0.8, independent=True), x=y * np.array([[0.2], [0.5], [1.0]]))
+    add("normalize_silence", "normalize", dict(sampleRate=48000, peak=0.8, independent=False), x=np.zeros((1, 16)))
+    add("normalize_nan", "normalize", dict(sampleRate=48000, peak=1.0, independent=False), x=np.array([[np.nan, 0.5, -0.25]]))
+
+    # ---- the auplay chain on a miniature of BASELINE config 1 (0.2 s): wav -> resample -> mono -> normalize(0.8)
+    pcm = tone_s16(8820, 2, 44100, seed=1)
+    for interp in ("linear", "cubic", "none"):
+        add("chain_c1_mini_%s" % interp, "chain", dict(targetRate=48000, interpolation=interp, peak=0.8, independent=None),
+            **{"in": wav_pcm(pcm.tobytes(), 2, 44100, 16)})
+
+    # ---- run everything through the reference
+    manifest = []
+    for i, case in enumerate(cases):
+        blobs = {}
+        for k in ("in", "x"):
+            key = "c%d/%s" % (i, k)
+            if key in store:
+                blobs[k] = store[key].tobytes() if k == "in" else store[key]
+        entry = dict(case)
+        t1 = time.time()
+        try:
+            a = run_case(R, case, blobs)
+            chans = Reference.audio_data(a)
+            fields = Reference.audio_fields(a)
+            entry["channels"] = len(chans)
+            entry["lengths"] = [int(c.size) for c in chans]
+            entry["sampleRate"] = fields["sampleRate"]
+            entry["metadata"] = {k: (v if not isinstance(v, float) or v == v else None) for k, v in fields["metadata"].items()}
+            entry["info"] = fields["info"]
+            for c, arr in enumerate(chans):
+                store["c%d/out%d" % (i, c)] = arr
+        except LuaError as ex:
+            entry["error"] = str(ex)
+        entry["seconds"] = round(time.time() - t1, 3)
+        manifest.append(entry)
+        print("%-40s %s" % (case["name"], entry.get("error") or entry.get("lengths")), flush=True)
+    store["manifest"] = np.frombuffer(json.dumps(manifest).encode(), dtype=np.uint8)
+    np.savez_compressed(OUT, **store)
+    print("wrote %s: %d cases, %.1f KB, %.1f s" % (OUT, len(cases), os.path.getsize(OUT) / 1024, time.time() - t0))
+
+
+if __name__ == "__main__":
+    main()
