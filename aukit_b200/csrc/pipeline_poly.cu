@@ -408,7 +408,17 @@ int launch_interp(aukit_ctx *ctx, const pipe_args &a, const poly_plan &pl, int i
 
 }  // namespace
 
+int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p, bool apply, long long L,
+                           long long M, double eps_r, bool pow2_ratio, unsigned long long *done_first,
+                           unsigned long long *done_count);
+
+static int poly_range(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p, bool apply, bool allow_run);
+
 int aukit_pipeline_poly_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p, bool apply) {
+    return poly_range(ctx, a, p, apply, true);
+}
+
+static int poly_range(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p, bool apply, bool allow_run) {
     // AUKIT_DISABLE_POLY=1 forces the generic fp64-position kernels (used by the tests to cross-check)
     static const bool disabled = getenv("AUKIT_DISABLE_POLY") && getenv("AUKIT_DISABLE_POLY")[0] == '1';
     if (disabled) return 0;
@@ -427,6 +437,29 @@ int aukit_pipeline_poly_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipe
     if (big && last_pos >= 1099511627776.0) return 0;                   // 2^40: beyond the proved range
     const int B = p->bitDepth / 8;
     if ((B == 2 || B == 4) && ((uintptr_t)a.in % B)) return 0;
+    if (allow_run) {
+        // headline shape: the run-per-lane kernel takes the interior, the kernels below the edges
+        const double eps = fma(-(double)M, a.ratio, (double)L) / ((double)M * a.ratio);
+        unsigned long long df = 0, dc = 0;
+        const int r = aukit_pipeline_run_try(ctx, a, p, apply, L, M, eps, pow2_ratio, &df, &dc);
+        if (r < 0) return -1;
+        if (r == 1) {
+            if (df > a.out_first) {
+                pipe_args h = a;
+                h.n_out = (size_t)(df - a.out_first);
+                if (poly_range(ctx, h, p, apply, false) != 1) return -1;
+            }
+            const unsigned long long end = a.out_first + a.n_out;
+            if (df + dc < end) {
+                pipe_args t = a;
+                t.out_first = df + dc;
+                t.n_out = (size_t)(end - (df + dc));
+                if (apply) t.out = a.out + (size_t)(df + dc - a.out_first);
+                if (poly_range(ctx, t, p, apply, false) != 1) return -1;
+            }
+            return 1;
+        }
+    }
     const int kind = p->dataType == AUKIT_FLOAT ? K_FLOAT : (p->dataType == AUKIT_UNSIGNED ? K_UNSIGNED : K_SIGNED);
     const int be = (p->bigEndian && B > 1) ? 1 : 0;
 

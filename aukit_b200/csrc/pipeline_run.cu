@@ -1,0 +1,349 @@
+// pipeline_run.cu -- "run per lane" variant of the fused pipeline (K10) for the headline case:
+// 16-bit little-endian STEREO input, cubic interpolation, mono mixdown, integer rates with
+// L = new/gcd a multiple of 32 and M = old/gcd odd (44.1 / 22.05 / 11.025 kHz -> 48 kHz).
+//
+// Why another kernel: pipeline_poly.cu maps lanes to consecutive outputs, so every output re-reads
+// its 4 taps from shared memory (32 B of the 128 B/clk/SM) -- measured 65 % shared-memory pipe,
+// 60 % issue, 42 instructions per output.  Here lane l of a warp owns one whole PERIOD of the
+// rational resampling pattern: outputs [l*L, (l+1)*L) of the warp's tile, i.e. input frames
+// [l*M - 1, (l+1)*M + 2).  All 32 lanes are therefore at the SAME phase at the same step:
+//   * the 4 Catmull-Rom weights of a step are warp-uniform: one broadcast LDS.128 from a table
+//     built once per CTA (in fp64, narrowed), not per-lane registers or per-lane reads;
+//   * the taps slide in registers: each input frame is loaded from shared memory and converted
+//     ONCE per lane (0.92 loads per output instead of 4), with row stride M words (odd => the 32
+//     lanes hit 32 different banks);
+//   * whether a new input frame yields 1 or 2 outputs is warp-uniform too (a byte script per
+//     frame, no divergence); the loop is unrolled over the 4 register slots so no moves are needed.
+// The warp's input tile (32*M + 3 contiguous frames) is staged by ONE bulk async copy (TMA,
+// cp.async.bulk + mbarrier).  Outputs are transposed through a small shared staging buffer and
+// written with one 128-byte bulk async store per lane (cp.async.bulk.global.shared::cta), so
+// stores stay coalesced although a lane's outputs are L samples apart from its neighbour's.
+// Warps are independent (own buffers, own mbarrier, own tile loop): no __syncthreads after setup.
+//
+// Positions: rational (n*M/L) plus a constant drift term per launch (delta = x*eps_r, see
+// pipeline_poly.cu / DESIGN.md 3.2); the host splits launches so delta stays within 3 % of its
+// true value.  Tiles that touch the ends of the signal or of the shard, other formats / modes and
+// exactness-sensitive cases stay on pipeline_poly.cu's kernels.
+#include "common.cuh"
+#include "pipeline.cuh"
+
+#include <math.h>
+
+namespace {
+
+struct run_plan {
+    int L, M;                     // outputs / input frames per lane (one period)
+    int raw_words;                // 32-bit words of raw input per warp buffer (multiple of 32)
+    int nwarps;
+    float delta;                  // drift of the reference's position in this launch's range (frames)
+    unsigned long long tile0;     // first warp tile (32*L outputs each) of this launch
+    unsigned long long ntiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk async copy (TMA), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global bulk async store
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- packed f32x2 helpers (sm_100 FFMA2: one issue slot for both channels)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float x, float y) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &x, float &y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// One stereo s16 frame -> (L, R) in the SCALED domain v * 2^15: u + max(u, 0) / 32767 is the correctly
+// rounded s * 32768 / 32767, i.e. 2^15 times the exactly rounded sample of A:1133 (same proof as
+// common.cuh::s16_to_float, scaled by a power of two).  The 2^-15 is folded into the final scale.
+__device__ __forceinline__ f32x2 cvt_frame(uint32_t w) {
+    const float ul = (float)(int)(int16_t)(w & 0xFFFFu), ur = (float)((int)w >> 16);
+    constexpr float c = 1.0f / 32767.0f;
+    return fma2(pack2(fmaxf(ul, 0.0f), fmaxf(ur, 0.0f)), pack2(c, c), pack2(ul, ur));
+}
+
+constexpr int STAGE_COLS = 32;        // outputs per lane per flush (one 128-byte line per lane-row)
+constexpr int STAGE_STRIDE = 36;      // floats per staging row: 16-byte aligned rows, 4-way conflict on the column writes
+
+// 32 outputs per lane are staged: transpose back so that 8 lanes write one full 128-byte line.
+// Kept out of line on purpose: inlined, the compiler hoists its 8 global address computations into
+// every output step.
+__device__ __noinline__ void flush_stage(const float *stage, float *g_tile_col, int L, int lane) {
+    __syncwarp();
+    float *g = g_tile_col + (size_t)(lane >> 3) * L + 4 * (lane & 7);
+    const float *sp = stage + (lane >> 3) * STAGE_STRIDE + 4 * (lane & 7);
+#pragma unroll
+    for (int it = 0; it < 8; it++)
+        stg_stream(reinterpret_cast<float4 *>(g + (size_t)it * 4 * L), *reinterpret_cast<const float4 *>(sp + it * 4 * STAGE_STRIDE));
+    __syncwarp();
+}
+
+// CMIN = floor(L / M): every new input frame yields CMIN outputs, some one more (bit flags per 4 frames)
+template <bool APPLY, int CMIN>
+__global__ void __launch_bounds__(384, 1) run_kernel(pipe_args a, run_plan rp) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int L = rp.L, M = rp.M;
+    // layout: weights[L] float4 | flags[M/4 + 4] bytes + tail counts (padded to 16) | mbar[nwarps] | per-warp: raw words | staging x2
+    float4 *W = reinterpret_cast<float4 *>(smem);
+    unsigned char *script = smem + (size_t)L * 16;
+    const int script_bytes = (M + 16 + 15) & ~15;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(script + script_bytes);
+    unsigned char *warp_base = reinterpret_cast<unsigned char *>(bars) + (((size_t)rp.nwarps * 8 + 127) & ~(size_t)127);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = (size_t)rp.raw_words * 4 + (APPLY ? 32 * STAGE_STRIDE * 4 : 0);
+    uint32_t *raw = reinterpret_cast<uint32_t *>(warp_base + (size_t)warp * per_warp);
+    float *stage = reinterpret_cast<float *>(raw + rp.raw_words);
+    const int G = M / 8;                               // full groups of 8 frames after the 3 priming frames
+
+    // ---- one-time tables (fp64 weights of A:265 at fraction j/L + delta, narrowed)
+    for (int e = threadIdx.x; e < L; e += blockDim.x) {
+        const int j = (int)(((long long)e * M) % L);
+        const double x = (double)j / (double)L + (double)rp.delta;
+        const double x2 = x * x, x3 = x2 * x;
+        W[e] = make_float4((float)(-0.5 * x3 + x2 - 0.5 * x), (float)(1.5 * x3 - 2.5 * x2 + 1.0),
+                           (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x), (float)(0.5 * x3 - 0.5 * x2));
+    }
+    // count(F) = number of outputs whose last tap (p3) is local frame F, i.e. floor(e*M/L) == F - 3
+    auto count_at = [&](int F) -> int {
+        if (F < 3 || F >= M + 3) return 0;
+        const long long lo = ((long long)(F - 3) * L + M - 1) / M;
+        long long hi = ((long long)(F - 2) * L + M - 1) / M;
+        if (hi > L) hi = L;
+        return (int)(hi - lo);
+    };
+    // script[g] (g < G): bit k set when frame 3 + 8g + k yields CMIN + 1 outputs; script[G + k]: count of tail frame k
+    for (int g = threadIdx.x; g < G + 8; g += blockDim.x) {
+        int v = 0;
+        if (g < G) {
+            for (int k = 0; k < 8; k++) v |= (count_at(3 + 8 * g + k) > CMIN) << k;
+        } else {
+            v = count_at(3 + 8 * G + (g - G));
+        }
+        script[g] = (unsigned char)v;
+    }
+    if (lane == 0) mbar_init(&bars[warp], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    float mult = 0.f;
+    if (APPLY) mult = (float)(a.peak / (double)a.d_max[0]) * (1.0f / 65536.0f);   // A:3444; 2^-15 (scale) * 1/2 (mono, A:687)
+    float mx = 0.f;
+    uint32_t parity = 0;
+    const unsigned long long warps_total = (unsigned long long)gridDim.x * rp.nwarps;
+
+    for (unsigned long long tile = rp.tile0 + (unsigned long long)blockIdx.x * rp.nwarps + warp; tile < rp.tile0 + rp.ntiles;
+         tile += warps_total) {
+        const unsigned long long out0 = tile * 32ull * (unsigned long long)L;          // first output of the warp tile
+        const long long gA = (long long)(tile * 32ull * (unsigned long long)M) - 1;    // first input frame needed
+        const size_t boff = (size_t)(gA - (long long)a.in_first) * 4;
+        const size_t a0 = boff & ~(size_t)15;
+        const int sh = (int)((boff - a0) >> 2);
+        const uint32_t bytes = (uint32_t)(((size_t)(32 * M + 3 + sh) * 4 + 15) & ~(size_t)15);
+        __syncwarp();
+        if (lane == 0) {
+            fence_async_smem();                       // earlier generic reads of this buffer vs the async write
+            mbar_expect_tx(&bars[warp], bytes);
+            bulk_load(raw, a.in + a0, bytes, &bars[warp]);
+        }
+        mbar_wait(&bars[warp], parity);
+        parity ^= 1;
+        const uint32_t *row = raw + sh + lane * M;    // local frame i of this lane = row[i]  (frame l*M - 1 + i)
+
+        // Converted frames live in 8 register slots, frame f in slot f % 8; the loop is unrolled over 8
+        // frames so every slot index is static.  Frame f + 3 is loaded and converted while the outputs
+        // of frame f are produced (software pipelining: the load -> convert chain is off the critical path).
+        f32x2 c0 = cvt_frame(row[0]), c1 = cvt_frame(row[1]), c2 = cvt_frame(row[2]), c3 = cvt_frame(row[3]);
+        f32x2 c4 = cvt_frame(row[4]), c5 = cvt_frame(row[5]), c6 = 0, c7 = 0;
+        int e = 0;
+        const float4 *wp = W;
+        float *out_tile = nullptr;
+        if (APPLY) out_tile = a.out + (size_t)(out0 - a.out_first);
+
+        // one output of this lane's period: the weights *wp are the same for every lane
+        auto emit = [&](f32x2 p0, f32x2 p1, f32x2 p2, f32x2 p3) {
+            const float4 w = *wp++;
+            f32x2 acc = mul2(p0, pack2(w.x, w.x));
+            acc = fma2(p1, pack2(w.y, w.y), acc);
+            acc = fma2(p2, pack2(w.z, w.z), acc);
+            acc = fma2(p3, pack2(w.w, w.w), acc);
+            float vl, vr;
+            unpack2(acc, vl, vr);
+            vl = fminf(fmaxf(vl, -32768.0f), 32768.0f);   // A:668 in the scaled domain (inputs finite, |v| <= 1)
+            vr = fminf(fmaxf(vr, -32768.0f), 32768.0f);
+            const float sum = vl + vr;                    // (0 + L) + R, A:686; the /2 is in the final scale
+            if (APPLY) {
+                stage[lane * STAGE_STRIDE + (e & (STAGE_COLS - 1))] = fminf(fmaxf(sum * mult, -1.0f), 1.0f);   // A:3455
+                if ((e & (STAGE_COLS - 1)) == STAGE_COLS - 1) flush_stage(stage, out_tile + (e - (STAGE_COLS - 1)), L, lane);
+            } else {
+                mx = fmaxf(mx, fabsf(sum));
+            }
+            e++;
+        };
+        // step for frame F (p3 = frame F): prefetch-convert frame F + 3 into NEXT, then CMIN (+1) outputs
+#define AUKIT_RUN_STEP(NEXT, P0, P1, P2, P3, F, EXTRA)                       \
+        NEXT = cvt_frame(row[(F) + 3]);                                      \
+        _Pragma("unroll")                                                    \
+        for (int c = 0; c < CMIN; c++) emit(P0, P1, P2, P3);                 \
+        if (EXTRA) emit(P0, P1, P2, P3);
+        int F = 3;
+#pragma unroll 1
+        for (int g = 0; g < G; g++, F += 8) {
+            const int fl = script[g];
+            AUKIT_RUN_STEP(c6, c0, c1, c2, c3, F, fl & 1)
+            AUKIT_RUN_STEP(c7, c1, c2, c3, c4, F + 1, fl & 2)
+            AUKIT_RUN_STEP(c0, c2, c3, c4, c5, F + 2, fl & 4)
+            AUKIT_RUN_STEP(c1, c3, c4, c5, c6, F + 3, fl & 8)
+            AUKIT_RUN_STEP(c2, c4, c5, c6, c7, F + 4, fl & 16)
+            AUKIT_RUN_STEP(c3, c5, c6, c7, c0, F + 5, fl & 32)
+            AUKIT_RUN_STEP(c4, c6, c7, c0, c1, F + 6, fl & 64)
+            AUKIT_RUN_STEP(c5, c7, c0, c1, c2, F + 7, fl & 128)
+        }
+#undef AUKIT_RUN_STEP
+        // tail: the last M % 8 frames, with explicit counts (the end of the period can yield fewer than CMIN)
+#define AUKIT_RUN_TAIL(NEXT, P0, P1, P2, P3, K)                              \
+        if (8 * G + K < M) {                                                 \
+            NEXT = cvt_frame(row[F + K + 3]);                                \
+            _Pragma("unroll 1")                                              \
+            for (int c = script[G + K]; c > 0; c--) emit(P0, P1, P2, P3);    \
+        }
+        AUKIT_RUN_TAIL(c6, c0, c1, c2, c3, 0)
+        AUKIT_RUN_TAIL(c7, c1, c2, c3, c4, 1)
+        AUKIT_RUN_TAIL(c0, c2, c3, c4, c5, 2)
+        AUKIT_RUN_TAIL(c1, c3, c4, c5, c6, 3)
+        AUKIT_RUN_TAIL(c2, c4, c5, c6, c7, 4)
+        AUKIT_RUN_TAIL(c3, c5, c6, c7, c0, 5)
+        AUKIT_RUN_TAIL(c4, c6, c7, c0, c1, 6)
+#undef AUKIT_RUN_TAIL
+    }
+    if (!APPLY) {
+        __shared__ float wm[16];
+        mx = warp_max(mx) * (1.0f / 65536.0f);         // back from the scaled domain: 2^-15, and /2 for the mono mean
+        if (lane == 0) wm[warp] = mx;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            mx = threadIdx.x < rp.nwarps ? wm[threadIdx.x] : 0.0f;
+            mx = warp_max(mx);
+            if (threadIdx.x == 0) atomic_max_nonneg(a.d_max, mx);
+        }
+    }
+}
+
+template <bool APPLY>
+int launch_run(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
+    const int L = rp.L, M = rp.M;
+    rp.raw_words = ((32 * M + 3 + 3 + 16) + 31) / 32 * 32;       // tile + halo + alignment shift + prefetch slack
+    const size_t fixed = (size_t)L * 16 + (size_t)((M + 16 + 15) & ~15);
+    const size_t per_warp = (size_t)rp.raw_words * 4 + (APPLY ? 32 * STAGE_STRIDE * 4 : 0);
+    const size_t budget = 224 * 1024;
+    int nw = (int)((budget - fixed - 128 - 256) / per_warp);
+    if (nw > 12) nw = 12;
+    if (nw < 2) return 0;                                         // not worth it: let the caller fall back
+    rp.nwarps = nw;
+    const size_t smem = fixed + (((size_t)nw * 8 + 127) & ~(size_t)127) + (size_t)nw * per_warp + 128;
+    const int cmin = L / M;
+    auto kern = cmin == 1 ? run_kernel<APPLY, 1> : (cmin == 2 ? run_kernel<APPLY, 2> : run_kernel<APPLY, 4>);
+    if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
+    unsigned long long g = (rp.ntiles + nw - 1) / nw;
+    if (g > (unsigned long long)ctx->num_sms) g = ctx->num_sms;
+    kern<<<(unsigned)g, nw * 32, smem, ctx->stream>>>(a, rp);
+    ctx->launches++;
+    return aukit_cuda_check(cudaGetLastError(), "run_kernel launch") ? -1 : 1;
+}
+
+}  // namespace
+
+// Tries the run-per-lane kernel on the interior of [a.out_first, a.out_first + a.n_out).  On success
+// returns 1 and sets [*done_first, *done_first + *done_count) to the outputs it produced (whole
+// warp tiles); the caller covers the rest with the polyphase kernels.  Returns 0 if not applicable.
+int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p, bool apply, long long L,
+                           long long M, double eps_r, bool pow2_ratio, unsigned long long *done_first,
+                           unsigned long long *done_count) {
+    static const bool disabled = getenv("AUKIT_DISABLE_RUN") && getenv("AUKIT_DISABLE_RUN")[0] == '1';
+    // measured (profiles/r1_*): the peak pass is faster here (0.25 ms vs 0.34 ms on config 2), the apply pass is
+    // faster on the polyphase kernel (0.40 ms vs 0.52 ms) until this kernel's occupancy is raised; AUKIT_RUN_APPLY=1
+    // forces the apply pass onto this kernel as well
+    static const bool run_apply = getenv("AUKIT_RUN_APPLY") && getenv("AUKIT_RUN_APPLY")[0] == '1';
+    if (disabled || (apply && !run_apply)) return 0;
+    if (p->bitDepth != 16 || p->dataType != AUKIT_SIGNED || p->bigEndian || p->channels != 2) return 0;
+    if (p->interpolation != AUKIT_INTERP_CUBIC || !p->mono) return 0;
+    if (L % 32 != 0 || L > 1024 || (M & 1) == 0 || M > 2048) return 0;
+    if (L / M != 1 && L / M != 2 && L / M != 4) return 0;          // outputs per input frame: CMIN or CMIN + 1
+    if (((uintptr_t)a.in & 15) != 0) return 0;
+    if (apply && ((((uintptr_t)a.out) & 15) != 0 || (a.out_first & 3) != 0)) return 0;   // 16-byte aligned bulk stores
+    const unsigned long long tile_out = 32ull * (unsigned long long)L, tile_in = 32ull * (unsigned long long)M;
+    // interior warp tiles: fully inside the output range, every tap inside [0, n_total) and inside the shard window
+    unsigned long long t_lo = (a.out_first + tile_out - 1) / tile_out;
+    if (t_lo == 0) t_lo = 1;                                       // tile 0 needs frame -1 (clamped): poly path
+    unsigned long long t_hi = (a.out_first + a.n_out) / tile_out;  // exclusive
+    const unsigned long long in_lo = a.in_first, in_hi = a.in_first + a.in_avail;
+    while (t_lo < t_hi && t_lo * tile_in < in_lo + 1 + 4) t_lo++;  // frame t*tile_in - 1 (and the 16-byte round-down) must exist
+    while (t_hi > t_lo && ((t_hi - 1) * tile_in + tile_in + 2 + 8 > in_hi || (t_hi - 1) * tile_in + tile_in + 2 >= a.n_total)) t_hi--;
+    if (t_hi <= t_lo || t_hi - t_lo < 8) return 0;
+    if (!pow2_ratio && (double)(t_hi * tile_in) >= 1518500249.0) return 0;              // beyond 2^30.5: exact-position kernels
+    run_plan rp{};
+    rp.L = (int)L; rp.M = (int)M;
+    // the drift x*eps_r is baked into the weight table: split the range so it stays within ~3 % of its value
+    unsigned long long t = t_lo;
+    int rc = 1;
+    while (t < t_hi && rc == 1) {
+        unsigned long long t_end = t_hi;
+        const double x0 = (double)(t * tile_in);
+        float delta = 0.f;
+        if (!pow2_ratio && (double)(t_hi * tile_in) >= 268435456.0) {
+            if (x0 < 268435456.0 / 1.06) {
+                // below 2^28 the drift is under 2^-25 and ignored; stop this launch where it starts to matter
+                const unsigned long long lim = (unsigned long long)(268435456.0 / 1.06 / (double)tile_in);
+                if (lim > t && lim < t_hi) t_end = lim;
+            } else {
+                const unsigned long long lim = (unsigned long long)(x0 * 1.06 / (double)tile_in) + 1;
+                if (lim < t_hi) t_end = lim;
+                delta = (float)(0.5 * (x0 + (double)(t_end * tile_in)) * eps_r);
+            }
+        }
+        rp.tile0 = t;
+        rp.ntiles = t_end - t;
+        rp.delta = delta;
+        rc = apply ? launch_run<true>(ctx, a, rp) : launch_run<false>(ctx, a, rp);
+        t = t_end;
+    }
+    if (rc != 1) return rc;
+    *done_first = t_lo * tile_out;
+    *done_count = (t_hi - t_lo) * tile_out;
+    return 1;
+}

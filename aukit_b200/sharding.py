@@ -37,7 +37,9 @@ def plan_time_shards(n_in_total: int, srcRate: float, dstRate: float, interpolat
     n_out = int(lib.aukit_resample_out_len(n_in_total, float(srcRate), float(dstRate)))
     shards = []
     for r in range(world):
-        o0, o1 = n_out * r // world, n_out * (r + 1) // world
+        # interior boundaries on multiples of 4 outputs keep every shard's stores 16-byte aligned
+        o0 = n_out * r // world // 4 * 4
+        o1 = n_out if r == world - 1 else n_out * (r + 1) // world // 4 * 4
         f, c = C.c_uint64(0), C.c_uint64(0)
         _lib.check(lib.aukit_resample_window(n_in_total, float(srcRate), float(dstRate), _INTERPS[interpolation], o0, o1 - o0,
                                              C.byref(f), C.byref(c)))

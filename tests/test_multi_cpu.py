@@ -1,0 +1,76 @@
+"""World-size-2 `gloo` tests of the multi-GPU host logic (no GPU): the time-shard planner, the halo
+windows and the one collective of the path (all-reduce MAX of the per-shard peaks).  The per-shard
+arithmetic is stood in for by the numpy restatement of the reference (tests/util.py), so the test
+checks exactly what the sharding layer adds: partitioning, halos, and the exchange."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, src, dst, interp, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from aukit_b200.sharding import allreduce_max_, plan_time_shards, shard_clips
+        from util import ref_resample_window
+        rng = np.random.default_rng(123)                    # same signal on every rank
+        n_in = 50_000
+        x = rng.uniform(-1, 1, (2, n_in))
+        shards = plan_time_shards(n_in, src, dst, interp, world)
+        sh = shards[rank]
+        # contiguous, disjoint, complete output partition
+        assert shards[0].out_first == 0 and all(shards[i].out_first + shards[i].n_out == shards[i + 1].out_first for i in range(world - 1))
+        window = x[:, sh.in_first: sh.in_first + sh.in_count]          # this rank holds ONLY its shard + halo
+        local = ref_resample_window(window, sh.in_first, n_in, src, dst, sh.out_first, sh.n_out, interp)
+        mono = (local[0] + local[1]) / 2
+        peak = torch.tensor([np.max(np.abs(mono))], dtype=torch.float64)
+        allreduce_max_(peak)                                            # the path's only collective
+        out = np.clip(mono * (0.8 / peak.item()), -1, 1)
+        # clip sharding: disjoint cover, greedy balance
+        mine = shard_clips(11, world, rank)
+        sized = shard_clips(6, world, rank, sizes=[9, 1, 1, 1, 4, 4])
+        q.put((rank, sh.out_first, out, peak.item(), mine, sized))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("src,dst,interp", [(44100, 48000, "cubic"), (96000, 44100, "linear"), (44100, 48000, "none")])
+def test_time_sharded_normalize_over_gloo(O, src, dst, interp):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, src, dst, interp, q)) for r in range(world)]
+    [p.start() for p in procs]
+    results = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    # single-process reference: the C oracle on the whole buffer
+    rng = np.random.default_rng(123)
+    x = rng.uniform(-1, 1, (2, 50_000))
+    whole = O.normalize(O.mono(O.resample(x, src, dst, interp)), 0.8)[0]
+    stitched = np.concatenate([r[2] for r in results])
+    assert stitched.shape == whole.shape
+    assert np.max(np.abs(stitched - whole)) <= 1e-14          # same fp64 expressions; pow() vs ** last-ulp only
+    assert results[0][3] == results[1][3]                      # both ranks ended with the global peak
+    assert sorted(results[0][4] + results[1][4]) == list(range(11))
+    assert sorted(results[0][5] + results[1][5]) == list(range(6))
+    loads = [sum([9, 1, 1, 1, 4, 4][i] for i in r[5]) for r in results]
+    assert max(loads) - min(loads) <= 2
