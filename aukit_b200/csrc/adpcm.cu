@@ -147,7 +147,7 @@ struct ms_coefs { int c1[256], c2[256]; int n; };
 __global__ void __launch_bounds__(128)
 ms_adpcm_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, int literal_mono,
                 size_t nblocks, size_t spb, const ms_coefs *__restrict__ coefs,
-                float *__restrict__ out, size_t stride, int *status) {
+                float *__restrict__ out, size_t stride, int *status, int vec_ok) {
     __shared__ int adapt[16];
     if (threadIdx.x < 16) adapt[threadIdx.x] = c_ms_adapt[threadIdx.x];
     __syncthreads();
@@ -172,12 +172,12 @@ ms_adpcm_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, int lit
         const uint8_t *np = data + start + 7 * (size_t)C;
         bool big = false;
         double ds1 = 0, ds2 = 0, dd = 0;                                // fp64 mirror once delta >= 2^31
-        for (size_t k = 0; k + 2 < spb; k++) {
+        // one sample of this chain (A:1319-1324 / A:1338-1347)
+        auto step = [&](size_t k) -> float {
             const size_t m = k * (size_t)C + (size_t)c;
             const int byte = np[m >> 1];
             const int un = (m & 1) ? (byte & 0xF) : (byte >> 4);
             const int nib = un >= 8 ? un - 16 : un;                     // A:1319-1320
-            float sample;
             if (!big) {
                 const long long lin = ((long long)s1 * c1 + (long long)s2 * c2) >> 8;   // floor(/256), A:1321
                 long long p = lin + (long long)nib * delta;
@@ -187,19 +187,32 @@ ms_adpcm_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, int lit
                 if (nd < 16) nd = 16;
                 if (nd >= (1ll << 31)) { big = true; ds1 = (double)s1; ds2 = (double)s2; dd = (double)nd; }
                 else delta = (int)nd;
-                sample = s16_to_float((int)p);
-            } else {
-                // the reference's own double arithmetic (Lua numbers), A:1321-1324
-                double p = floor(__dadd_rn(__dmul_rn(ds1, (double)c1), __dmul_rn(ds2, (double)c2)) / 256.0);
-                p = __dadd_rn(p, __dmul_rn((double)nib, dd));
-                p = p < -32768.0 ? -32768.0 : (p > 32767.0 ? 32767.0 : p);   // NaN passes, A:228
-                ds2 = ds1; ds1 = p;
-                const double nd = floor(__dmul_rn((double)adapt[un], dd) / 256.0);
-                dd = (16.0 > nd) ? 16.0 : nd;                                  // math.max(nd, 16)
-                sample = (float)(p / (p < 0 ? 32768.0 : 32767.0));
+                return s16_to_float((int)p);
             }
-            o[2 + k] = sample;
+            // the reference's own double arithmetic (Lua numbers), A:1321-1324
+            double p = floor(__dadd_rn(__dmul_rn(ds1, (double)c1), __dmul_rn(ds2, (double)c2)) / 256.0);
+            p = __dadd_rn(p, __dmul_rn((double)nib, dd));
+            p = p < -32768.0 ? -32768.0 : (p > 32767.0 ? 32767.0 : p);   // NaN passes, A:228
+            ds2 = ds1; ds1 = p;
+            const double nd = floor(__dmul_rn((double)adapt[un], dd) / 256.0);
+            dd = (16.0 > nd) ? 16.0 : nd;                                  // math.max(nd, 16)
+            return (float)(p / (p < 0 ? 32768.0 : 32767.0));
+        };
+        // stores: each lane owns its own output row, so 4-byte stores would touch 32 sectors per warp
+        // instruction; group 4 samples into one 16-byte store once the row position is 16-byte aligned
+        const size_t nk = spb - 2;
+        float *os = o + 2;
+        size_t k = 0;
+        if (vec_ok) {
+            const size_t head = (4 - ((b * spb + 2) & 3)) & 3;
+            for (; k < head && k < nk; k++) os[k] = step(k);
+            for (; k + 4 <= nk; k += 4) {
+                float4 v;
+                v.x = step(k); v.y = step(k + 1); v.z = step(k + 2); v.w = step(k + 3);
+                stg_stream(reinterpret_cast<float4 *>(os + k), v);
+            }
         }
+        for (; k < nk; k++) os[k] = step(k);
     }
 }
 
@@ -305,7 +318,7 @@ extern "C" int aukit_cuda_dev_msadpcm(aukit_ctx *ctx, const void *d_in, size_t n
     ms_adpcm_kernel<<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels,
                                                        dialect == AUKIT_DIALECT_LITERAL && channels == 1, nblocks, spb,
                                                        static_cast<const ms_coefs *>(d_coefs), d_out, out_stride,
-                                                       ctx->d_status);
+                                                       ctx->d_status, ((uintptr_t)d_out % 16 == 0) && (out_stride % 4 == 0));
     ctx->launches++;
     int rc = aukit_cuda_check(cudaGetLastError(), "ms_adpcm_kernel launch");
     aukit_dev_free(ctx, d_coefs);

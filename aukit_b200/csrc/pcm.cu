@@ -31,11 +31,38 @@ pcm_unpack_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_
     float *dst = out + (size_t)blockIdx.y * out_stride;
     constexpr int CC = C > 0 ? C : 1;
     constexpr int FPT = C > 0 ? frames_per_thread(B, CC) : 4;
+    if (C == 0) {
+        // runtime channel count: one thread per (4 frames, channel), channel fastest, so the lanes of a warp
+        // read runs of C consecutive samples (full sectors) and every thread stores one float4
+        const int nc = channels_rt;
+        const size_t nquads = (frames + 3) / 4, items = nquads * (size_t)nc;
+        for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < items; id += (size_t)gridDim.x * blockDim.x) {
+            const size_t q = id / (size_t)nc;
+            const int c = (int)(id % (size_t)nc);
+            const size_t f0 = q * 4;
+            const uint8_t *p = src + (f0 * (size_t)nc + c) * B;
+            const size_t fs = (size_t)nc * B;
+            if (f0 + 4 <= frames) {
+                float4 o;
+                o.x = convert<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p, vec_ok), lut);
+                o.y = convert<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p + fs, vec_ok), lut);
+                o.z = convert<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p + 2 * fs, vec_ok), lut);
+                o.w = convert<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p + 3 * fs, vec_ok), lut);
+                float *d = dst + (size_t)c * out_stride + f0;
+                if (vec_ok) stg_stream(reinterpret_cast<float4 *>(d), o);
+                else { d[0] = o.x; d[1] = o.y; d[2] = o.z; d[3] = o.w; }
+            } else {
+                for (size_t f = f0; f < frames; f++)
+                    dst[(size_t)c * out_stride + f] = convert<B, KIND>(load_raw<B, BE>(src + (f * (size_t)nc + c) * B), lut);
+            }
+        }
+        return;
+    }
     const size_t nchunks = (frames + FPT - 1) / FPT;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nchunks;
          t += (size_t)gridDim.x * blockDim.x) {
         const size_t f0 = t * FPT;
-        if (C > 0 && vec_ok && f0 + FPT <= frames) {
+        if (vec_ok && f0 + FPT <= frames) {
             constexpr int WORDS = FPT * CC * B / 4;
             uint32_t w[WORDS + 1];
             const uint4 *p = reinterpret_cast<const uint4 *>(src + f0 * (size_t)(CC * B));
@@ -58,12 +85,11 @@ pcm_unpack_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_
                 }
             }
         } else {
-            const int nc = C > 0 ? CC : channels_rt;
             const size_t fend = f0 + FPT < frames ? f0 + FPT : frames;
-            for (int c = 0; c < nc; c++)
+            for (int c = 0; c < CC; c++)
                 for (size_t f = f0; f < fend; f++)
                     dst[(size_t)c * out_stride + f] =
-                        convert<B, KIND>(load_raw<B, BE>(src + (f * (size_t)nc + c) * B), lut);
+                        convert<B, KIND>(load_raw<B, BE>(src + (f * (size_t)CC + c) * B), lut);
         }
     }
 }
@@ -89,8 +115,11 @@ int launch_c(aukit_ctx *ctx, const uint8_t *d_in, float *d_out, size_t frames, s
         pcm_unpack_kernel<B, KIND, BE, 2><<<grid_for(frames_per_thread(B, 2)), threads, 0, ctx->stream>>>(
             d_in, d_out, frames, out_stride, 2, 0, vec_ok);
     } else {
-        pcm_unpack_kernel<B, KIND, BE, 0><<<grid_for(4), threads, 0, ctx->stream>>>(d_in, d_out, frames,
-                                                                                   out_stride, channels, 0, 0);
+        // vec_ok here = samples are naturally aligned (natural-width loads) and float4 stores are legal
+        const int vok = ((uintptr_t)d_in % B == 0 || B == 3) && ((uintptr_t)d_out % 16 == 0) && (out_stride % 4 == 0);
+        const size_t items = (frames + 3) / 4 * (size_t)channels;
+        pcm_unpack_kernel<B, KIND, BE, 0><<<aukit_grid(items, threads, (size_t)ctx->num_sms * 8 * 16), threads, 0, ctx->stream>>>(
+            d_in, d_out, frames, out_stride, channels, 0, vok);
     }
     ctx->launches++;
     return aukit_cuda_check(cudaGetLastError(), "pcm_unpack launch");

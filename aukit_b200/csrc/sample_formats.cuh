@@ -80,6 +80,11 @@ __device__ __forceinline__ uint32_t load_raw_aligned(const uint8_t *p) {
     return load_raw<B, BE>(p);
 }
 
+template <int B, bool BE>
+__device__ __forceinline__ uint32_t load_raw_aligned_or_bytes(const uint8_t *p, int aligned) {
+    return aligned ? load_raw_aligned<B, BE>(p) : load_raw<B, BE>(p);
+}
+
 // sample at static byte offset `off` of a register-resident chunk
 template <int B, bool BE>
 __device__ __forceinline__ uint32_t extract(const uint32_t *w, int off) {

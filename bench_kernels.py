@@ -1,0 +1,125 @@
+#!/usr/bin/env python
+"""Per-kernel throughput / roofline table for K1..K9 (auxiliary to bench.py, which times the fused
+K10 chain the headline metric is quoted on).  Device-resident inputs, CUDA events, inputs larger
+than L2.  One JSON line per kernel: algorithmic bytes (B_in + B_out), achieved GB/s,
+fraction of the measured HBM copy rate.
+
+    python bench_kernels.py [--scale 1.0] > profiles/rNN_kernels.jsonl
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--iters", type=int, default=10)
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import aukit_b200 as ak
+    from bench import hbm_peak
+    from util import ima_blocks, ms_blocks
+
+    ctx = ak.context()
+    ctx.use_torch_stream()
+    lib = ctx.lib
+    peak, src = hbm_peak()
+    stream = torch.cuda.current_stream()
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.iters):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ctx.synchronize()
+        return e0.elapsed_time(e1) / args.iters
+
+    def report(name, ms, bytes_, units, unit_name, note=""):
+        gbs = bytes_ / (ms * 1e-3) / 1e9
+        print(json.dumps({"kernel": name, "ms": round(ms, 4), "algorithmic_bytes": int(bytes_), "GB/s": round(gbs, 1),
+                          "frac_of_measured_peak": round(gbs / peak, 3), "peak_GB/s": peak, unit_name + "/s": units / (ms * 1e-3),
+                          "note": note}), flush=True)
+
+    frames = int(158_760_000 * args.scale) // 64 * 64            # config 2: 1 h at 44.1 kHz
+
+    def rand_bytes(n):
+        return torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
+
+    # ---- K1 pcm_unpack
+    for bits, dt, ch, be, label in ((16, 0, 2, 0, "s16le stereo (config 2 input)"), (24, 0, 2, 1, "s24be stereo (config 3 input)"),
+                                    (32, 2, 8, 0, "f32le 8ch (config 5 input)"), (8, 1, 1, 0, "u8 mono")):
+        n = frames if ch <= 2 else frames // 4
+        nbytes = n * ch * bits // 8
+        d_in = rand_bytes(nbytes)
+        stride = (n + 31) // 32 * 32
+        d_out = torch.empty((ch, stride), dtype=torch.float32, device="cuda")
+        ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_pcm(ctx.handle, d_in.data_ptr(), nbytes, bits, dt, ch, 1, be, d_out.data_ptr(), stride)))
+        report("K1 pcm_unpack " + label, ms, nbytes + n * ch * 4, n * ch, "samples")
+        del d_in, d_out
+    # ---- K2 g711
+    n = frames * 2
+    d_in = rand_bytes(n)
+    d_out = torch.empty((2, n // 2), dtype=torch.float32, device="cuda")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_g711(ctx.handle, d_in.data_ptr(), n, 1, 2, d_out.data_ptr(), n // 2)))
+    report("K2 g711 ulaw stereo", ms, n * 5, n, "samples")
+    del d_in, d_out
+    # ---- K3 / K4 ADPCM, 8 channels, blockAlign 8192 (config 4), 1/10 of its length by default
+    nblocks = int(77_824 * args.scale)
+    for kind in ("ima", "ms"):
+        proto = (ima_blocks if kind == "ima" else ms_blocks)(512, 8192, 8, seed=4)
+        d_in = torch.from_numpy(np.tile(proto, nblocks // 512)).cuda()
+        nb = d_in.numel()
+        if kind == "ima":
+            fr = int(lib.aukit_ima_adpcm_wav_frames(nb, 8192, 8, 1))
+        else:
+            fr = int(lib.aukit_msadpcm_frames(nb, 8192, 8))
+        stride = (fr + 31) // 32 * 32
+        d_out = torch.empty((8, stride), dtype=torch.float32, device="cuda")
+        if kind == "ima":
+            f = lambda: ak._lib.check(lib.aukit_cuda_dev_ima_adpcm_wav(ctx.handle, d_in.data_ptr(), nb, 8192, 8, 1, d_out.data_ptr(), stride))
+        else:
+            f = lambda: ak._lib.check(lib.aukit_cuda_dev_msadpcm(ctx.handle, d_in.data_ptr(), nb, 8192, 8, None, None, 0, 1, d_out.data_ptr(), stride))
+        ms = timed(f)
+        report("K%d %s_adpcm 8ch blockAlign 8192" % (3 if kind == "ima" else 4, kind), ms, nb + fr * 8 * 4, fr * 8, "samples",
+               "serial chain per (block, channel); integer-issue co-limited")
+        del d_in, d_out
+    # ---- K5 resample f32 stereo 44.1 -> 48 kHz
+    n = frames // 2
+    x = torch.rand((2, n), device="cuda") * 2 - 1
+    for mode, name in ((2, "cubic"), (1, "linear"), (0, "none")):
+        n_out = int(lib.aukit_resample_out_len(n, 44100.0, 48000.0))
+        stride = (n_out + 31) // 32 * 32
+        y = torch.empty((2, stride), dtype=torch.float32, device="cuda")
+        ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_resample(ctx.handle, x.data_ptr(), n, 2, n, 0, n, 44100.0, 48000.0, mode, 0, n_out,
+                                                                     y.data_ptr(), stride)))
+        report("K5 resample %s f32 stereo 44.1->48k" % name, ms, (n + n_out) * 2 * 4, n_out * 2, "samples", "fp64 position per output frame (IEEE division)")
+    # ---- K6 mono, K7 amplify, K8 absmax, K9 scale_clamp
+    m = torch.empty(n, dtype=torch.float32, device="cuda")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_mono(ctx.handle, x.data_ptr(), n, 2, n, m.data_ptr())))
+    report("K6 mono 2ch", ms, n * 12, n, "samples")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_amplify(ctx.handle, x.data_ptr(), n, 2, n, 0.999)))
+    report("K7 amplify 2ch", ms, n * 2 * 8, n * 2, "samples")
+    dmax = torch.zeros(2, dtype=torch.float32, device="cuda")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_absmax(ctx.handle, x.data_ptr(), n, 2, n, 0, dmax.data_ptr())))
+    report("K8 absmax 2ch", ms, n * 2 * 4, n * 2, "samples")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_scale_clamp(ctx.handle, x.data_ptr(), n, 2, n, 1.0, 0, dmax.data_ptr())))
+    report("K9 scale_clamp 2ch", ms, n * 2 * 8, n * 2, "samples")
+
+
+if __name__ == "__main__":
+    main()

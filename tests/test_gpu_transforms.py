@@ -316,3 +316,28 @@ def test_run_per_lane_kernel_matches_oracle_and_polyphase(ak, O, src, monkeypatc
     ref = O.chain_s16(pcm.tobytes(), 2, src, 48000, "cubic", 0.8)
     assert got.shape == ref.shape
     assert np.max(np.abs(got - ref)) <= TOL
+
+
+def test_run_per_lane_apply_pass_in_subprocess(O):
+    """The apply pass of the run-per-lane kernel is opt-in (AUKIT_RUN_APPLY=1, read once per process):
+    exercise it in a child process against the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import aukit_b200 as ak
+from oracle import oracle as O
+pcm = np.random.default_rng(9).integers(-32768, 32768, (900011, 2)).astype(np.int16)
+got = ak.preload(pcm.tobytes(), 16, "signed", 2, 44100, 48000, "cubic", True, 0.8)[0]
+ref = O.chain_s16(pcm.tobytes(), 2, 44100, 48000, "cubic", 0.8)
+assert got.shape == ref.shape
+err = float(np.max(np.abs(got - ref)))
+assert err <= 2.0 ** -20, err
+print("ok", err)
+''' % root
+    env = dict(os.environ, AUKIT_RUN_APPLY="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
