@@ -75,8 +75,10 @@ ima_wav_kernel(const uint8_t *__restrict__ data, size_t nbytes, int blockAlign, 
         if (mode != IMA_LITERAL_MONO) {
             const size_t hdr = 4 * (size_t)C;
             const uint8_t *gp = data + start + hdr + 4 * (size_t)c;
-            for (int g = 0; g < groups; g++, gp += hdr, o += 8) {
-                const uint32_t w = load_u32_any(gp, word_aligned);
+            uint32_t w = groups > 0 ? load_u32_any(gp, word_aligned) : 0u;
+            for (int g = 0; g < groups; g++, o += 8) {
+                gp += hdr;
+                const uint32_t wn = (g + 1 < groups) ? load_u32_any(gp, word_aligned) : 0u;   // prefetch: the chain is serial
                 float v[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) v[k] = s16_to_float(ima_step((w >> (4 * k)) & 0xF, pred, idx, steps));
@@ -87,6 +89,7 @@ ima_wav_kernel(const uint8_t *__restrict__ data, size_t nbytes, int blockAlign, 
 #pragma unroll
                     for (int k = 0; k < 8; k++) o[k] = v[k];
                 }
+                w = wn;
             }
         } else {
             size_t end = start + (size_t)blockAlign;
@@ -172,22 +175,44 @@ ms_adpcm_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, int lit
         const uint8_t *np = data + start + 7 * (size_t)C;
         bool big = false;
         double ds1 = 0, ds2 = 0, dd = 0;                                // fp64 mirror once delta >= 2^31
+        // Integer fast path in 32 bits: s1*c1 + s2*c2 fits when |c1| + |c2| <= 65535; nib * delta is evaluated
+        // with delta saturated at 2^24 (any larger delta drives the clamp to the same side: |lin| < 2^24); the
+        // delta update uses 32 bits while |delta| < 2^21 and 64 bits above.
+        const bool narrow = (abs(c1) + abs(c2)) <= 65535;
+        const bool evenC = (C & 1) == 0;
+        const uint8_t *bp = np + (c >> 1);                              // even C: one byte per sample, C/2 apart
+        const int bstride = C >> 1, hi_nib = (c & 1) == 0;
         // one sample of this chain (A:1319-1324 / A:1338-1347)
         auto step = [&](size_t k) -> float {
-            const size_t m = k * (size_t)C + (size_t)c;
-            const int byte = np[m >> 1];
-            const int un = (m & 1) ? (byte & 0xF) : (byte >> 4);
+            int byte;
+            bool hi;
+            if (evenC) { byte = bp[k * (size_t)bstride]; hi = hi_nib; }
+            else { const size_t m = k * (size_t)C + (size_t)c; byte = np[m >> 1]; hi = (m & 1) == 0; }
+            const int un = hi ? (byte >> 4) : (byte & 0xF);
             const int nib = un >= 8 ? un - 16 : un;                     // A:1319-1320
             if (!big) {
-                const long long lin = ((long long)s1 * c1 + (long long)s2 * c2) >> 8;   // floor(/256), A:1321
-                long long p = lin + (long long)nib * delta;
+                int p;
+                if (narrow) {
+                    const int lin = (s1 * c1 + s2 * c2) >> 8;           // floor(/256), A:1321
+                    const int dsat = delta > (1 << 24) ? (1 << 24) : delta;
+                    p = lin + nib * dsat;
+                } else {
+                    const long long lin = ((long long)s1 * c1 + (long long)s2 * c2) >> 8;
+                    long long pl = lin + (long long)nib * delta;
+                    p = pl < -32768 ? -32768 : (pl > 32767 ? 32767 : (int)pl);
+                }
                 p = p < -32768 ? -32768 : (p > 32767 ? 32767 : p);
-                s2 = s1; s1 = (int)p;
-                long long nd = ((long long)adapt[un] * delta) >> 8;                     // A:1324
-                if (nd < 16) nd = 16;
-                if (nd >= (1ll << 31)) { big = true; ds1 = (double)s1; ds2 = (double)s2; dd = (double)nd; }
-                else delta = (int)nd;
-                return s16_to_float((int)p);
+                s2 = s1; s1 = p;
+                if (delta < (1 << 21) && delta > -(1 << 21)) {
+                    const int nd = (adapt[un] * delta) >> 8;            // A:1324
+                    delta = nd < 16 ? 16 : nd;
+                } else {
+                    long long nd = ((long long)adapt[un] * delta) >> 8;
+                    if (nd < 16) nd = 16;
+                    if (nd >= (1ll << 31)) { big = true; ds1 = (double)s1; ds2 = (double)s2; dd = (double)nd; }
+                    else delta = (int)nd;
+                }
+                return s16_to_float(p);
             }
             // the reference's own double arithmetic (Lua numbers), A:1321-1324
             double p = floor(__dadd_rn(__dmul_rn(ds1, (double)c1), __dmul_rn(ds2, (double)c2)) / 256.0);

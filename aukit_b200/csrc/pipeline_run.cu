@@ -98,38 +98,51 @@ __device__ __forceinline__ f32x2 cvt_frame(uint32_t w) {
     return fma2(pack2(fmaxf(ul, 0.0f), fmaxf(ur, 0.0f)), pack2(c, c), pack2(ul, ur));
 }
 
-constexpr int STAGE_COLS = 32;        // outputs per lane per flush (one 128-byte line per lane-row)
-constexpr int STAGE_STRIDE = 36;      // floats per staging row: 16-byte aligned rows, 4-way conflict on the column writes
+constexpr int STAGE_COLS = 16;        // outputs per lane per flush (64 bytes per lane-row)
+constexpr int STAGE_STRIDE = 20;      // floats per staging row: 16-byte aligned rows
+constexpr int PERIODS = 16;           // periods per warp tile: two lanes (half-periods) per period
 
-// 32 outputs per lane are staged: transpose back so that 8 lanes write one full 128-byte line.
-// Kept out of line on purpose: inlined, the compiler hoists its 8 global address computations into
-// every output step.
-__device__ __noinline__ void flush_stage(const float *stage, float *g_tile_col, int L, int lane) {
-    __syncwarp();
-    float *g = g_tile_col + (size_t)(lane >> 3) * L + 4 * (lane & 7);
-    const float *sp = stage + (lane >> 3) * STAGE_STRIDE + 4 * (lane & 7);
+// 16 outputs per lane of ONE class (16 lanes) are staged: transpose back so that 4 lanes write 64 contiguous
+// bytes.  `cls_stage` = staging rows of the class, `g` = global address of (row 0, first staged column).
+// Kept out of line on purpose: inlined, the compiler hoists the address computations into every output step.
+__device__ __noinline__ void flush_stage(const float *cls_stage, float *g, int L, int j, unsigned mask) {
+    __syncwarp(mask);
+    g += (size_t)(j >> 2) * L + 4 * (j & 3);
+    const float *sp = cls_stage + (j >> 2) * STAGE_STRIDE + 4 * (j & 3);
 #pragma unroll
-    for (int it = 0; it < 8; it++)
+    for (int it = 0; it < 4; it++)
         stg_stream(reinterpret_cast<float4 *>(g + (size_t)it * 4 * L), *reinterpret_cast<const float4 *>(sp + it * 4 * STAGE_STRIDE));
-    __syncwarp();
+    __syncwarp(mask);
 }
 
-// CMIN = floor(L / M): every new input frame yields CMIN outputs, some one more (bit flags per 4 frames)
+// Lane (h, p): class h = lane >> 4 owns HALF of period p = lane & 15 of the warp tile: outputs
+// [h*L/2, (h+1)*L/2) of the period.  All lanes of a class are at the same phase at the same step, the two
+// classes half a period apart (two weight addresses per LDS.128, two script bytes).  Halving the run per lane
+// halves the shared memory per warp, which is what bounds the number of resident warps.
+// CMIN = floor(L / M): every new input frame yields CMIN outputs, some one more (bit flags per 8 frames).
 template <bool APPLY, int CMIN>
-__global__ void __launch_bounds__(384, 1) run_kernel(pipe_args a, run_plan rp) {
+__global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int L = rp.L, M = rp.M;
-    // layout: weights[L] float4 | flags[M/4 + 4] bytes + tail counts (padded to 16) | mbar[nwarps] | per-warp: raw words | staging x2
+    const int L = rp.L, M = rp.M, LH = L / 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = lane >> 4, pp = lane & 15;
+    // per-class geometry
+    const int e_begin = h * LH;
+    const int fbase = (int)(((long long)e_begin * M) / L);                 // floor position of the class's first output
+    const int nsteps0 = (int)(((long long)(LH - 1) * M) / L) + 1;         // distinct floors of class 0 / class 1
+    const int nsteps1 = (int)(((long long)(L - 1) * M) / L) - (int)(((long long)LH * M) / L) + 1;
+    const int NSmin = nsteps0 < nsteps1 ? nsteps0 : nsteps1, NSmax = nsteps0 < nsteps1 ? nsteps1 : nsteps0;
+    const int G = NSmin / 8;                                               // full groups of 8 steps both classes share
+    const int tail_steps = NSmax - 8 * G;                                  // <= 15, handled with explicit counts
+    const int SCR = 64;                                                    // bytes per class: flags[G] then tail counts
+    // layout: weights[L] float4 | script[2][SCR] | mbar[nwarps] | per-warp: raw words | staging
     float4 *W = reinterpret_cast<float4 *>(smem);
     unsigned char *script = smem + (size_t)L * 16;
-    const int script_bytes = (M + 16 + 15) & ~15;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(script + script_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(script + 2 * SCR);
     unsigned char *warp_base = reinterpret_cast<unsigned char *>(bars) + (((size_t)rp.nwarps * 8 + 127) & ~(size_t)127);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = (size_t)rp.raw_words * 4 + (APPLY ? 32 * STAGE_STRIDE * 4 : 0);
     uint32_t *raw = reinterpret_cast<uint32_t *>(warp_base + (size_t)warp * per_warp);
     float *stage = reinterpret_cast<float *>(raw + rp.raw_words);
-    const int G = M / 8;                               // full groups of 8 frames after the 3 priming frames
 
     // ---- one-time tables (fp64 weights of A:265 at fraction j/L + delta, narrowed)
     for (int e = threadIdx.x; e < L; e += blockDim.x) {
@@ -139,23 +152,24 @@ __global__ void __launch_bounds__(384, 1) run_kernel(pipe_args a, run_plan rp) {
         W[e] = make_float4((float)(-0.5 * x3 + x2 - 0.5 * x), (float)(1.5 * x3 - 2.5 * x2 + 1.0),
                            (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x), (float)(0.5 * x3 - 0.5 * x2));
     }
-    // count(F) = number of outputs whose last tap (p3) is local frame F, i.e. floor(e*M/L) == F - 3
-    auto count_at = [&](int F) -> int {
-        if (F < 3 || F >= M + 3) return 0;
-        const long long lo = ((long long)(F - 3) * L + M - 1) / M;
-        long long hi = ((long long)(F - 2) * L + M - 1) / M;
-        if (hi > L) hi = L;
-        return (int)(hi - lo);
+    // count(cls, s) = outputs of class cls whose floor position is fbase_cls + s  (s = step index, 0-based)
+    auto count_at = [&](int cls, int s) -> int {
+        const int eb = cls * LH, ee = eb + LH;
+        const long long f = ((long long)eb * M) / L + s;
+        long long lo = (f * L + M - 1) / M, hi = ((f + 1) * L + M - 1) / M;  // e with floor(e*M/L) == f
+        if (lo < eb) lo = eb;
+        if (hi > ee) hi = ee;
+        return hi > lo ? (int)(hi - lo) : 0;
     };
-    // script[g] (g < G): bit k set when frame 3 + 8g + k yields CMIN + 1 outputs; script[G + k]: count of tail frame k
-    for (int g = threadIdx.x; g < G + 8; g += blockDim.x) {
+    for (int i = threadIdx.x; i < 2 * SCR; i += blockDim.x) {
+        const int cls = i / SCR, g = i % SCR;
         int v = 0;
         if (g < G) {
-            for (int k = 0; k < 8; k++) v |= (count_at(3 + 8 * g + k) > CMIN) << k;
-        } else {
-            v = count_at(3 + 8 * G + (g - G));
+            for (int k = 0; k < 8; k++) v |= (count_at(cls, 8 * g + k) > CMIN) << k;
+        } else if (g - G < tail_steps) {
+            v = count_at(cls, 8 * G + (g - G));
         }
-        script[g] = (unsigned char)v;
+        script[i] = (unsigned char)v;
     }
     if (lane == 0) mbar_init(&bars[warp], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -166,15 +180,19 @@ __global__ void __launch_bounds__(384, 1) run_kernel(pipe_args a, run_plan rp) {
     float mx = 0.f;
     uint32_t parity = 0;
     const unsigned long long warps_total = (unsigned long long)gridDim.x * rp.nwarps;
+    const unsigned char *myscript = script + h * SCR;
+    const unsigned cls_mask = h ? 0xFFFF0000u : 0x0000FFFFu;
+    float *my_stage = stage + lane * STAGE_STRIDE;
+    const float *cls_stage = stage + (h * 16) * STAGE_STRIDE;
 
     for (unsigned long long tile = rp.tile0 + (unsigned long long)blockIdx.x * rp.nwarps + warp; tile < rp.tile0 + rp.ntiles;
          tile += warps_total) {
-        const unsigned long long out0 = tile * 32ull * (unsigned long long)L;          // first output of the warp tile
-        const long long gA = (long long)(tile * 32ull * (unsigned long long)M) - 1;    // first input frame needed
+        const unsigned long long out0 = tile * (unsigned long long)(PERIODS * L);          // first output of the warp tile
+        const long long gA = (long long)(tile * (unsigned long long)(PERIODS * M)) - 1;    // first input frame needed
         const size_t boff = (size_t)(gA - (long long)a.in_first) * 4;
         const size_t a0 = boff & ~(size_t)15;
         const int sh = (int)((boff - a0) >> 2);
-        const uint32_t bytes = (uint32_t)(((size_t)(32 * M + 3 + sh) * 4 + 15) & ~(size_t)15);
+        const uint32_t bytes = (uint32_t)(((size_t)(PERIODS * M + 3 + sh) * 4 + 15) & ~(size_t)15);
         __syncwarp();
         if (lane == 0) {
             fence_async_smem();                       // earlier generic reads of this buffer vs the async write
@@ -183,19 +201,20 @@ __global__ void __launch_bounds__(384, 1) run_kernel(pipe_args a, run_plan rp) {
         }
         mbar_wait(&bars[warp], parity);
         parity ^= 1;
-        const uint32_t *row = raw + sh + lane * M;    // local frame i of this lane = row[i]  (frame l*M - 1 + i)
+        // local frame i of this lane = row[i] = global frame (tile start + p*M + fbase - 1 + i)
+        const uint32_t *row = raw + sh + pp * M + fbase;
 
         // Converted frames live in 8 register slots, frame f in slot f % 8; the loop is unrolled over 8
         // frames so every slot index is static.  Frame f + 3 is loaded and converted while the outputs
         // of frame f are produced (software pipelining: the load -> convert chain is off the critical path).
         f32x2 c0 = cvt_frame(row[0]), c1 = cvt_frame(row[1]), c2 = cvt_frame(row[2]), c3 = cvt_frame(row[3]);
         f32x2 c4 = cvt_frame(row[4]), c5 = cvt_frame(row[5]), c6 = 0, c7 = 0;
-        int e = 0;
-        const float4 *wp = W;
-        float *out_tile = nullptr;
-        if (APPLY) out_tile = a.out + (size_t)(out0 - a.out_first);
+        int er = 0;                                   // outputs produced so far by this lane (relative to e_begin)
+        const float4 *wp = W + e_begin;
+        float *out_cls = nullptr;                     // global address of (class row 0, column 0)
+        if (APPLY) out_cls = a.out + (size_t)(out0 - a.out_first) + e_begin;
 
-        // one output of this lane's period: the weights *wp are the same for every lane
+        // one output of this lane's half period: the weights *wp are the same for every lane of the class
         auto emit = [&](f32x2 p0, f32x2 p1, f32x2 p2, f32x2 p3) {
             const float4 w = *wp++;
             f32x2 acc = mul2(p0, pack2(w.x, w.x));
@@ -208,12 +227,12 @@ __global__ void __launch_bounds__(384, 1) run_kernel(pipe_args a, run_plan rp) {
             vr = fminf(fmaxf(vr, -32768.0f), 32768.0f);
             const float sum = vl + vr;                    // (0 + L) + R, A:686; the /2 is in the final scale
             if (APPLY) {
-                stage[lane * STAGE_STRIDE + (e & (STAGE_COLS - 1))] = fminf(fmaxf(sum * mult, -1.0f), 1.0f);   // A:3455
-                if ((e & (STAGE_COLS - 1)) == STAGE_COLS - 1) flush_stage(stage, out_tile + (e - (STAGE_COLS - 1)), L, lane);
+                my_stage[er & (STAGE_COLS - 1)] = fminf(fmaxf(sum * mult, -1.0f), 1.0f);   // A:3455
+                if ((er & (STAGE_COLS - 1)) == STAGE_COLS - 1) flush_stage(cls_stage, out_cls + (er - (STAGE_COLS - 1)), L, pp, cls_mask);
             } else {
                 mx = fmaxf(mx, fabsf(sum));
             }
-            e++;
+            er++;
         };
         // step for frame F (p3 = frame F): prefetch-convert frame F + 3 into NEXT, then CMIN (+1) outputs
 #define AUKIT_RUN_STEP(NEXT, P0, P1, P2, P3, F, EXTRA)                       \
@@ -224,7 +243,7 @@ __global__ void __launch_bounds__(384, 1) run_kernel(pipe_args a, run_plan rp) {
         int F = 3;
 #pragma unroll 1
         for (int g = 0; g < G; g++, F += 8) {
-            const int fl = script[g];
+            const int fl = myscript[g];
             AUKIT_RUN_STEP(c6, c0, c1, c2, c3, F, fl & 1)
             AUKIT_RUN_STEP(c7, c1, c2, c3, c4, F + 1, fl & 2)
             AUKIT_RUN_STEP(c0, c2, c3, c4, c5, F + 2, fl & 4)
@@ -235,12 +254,12 @@ __global__ void __launch_bounds__(384, 1) run_kernel(pipe_args a, run_plan rp) {
             AUKIT_RUN_STEP(c5, c7, c0, c1, c2, F + 7, fl & 128)
         }
 #undef AUKIT_RUN_STEP
-        // tail: the last M % 8 frames, with explicit counts (the end of the period can yield fewer than CMIN)
+        // tail: the remaining steps (up to 15), with explicit per-class counts (may be 0 for one class)
 #define AUKIT_RUN_TAIL(NEXT, P0, P1, P2, P3, K)                              \
-        if (8 * G + K < M) {                                                 \
-            NEXT = cvt_frame(row[F + K + 3]);                                \
+        if ((K) < tail_steps) {                                              \
+            NEXT = cvt_frame(row[F + (K) + 3]);                              \
             _Pragma("unroll 1")                                              \
-            for (int c = script[G + K]; c > 0; c--) emit(P0, P1, P2, P3);    \
+            for (int c = myscript[G + (K)]; c > 0; c--) emit(P0, P1, P2, P3); \
         }
         AUKIT_RUN_TAIL(c6, c0, c1, c2, c3, 0)
         AUKIT_RUN_TAIL(c7, c1, c2, c3, c4, 1)
@@ -249,10 +268,18 @@ __global__ void __launch_bounds__(384, 1) run_kernel(pipe_args a, run_plan rp) {
         AUKIT_RUN_TAIL(c2, c4, c5, c6, c7, 4)
         AUKIT_RUN_TAIL(c3, c5, c6, c7, c0, 5)
         AUKIT_RUN_TAIL(c4, c6, c7, c0, c1, 6)
+        AUKIT_RUN_TAIL(c5, c7, c0, c1, c2, 7)
+        AUKIT_RUN_TAIL(c6, c0, c1, c2, c3, 8)
+        AUKIT_RUN_TAIL(c7, c1, c2, c3, c4, 9)
+        AUKIT_RUN_TAIL(c0, c2, c3, c4, c5, 10)
+        AUKIT_RUN_TAIL(c1, c3, c4, c5, c6, 11)
+        AUKIT_RUN_TAIL(c2, c4, c5, c6, c7, 12)
+        AUKIT_RUN_TAIL(c3, c5, c6, c7, c0, 13)
+        AUKIT_RUN_TAIL(c4, c6, c7, c0, c1, 14)
 #undef AUKIT_RUN_TAIL
     }
     if (!APPLY) {
-        __shared__ float wm[16];
+        __shared__ float wm[32];
         mx = warp_max(mx) * (1.0f / 65536.0f);         // back from the scaled domain: 2^-15, and /2 for the mono mean
         if (lane == 0) wm[warp] = mx;
         __syncthreads();
@@ -267,12 +294,12 @@ __global__ void __launch_bounds__(384, 1) run_kernel(pipe_args a, run_plan rp) {
 template <bool APPLY>
 int launch_run(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     const int L = rp.L, M = rp.M;
-    rp.raw_words = ((32 * M + 3 + 3 + 16) + 31) / 32 * 32;       // tile + halo + alignment shift + prefetch slack
-    const size_t fixed = (size_t)L * 16 + (size_t)((M + 16 + 15) & ~15);
+    rp.raw_words = ((PERIODS * M + 3 + 3 + 24) + 31) / 32 * 32;  // tile + halo + alignment shift + prefetch slack
+    const size_t fixed = (size_t)L * 16 + 2 * 64;
     const size_t per_warp = (size_t)rp.raw_words * 4 + (APPLY ? 32 * STAGE_STRIDE * 4 : 0);
     const size_t budget = 224 * 1024;
-    int nw = (int)((budget - fixed - 128 - 256) / per_warp);
-    if (nw > 12) nw = 12;
+    int nw = (int)((budget - fixed - 256 - 256) / per_warp);
+    if (nw > 24) nw = 24;
     if (nw < 2) return 0;                                         // not worth it: let the caller fall back
     rp.nwarps = nw;
     const size_t smem = fixed + (((size_t)nw * 8 + 127) & ~(size_t)127) + (size_t)nw * per_warp + 128;
@@ -303,10 +330,11 @@ int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipel
     if (p->bitDepth != 16 || p->dataType != AUKIT_SIGNED || p->bigEndian || p->channels != 2) return 0;
     if (p->interpolation != AUKIT_INTERP_CUBIC || !p->mono) return 0;
     if (L % 32 != 0 || L > 1024 || (M & 1) == 0 || M > 2048) return 0;
+    if ((L / 2 - 1) * M / L + 1 - 8 * (((L / 2 - 1) * M / L + 1) / 8) + 2 > 15) return 0;   // tail steps must fit the unrolled tail
     if (L / M != 1 && L / M != 2 && L / M != 4) return 0;          // outputs per input frame: CMIN or CMIN + 1
     if (((uintptr_t)a.in & 15) != 0) return 0;
     if (apply && ((((uintptr_t)a.out) & 15) != 0 || (a.out_first & 3) != 0)) return 0;   // 16-byte aligned bulk stores
-    const unsigned long long tile_out = 32ull * (unsigned long long)L, tile_in = 32ull * (unsigned long long)M;
+    const unsigned long long tile_out = (unsigned long long)PERIODS * L, tile_in = (unsigned long long)PERIODS * M;
     // interior warp tiles: fully inside the output range, every tap inside [0, n_total) and inside the shard window
     unsigned long long t_lo = (a.out_first + tile_out - 1) / tile_out;
     if (t_lo == 0) t_lo = 1;                                       // tile 0 needs frame -1 (clamped): poly path
@@ -314,7 +342,7 @@ int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipel
     const unsigned long long in_lo = a.in_first, in_hi = a.in_first + a.in_avail;
     while (t_lo < t_hi && t_lo * tile_in < in_lo + 1 + 4) t_lo++;  // frame t*tile_in - 1 (and the 16-byte round-down) must exist
     while (t_hi > t_lo && ((t_hi - 1) * tile_in + tile_in + 2 + 8 > in_hi || (t_hi - 1) * tile_in + tile_in + 2 >= a.n_total)) t_hi--;
-    if (t_hi <= t_lo || t_hi - t_lo < 8) return 0;
+    if (t_hi <= t_lo || t_hi - t_lo < 16) return 0;
     if (!pow2_ratio && (double)(t_hi * tile_in) >= 1518500249.0) return 0;              // beyond 2^30.5: exact-position kernels
     run_plan rp{};
     rp.L = (int)L; rp.M = (int)M;
