@@ -94,25 +94,31 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 // common.cuh::s16_to_float, scaled by a power of two).  The 2^-15 is folded into the final scale.
 __device__ __forceinline__ f32x2 cvt_frame(uint32_t w) {
     const float ul = (float)(int)(int16_t)(w & 0xFFFFu), ur = (float)((int)w >> 16);
-    constexpr float c = 1.0f / 32767.0f;
-    return fma2(pack2(fmaxf(ul, 0.0f), fmaxf(ur, 0.0f)), pack2(c, c), pack2(ul, ur));
+    constexpr float c = 0.5f / 32767.0f;
+    // max(u, 0) = (u + |u|) / 2, evaluated as an FADD with an |.| operand (FMA pipe, exact) instead of an
+    // FMNMX (ALU pipe, the busier one here); the 1/2 is folded into c
+    return fma2(pack2(ul + fabsf(ul), ur + fabsf(ur)), pack2(c, c), pack2(ul, ur));
 }
 
 constexpr int STAGE_COLS = 16;        // outputs per lane per flush (64 bytes per lane-row)
-constexpr int STAGE_STRIDE = 20;      // floats per staging row: 16-byte aligned rows
+constexpr int STAGE_RING = 32;        // staged columns per lane (ring): the two classes drift by a few outputs
+constexpr int STAGE_STRIDE = 36;      // floats per staging row: 16-byte aligned rows
 constexpr int PERIODS = 16;           // periods per warp tile: two lanes (half-periods) per period
 
-// 16 outputs per lane of ONE class (16 lanes) are staged: transpose back so that 4 lanes write 64 contiguous
-// bytes.  `cls_stage` = staging rows of the class, `g` = global address of (row 0, first staged column).
+// The whole warp flushes 16 staged outputs of every lane-row: transpose back so that 4 lanes write 64
+// contiguous bytes of one row.  Row r = lane index that produced it (class r >> 4, period r & 15); columns are
+// XOR-swizzled by 4 * ((r >> 3) & 3) so that the column writes of 32 lanes hit 32 banks.
 // Kept out of line on purpose: inlined, the compiler hoists the address computations into every output step.
-__device__ __noinline__ void flush_stage(const float *cls_stage, float *g, int L, int j, unsigned mask) {
-    __syncwarp(mask);
-    g += (size_t)(j >> 2) * L + 4 * (j & 3);
-    const float *sp = cls_stage + (j >> 2) * STAGE_STRIDE + 4 * (j & 3);
+__device__ __noinline__ void flush_stage(const float *stage, float *g_tile, int L, int col0, int lane) {
+    __syncwarp();
+    const int q = lane & 3;
 #pragma unroll
-    for (int it = 0; it < 4; it++)
-        stg_stream(reinterpret_cast<float4 *>(g + (size_t)it * 4 * L), *reinterpret_cast<const float4 *>(sp + it * 4 * STAGE_STRIDE));
-    __syncwarp(mask);
+    for (int it = 0; it < 4; it++) {
+        const int r = (lane >> 2) + 8 * it;
+        const float4 v = *reinterpret_cast<const float4 *>(stage + r * STAGE_STRIDE + (col0 & (STAGE_RING - 1)) + 4 * (q ^ ((r >> 3) & 3)));
+        stg_stream(reinterpret_cast<float4 *>(g_tile + (size_t)(r & 15) * L + (size_t)(r >> 4) * (L >> 1) + col0 + 4 * q), v);
+    }
+    __syncwarp();
 }
 
 // Lane (h, p): class h = lane >> 4 owns HALF of period p = lane & 15 of the warp tile: outputs
@@ -181,9 +187,8 @@ __global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
     uint32_t parity = 0;
     const unsigned long long warps_total = (unsigned long long)gridDim.x * rp.nwarps;
     const unsigned char *myscript = script + h * SCR;
-    const unsigned cls_mask = h ? 0xFFFF0000u : 0x0000FFFFu;
     float *my_stage = stage + lane * STAGE_STRIDE;
-    const float *cls_stage = stage + (h * 16) * STAGE_STRIDE;
+    const int swz = 4 * ((lane >> 3) & 3);
 
     for (unsigned long long tile = rp.tile0 + (unsigned long long)blockIdx.x * rp.nwarps + warp; tile < rp.tile0 + rp.ntiles;
          tile += warps_total) {
@@ -211,8 +216,9 @@ __global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
         f32x2 c4 = cvt_frame(row[4]), c5 = cvt_frame(row[5]), c6 = 0, c7 = 0;
         int er = 0;                                   // outputs produced so far by this lane (relative to e_begin)
         const float4 *wp = W + e_begin;
-        float *out_cls = nullptr;                     // global address of (class row 0, column 0)
-        if (APPLY) out_cls = a.out + (size_t)(out0 - a.out_first) + e_begin;
+        int nfl = 0;                                  // flushes done in this tile (16 outputs per lane each)
+        float *out_tile = nullptr;
+        if (APPLY) out_tile = a.out + (size_t)(out0 - a.out_first);
 
         // one output of this lane's half period: the weights *wp are the same for every lane of the class
         auto emit = [&](f32x2 p0, f32x2 p1, f32x2 p2, f32x2 p3) {
@@ -227,19 +233,30 @@ __global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
             vr = fminf(fmaxf(vr, -32768.0f), 32768.0f);
             const float sum = vl + vr;                    // (0 + L) + R, A:686; the /2 is in the final scale
             if (APPLY) {
-                my_stage[er & (STAGE_COLS - 1)] = fminf(fmaxf(sum * mult, -1.0f), 1.0f);   // A:3455
-                if ((er & (STAGE_COLS - 1)) == STAGE_COLS - 1) flush_stage(cls_stage, out_cls + (er - (STAGE_COLS - 1)), L, pp, cls_mask);
+                my_stage[(er & (STAGE_RING - 1)) ^ swz] = fminf(fmaxf(sum * mult, -1.0f), 1.0f);   // A:3455
             } else {
                 mx = fmaxf(mx, fabsf(sum));
             }
             er++;
+        };
+        // uniform point: flush once BOTH classes have 16 outputs staged (they drift by a few outputs at most;
+        // the ring holds 32).  Called after every 8-frame group (CMIN == 1: <= 16 new outputs), after every
+        // step when a step can produce more, and after every tail step.
+        auto maybe_flush = [&]() {
+            const int pend = er - STAGE_COLS * nfl;
+            const int other = __shfl_xor_sync(0xffffffffu, pend, 16);
+            if ((pend < other ? pend : other) >= STAGE_COLS) {
+                flush_stage(stage, out_tile, L, STAGE_COLS * nfl, lane);
+                nfl++;
+            }
         };
         // step for frame F (p3 = frame F): prefetch-convert frame F + 3 into NEXT, then CMIN (+1) outputs
 #define AUKIT_RUN_STEP(NEXT, P0, P1, P2, P3, F, EXTRA)                       \
         NEXT = cvt_frame(row[(F) + 3]);                                      \
         _Pragma("unroll")                                                    \
         for (int c = 0; c < CMIN; c++) emit(P0, P1, P2, P3);                 \
-        if (EXTRA) emit(P0, P1, P2, P3);
+        if (EXTRA) emit(P0, P1, P2, P3);                                     \
+        if (APPLY && CMIN > 1) maybe_flush();
         int F = 3;
 #pragma unroll 1
         for (int g = 0; g < G; g++, F += 8) {
@@ -252,6 +269,7 @@ __global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
             AUKIT_RUN_STEP(c3, c5, c6, c7, c0, F + 5, fl & 32)
             AUKIT_RUN_STEP(c4, c6, c7, c0, c1, F + 6, fl & 64)
             AUKIT_RUN_STEP(c5, c7, c0, c1, c2, F + 7, fl & 128)
+            if (APPLY && CMIN == 1) maybe_flush();
         }
 #undef AUKIT_RUN_STEP
         // tail: the remaining steps (up to 15), with explicit per-class counts (may be 0 for one class)
@@ -260,6 +278,7 @@ __global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
             NEXT = cvt_frame(row[F + (K) + 3]);                              \
             _Pragma("unroll 1")                                              \
             for (int c = myscript[G + (K)]; c > 0; c--) emit(P0, P1, P2, P3); \
+            if (APPLY) maybe_flush();                                        \
         }
         AUKIT_RUN_TAIL(c6, c0, c1, c2, c3, 0)
         AUKIT_RUN_TAIL(c7, c1, c2, c3, c4, 1)
@@ -277,6 +296,10 @@ __global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
         AUKIT_RUN_TAIL(c3, c5, c6, c7, c0, 13)
         AUKIT_RUN_TAIL(c4, c6, c7, c0, c1, 14)
 #undef AUKIT_RUN_TAIL
+        if (APPLY) {
+            // every lane has now produced its L/2 outputs (a multiple of 16): drain the staging ring
+            for (; STAGE_COLS * nfl < LH; nfl++) flush_stage(stage, out_tile, L, STAGE_COLS * nfl, lane);
+        }
     }
     if (!APPLY) {
         __shared__ float wm[32];
@@ -322,11 +345,9 @@ int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipel
                            long long M, double eps_r, bool pow2_ratio, unsigned long long *done_first,
                            unsigned long long *done_count) {
     static const bool disabled = getenv("AUKIT_DISABLE_RUN") && getenv("AUKIT_DISABLE_RUN")[0] == '1';
-    // measured (profiles/r1_*): the peak pass is faster here (0.25 ms vs 0.34 ms on config 2), the apply pass is
-    // faster on the polyphase kernel (0.40 ms vs 0.52 ms) until this kernel's occupancy is raised; AUKIT_RUN_APPLY=1
-    // forces the apply pass onto this kernel as well
-    static const bool run_apply = getenv("AUKIT_RUN_APPLY") && getenv("AUKIT_RUN_APPLY")[0] == '1';
-    if (disabled || (apply && !run_apply)) return 0;
+    // AUKIT_RUN_APPLY=0 keeps the apply pass on the polyphase kernel (A/B measurements, profiles/r1_*)
+    static const bool no_run_apply = getenv("AUKIT_RUN_APPLY") && getenv("AUKIT_RUN_APPLY")[0] == '0';
+    if (disabled || (apply && no_run_apply)) return 0;
     if (p->bitDepth != 16 || p->dataType != AUKIT_SIGNED || p->bigEndian || p->channels != 2) return 0;
     if (p->interpolation != AUKIT_INTERP_CUBIC || !p->mono) return 0;
     if (L % 32 != 0 || L > 1024 || (M & 1) == 0 || M > 2048) return 0;

@@ -318,9 +318,9 @@ def test_run_per_lane_kernel_matches_oracle_and_polyphase(ak, O, src, monkeypatc
     assert np.max(np.abs(got - ref)) <= TOL
 
 
-def test_run_per_lane_apply_pass_in_subprocess(O):
-    """The apply pass of the run-per-lane kernel is opt-in (AUKIT_RUN_APPLY=1, read once per process):
-    exercise it in a child process against the oracle."""
+def test_polyphase_only_paths_in_subprocess(O):
+    """The kernel-selection switches are read once per process: exercise the polyphase-only apply pass
+    (AUKIT_RUN_APPLY=0) and the polyphase-only pipeline (AUKIT_DISABLE_RUN=1) in child processes."""
     import os
     import subprocess
     import sys
@@ -338,6 +338,6 @@ err = float(np.max(np.abs(got - ref)))
 assert err <= 2.0 ** -20, err
 print("ok", err)
 ''' % root
-    env = dict(os.environ, AUKIT_RUN_APPLY="1")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
-    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+    for extra in ({"AUKIT_RUN_APPLY": "0"}, {"AUKIT_DISABLE_RUN": "1"}, {"AUKIT_DISABLE_POLY": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **extra), timeout=600)
+        assert r.returncode == 0 and "ok" in r.stdout, (extra, r.stdout + r.stderr)
