@@ -271,7 +271,7 @@ def run_b200(args):
                 "parallelism": "time-shard x%d" % world, "output_peak_check": checksum,
             },
             "roofline": {
-                "bound": "hbm", "kernel": "pipeline apply pass (pipeline_kernel<..., APPLY=true>)", "achieved": achieved, "peak": peak_gbs,
+                "bound": "hbm", "kernel": "fused apply pass: run_kernel<APPLY=true> (interior) + poly_kernel edges", "achieved": achieved, "peak": peak_gbs,
                 "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": apply_bytes, "ms_per_launch": ms_apply,
                 "peak_pass": {"algorithmic_bytes_per_launch": peak_bytes, "ms_per_launch": ms_peak,
