@@ -54,6 +54,10 @@ int aukit_upload_bytes(aukit_ctx *ctx, const void *h, size_t nbytes, void **d_ou
 int aukit_dev_alloc(aukit_ctx *ctx, size_t nbytes, void **d_out);
 void aukit_dev_free(aukit_ctx *ctx, void *d);
 
+// Host proof that the 3-operation FMA quotient equals RN(n / r) for every integer n with n / r < 2^max_k
+// (resample.cu; used by the resampler and the fused pipeline).
+bool aukit_quotient_fma_is_exact(double r, int max_k);
+
 // grid sizing: enough CTAs to cover `work_items` at `per_cta`, capped to waves*num_sms*occupancy
 static inline unsigned aukit_grid(size_t work_items, size_t per_cta, size_t cap) {
     size_t g = (work_items + per_cta - 1) / per_cta;

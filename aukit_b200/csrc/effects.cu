@@ -24,6 +24,22 @@ mono_kernel(const float *__restrict__ in, size_t in_stride, int C, size_t n, flo
     const double inv = 1.0 / cn;
     auto div_cn = [&](double s) { return pow2 ? s * inv : s / cn; };
     const size_t nvec = vec_ok ? n / 4 : 0;
+    if (C == 2) {
+        // two channels: (0 + a) + b is exact in fp64 and the division by 2 is exact, so the reference value is
+        // the correctly rounded (a + b) / 2 -- which is exactly what one fp32 add and an exact halving produce
+        for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nvec; t += (size_t)gridDim.x * blockDim.x) {
+            const uint4 a4 = ldg_stream(reinterpret_cast<const uint4 *>(in) + t);
+            const uint4 b4 = ldg_stream(reinterpret_cast<const uint4 *>(in + in_stride) + t);
+            stg_stream(reinterpret_cast<float4 *>(out) + t,
+                       make_float4(__fadd_rn(__fadd_rn(0.0f, __uint_as_float(a4.x)), __uint_as_float(b4.x)) * 0.5f,
+                                   __fadd_rn(__fadd_rn(0.0f, __uint_as_float(a4.y)), __uint_as_float(b4.y)) * 0.5f,
+                                   __fadd_rn(__fadd_rn(0.0f, __uint_as_float(a4.z)), __uint_as_float(b4.z)) * 0.5f,
+                                   __fadd_rn(__fadd_rn(0.0f, __uint_as_float(a4.w)), __uint_as_float(b4.w)) * 0.5f));
+        }
+        for (size_t i = nvec * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+            out[i] = __fadd_rn(__fadd_rn(0.0f, in[i]), in[in_stride + i]) * 0.5f;   // (0 + a) + b keeps the reference's zero sign
+        return;
+    }
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nvec; t += (size_t)gridDim.x * blockDim.x) {
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0;                          // local s = 0, A:685
         for (int c = 0; c < C; c++) {

@@ -14,6 +14,12 @@
 namespace {
 using namespace aukit_fmt;
 
+template <int B, int KIND>
+__device__ __forceinline__ float conv_lut(uint32_t raw, const float *lut) {
+    if (B == 1) return lut[raw & 0xFFu];
+    return convert<B, KIND>(raw, lut);
+}
+
 // C > 0: interleaved with compile-time channel count (vector path).
 // C == 0: runtime channel count (per-sample loads, L1-served).
 // Grid: x over chunks of frames; y over planar channel rows (planar layout runs as C == 1
@@ -22,9 +28,13 @@ template <int B, int KIND, bool BE, int C>
 __global__ void __launch_bounds__(256)
 pcm_unpack_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_t frames,
                   size_t out_stride, int channels_rt, size_t planar_row_bytes, int vec_ok) {
-    __shared__ float lut[(KIND == K_ALAW || KIND == K_ULAW) ? 256 : 1];
-    if (KIND == K_ALAW || KIND == K_ULAW) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = g711_value(i, KIND == K_ULAW);
+    // 8-bit formats (G.711 and 8-bit PCM) decode through a 256-entry shared table built with the exact
+    // per-sample formula (A:1374-1379 / A:1133 / A:1152); wider formats compute in registers
+    constexpr bool USE_LUT = (B == 1);
+    __shared__ float lut[USE_LUT ? 256 : 1];
+    if (USE_LUT) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x)
+            lut[i] = (KIND == K_ALAW || KIND == K_ULAW) ? g711_value(i, KIND == K_ULAW) : convert<B, KIND>((uint32_t)i, nullptr);
         __syncthreads();
     }
     const uint8_t *src = in + (size_t)blockIdx.y * planar_row_bytes;
@@ -44,16 +54,16 @@ pcm_unpack_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_
             const size_t fs = (size_t)nc * B;
             if (f0 + 4 <= frames) {
                 float4 o;
-                o.x = convert<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p, vec_ok), lut);
-                o.y = convert<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p + fs, vec_ok), lut);
-                o.z = convert<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p + 2 * fs, vec_ok), lut);
-                o.w = convert<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p + 3 * fs, vec_ok), lut);
+                o.x = conv_lut<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p, vec_ok), lut);
+                o.y = conv_lut<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p + fs, vec_ok), lut);
+                o.z = conv_lut<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p + 2 * fs, vec_ok), lut);
+                o.w = conv_lut<B, KIND>(load_raw_aligned_or_bytes<B, BE>(p + 3 * fs, vec_ok), lut);
                 float *d = dst + (size_t)c * out_stride + f0;
                 if (vec_ok) stg_stream(reinterpret_cast<float4 *>(d), o);
                 else { d[0] = o.x; d[1] = o.y; d[2] = o.z; d[3] = o.w; }
             } else {
                 for (size_t f = f0; f < frames; f++)
-                    dst[(size_t)c * out_stride + f] = convert<B, KIND>(load_raw<B, BE>(src + (f * (size_t)nc + c) * B), lut);
+                    dst[(size_t)c * out_stride + f] = conv_lut<B, KIND>(load_raw<B, BE>(src + (f * (size_t)nc + c) * B), lut);
             }
         }
         return;
@@ -77,10 +87,10 @@ pcm_unpack_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_
 #pragma unroll
                 for (int q = 0; q < FPT / 4; q++) {
                     float4 o;
-                    o.x = convert<B, KIND>(extract<B, BE>(w, ((4 * q + 0) * CC + c) * B), lut);
-                    o.y = convert<B, KIND>(extract<B, BE>(w, ((4 * q + 1) * CC + c) * B), lut);
-                    o.z = convert<B, KIND>(extract<B, BE>(w, ((4 * q + 2) * CC + c) * B), lut);
-                    o.w = convert<B, KIND>(extract<B, BE>(w, ((4 * q + 3) * CC + c) * B), lut);
+                    o.x = conv_lut<B, KIND>(extract<B, BE>(w, ((4 * q + 0) * CC + c) * B), lut);
+                    o.y = conv_lut<B, KIND>(extract<B, BE>(w, ((4 * q + 1) * CC + c) * B), lut);
+                    o.z = conv_lut<B, KIND>(extract<B, BE>(w, ((4 * q + 2) * CC + c) * B), lut);
+                    o.w = conv_lut<B, KIND>(extract<B, BE>(w, ((4 * q + 3) * CC + c) * B), lut);
                     stg_stream(reinterpret_cast<float4 *>(dst + (size_t)c * out_stride + f0 + 4 * q), o);
                 }
             }
@@ -89,7 +99,7 @@ pcm_unpack_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_
             for (int c = 0; c < CC; c++)
                 for (size_t f = f0; f < fend; f++)
                     dst[(size_t)c * out_stride + f] =
-                        convert<B, KIND>(load_raw<B, BE>(src + (f * (size_t)CC + c) * B), lut);
+                        conv_lut<B, KIND>(load_raw<B, BE>(src + (f * (size_t)CC + c) * B), lut);
         }
     }
 }

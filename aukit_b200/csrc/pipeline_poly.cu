@@ -334,41 +334,6 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
     }
 }
 
-// Is q1 = fma(fma(-q0, r, n), y, q0) with q0 = RN(n * y), y = RN(1 / r) the correctly rounded n / r for
-// EVERY integer n with n / r < 2^max_k?  The value v = q0 + rem * y differs from n / r by at most
-// 1.5 * 2^(k-105) in binade k, so RN(v) can differ from RN(n / r) only if n / r lies that close to a
-// rounding midpoint mu = U * 2^(k-53) (U odd).  With r = R * 2^g (R odd) and s = 53 - g - k that means
-// |n * 2^s - R * U| < 3, i.e. R * U = n * 2^s -+ 1 (the left side is odd, the right side's first term
-// even).  For s >= 54 there is exactly one residue U mod 2^s that satisfies it, and it is a midpoint
-// only if it falls in [2^53, 2^54).  If no binade has such a U the three-operation quotient is exact
-// everywhere in range; otherwise (or when s < 54) the kernel uses the IEEE division instead.
-bool quotient_fma_is_exact(double r, int max_k) {
-    typedef unsigned __int128 u128;
-    if (!(r > 0) || !isfinite(r)) return false;
-    int e = 0;
-    const double fr = frexp(r, &e);                       // r = fr * 2^e, fr in [0.5, 1)
-    unsigned long long R = (unsigned long long)ldexp(fr, 53);
-    int g = e - 53;
-    while ((R & 1) == 0) { R >>= 1; g++; }
-    // inverse of R modulo 2^128 (Newton), R odd
-    u128 inv = R;
-    for (int i = 0; i < 8; i++) inv *= (u128)2 - (u128)R * inv;
-    int kmin = 0;
-    frexp(1.0 / r, &kmin);                                // smallest non-zero quotient is 1 / r
-    for (int k = kmin - 2; k <= max_k; k++) {
-        const int s = 53 - g - k;
-        if (s < 54) return false;                         // several candidates per binade: do not claim exactness
-        if (s > 127) return false;                        // residue not decidable in 128 bits
-        const u128 mask = (((u128)1) << s) - 1;
-        for (int sign = 0; sign < 2; sign++) {
-            // R * U == -+1 (mod 2^s)  =>  U == -+inv (mod 2^s)
-            u128 U = sign ? (inv & mask) : ((~inv + 1) & mask);
-            if (U >= (((u128)1) << 53) && U < (((u128)1) << 54)) return false;
-        }
-    }
-    return true;
-}
-
 long long gcd_ll(long long x, long long y) { while (y) { long long r = x % y; x = y; y = r; } return x; }
 
 template <int CT, int MODE, bool MONO, bool APPLY>
@@ -490,7 +455,7 @@ static int poly_range(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_d
     const bool unbounded = kind == K_FLOAT || (kind == K_UNSIGNED && B > 1);
     const int small_px = (unbounded || p->interpolation == AUKIT_INTERP_NONE) ? PX_TABLE : PX_RATIONAL;
     pl.y = 1.0 / a.ratio;
-    pl.quotient_fma_ok = big ? (quotient_fma_is_exact(a.ratio, 41) ? 1 : 0) : 0;
+    pl.quotient_fma_ok = big ? (aukit_quotient_fma_is_exact(a.ratio, 41) ? 1 : 0) : 0;
     pl.eps_r = (float)(fma(-(double)M, a.ratio, (double)L) / ((double)M * a.ratio));   // L/M / ratio_d - 1, numerator exact
     // position mode of a tile = f(largest input position it touches); tiles in which x crosses a power of
     // two >= 2^28 (the "+ 1" of A:666 rounds there) are evaluated exactly

@@ -367,7 +367,8 @@ int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipel
     if (!pow2_ratio && (double)(t_hi * tile_in) >= 1518500249.0) return 0;              // beyond 2^30.5: exact-position kernels
     run_plan rp{};
     rp.L = (int)L; rp.M = (int)M;
-    // the drift x*eps_r is baked into the weight table: split the range so it stays within ~3 % of its value
+    // the drift x*eps_r (<= 2^-22.5) is baked into the weight table: split the range so it stays within ~11 % of its
+    // value (an error below 2^-25.5 in the position, i.e. < 6e-8 in the output)
     unsigned long long t = t_lo;
     int rc = 1;
     while (t < t_hi && rc == 1) {
@@ -375,12 +376,12 @@ int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipel
         const double x0 = (double)(t * tile_in);
         float delta = 0.f;
         if (!pow2_ratio && (double)(t_hi * tile_in) >= 268435456.0) {
-            if (x0 < 268435456.0 / 1.06) {
+            if (x0 < 268435456.0 / 1.25) {
                 // below 2^28 the drift is under 2^-25 and ignored; stop this launch where it starts to matter
-                const unsigned long long lim = (unsigned long long)(268435456.0 / 1.06 / (double)tile_in);
+                const unsigned long long lim = (unsigned long long)(268435456.0 / 1.25 / (double)tile_in);
                 if (lim > t && lim < t_hi) t_end = lim;
             } else {
-                const unsigned long long lim = (unsigned long long)(x0 * 1.06 / (double)tile_in) + 1;
+                const unsigned long long lim = (unsigned long long)(x0 * 1.25 / (double)tile_in) + 1;
                 if (lim < t_hi) t_end = lim;
                 delta = (float)(0.5 * (x0 + (double)(t_end * tile_in)) * eps_r);
             }

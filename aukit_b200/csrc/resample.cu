@@ -29,14 +29,27 @@ struct resample_args {
     size_t n_out;
     float *out;
     size_t out_stride;
+    double y;             // RN(1 / ratio)
+    int quotient_fma_ok;  // host-proved: fma(fma(-q0, r, n), y, q0) == RN(n / r) over the whole index range
+    double base_d;        // (double)(in_first + 1): 1-based index of the first frame held in `in`
 };
 
-template <int MODE>
+template <int MODE, bool QFMA>
 __global__ void __launch_bounds__(256) resample_kernel(resample_args a) {
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < a.n_out;
          o += (size_t)gridDim.x * blockDim.x) {
         const unsigned long long i0 = a.out_first + o;                 // = i - 1
-        const double x = __dadd_rn(__ddiv_rn((double)i0, a.ratio), 1.0);  // A:666
+        const double nd = (double)i0;
+        // x = (i - 1) / ratio + 1 (A:666): the correctly rounded quotient, either by the 3-operation FMA
+        // sequence the host proved exact for this ratio and range, or by the IEEE division
+        double q;
+        if (QFMA) {
+            const double q0 = __dmul_rn(nd, a.y);
+            q = __fma_rn(__fma_rn(-q0, a.ratio, nd), a.y, q0);
+        } else {
+            q = __ddiv_rn(nd, a.ratio);
+        }
+        const double x = __dadd_rn(q, 1.0);
         const double fl = floor(x);
         const bool hit = (x == fl);                                    // x % 1 == 0, A:667
         const long long f = (long long)fl;                             // 1-based index of p1
@@ -76,6 +89,42 @@ __global__ void __launch_bounds__(256) resample_kernel(resample_args a) {
 }
 
 }  // namespace
+
+// Is q1 = fma(fma(-q0, r, n), y, q0) with q0 = RN(n * y), y = RN(1 / r) the correctly rounded n / r for
+// EVERY integer n with n / r < 2^max_k?  The value v = q0 + rem * y differs from n / r by at most
+// 1.5 * 2^(k-105) in binade k, so RN(v) can differ from RN(n / r) only if n / r lies that close to a
+// rounding midpoint mu = U * 2^(k-53) (U odd).  With r = R * 2^g (R odd) and s = 53 - g - k that means
+// |n * 2^s - R * U| < 3, i.e. R * U = n * 2^s -+ 1 (the left side is odd, the right side's first term
+// even).  For s >= 54 there is exactly one residue U mod 2^s that satisfies it, and it is a midpoint
+// only if it falls in [2^53, 2^54).  If no binade has such a U the three-operation quotient is exact
+// everywhere in range; otherwise (or when s < 54) the kernel uses the IEEE division instead.
+bool aukit_quotient_fma_is_exact(double r, int max_k) {
+    typedef unsigned __int128 u128;
+    if (!(r > 0) || !isfinite(r)) return false;
+    int e = 0;
+    const double fr = frexp(r, &e);                       // r = fr * 2^e, fr in [0.5, 1)
+    unsigned long long R = (unsigned long long)ldexp(fr, 53);
+    int g = e - 53;
+    while ((R & 1) == 0) { R >>= 1; g++; }
+    // inverse of R modulo 2^128 (Newton), R odd
+    u128 inv = R;
+    for (int i = 0; i < 8; i++) inv *= (u128)2 - (u128)R * inv;
+    int kmin = 0;
+    frexp(1.0 / r, &kmin);                                // smallest non-zero quotient is 1 / r
+    for (int k = kmin - 2; k <= max_k; k++) {
+        const int s = 53 - g - k;
+        if (s < 54) return false;                         // several candidates per binade: do not claim exactness
+        if (s > 127) return false;                        // residue not decidable in 128 bits
+        const u128 mask = (((u128)1) << s) - 1;
+        for (int sign = 0; sign < 2; sign++) {
+            // R * U == -+1 (mod 2^s)  =>  U == -+inv (mod 2^s)
+            u128 U = sign ? (inv & mask) : ((~inv + 1) & mask);
+            if (U >= (((u128)1) << 53) && U < (((u128)1) << 54)) return false;
+        }
+    }
+    return true;
+}
+
 
 extern "C" uint64_t aukit_resample_out_len(uint64_t n_in, double srcRate, double dstRate) {
     const double ratio = dstRate / srcRate;              // A:658
@@ -130,13 +179,20 @@ extern "C" int aukit_cuda_dev_resample(aukit_ctx *ctx, const float *d_in, size_t
                           (unsigned long long)in_first, (unsigned long long)(in_first + in_avail),
                           (unsigned long long)need_first, (unsigned long long)(need_first + need_count));
     resample_args a{d_in, in_stride, channels, n_in_total, in_first, dstRate / srcRate, out_first, n_out, d_out, out_stride};
+    a.y = 1.0 / a.ratio;
+    a.quotient_fma_ok = aukit_quotient_fma_is_exact(a.ratio, 44) ? 1 : 0;
+    a.base_d = (double)(in_first + 1);
     const int threads = 256;
     const unsigned grid = aukit_grid(n_out, threads, (size_t)ctx->num_sms * 8 * 8);
+#define AUKIT_RS(MODE) \
+    if (a.quotient_fma_ok) resample_kernel<MODE, true><<<grid, threads, 0, ctx->stream>>>(a); \
+    else resample_kernel<MODE, false><<<grid, threads, 0, ctx->stream>>>(a)
     switch (interpolation) {
-    case AUKIT_INTERP_NONE: resample_kernel<AUKIT_INTERP_NONE><<<grid, threads, 0, ctx->stream>>>(a); break;
-    case AUKIT_INTERP_LINEAR: resample_kernel<AUKIT_INTERP_LINEAR><<<grid, threads, 0, ctx->stream>>>(a); break;
-    default: resample_kernel<AUKIT_INTERP_CUBIC><<<grid, threads, 0, ctx->stream>>>(a); break;
+    case AUKIT_INTERP_NONE: AUKIT_RS(AUKIT_INTERP_NONE); break;
+    case AUKIT_INTERP_LINEAR: AUKIT_RS(AUKIT_INTERP_LINEAR); break;
+    default: AUKIT_RS(AUKIT_INTERP_CUBIC); break;
     }
+#undef AUKIT_RS
     ctx->launches++;
     return aukit_cuda_check(cudaGetLastError(), "resample_kernel launch");
 }

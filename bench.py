@@ -195,7 +195,14 @@ def run_b200(args):
 
     n_in_total = int(args.seconds * SRC_RATE) * world
     shard = plan_time_shards(n_in_total, SRC_RATE, DST_RATE, INTERP, world)[rank]
+    if args.emulate_shard:
+        # diagnostics: time ONE GPU on shard r of a w-hour buffer (no collective); not a bench line
+        r, w = (int(v) for v in args.emulate_shard.split("/"))
+        n_in_total = int(args.seconds * SRC_RATE) * w
+        shard = plan_time_shards(n_in_total, SRC_RATE, DST_RATE, INTERP, w)[r]
     n_out_total = int(lib.aukit_resample_out_len(n_in_total, float(SRC_RATE), float(DST_RATE)))
+    if args.emulate_shard:
+        n_out_total = shard.n_out
     sp = ShardedPreload(ctx, shard, n_in_total, BITS, "signed", CHANNELS, SRC_RATE, DST_RATE, INTERP, True, PEAK)
     d_in = synth_frames_cuda(shard.in_first, shard.in_count, torch).view(torch.uint8).reshape(-1)
     in_bytes, out_bytes = d_in.numel(), shard.n_out * 4
@@ -307,6 +314,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=1200.0, help="audio seconds of the 1-core cpu_baseline sample")
     ap.add_argument("--cpu-clip-seconds", type=float, default=30.0, help="--impl reference: audio seconds per thread per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--emulate-shard", default="", help="diagnostics: 'r/w' = run shard r of a w-GPU time-sharded buffer on one GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
