@@ -17,8 +17,16 @@ struct pipe_args {
     double peak;
     float *out;
     size_t out_stride;
+    // standalone Audio:resample through the polyphase kernels: planar float32 input rows, raw output
+    int planar_f32;               // `in` holds float rows, in_stride floats apart (instead of packed interleaved bytes)
+    size_t in_stride;
+    int raw_out;                  // store the resampled value itself (no normalize scale / clamp)
 };
 
 // implemented in pipeline_poly.cu; returns 1 when it handled the launch, 0 when the generic
 // path must run, -1 on error
 int aukit_pipeline_poly_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p, bool apply);
+// Audio:resample on planar float32 through the same polyphase kernels (resample.cu calls it first); same return convention
+int aukit_poly_resample_try(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels, unsigned long long n_in_total,
+                            unsigned long long in_first, size_t in_avail, double srcRate, double dstRate, int interpolation,
+                            unsigned long long out_first, size_t n_out, float *d_out, size_t out_stride);

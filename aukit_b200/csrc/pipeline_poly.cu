@@ -100,8 +100,31 @@ __device__ __forceinline__ void stage_tile(const pipe_args &a, const poly_plan &
     }
 }
 
+// phase A for planar float32 input (standalone Audio:resample): value pass-through, same clamped indexing
+template <int CT>
+__device__ __forceinline__ void stage_planar(const pipe_args &a, const poly_plan &pl, long long g0, float *sm, int plane) {
+    const int C = CT ? CT : a.channels;
+    const long long n_total = (long long)a.n_total;
+    const long long lo = (long long)a.in_first, hi = lo + (long long)a.in_avail;
+    const float *in = reinterpret_cast<const float *>(a.in);
+    for (int i = threadIdx.x; i < pl.nfr; i += blockDim.x) {
+        long long g = g0 + i;
+        g = g < 0 ? 0 : (g >= n_total ? n_total - 1 : g);
+        const bool ok = g >= lo && g < hi;
+        const size_t off = (size_t)(g - lo);
+        if (CT == 2) {
+            reinterpret_cast<float2 *>(sm)[i] = ok ? make_float2(in[off], in[a.in_stride + off]) : make_float2(0.f, 0.f);
+        } else if (CT == 1) {
+            sm[i] = ok ? in[off] : 0.f;
+        } else {
+            for (int c = 0; c < C; c++) sm[(size_t)c * plane + i] = ok ? in[(size_t)c * a.in_stride + off] : 0.f;
+        }
+    }
+}
+
 template <int CT>
 __device__ __forceinline__ void stage_dispatch(const pipe_args &a, const poly_plan &pl, long long g0, float *sm, int plane) {
+    if (a.planar_f32) { stage_planar<CT>(a, pl, g0, sm, plane); return; }
     switch (pl.fmt) {
 #define AUKIT_STAGE(BB, KK, EE) case ((BB << 8) | (KK << 4) | EE): stage_tile<BB, KK, (EE != 0), CT>(a, pl, g0, sm, plane); break;
         AUKIT_STAGE(1, K_SIGNED, 0) AUKIT_STAGE(1, K_UNSIGNED, 0)
@@ -157,14 +180,14 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
         }
     }
     float mult = 0.f;
-    if (APPLY) mult = (float)(a.peak / (double)a.d_max[0]);             // A:3444
+    if (APPLY && !a.raw_out) mult = (float)(a.peak / (double)a.d_max[0]);   // A:3444
     const float inv_cn = a.inv_cn;                                      // s / cn (A:687) as a multiply
     float mx = 0.f;
     const unsigned long long out_lo = a.out_first, out_hi = a.out_first + a.n_out;
     const unsigned long long tile_out = (unsigned long long)pl.Sp * pl.K;
     const long long n_total = (long long)a.n_total;
     const long long in_lo = (long long)a.in_first, in_hi = in_lo + (long long)a.in_avail;
-    const bool s16le = pl.fmt == ((2 << 8) | (K_SIGNED << 4) | 0);
+    const bool s16le = !a.planar_f32 && pl.fmt == ((2 << 8) | (K_SIGNED << 4) | 0);
 
     auto clampv = [](float v) {
         if (PX != PX_RATIONAL) return clamp_ref(v);                     // NaN passes through like A:228-232
@@ -299,7 +322,10 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
                 const float2 f3 = (MODE == AUKIT_INTERP_CUBIC) ? f[3] : z;
                 const float vl = value(f0.x, f1.x, f2.x, f3.x), vr = value(f0.y, f1.y, f2.y, f3.y);
                 if (MONO) acc = vl + vr;                                // (0 + L) + R, A:686
-                else if (APPLY) { outp[0] = clampv(vl * mult); outp[a.out_stride] = clampv(vr * mult); }
+                else if (APPLY) {
+                    if (a.raw_out) { outp[0] = vl; outp[a.out_stride] = vr; }
+                    else { outp[0] = clampv(vl * mult); outp[a.out_stride] = clampv(vr * mult); }
+                }
                 else mx = fmaxf(mx, fmaxf(fabsf(vl), fabsf(vr)));
             } else {
                 for (int c = 0; c < C; c++) {
@@ -310,7 +336,7 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
                     const float p3 = (MODE == AUKIT_INTERP_CUBIC) ? f[3] : 0.f;
                     const float v = value(p0, p1, p2, p3);
                     if (MONO) acc += v;
-                    else if (APPLY) outp[(size_t)c * a.out_stride] = clampv(v * mult);
+                    else if (APPLY) outp[(size_t)c * a.out_stride] = a.raw_out ? v : clampv(v * mult);
                     else mx = fmaxf(mx, fabsf(v));
                 }
             }
@@ -381,6 +407,28 @@ static int poly_range(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_d
 
 int aukit_pipeline_poly_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p, bool apply) {
     return poly_range(ctx, a, p, apply, true);
+}
+
+int aukit_poly_resample_try(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels, unsigned long long n_in_total,
+                            unsigned long long in_first, size_t in_avail, double srcRate, double dstRate, int interpolation,
+                            unsigned long long out_first, size_t n_out, float *d_out, size_t out_stride) {
+    static const bool disabled = getenv("AUKIT_DISABLE_POLY") && getenv("AUKIT_DISABLE_POLY")[0] == '1';
+    if (disabled) return 0;
+    aukit_pipeline_desc d{};
+    d.bitDepth = 32; d.dataType = AUKIT_FLOAT; d.channels = channels; d.bigEndian = 0;
+    d.srcRate = srcRate; d.dstRate = dstRate; d.interpolation = interpolation; d.mono = 0;
+    d.n_in_total = n_in_total; d.in_first = in_first; d.in_avail = in_avail; d.out_first = out_first; d.n_out = n_out;
+    pipe_args a{};
+    a.in = reinterpret_cast<const uint8_t *>(d_in);
+    a.channels = channels;
+    a.n_total = n_in_total; a.in_first = in_first; a.in_avail = in_avail;
+    a.ratio = dstRate / srcRate;
+    a.out_first = out_first; a.n_out = n_out;
+    a.mono = 0; a.inv_cn = 1.0f; a.cn_pow2 = 1;
+    a.d_max = nullptr; a.peak = 1.0;
+    a.out = d_out; a.out_stride = out_stride;
+    a.planar_f32 = 1; a.in_stride = in_stride; a.raw_out = 1;
+    return poly_range(ctx, a, &d, true, false);
 }
 
 static int poly_range(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p, bool apply, bool allow_run) {

@@ -13,6 +13,7 @@
 //
 // One thread per output frame: the position is computed once and shared by all channels.
 #include "common.cuh"
+#include "pipeline.cuh"
 
 #include <math.h>
 
@@ -178,6 +179,13 @@ extern "C" int aukit_cuda_dev_resample(aukit_ctx *ctx, const float *d_in, size_t
         return aukit_fail("aukit_cuda: input window [%llu, %llu) does not cover the needed frames [%llu, %llu)",
                           (unsigned long long)in_first, (unsigned long long)(in_first + in_avail),
                           (unsigned long long)need_first, (unsigned long long)(need_first + need_count));
+    // integer rates with a short period: the polyphase kernels (pipeline_poly.cu) do the same arithmetic with
+    // shared-memory tap reuse and loop-invariant weights; everything else takes the per-frame fp64 kernel below
+    {
+        const int r = aukit_poly_resample_try(ctx, d_in, in_stride, channels, n_in_total, in_first, in_avail, srcRate, dstRate,
+                                              interpolation, out_first, n_out, d_out, out_stride);
+        if (r != 0) return r < 0 ? -1 : 0;
+    }
     resample_args a{d_in, in_stride, channels, n_in_total, in_first, dstRate / srcRate, out_first, n_out, d_out, out_stride};
     a.y = 1.0 / a.ratio;
     a.quotient_fma_ok = aukit_quotient_fma_is_exact(a.ratio, 44) ? 1 : 0;

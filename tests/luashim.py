@@ -1,0 +1,123 @@
+"""Python stand-in for the Lua C module `aukit_cuda` (csrc/lua_binding.c), for running the Lua FACADE
+(aukit_b200/lua/aukit.lua) inside oracle/luavm on the GPU box, where no Lua interpreter exists.  It
+exposes exactly the functions luaopen_aukit_cuda registers, with the same argument conventions, but
+reaches libaukit_cuda.so through the Python ctypes layer instead of the C binding."""
+import ctypes as C
+
+import numpy as np
+
+from oracle.luavm.lua import LuaError, LuaFunction, LuaTable, to_lua
+
+
+class Handle:
+    """Lua userdata standing for an aukit_audio*."""
+
+    def __init__(self, audio):
+        self.audio = audio
+
+
+def make_module(ak):
+    ctx = ak.context()
+    lib = ctx.lib
+
+    def wrap(call, *args):
+        out = C.c_void_p()
+        rc = call(ctx.handle, *args, C.byref(out))
+        if rc != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        return Handle(ak.Audio(ctx, out))
+
+    def num(v, default=None):
+        return default if v is None else v
+
+    def ints(t, n):
+        if not isinstance(t, LuaTable):
+            return None
+        return (C.c_int * n)(*[int(t.get(i + 1)) for i in range(n)])
+
+    def buf(b):
+        return C.cast(C.c_char_p(b), C.c_void_p), len(b)
+
+    def l_pcm(a):
+        p, n = buf(a[0])
+        return [wrap(lib.aukit_cuda_pcm, p, n, int(num(a[1] if len(a) > 1 else None, 8)), int(num(a[2] if len(a) > 2 else None, 0)),
+                     int(num(a[3] if len(a) > 3 else None, 1)), float(num(a[4] if len(a) > 4 else None, 48000)),
+                     int(bool(num(a[5] if len(a) > 5 else None, True))), int(bool(num(a[6] if len(a) > 6 else None, False))))]
+
+    def l_g711(a):
+        p, n = buf(a[0])
+        return [wrap(lib.aukit_cuda_g711, p, n, int(bool(a[1])), int(num(a[2] if len(a) > 2 else None, 1)), float(num(a[3] if len(a) > 3 else None, 8000)))]
+
+    def l_wav(a):
+        data = a[0]
+        p, n = buf(data)
+        info = ak.WavInfo()
+        out = C.c_void_p()
+        rc = lib.aukit_cuda_wav(ctx.handle, p, n, int(bool(a[1] if len(a) > 1 else False)), int(num(a[2] if len(a) > 2 else None, 0)),
+                                C.byref(info), C.byref(out))
+        if rc != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        names = [b"signed", b"unsigned", b"float", b"alaw", b"ulaw", b"adpcm", b"msadpcm", b"dfpwm", None]
+        t = LuaTable()
+        if names[info.format] is not None:
+            t.set(b"dataType", names[info.format])
+        t.set(b"channels", float(info.channels))
+        t.set(b"sampleRate", float(info.sampleRate))
+        t.set(b"blockAlign", float(info.blockAlign))
+        if info.have_fmt:
+            t.set(b"bitDepth", float(info.bitDepth))
+        tags = LuaTable()
+        for i in range(info.ntags):
+            tg = info.tags[i]
+            e = LuaTable()
+            e.arr = [tg.id, data[tg.off: tg.off + tg.len]]
+            tags.set(i + 1, e)
+        t.set(b"tags", tags)
+        return [Handle(ak.Audio(ctx, out)), t]
+
+    def l_resample(a):
+        return [wrap(lib.aukit_cuda_resample, a[0].audio._h, float(a[1]), int(a[2]))]
+
+    def l_mono(a):
+        return [wrap(lib.aukit_cuda_mono, a[0].audio._h)]
+
+    def l_amplify(a):
+        if lib.aukit_cuda_amplify(ctx.handle, a[0].audio._h, float(a[1])) != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        return []
+
+    def l_normalize(a):
+        if lib.aukit_cuda_normalize(ctx.handle, a[0].audio._h, float(num(a[1] if len(a) > 1 else None, 1.0)),
+                                    int(bool(a[2] if len(a) > 2 else False))) != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        return []
+
+    def l_frames(a):
+        au = a[0].audio
+        if len(a) > 1 and a[1] is not None:
+            return [float(lib.aukit_cuda_audio_channel_frames(au._h, int(a[1]) - 1))]
+        return [float(au.frames)]
+
+    def l_read(a):
+        au, c, first, count = a[0].audio, int(a[1]) - 1, int(a[2]) - 1, int(a[3])
+        out = np.empty(count, dtype=np.float32)
+        if lib.aukit_cuda_audio_download(ctx.handle, au._h, c, first, count, C.c_void_p(out.ctypes.data)) != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        t = LuaTable()
+        t.arr = [float(v) for v in out]
+        return [t]
+
+    def l_new(a):
+        out = C.c_void_p()
+        if lib.aukit_cuda_audio_new(ctx.handle, int(a[0]), int(a[1]), float(a[2]), C.byref(out)) != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        return [Handle(ak.Audio(ctx, out))]
+
+    mod = LuaTable()
+    for name, f in {"pcm": l_pcm, "g711": l_g711, "wav": l_wav, "resample": l_resample, "mono": l_mono, "amplify": l_amplify,
+                    "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
+                    "channels": lambda a: [float(a[0].audio.channels())],
+                    "sample_rate": lambda a: [float(lib.aukit_cuda_audio_sample_rate(a[0].audio._h))]}.items():
+        mod.set(name.encode(), LuaFunction(f, "aukit_cuda." + name))
+    mod.set(b"abi_version", 1.0)
+    return mod

@@ -1,0 +1,73 @@
+"""The Lua facade (aukit_b200/lua/aukit.lua) executed by oracle/luavm against the real CUDA library: the
+auplay.lua call chain (auplay.lua:12-27) written in Lua, unchanged from how a ComputerCraft script would
+write it, must reproduce the reference's own golden output.  The C binding (csrc/lua_binding.c) is
+replaced by tests/luashim.py because no Lua interpreter that could dlopen() it exists in the image."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from util import TOL
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+AUPLAY_CHAIN = r'''
+local aukit = require "aukit"
+local data = ...
+local audio = aukit.wav(data)                    -- auplay.lua:12
+local resamp = audio:resample(48000)             -- auplay.lua:21 (aukit.defaultInterpolation = "linear")
+local mono = resamp:mono()                       -- auplay.lua:24
+local ret = aukit.effects.normalize(mono, 0.8)   -- auplay.lua:27: relies on in-place mutation
+assert(ret == mono)
+local out = {}
+for i = 1, #mono.data[1] do out[i] = mono.data[1][i] end
+return out, #mono.data, mono:len(), mono.sampleRate, audio.info.dataType, audio.info.bitDepth, #audio.data, #audio.data[1]
+'''
+
+
+@pytest.fixture(scope="module")
+def lua(ak):
+    from oracle.luavm.aukit_ref import EXPECT_LUA
+    from oracle.luavm.lua import Interpreter
+    import luashim
+    I = Interpreter()
+    I.preload[b"cc.expect"] = lambda: I.run(EXPECT_LUA, "cc.expect")[0]
+    I.preload[b"aukit_cuda"] = lambda: luashim.make_module(ak)
+    src = open(os.path.join(ROOT, "aukit_b200", "lua", "aukit.lua"), "rb").read()
+    I.preload[b"aukit"] = lambda: I.run(src, "aukit.lua(facade)")[0]
+    return I
+
+
+def test_auplay_chain_through_the_lua_facade(lua):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+    manifest = json.loads(z["manifest"].tobytes().decode())
+    i = [m["name"] for m in manifest].index("chain_c1_mini_linear")
+    wav = z["c%d/in" % i].tobytes()
+    ref = z["c%d/out0" % i]                          # what the reference's aukit.lua produced for the same chain
+    r = lua.run(AUPLAY_CHAIN, "auplay_chain", [wav])
+    got = np.array(r[0].arr)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= TOL
+    assert r[1:] == [1.0, len(ref) / 48000.0, 48000.0, b"signed", 16.0, 2.0, 8820.0]
+
+
+def test_facade_errors_and_effects_semantics(lua):
+    from oracle.luavm.lua import LuaError
+    with pytest.raises(LuaError, match=r"bad argument #2 \(invalid bit depth\)"):
+        lua.run('local aukit = require "aukit" return aukit.pcm("\\0\\0", 12)')
+    with pytest.raises(LuaError, match=r"uneven amount of data per channel"):
+        lua.run('local aukit = require "aukit" return aukit.pcm("\\0\\0\\0\\0\\0\\0", 16, "signed", 2)')
+    with pytest.raises(LuaError, match=r"invalid interpolation type"):
+        lua.run('local aukit = require "aukit" return aukit.pcm("\\0\\0\\0\\0", 16):resample(48000, "bogus")')
+    with pytest.raises(LuaError, match=r"not a WAV file"):
+        lua.run('local aukit = require "aukit" return aukit.wav("RIFXxxxxxxxxxxxxxxxx")')
+    r = lua.run('''
+        local aukit = require "aukit"
+        local a = aukit.pcm("\\0\\64\\0\\192", 16, "signed", 1, 8000)       -- 0.5, -0.5
+        local b = aukit.effects.amplify(a, 1)                               -- multiplier 1: untouched, same object
+        local c = aukit.effects.amplify(a, 4)                               -- in place, clamped
+        return b == a, c == a, a.data[1][1], a.data[1][2], #a.data[1], a:len(), a:channels()
+    ''')
+    assert r == [True, True, 1.0, -1.0, 2.0, 2 / 8000.0, 1.0]
