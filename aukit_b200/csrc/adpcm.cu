@@ -16,6 +16,7 @@
 //     32-bit integers while delta < 2^31 and switches that chain to the same fp64
 //     operations the reference performs once it grows past that.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -143,19 +144,19 @@ __global__ void adpcm_stream_kernel(const uint8_t *__restrict__ data, size_t len
 __constant__ int c_ms_adapt[16] = {230, 230, 230, 230, 307, 409, 512, 614,      // nibble 0..7
                                    768, 614, 512, 409, 307, 230, 230, 230};     // nibble 8..15 = -8..-1
 
-struct ms_coefs { int c1[256], c2[256]; int n; };
+struct ms_coefs { int c1[256], c2[256]; int n; };   // 2052 bytes: passed by value as a __grid_constant__ kernel parameter
 
 // One thread per (block, channel) chain.  Nibble stream after the 7*C-byte header is
 // high-nibble-first; nibble m belongs to channel m % C (A:1317-1347 for C = 1, 2).
 __global__ void __launch_bounds__(128)
 ms_adpcm_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, int literal_mono,
-                size_t nblocks, size_t spb, const ms_coefs *__restrict__ coefs,
+                size_t nblocks, size_t spb, const __grid_constant__ ms_coefs coefs,
                 float *__restrict__ out, size_t stride, int *status, int vec_ok) {
     __shared__ int adapt[16];
     if (threadIdx.x < 16) adapt[threadIdx.x] = c_ms_adapt[threadIdx.x];
     __syncthreads();
     const size_t nchains = nblocks * (size_t)C;
-    const int ncoef = coefs->n;
+    const int ncoef = coefs.n;
     for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < nchains;
          id += (size_t)gridDim.x * blockDim.x) {
         const size_t b = id / (size_t)C;
@@ -164,7 +165,7 @@ ms_adpcm_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, int lit
         const uint8_t *hp = data + (literal_mono ? 0 : start);         // A:1331: block 1's header
         int pi = hp[c];
         if (pi >= ncoef) { atomicOr(status, AUKIT_DEVERR_MS_PREDICTOR); pi = 0; }
-        const int c1 = coefs->c1[pi], c2 = coefs->c2[pi];
+        const int c1 = coefs.c1[pi], c2 = coefs.c2[pi];
         auto rd16 = [&](size_t off) { return (int)(int16_t)((uint32_t)hp[off] | ((uint32_t)hp[off + 1] << 8)); };
         int delta = rd16((size_t)C + 2 * (size_t)c);
         int s1 = rd16(3 * (size_t)C + 2 * (size_t)c);
@@ -241,6 +242,271 @@ ms_adpcm_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, int lit
     }
 }
 
+// ------------------------------------------------------------------ warp-tiled variants (the fast paths)
+// The chain-per-lane kernels above store 16 bytes per lane per instruction into 32 different rows:
+// 32 sector requests per STG, which fills the LSU queue (ncu: lg_throttle + mio_throttle were the top
+// stalls).  The tiled kernels keep lane <-> chain but stage 16 samples per chain in shared memory
+// (32 rows x 64 B per warp, XOR-swizzled so both the row-wise STS.128 and the transposed LDS.128 are
+// conflict-free) and flush with each quarter-warp writing two whole 64 B row pieces: 16 full-sector
+// requests per STG instead of 32 half-sector ones.
+
+constexpr size_t ROW_NONE = ~(size_t)0;
+
+__device__ __forceinline__ void stage_put(float4 *st, int lane, int q, float4 v) {
+    st[lane * 4 + (q ^ ((lane >> 1) & 3))] = v;
+}
+
+// rows r = i*8 + lane/4 (i = 0..3), 16-byte column q = lane%4; nq = valid columns (1..4)
+__device__ __forceinline__ void stage_flush(const float4 *st, float *out, const size_t (&rowbase)[4], size_t col0,
+                                            int lane, int nq) {
+    const int q = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = i * 8 + (lane >> 2);
+        const float4 v = st[r * 4 + (q ^ ((r >> 1) & 3))];
+        if (q < nq && rowbase[i] != ROW_NONE) stg_stream(reinterpret_cast<float4 *>(out + rowbase[i] + col0) + q, v);
+    }
+}
+
+// IMA transition table: entry(idx, nib) = (signed diff << 13) | (next_idx * 64); the low 13 bits are the
+// byte offset of the next row, so one LDS replaces the step lookup, the diff arithmetic (A:1252), the
+// sign select and the index update + clamp (A:1250-1254).  1424 entries, rebuilt per CTA from the step table.
+constexpr int IMA_TAB = 89 * 16;
+
+__device__ __forceinline__ void ima_build_tab(int *tab) {
+    for (int e = threadIdx.x; e < IMA_TAB; e += blockDim.x) {
+        const int idx = e >> 4, nib = e & 15, t = nib & 7;
+        const int step = c_ima_steps[idx];
+        const int diff = ((t * step) >> 2) + (step >> 3);
+        int nidx = idx + ((t < 4) ? -1 : (2 * t - 6));
+        nidx = min(max(nidx, 0), 88);
+        tab[e] = ((nib & 8) ? -diff : diff) * 8192 + nidx * 64;
+    }
+}
+
+// state: pred, and `row` = idx * 64 (byte offset of the table row); nib4 = nibble * 4 (byte offset in the row)
+__device__ __forceinline__ float ima_tab_step(const char *tab, int nib4, int &pred, int &row) {
+    const int e = *reinterpret_cast<const int *>(tab + (row | nib4));
+    row = e & 0x1FC0;
+    pred = min(max(pred + (e >> 13), -32768), 32767);
+    return s16_to_float(pred);
+}
+
+__device__ __forceinline__ void ima_word(const char *tab, uint32_t w, int &pred, int &row, float4 &a, float4 &b) {
+    a.x = ima_tab_step(tab, (w << 2) & 0x3C, pred, row);
+    a.y = ima_tab_step(tab, (w >> 2) & 0x3C, pred, row);
+    a.z = ima_tab_step(tab, (w >> 6) & 0x3C, pred, row);
+    a.w = ima_tab_step(tab, (w >> 10) & 0x3C, pred, row);
+    b.x = ima_tab_step(tab, (w >> 14) & 0x3C, pred, row);
+    b.y = ima_tab_step(tab, (w >> 18) & 0x3C, pred, row);
+    b.z = ima_tab_step(tab, (w >> 22) & 0x3C, pred, row);
+    b.w = ima_tab_step(tab, (w >> 26) & 0x3C, pred, row);
+}
+
+// general / literal-stereo block layout, 4-byte aligned input, 16-byte aligned output rows
+__global__ void __launch_bounds__(128)
+ima_wav_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, size_t nblocks, size_t spb,
+                     int groups, float *__restrict__ out, size_t stride, int *status) {
+    __shared__ __align__(16) int tab[IMA_TAB];
+    __shared__ float4 stage_all[4][128];
+    ima_build_tab(tab);
+    __syncthreads();
+    const char *tb = reinterpret_cast<const char *>(tab);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *st = stage_all[warp];
+    const size_t nchains = nblocks * (size_t)C;
+    const size_t ntiles = (nchains + 31) / 32;
+    const size_t hdr = 4 * (size_t)C;
+    for (size_t tile = (size_t)blockIdx.x * 4 + warp; tile < ntiles; tile += (size_t)gridDim.x * 4) {
+        const size_t id0 = tile * 32;
+        size_t rowbase[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const size_t rid = id0 + i * 8 + (lane >> 2);
+            rowbase[i] = rid < nchains ? (rid % (size_t)C) * stride + (rid / (size_t)C) * spb : ROW_NONE;
+        }
+        const size_t id = min(id0 + lane, nchains - 1);                  // surplus lanes shadow the last chain
+        const size_t b = id / (size_t)C;
+        const int c = (int)(id % (size_t)C);
+        const uint8_t *gp = data + b * (size_t)blockAlign + 4 * (size_t)c;
+        const uint32_t hw = *reinterpret_cast<const uint32_t *>(gp);
+        int pred = (int)(int16_t)(hw & 0xFFFF);
+        int idx = (hw >> 16) & 0xFF;
+        if (idx > 88) { atomicOr(status, AUKIT_DEVERR_IMA_INDEX); idx = 88; }
+        int row = idx * 64;
+        const int pairs = groups >> 1;
+        uint32_t w0 = 0, w1 = 0;
+        if (pairs > 0) {
+            w0 = *reinterpret_cast<const uint32_t *>(gp + hdr);
+            w1 = *reinterpret_cast<const uint32_t *>(gp + 2 * hdr);
+        }
+        gp += 2 * hdr;
+        size_t col = 0;
+        for (int pr = 0; pr < pairs; pr++, col += 16) {
+            uint32_t n0 = 0, n1 = 0;
+            if (pr + 1 < pairs) {                                        // prefetch: the chain itself is serial
+                n0 = *reinterpret_cast<const uint32_t *>(gp + hdr);
+                n1 = *reinterpret_cast<const uint32_t *>(gp + 2 * hdr);
+            }
+            gp += 2 * hdr;
+            float4 a, bq;
+            ima_word(tb, w0, pred, row, a, bq);
+            stage_put(st, lane, 0, a);
+            stage_put(st, lane, 1, bq);
+            ima_word(tb, w1, pred, row, a, bq);
+            stage_put(st, lane, 2, a);
+            stage_put(st, lane, 3, bq);
+            __syncwarp();
+            stage_flush(st, out, rowbase, col, lane, 4);
+            __syncwarp();
+            w0 = n0; w1 = n1;
+        }
+        if (groups & 1) {
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(gp - hdr);
+            float4 a, bq;
+            ima_word(tb, w, pred, row, a, bq);
+            stage_put(st, lane, 0, a);
+            stage_put(st, lane, 1, bq);
+            __syncwarp();
+            stage_flush(st, out, rowbase, col, lane, 2);
+            __syncwarp();
+        }
+    }
+}
+
+// ---- MS-ADPCM, warp-tiled.  Fast path per 4 samples in 32-bit integers while delta < 2^14 (then
+// delta < 2^14 * 3^4 < 2^21 inside the quad, so adapt*delta and nib*delta cannot overflow) and
+// |c1| + |c2| <= 65535; anything else (huge deltas, the fp64 continuation) goes through the
+// out-of-line general step, which carries the same state the chain-per-lane kernel does.
+struct ms_state { int s1, s2, delta, big; double ds1, ds2, dd; };
+
+__device__ __noinline__ float ms_general_step(ms_state *st, int un, int c1, int c2) {
+    const int nib = un >= 8 ? un - 16 : un;                             // A:1319-1320
+    const int ad = c_ms_adapt[un];
+    if (!st->big) {
+        const long long lin = ((long long)st->s1 * c1 + (long long)st->s2 * c2) >> 8;   // floor(/256), A:1321
+        const long long pl = lin + (long long)nib * st->delta;
+        const int p = pl < -32768 ? -32768 : (pl > 32767 ? 32767 : (int)pl);
+        st->s2 = st->s1; st->s1 = p;
+        long long nd = ((long long)ad * st->delta) >> 8;                                // A:1324
+        if (nd < 16) nd = 16;
+        if (nd >= (1ll << 31)) {
+            st->big = 1; st->ds1 = (double)st->s1; st->ds2 = (double)st->s2; st->dd = (double)nd;
+            st->delta = 0x7FFFFFFF;                                     // keeps the caller on this path
+        } else st->delta = (int)nd;
+        return s16_to_float(p);
+    }
+    // the reference's own double arithmetic (Lua numbers), A:1321-1324
+    double p = floor(__dadd_rn(__dmul_rn(st->ds1, (double)c1), __dmul_rn(st->ds2, (double)c2)) / 256.0);
+    p = __dadd_rn(p, __dmul_rn((double)nib, st->dd));
+    p = p < -32768.0 ? -32768.0 : (p > 32767.0 ? 32767.0 : p);          // NaN passes, A:228
+    st->ds2 = st->ds1; st->ds1 = p;
+    const double nd = floor(__dmul_rn((double)ad, st->dd) / 256.0);
+    st->dd = (16.0 > nd) ? 16.0 : nd;                                   // math.max(nd, 16)
+    return (float)(p / (p < 0 ? 32768.0 : 32767.0));
+}
+
+// requires spb % 4 == 0 and 16-byte aligned output rows; chain layout as ms_adpcm_kernel
+__global__ void __launch_bounds__(128)
+ms_adpcm_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, int literal_mono,
+                      size_t nblocks, size_t spb, const __grid_constant__ ms_coefs coefs,
+                      float *__restrict__ out, size_t stride, int *status) {
+    __shared__ int adapt[16];
+    __shared__ float4 stage_all[4][128];
+    if (threadIdx.x < 16) adapt[threadIdx.x] = c_ms_adapt[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *st = stage_all[warp];
+    const size_t nchains = nblocks * (size_t)C;
+    const size_t ntiles = (nchains + 31) / 32;
+    const int ncoef = coefs.n;
+    const bool evenC = (C & 1) == 0;
+    const int bstride = C >> 1;
+    const int nquads = (int)(spb / 4);
+    for (size_t tile = (size_t)blockIdx.x * 4 + warp; tile < ntiles; tile += (size_t)gridDim.x * 4) {
+        const size_t id0 = tile * 32;
+        size_t rowbase[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const size_t rid = id0 + i * 8 + (lane >> 2);
+            rowbase[i] = rid < nchains ? (rid % (size_t)C) * stride + (rid / (size_t)C) * spb : ROW_NONE;
+        }
+        const size_t id = min(id0 + lane, nchains - 1);
+        const size_t b = id / (size_t)C;
+        const int c = (int)(id % (size_t)C);
+        const size_t start = b * (size_t)blockAlign;
+        const uint8_t *hp = data + (literal_mono ? 0 : start);         // A:1331: block 1's header
+        int pi = hp[c];
+        if (pi >= ncoef) { atomicOr(status, AUKIT_DEVERR_MS_PREDICTOR); pi = 0; }
+        const int c1 = coefs.c1[pi], c2 = coefs.c2[pi];
+        auto rd16 = [&](size_t off) { return (int)(int16_t)((uint32_t)hp[off] | ((uint32_t)hp[off + 1] << 8)); };
+        int delta = rd16((size_t)C + 2 * (size_t)c);
+        int s1 = rd16(3 * (size_t)C + 2 * (size_t)c);
+        int s2 = rd16(5 * (size_t)C + 2 * (size_t)c);
+        const uint8_t *np = data + start + 7 * (size_t)C;
+        const uint8_t *bp = np + (c >> 1);                              // even C: one byte per sample, C/2 apart
+        const int sh = (c & 1) ? 0 : 4;
+        const bool narrow = (abs(c1) + abs(c2)) <= 65535;
+        ms_state gs;
+        gs.big = 0;
+        // nibble k of this chain (0-based after the two header samples)
+        auto fetch = [&](int k) -> int {
+            if (evenC) return (bp[(size_t)k * (size_t)bstride] >> sh) & 0xF;
+            const size_t m = (size_t)k * (size_t)C + (size_t)c;
+            const int byte = np[m >> 1];
+            return (m & 1) ? (byte & 0xF) : (byte >> 4);
+        };
+        auto fast = [&](int un) -> float {
+            const int nib = (un ^ 8) - 8;
+            int p = ((s1 * c1 + s2 * c2) >> 8) + nib * delta;           // A:1321-1322
+            p = min(max(p, -32768), 32767);
+            s2 = s1; s1 = p;
+            delta = max((adapt[un] * delta) >> 8, 16);                  // A:1324
+            return s16_to_float(p);
+        };
+        auto general = [&](int un) -> float {
+            gs.s1 = s1; gs.s2 = s2; gs.delta = delta;
+            const float v = ms_general_step(&gs, un, c1, c2);
+            s1 = gs.s1; s2 = gs.s2; delta = gs.delta;
+            return v;
+        };
+        auto quad = [&](int k) -> float4 {                              // samples k..k+3
+            const int u0 = fetch(k), u1 = fetch(k + 1), u2 = fetch(k + 2), u3 = fetch(k + 3);
+            float4 v;
+            if (narrow && delta < (1 << 14) && delta > -(1 << 16)) {
+                v.x = fast(u0); v.y = fast(u1); v.z = fast(u2); v.w = fast(u3);
+            } else {
+                v.x = general(u0); v.y = general(u1); v.z = general(u2); v.w = general(u3);
+            }
+            return v;
+        };
+        // quad 0 = the two header samples (A:1312-1315) + the first two decoded ones
+        {
+            const int u0 = fetch(0), u1 = fetch(1);
+            float4 v;
+            v.x = s16_to_float(s2); v.y = s16_to_float(s1);
+            v.z = general(u0); v.w = general(u1);
+            stage_put(st, lane, 0, v);
+        }
+        size_t col = 0;
+        int q = 1;
+        for (int j = 1; j < nquads; j++) {
+            stage_put(st, lane, q, quad(4 * j - 2));
+            if (++q == 4) {
+                __syncwarp();
+                stage_flush(st, out, rowbase, col, lane, 4);
+                __syncwarp();
+                q = 0; col += 16;
+            }
+        }
+        if (q) {
+            __syncwarp();
+            stage_flush(st, out, rowbase, col, lane, q);
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" size_t aukit_ima_adpcm_wav_frames(size_t nbytes, int blockAlign, int channels, int dialect) {
@@ -303,9 +569,16 @@ extern "C" int aukit_cuda_dev_ima_adpcm_wav(aukit_ctx *ctx, const void *d_in, si
     const int word_aligned = ((uintptr_t)d_in % 4 == 0) && (blockAlign % 4 == 0);
     const int threads = 128;
     const unsigned grid = aukit_grid(nblocks * (size_t)channels, threads, (size_t)ctx->num_sms * 64);
+    const int out_aligned = ((uintptr_t)d_out % 16 == 0) && (out_stride % 4 == 0);
+    if (mode != IMA_LITERAL_MONO && word_aligned && out_aligned && groups > 0 && !getenv("AUKIT_DISABLE_TILED_ADPCM")) {
+        ima_wav_tiled_kernel<<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels,
+                                                                nblocks, spb, groups, d_out, out_stride, ctx->d_status);
+        ctx->launches++;
+        return aukit_cuda_check(cudaGetLastError(), "ima_wav_tiled_kernel launch");
+    }
     ima_wav_kernel<<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), nbytes, blockAlign, channels,
                                                       mode, nblocks, spb, groups, d_out, out_stride, ctx->d_status,
-                                                      word_aligned, ((uintptr_t)d_out % 16 == 0) && (out_stride % 4 == 0));
+                                                      word_aligned, out_aligned);
     ctx->launches++;
     return aukit_cuda_check(cudaGetLastError(), "ima_wav_kernel launch");
 }
@@ -333,21 +606,25 @@ extern "C" int aukit_cuda_dev_msadpcm(aukit_ctx *ctx, const void *d_in, size_t n
     if (ncoef > 256) return aukit_fail("aukit_cuda: more than 256 coefficient pairs");
     for (int i = 0; i < ncoef; i++) { h.c1[i] = coef1[i]; h.c2[i] = coef2[i]; }
     h.n = ncoef;
-    void *d_coefs = nullptr;
-    if (aukit_upload_bytes(ctx, &h, sizeof h, &d_coefs)) return -1;
     const size_t nblocks = nbytes / bA;
     const size_t spb = 2 + (bA - 7 * C) * 2 / C;
-    if (channels > 1 && out_stride < nblocks * spb) { aukit_dev_free(ctx, d_coefs); return aukit_fail("aukit_cuda: out_stride < frames"); }
+    if (channels > 1 && out_stride < nblocks * spb) return aukit_fail("aukit_cuda: out_stride < frames");
     const int threads = 128;
     const unsigned grid = aukit_grid(nblocks * C, threads, (size_t)ctx->num_sms * 64);
+    const int vec_ok = ((uintptr_t)d_out % 16 == 0) && (out_stride % 4 == 0);
+    if (vec_ok && spb % 4 == 0 && !getenv("AUKIT_DISABLE_TILED_ADPCM")) {
+        ms_adpcm_tiled_kernel<<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels,
+                                                                 dialect == AUKIT_DIALECT_LITERAL && channels == 1, nblocks,
+                                                                 spb, h, d_out, out_stride, ctx->d_status);
+        ctx->launches++;
+        return aukit_cuda_check(cudaGetLastError(), "ms_adpcm_tiled_kernel launch");
+    }
     ms_adpcm_kernel<<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels,
                                                        dialect == AUKIT_DIALECT_LITERAL && channels == 1, nblocks, spb,
-                                                       static_cast<const ms_coefs *>(d_coefs), d_out, out_stride,
-                                                       ctx->d_status, ((uintptr_t)d_out % 16 == 0) && (out_stride % 4 == 0));
+                                                       h, d_out, out_stride,
+                                                       ctx->d_status, vec_ok);
     ctx->launches++;
-    int rc = aukit_cuda_check(cudaGetLastError(), "ms_adpcm_kernel launch");
-    aukit_dev_free(ctx, d_coefs);
-    return rc;
+    return aukit_cuda_check(cudaGetLastError(), "ms_adpcm_kernel launch");
 }
 
 // used by capi.cu for aukit_cuda_adpcm (headerless nibble strings)
