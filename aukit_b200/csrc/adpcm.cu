@@ -252,123 +252,140 @@ ms_adpcm_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, int lit
 
 constexpr size_t ROW_NONE = ~(size_t)0;
 
+// Per-warp staging tile: 32 rows (one per chain) x NQ float4.  Row-wise STS.128 (lane = row, fixed column)
+// and transposed LDS.128 (consecutive lanes = consecutive columns of a row) are both conflict-free under
+// the XOR swizzle below.  NQ = 4, 8 or 16: 64, 128 or 256 bytes per row per flush.
+template <int NQ> __device__ __forceinline__ int stage_swz(int r) { return NQ == 4 ? ((r >> 1) & 3) : (r & 7); }
+
+template <int NQ>
 __device__ __forceinline__ void stage_put(float4 *st, int lane, int q, float4 v) {
-    st[lane * 4 + (q ^ ((lane >> 1) & 3))] = v;
+    st[lane * NQ + (q ^ stage_swz<NQ>(lane))] = v;
 }
 
-// rows r = i*8 + lane/4 (i = 0..3), 16-byte column q = lane%4; nq = valid columns (1..4)
-__device__ __forceinline__ void stage_flush(const float4 *st, float *out, const size_t (&rowbase)[4], size_t col0,
-                                            int lane, int nq) {
-    const int q = lane & 3;
+// nq = valid float4 columns (1..NQ); rowb[r] = output float index of row r's block start (ROW_NONE = no chain)
+template <int NQ>
+__device__ __forceinline__ void stage_flush(const float4 *st, float *out, const size_t *rowb, size_t col0, int lane, int nq) {
+    constexpr int RPI = 32 / NQ;                                        // rows per instruction
+    const int q = lane % NQ;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int r = i * 8 + (lane >> 2);
-        const float4 v = st[r * 4 + (q ^ ((r >> 1) & 3))];
-        if (q < nq && rowbase[i] != ROW_NONE) stg_stream(reinterpret_cast<float4 *>(out + rowbase[i] + col0) + q, v);
+    for (int i = 0; i < NQ; i++) {
+        const int r = i * RPI + lane / NQ;
+        const float4 v = st[r * NQ + (q ^ stage_swz<NQ>(r))];
+        const size_t base = rowb[r];
+        if (q < nq && base != ROW_NONE) stg_stream(reinterpret_cast<float4 *>(out + base + col0) + q, v);
     }
 }
 
-// IMA transition table: entry(idx, nib) = (signed diff << 13) | (next_idx * 64); the low 13 bits are the
-// byte offset of the next row, so one LDS replaces the step lookup, the diff arithmetic (A:1252), the
-// sign select and the index update + clamp (A:1250-1254).  1424 entries, rebuilt per CTA from the step table.
+// IMA transition table: entry(idx, nib) = float bits of (signed diff * 2^-16) with next_idx in the low 7
+// bits (the float needs 16 significant bits, so its low 8 mantissa bits are free).  One LDS.32 replaces
+// the step lookup, the diff arithmetic (A:1252), the sign select and the index update + clamp
+// (A:1250-1254).  1424 entries (5.6 KB), rebuilt per CTA.  32-bit entries on purpose: with 8-byte
+// entries the random (idx, nibble) accesses cost ~5 shared-memory wavefronts per sample and the kernel
+// became shared-memory bound (ncu, r1); 4-byte ones cost ~2.3.
+//
+// The predictor is carried as u = (pred + 32768) * 2^-16 in [0, 65535/65536]: u + d is exact in fp32
+// (both are multiples of 2^-16 below 2), the lower clamp (A:1253) is the saturate of the add, the upper
+// one a single min, and the output p / (p < 0 and 32768 or 32767) follows without an int->float convert:
+//   p * 2^-15 = 2u - 1 (exact),  max(p, 0) * 2^-16 = saturate(u - 1/2) (exact),
+//   out = fma(max(p,0) * 2^-16, 2^16 / (32767 * 32768), p * 2^-15)  -- the same FMA s16_to_float does.
 constexpr int IMA_TAB = 89 * 16;
 
-__device__ __forceinline__ void ima_build_tab(int *tab) {
+__device__ __forceinline__ void ima_build_tab(uint32_t *tab) {
     for (int e = threadIdx.x; e < IMA_TAB; e += blockDim.x) {
         const int idx = e >> 4, nib = e & 15, t = nib & 7;
         const int step = c_ima_steps[idx];
         const int diff = ((t * step) >> 2) + (step >> 3);
         int nidx = idx + ((t < 4) ? -1 : (2 * t - 6));
         nidx = min(max(nidx, 0), 88);
-        tab[e] = ((nib & 8) ? -diff : diff) * 8192 + nidx * 64;
+        tab[e] = __float_as_uint((float)((nib & 8) ? -diff : diff) * (1.0f / 65536.0f)) | (uint32_t)nidx;
     }
 }
 
-// state: pred, and `row` = idx * 64 (byte offset of the table row); nib4 = nibble * 4 (byte offset in the row)
-__device__ __forceinline__ float ima_tab_step(const char *tab, int nib4, int &pred, int &row) {
-    const int e = *reinterpret_cast<const int *>(tab + (row | nib4));
-    row = e & 0x1FC0;
-    pred = min(max(pred + (e >> 13), -32768), 32767);
-    return s16_to_float(pred);
+// state: u, and e = the previous table entry (its low 7 bits = current step index); x4 = nibble * 4
+__device__ __forceinline__ float ima_tab_step(const char *tab, uint32_t x4, float &u, uint32_t &e) {
+    e = *reinterpret_cast<const uint32_t *>(tab + ((e & 0x7F) * 64 + x4));
+    u = fminf(__saturatef(__fadd_rn(u, __uint_as_float(e & 0xFFFFFF80u))), 65535.0f / 65536.0f);
+    const float lo = __fmaf_rn(u, 2.0f, -1.0f);
+    return __fmaf_rn(__saturatef(__fadd_rn(u, -0.5f)), (1.0f / (32767.0f * 32768.0f)) * 65536.0f, lo);
 }
 
-__device__ __forceinline__ void ima_word(const char *tab, uint32_t w, int &pred, int &row, float4 &a, float4 &b) {
-    a.x = ima_tab_step(tab, (w << 2) & 0x3C, pred, row);
-    a.y = ima_tab_step(tab, (w >> 2) & 0x3C, pred, row);
-    a.z = ima_tab_step(tab, (w >> 6) & 0x3C, pred, row);
-    a.w = ima_tab_step(tab, (w >> 10) & 0x3C, pred, row);
-    b.x = ima_tab_step(tab, (w >> 14) & 0x3C, pred, row);
-    b.y = ima_tab_step(tab, (w >> 18) & 0x3C, pred, row);
-    b.z = ima_tab_step(tab, (w >> 22) & 0x3C, pred, row);
-    b.w = ima_tab_step(tab, (w >> 26) & 0x3C, pred, row);
+__device__ __forceinline__ void ima_word(const char *tab, uint32_t w, float &u, uint32_t &e, float4 &a, float4 &b) {
+    a.x = ima_tab_step(tab, (w << 2) & 0x3C, u, e);
+    a.y = ima_tab_step(tab, (w >> 2) & 0x3C, u, e);
+    a.z = ima_tab_step(tab, (w >> 6) & 0x3C, u, e);
+    a.w = ima_tab_step(tab, (w >> 10) & 0x3C, u, e);
+    b.x = ima_tab_step(tab, (w >> 14) & 0x3C, u, e);
+    b.y = ima_tab_step(tab, (w >> 18) & 0x3C, u, e);
+    b.z = ima_tab_step(tab, (w >> 22) & 0x3C, u, e);
+    b.w = ima_tab_step(tab, (w >> 26) & 0x3C, u, e);
 }
 
 // general / literal-stereo block layout, 4-byte aligned input, 16-byte aligned output rows
-__global__ void __launch_bounds__(128)
+template <int NQ, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 ima_wav_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, size_t nblocks, size_t spb,
                      int groups, float *__restrict__ out, size_t stride, int *status) {
-    __shared__ __align__(16) int tab[IMA_TAB];
-    __shared__ float4 stage_all[4][128];
+    constexpr int GP = NQ / 2;                                          // 8-sample groups per flush
+    __shared__ __align__(16) uint32_t tab[IMA_TAB];
+    __shared__ float4 stage_all[4][32 * NQ];
+    __shared__ size_t rowb_all[4][32];
     ima_build_tab(tab);
     __syncthreads();
     const char *tb = reinterpret_cast<const char *>(tab);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *st = stage_all[warp];
+    size_t *rowb = rowb_all[warp];
     const size_t nchains = nblocks * (size_t)C;
     const size_t ntiles = (nchains + 31) / 32;
     const size_t hdr = 4 * (size_t)C;
     for (size_t tile = (size_t)blockIdx.x * 4 + warp; tile < ntiles; tile += (size_t)gridDim.x * 4) {
-        const size_t id0 = tile * 32;
-        size_t rowbase[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const size_t rid = id0 + i * 8 + (lane >> 2);
-            rowbase[i] = rid < nchains ? (rid % (size_t)C) * stride + (rid / (size_t)C) * spb : ROW_NONE;
-        }
-        const size_t id = min(id0 + lane, nchains - 1);                  // surplus lanes shadow the last chain
+        const size_t id = min(tile * 32 + lane, nchains - 1);            // surplus lanes shadow the last chain
         const size_t b = id / (size_t)C;
         const int c = (int)(id % (size_t)C);
+        rowb[lane] = tile * 32 + lane < nchains ? (size_t)c * stride + b * spb : ROW_NONE;
         const uint8_t *gp = data + b * (size_t)blockAlign + 4 * (size_t)c;
         const uint32_t hw = *reinterpret_cast<const uint32_t *>(gp);
-        int pred = (int)(int16_t)(hw & 0xFFFF);
+        float pred = (float)((int)(int16_t)(hw & 0xFFFF) + 32768) * (1.0f / 65536.0f);      // u, see above
         int idx = (hw >> 16) & 0xFF;
         if (idx > 88) { atomicOr(status, AUKIT_DEVERR_IMA_INDEX); idx = 88; }
-        int row = idx * 64;
-        const int pairs = groups >> 1;
-        uint32_t w0 = 0, w1 = 0;
-        if (pairs > 0) {
-            w0 = *reinterpret_cast<const uint32_t *>(gp + hdr);
-            w1 = *reinterpret_cast<const uint32_t *>(gp + 2 * hdr);
+        uint32_t row = (uint32_t)idx;                                    // "previous entry": only its index bits matter
+        const int nper = groups / GP;
+        uint32_t w[GP];
+        gp += hdr;                                                       // first group word of this chain
+        if (nper > 0) {
+#pragma unroll
+            for (int g = 0; g < GP; g++) w[g] = *reinterpret_cast<const uint32_t *>(gp + (size_t)g * hdr);
         }
-        gp += 2 * hdr;
         size_t col = 0;
-        for (int pr = 0; pr < pairs; pr++, col += 16) {
-            uint32_t n0 = 0, n1 = 0;
-            if (pr + 1 < pairs) {                                        // prefetch: the chain itself is serial
-                n0 = *reinterpret_cast<const uint32_t *>(gp + hdr);
-                n1 = *reinterpret_cast<const uint32_t *>(gp + 2 * hdr);
+        for (int per = 0; per < nper; per++, col += 4 * NQ) {
+            gp += GP * hdr;
+            uint32_t n[GP];
+#pragma unroll
+            for (int g = 0; g < GP; g++)                                 // prefetch: the chain itself is serial
+                n[g] = (per + 1 < nper) ? *reinterpret_cast<const uint32_t *>(gp + (size_t)g * hdr) : 0u;
+#pragma unroll
+            for (int g = 0; g < GP; g++) {
+                float4 a, bq;
+                ima_word(tb, w[g], pred, row, a, bq);
+                stage_put<NQ>(st, lane, 2 * g, a);
+                stage_put<NQ>(st, lane, 2 * g + 1, bq);
             }
-            gp += 2 * hdr;
-            float4 a, bq;
-            ima_word(tb, w0, pred, row, a, bq);
-            stage_put(st, lane, 0, a);
-            stage_put(st, lane, 1, bq);
-            ima_word(tb, w1, pred, row, a, bq);
-            stage_put(st, lane, 2, a);
-            stage_put(st, lane, 3, bq);
             __syncwarp();
-            stage_flush(st, out, rowbase, col, lane, 4);
+            stage_flush<NQ>(st, out, rowb, col, lane, NQ);
             __syncwarp();
-            w0 = n0; w1 = n1;
+#pragma unroll
+            for (int g = 0; g < GP; g++) w[g] = n[g];
         }
-        if (groups & 1) {
-            const uint32_t w = *reinterpret_cast<const uint32_t *>(gp - hdr);
-            float4 a, bq;
-            ima_word(tb, w, pred, row, a, bq);
-            stage_put(st, lane, 0, a);
-            stage_put(st, lane, 1, bq);
+        const int rem = groups - nper * GP;
+        if (rem) {
+            for (int g = 0; g < rem; g++) {
+                float4 a, bq;
+                ima_word(tb, *reinterpret_cast<const uint32_t *>(gp + (size_t)g * hdr), pred, row, a, bq);
+                stage_put<NQ>(st, lane, 2 * g, a);
+                stage_put<NQ>(st, lane, 2 * g + 1, bq);
+            }
             __syncwarp();
-            stage_flush(st, out, rowbase, col, lane, 2);
+            stage_flush<NQ>(st, out, rowb, col, lane, 2 * rem);
             __syncwarp();
         }
     }
@@ -378,11 +395,15 @@ ima_wav_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, si
 // delta < 2^14 * 3^4 < 2^21 inside the quad, so adapt*delta and nib*delta cannot overflow) and
 // |c1| + |c2| <= 65535; anything else (huge deltas, the fp64 continuation) goes through the
 // out-of-line general step, which carries the same state the chain-per-lane kernel does.
+//
+// Input records: with the two header samples counted as samples 0 and 1 of the block, the nibbles of
+// samples 4j..4j+3 of ALL channels are the 2C bytes at block offset 2C(3 + j) (record 0 starts inside
+// the header: its second half holds the first two coded frames).  For C in {1, 2, 4, 8} one aligned
+// 2C-byte load per quad fetches the record and the chain's four nibbles come out with constant shifts.
 struct ms_state { int s1, s2, delta, big; double ds1, ds2, dd; };
 
-__device__ __noinline__ float ms_general_step(ms_state *st, int un, int c1, int c2) {
-    const int nib = un >= 8 ? un - 16 : un;                             // A:1319-1320
-    const int ad = c_ms_adapt[un];
+__device__ __noinline__ float ms_general_step(ms_state *st, int nib, int c1, int c2) {
+    const int ad = c_ms_adapt[nib & 15];
     if (!st->big) {
         const long long lin = ((long long)st->s1 * c1 + (long long)st->s2 * c2) >> 8;   // floor(/256), A:1321
         const long long pl = lin + (long long)nib * st->delta;
@@ -406,36 +427,88 @@ __device__ __noinline__ float ms_general_step(ms_state *st, int un, int c1, int 
     return (float)(p / (p < 0 ? 32768.0 : 32767.0));
 }
 
+__device__ __forceinline__ int sx4(uint32_t w, int left) { return (int)(w << left) >> 28; }   // signed nibble
+
+// One input record (the nibbles of 4 consecutive samples of all channels).  TC = channel count when it
+// is 1, 2, 4 or 8 and the records are 2C-aligned: a single vector load, issued one quad ahead of its use;
+// TC = 0 reads byte by byte for any C.  cs = bit offset of the chain's nibble inside a frame (high
+// nibble first: 8*(c/2) + (c odd ? 0 : 4)).
+template <int TC> struct ms_rec { uint32_t w[TC == 8 ? 4 : (TC == 4 ? 2 : 1)]; };
+
+template <int TC>
+__device__ __forceinline__ ms_rec<TC> ms_load_rec(const uint8_t *blk, int j) {
+    ms_rec<TC> r;
+    if (TC == 8) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(blk + 16 * (3 + j));
+        r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+    } else if (TC == 4) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(blk + 8 * (3 + j));
+        r.w[0] = v.x; r.w[1] = v.y;
+    } else if (TC == 2) {
+        r.w[0] = *reinterpret_cast<const uint32_t *>(blk + 4 * (3 + j));
+    } else if (TC == 1) {
+        r.w[0] = *reinterpret_cast<const uint16_t *>(blk + 2 * (3 + j));
+    } else {
+        r.w[0] = 0;
+    }
+    return r;
+}
+
+template <int TC>
+__device__ __forceinline__ void ms_record_nibs(const ms_rec<TC> &r, const uint8_t *blk, int C, int c, int cs, int j,
+                                               int (&nb)[4]) {
+    if (TC == 8) {
+        const uint32_t mul = 1u << (28 - cs);                           // shift as a multiply: IMAD runs on the FMA pipe
+        nb[0] = (int)(r.w[0] * mul) >> 28; nb[1] = (int)(r.w[1] * mul) >> 28;
+        nb[2] = (int)(r.w[2] * mul) >> 28; nb[3] = (int)(r.w[3] * mul) >> 28;
+    } else if (TC == 4) {
+        const uint32_t a = r.w[0] >> cs, b = r.w[TC == 4 ? 1 : 0] >> cs;
+        nb[0] = sx4(a, 28); nb[1] = sx4(a, 12); nb[2] = sx4(b, 28); nb[3] = sx4(b, 12);
+    } else if (TC == 2) {
+        const uint32_t a = r.w[0] >> cs;
+        nb[0] = sx4(a, 28); nb[1] = sx4(a, 20); nb[2] = sx4(a, 12); nb[3] = sx4(a, 4);
+    } else if (TC == 1) {
+        const uint32_t a = r.w[0];
+        nb[0] = sx4(a, 24); nb[1] = sx4(a, 28); nb[2] = sx4(a, 16); nb[3] = sx4(a, 20);
+    } else {
+        const uint8_t *rec = blk + 2 * (size_t)C * (size_t)(3 + j);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int n = i * C + c;
+            const int byte = rec[n >> 1];
+            nb[i] = sx4((uint32_t)byte, (n & 1) ? 28 : 24);
+        }
+    }
+}
+
 // requires spb % 4 == 0 and 16-byte aligned output rows; chain layout as ms_adpcm_kernel
-__global__ void __launch_bounds__(128)
+template <int TC, int NQ>
+__global__ void __launch_bounds__(128, 8)
 ms_adpcm_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, int literal_mono,
                       size_t nblocks, size_t spb, const __grid_constant__ ms_coefs coefs,
                       float *__restrict__ out, size_t stride, int *status) {
-    __shared__ int adapt[16];
-    __shared__ float4 stage_all[4][128];
-    if (threadIdx.x < 16) adapt[threadIdx.x] = c_ms_adapt[threadIdx.x];
+    // adaptation table indexed by the signed nibble, 3 words apart: the odd stride keeps the 16 entries in
+    // 16 different banks and makes the address an IMAD (FMA pipe) instead of a LEA (ALU pipe)
+    __shared__ int adapt_s[48];
+    __shared__ float4 stage_all[4][32 * NQ];
+    __shared__ size_t rowb_all[4][32];
+    if (threadIdx.x < 16) adapt_s[threadIdx.x * 3] = c_ms_adapt[(threadIdx.x - 8) & 15];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *st = stage_all[warp];
+    size_t *rowb = rowb_all[warp];
     const size_t nchains = nblocks * (size_t)C;
     const size_t ntiles = (nchains + 31) / 32;
     const int ncoef = coefs.n;
-    const bool evenC = (C & 1) == 0;
-    const int bstride = C >> 1;
     const int nquads = (int)(spb / 4);
+    const int *adapt_mid = adapt_s + 24;
     for (size_t tile = (size_t)blockIdx.x * 4 + warp; tile < ntiles; tile += (size_t)gridDim.x * 4) {
-        const size_t id0 = tile * 32;
-        size_t rowbase[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const size_t rid = id0 + i * 8 + (lane >> 2);
-            rowbase[i] = rid < nchains ? (rid % (size_t)C) * stride + (rid / (size_t)C) * spb : ROW_NONE;
-        }
-        const size_t id = min(id0 + lane, nchains - 1);
+        const size_t id = min(tile * 32 + lane, nchains - 1);
         const size_t b = id / (size_t)C;
         const int c = (int)(id % (size_t)C);
-        const size_t start = b * (size_t)blockAlign;
-        const uint8_t *hp = data + (literal_mono ? 0 : start);         // A:1331: block 1's header
+        rowb[lane] = tile * 32 + lane < nchains ? (size_t)c * stride + b * spb : ROW_NONE;
+        const uint8_t *blk = data + b * (size_t)blockAlign;
+        const uint8_t *hp = literal_mono ? data : blk;                  // A:1331: block 1's header
         int pi = hp[c];
         if (pi >= ncoef) { atomicOr(status, AUKIT_DEVERR_MS_PREDICTOR); pi = 0; }
         const int c1 = coefs.c1[pi], c2 = coefs.c2[pi];
@@ -443,65 +516,59 @@ ms_adpcm_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, i
         int delta = rd16((size_t)C + 2 * (size_t)c);
         int s1 = rd16(3 * (size_t)C + 2 * (size_t)c);
         int s2 = rd16(5 * (size_t)C + 2 * (size_t)c);
-        const uint8_t *np = data + start + 7 * (size_t)C;
-        const uint8_t *bp = np + (c >> 1);                              // even C: one byte per sample, C/2 apart
-        const int sh = (c & 1) ? 0 : 4;
+        const int cs = 8 * (c >> 1) + ((c & 1) ? 0 : 4);
         const bool narrow = (abs(c1) + abs(c2)) <= 65535;
         ms_state gs;
         gs.big = 0;
-        // nibble k of this chain (0-based after the two header samples)
-        auto fetch = [&](int k) -> int {
-            if (evenC) return (bp[(size_t)k * (size_t)bstride] >> sh) & 0xF;
-            const size_t m = (size_t)k * (size_t)C + (size_t)c;
-            const int byte = np[m >> 1];
-            return (m & 1) ? (byte & 0xF) : (byte >> 4);
-        };
-        auto fast = [&](int un) -> float {
-            const int nib = (un ^ 8) - 8;
+        auto fast = [&](int nib) -> float {
             int p = ((s1 * c1 + s2 * c2) >> 8) + nib * delta;           // A:1321-1322
             p = min(max(p, -32768), 32767);
             s2 = s1; s1 = p;
-            delta = max((adapt[un] * delta) >> 8, 16);                  // A:1324
+            delta = max((adapt_mid[nib * 3] * delta) >> 8, 16);         // A:1324
             return s16_to_float(p);
         };
-        auto general = [&](int un) -> float {
+        auto general = [&](int nib) -> float {
             gs.s1 = s1; gs.s2 = s2; gs.delta = delta;
-            const float v = ms_general_step(&gs, un, c1, c2);
+            const float v = ms_general_step(&gs, nib, c1, c2);
             s1 = gs.s1; s2 = gs.s2; delta = gs.delta;
             return v;
         };
-        auto quad = [&](int k) -> float4 {                              // samples k..k+3
-            const int u0 = fetch(k), u1 = fetch(k + 1), u2 = fetch(k + 2), u3 = fetch(k + 3);
+        ms_rec<TC> rec = ms_load_rec<TC>(blk, 0);
+        ms_rec<TC> rec_next = ms_load_rec<TC>(blk, nquads > 1 ? 1 : 0);
+        // samples 4j..4j+3 of the block; `first`: the two header samples lead (A:1312-1315)
+        auto quad = [&](int j, bool first) -> float4 {
+            int nb[4];
+            ms_record_nibs<TC>(rec, blk, C, c, cs, j, nb);
+            rec = rec_next;
+            if (j + 2 < nquads) rec_next = ms_load_rec<TC>(blk, j + 2); // two quads in flight while the chain runs
+            const bool quick = narrow && delta < (1 << 14) && delta > -(1 << 16);
             float4 v;
-            if (narrow && delta < (1 << 14) && delta > -(1 << 16)) {
-                v.x = fast(u0); v.y = fast(u1); v.z = fast(u2); v.w = fast(u3);
+            if (first) {
+                v.x = s16_to_float(s2); v.y = s16_to_float(s1);
+                if (quick) { v.z = fast(nb[2]); v.w = fast(nb[3]); }
+                else { v.z = general(nb[2]); v.w = general(nb[3]); }
+            } else if (quick) {
+                v.x = fast(nb[0]); v.y = fast(nb[1]); v.z = fast(nb[2]); v.w = fast(nb[3]);
             } else {
-                v.x = general(u0); v.y = general(u1); v.z = general(u2); v.w = general(u3);
+                v.x = general(nb[0]); v.y = general(nb[1]); v.z = general(nb[2]); v.w = general(nb[3]);
             }
             return v;
         };
-        // quad 0 = the two header samples (A:1312-1315) + the first two decoded ones
-        {
-            const int u0 = fetch(0), u1 = fetch(1);
-            float4 v;
-            v.x = s16_to_float(s2); v.y = s16_to_float(s1);
-            v.z = general(u0); v.w = general(u1);
-            stage_put(st, lane, 0, v);
-        }
         size_t col = 0;
-        int q = 1;
-        for (int j = 1; j < nquads; j++) {
-            stage_put(st, lane, q, quad(4 * j - 2));
-            if (++q == 4) {
-                __syncwarp();
-                stage_flush(st, out, rowbase, col, lane, 4);
-                __syncwarp();
-                q = 0; col += 16;
-            }
-        }
-        if (q) {
+        const int nper = nquads / NQ;
+        for (int per = 0; per < nper; per++, col += 4 * NQ) {
+            stage_put<NQ>(st, lane, 0, quad(NQ * per, per == 0));
+#pragma unroll
+            for (int q = 1; q < NQ; q++) stage_put<NQ>(st, lane, q, quad(NQ * per + q, false));
             __syncwarp();
-            stage_flush(st, out, rowbase, col, lane, q);
+            stage_flush<NQ>(st, out, rowb, col, lane, NQ);
+            __syncwarp();
+        }
+        const int rem = nquads - nper * NQ;
+        if (rem) {
+            for (int q = 0; q < rem; q++) stage_put<NQ>(st, lane, q, quad(NQ * nper + q, nper == 0 && q == 0));
+            __syncwarp();
+            stage_flush<NQ>(st, out, rowb, col, lane, rem);
             __syncwarp();
         }
     }
@@ -568,11 +635,19 @@ extern "C" int aukit_cuda_dev_ima_adpcm_wav(aukit_ctx *ctx, const void *d_in, si
     if (channels > 1 && out_stride < frames) return aukit_fail("aukit_cuda: out_stride < frames");
     const int word_aligned = ((uintptr_t)d_in % 4 == 0) && (blockAlign % 4 == 0);
     const int threads = 128;
-    const unsigned grid = aukit_grid(nblocks * (size_t)channels, threads, (size_t)ctx->num_sms * 64);
+    unsigned grid = aukit_grid(nblocks * (size_t)channels, threads, (size_t)ctx->num_sms * 64);
+    if (const char *g = getenv("AUKIT_ADPCM_CTAS_PER_SM")) grid = aukit_grid(nblocks * (size_t)channels, threads, (size_t)ctx->num_sms * atoi(g));
     const int out_aligned = ((uintptr_t)d_out % 16 == 0) && (out_stride % 4 == 0);
     if (mode != IMA_LITERAL_MONO && word_aligned && out_aligned && groups > 0 && !getenv("AUKIT_DISABLE_TILED_ADPCM")) {
-        ima_wav_tiled_kernel<<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels,
-                                                                nblocks, spb, groups, d_out, out_stride, ctx->d_status);
+        const char *e = getenv("AUKIT_ADPCM_NQ");
+        const int nq = e ? atoi(e) : 16;
+#define AUKIT_IMA_TILED(NQ, MB)                                                                                              \
+    ima_wav_tiled_kernel<NQ, MB><<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels, \
+                                                                    nblocks, spb, groups, d_out, out_stride, ctx->d_status)
+        if (nq >= 16) AUKIT_IMA_TILED(16, 4);
+        else if (nq >= 8) AUKIT_IMA_TILED(8, 8);
+        else AUKIT_IMA_TILED(4, 9);
+#undef AUKIT_IMA_TILED
         ctx->launches++;
         return aukit_cuda_check(cudaGetLastError(), "ima_wav_tiled_kernel launch");
     }
@@ -610,12 +685,29 @@ extern "C" int aukit_cuda_dev_msadpcm(aukit_ctx *ctx, const void *d_in, size_t n
     const size_t spb = 2 + (bA - 7 * C) * 2 / C;
     if (channels > 1 && out_stride < nblocks * spb) return aukit_fail("aukit_cuda: out_stride < frames");
     const int threads = 128;
-    const unsigned grid = aukit_grid(nblocks * C, threads, (size_t)ctx->num_sms * 64);
+    unsigned grid = aukit_grid(nblocks * C, threads, (size_t)ctx->num_sms * 64);
+    if (const char *g = getenv("AUKIT_ADPCM_CTAS_PER_SM")) grid = aukit_grid(nblocks * C, threads, (size_t)ctx->num_sms * atoi(g));
     const int vec_ok = ((uintptr_t)d_out % 16 == 0) && (out_stride % 4 == 0);
     if (vec_ok && spb % 4 == 0 && !getenv("AUKIT_DISABLE_TILED_ADPCM")) {
-        ms_adpcm_tiled_kernel<<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels,
-                                                                 dialect == AUKIT_DIALECT_LITERAL && channels == 1, nblocks,
-                                                                 spb, h, d_out, out_stride, ctx->d_status);
+        const bool rec_aligned = ((uintptr_t)d_in % 16 == 0) && (bA % (2 * C) == 0);
+        const int tc = (rec_aligned && (channels == 1 || channels == 2 || channels == 4 || channels == 8)) ? channels : 0;
+        const char *e = getenv("AUKIT_ADPCM_NQ");
+        const int nq = e ? atoi(e) : 16;
+#define AUKIT_MS_LAUNCH(TC, NQ)                                                                                          \
+    ms_adpcm_tiled_kernel<TC, NQ><<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels, \
+                                                                 dialect == AUKIT_DIALECT_LITERAL && channels == 1, nblocks, \
+                                                                 spb, h, d_out, out_stride, ctx->d_status)
+#define AUKIT_MS_TILED(TC)                                                                                               \
+    if (nq >= 16) AUKIT_MS_LAUNCH(TC, 16); else if (nq >= 8) AUKIT_MS_LAUNCH(TC, 8); else AUKIT_MS_LAUNCH(TC, 4)
+        switch (tc) {
+            case 8: AUKIT_MS_TILED(8); break;
+            case 4: AUKIT_MS_TILED(4); break;
+            case 2: AUKIT_MS_TILED(2); break;
+            case 1: AUKIT_MS_TILED(1); break;
+            default: AUKIT_MS_TILED(0); break;
+        }
+#undef AUKIT_MS_LAUNCH
+#undef AUKIT_MS_TILED
         ctx->launches++;
         return aukit_cuda_check(cudaGetLastError(), "ms_adpcm_tiled_kernel launch");
     }

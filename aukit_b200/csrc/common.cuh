@@ -77,9 +77,12 @@ __device__ __forceinline__ double clamp_ref(double v) { return v < -1.0 ? -1.0 :
 // Branch-free: p * 2^-15 is exact, and for p > 0 one FMA adds p / (32767 * 32768); the result is
 // bit-identical to (float)((double)p / 32767.0) for every p in [0, 32767] (checked exhaustively
 // on the host with exact rationals and on the device by tests/test_gpu_decode.py).
+// max(p, 0) * 2^-15 is taken as saturate(p * 2^-15): the clamp rides on the multiply (FMA pipe) instead
+// of a separate FMNMX on the half-rate ALU pipe; the constant is scaled by 2^15 to match, so the FMA sees
+// the same real product and rounds identically.
 __device__ __forceinline__ float s16_to_float(int p) {
-    const float f = (float)p;
-    return __fmaf_rn(fmaxf(f, 0.0f), 1.0f / (32767.0f * 32768.0f), __fmul_rn(f, 1.0f / 32768.0f));
+    const float lo = __fmul_rn((float)p, 1.0f / 32768.0f);
+    return __fmaf_rn(__saturatef(lo), (1.0f / (32767.0f * 32768.0f)) * 32768.0f, lo);
 }
 
 // streaming 128-bit accesses: inputs are read once, outputs written once

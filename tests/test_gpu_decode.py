@@ -133,6 +133,40 @@ def test_msadpcm(ak, O, channels, block_align, dialect, tame):
     _check(got, ref)
 
 
+@pytest.mark.parametrize("channels,block_align,nblocks,tame", [
+    (1, 256, 37, True), (1, 258, 5, False), (2, 256, 33, True), (2, 1028, 7, False), (4, 512, 9, True), (4, 520, 3, False),
+    (8, 2048, 5, True), (8, 2064, 4, False), (3, 300, 11, True), (5, 1000, 3, False), (6, 516, 7, True), (2, 254, 9, True)])
+def test_msadpcm_tiled_and_chain_kernels_agree(ak, O, monkeypatch, channels, block_align, nblocks, tame):
+    """The warp-tiled kernel (aligned record loads for 1/2/4/8 channels, byte reads otherwise), the
+    chain-per-lane kernel and the oracle agree bit for bit; chains not a multiple of 32, partial last
+    flush, deltas that leave the 32-bit fast path mid-block."""
+    raw = ms_blocks(nblocks, block_align, channels, seed=7 * block_align + channels, tame=tame)
+    blocks = raw.reshape(nblocks, block_align)
+    blocks[::3, channels:3 * channels] = np.array([0xFF, 0x7F] * channels, dtype=np.uint8)      # delta 32767 in the header
+    blocks[1::3, 7 * channels:7 * channels + 8] = 0x88                                           # nibble -8: delta triples
+    ref = O.msadpcm(raw, block_align, channels, None, 1)
+    got = ak.msadpcm(raw, block_align, channels, 44100, None, 1).numpy()
+    _check(got, ref)
+    monkeypatch.setenv("AUKIT_DISABLE_TILED_ADPCM", "1")
+    _check(ak.msadpcm(raw, block_align, channels, 44100, None, 1).numpy(), ref)
+
+
+@pytest.mark.parametrize("channels,block_align,nblocks", [(1, 256, 37), (1, 36, 70), (2, 264, 33), (2, 1024, 3), (3, 600, 9),
+                                                          (8, 2048, 5), (8, 96, 13), (5, 40, 7)])
+def test_ima_tiled_and_chain_kernels_agree(ak, O, monkeypatch, channels, block_align, nblocks):
+    """Transition-table + transposed-store kernel vs the chain-per-lane kernel vs the oracle: odd and
+    even group counts, a single group, chains not a multiple of 32, every step index reached."""
+    raw = ima_blocks(nblocks, block_align, channels, seed=block_align + channels)
+    rng = np.random.default_rng(block_align)
+    blocks = raw.reshape(nblocks, block_align)
+    blocks[:, 4 * channels:] = rng.integers(0, 256, blocks[:, 4 * channels:].shape, dtype=np.uint8)   # wild nibbles
+    ref = O.wav_ima(raw, block_align, channels, 1)
+    got = ak._aukit.Audio(ak.context(), _ima_handle(ak, raw, block_align, channels, 1)).numpy()
+    _check(got, ref)
+    monkeypatch.setenv("AUKIT_DISABLE_TILED_ADPCM", "1")
+    _check(ak._aukit.Audio(ak.context(), _ima_handle(ak, raw, block_align, channels, 1)).numpy(), ref)
+
+
 def test_msadpcm_custom_coefficients_and_wav(ak, O):
     coefs = [[256, 512, 0, 192, 240, 460, 392, -300], [0, -256, 0, 64, 0, -208, -232, 77]]
     raw = ms_blocks(9, 256, 2, seed=3)
