@@ -81,6 +81,16 @@ SIGNATURES = {
     "aukit_cuda_dev_pipeline_peak": (_I, [_P, C.POINTER(PipelineDesc), _P, _P]),
     "aukit_cuda_dev_pipeline_apply": (_I, [_P, C.POINTER(PipelineDesc), _P, _D, _P, _P, _SZ]),
     "aukit_cuda_pipeline_host": (_I, [_P, C.POINTER(PipelineDesc), _P, _SZ, _D, _P]),
+    "aukit_cuda_preloader_create": (_I, [_P, _SZ, _SZ, _I, C.POINTER(_P)]),
+    "aukit_cuda_preloader_destroy": (None, [_P]),
+    "aukit_cuda_preloader_begin": (_I, [_P, C.POINTER(PipelineDesc), _P, _SZ, C.POINTER(_I)]),
+    "aukit_cuda_preloader_peak_ptr": (_P, [_P, _I]),
+    "aukit_cuda_preloader_stream": (_P, [_P]),
+    "aukit_cuda_preloader_finish": (_I, [_P, _I, _D, _P]),
+    "aukit_cuda_preloader_submit": (_I, [_P, C.POINTER(PipelineDesc), _P, _SZ, _D, _P]),
+    "aukit_cuda_preloader_drain": (_I, [_P]),
+    "aukit_cuda_host_alloc": (_I, [_SZ, C.POINTER(_P)]),
+    "aukit_cuda_host_free": (None, [_P]),
     "aukit_resample_out_len": (_U64, [_U64, _D, _D]),
     "aukit_resample_position": (_D, [_U64, _D, _D]),
     "aukit_resample_window": (_I, [_U64, _D, _D, _I, _U64, _U64, C.POINTER(_U64), C.POINTER(_U64)]),

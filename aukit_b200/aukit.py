@@ -483,3 +483,97 @@ def preload(data, bitDepth=16, dataType="signed", channels=2, sampleRate=44100, 
     _lib.check(ctx.lib.aukit_cuda_pipeline_host(ctx.handle, C.byref(d), p, n, float(peakAmplitude),
                                                 C.c_void_p(out.ctypes.data)))
     return out
+
+
+class Preloader:
+    """Pipelined preload() for a playlist of clips (aukit_cuda_preloader_*): clip i's download overlaps
+    clip i+1's upload, `slots` device buffers in rotation.  submit() is asynchronous; results are valid
+    after drain().  Host arrays should come from pinned() so the copies really are asynchronous.
+
+        pl = Preloader(max_in_bytes, max_out_samples)
+        for clip, out in zip(clips, outs): pl.submit(clip, out, sampleRate=44100)
+        pl.drain()
+    """
+
+    def __init__(self, max_in_bytes: int, max_out_samples: int, slots: int = 2, ctx: Optional[Context] = None):
+        self.ctx = ctx or context()
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.aukit_cuda_preloader_create(self.ctx.handle, int(max_in_bytes), int(max_out_samples), int(slots),
+                                                            C.byref(h)))
+        self.handle = h
+        self._keep = []
+
+    @staticmethod
+    def pinned(shape, dtype) -> np.ndarray:
+        """numpy array over pinned host memory (aukit_cuda_host_alloc); freed with the array."""
+        lib = _lib.load()
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        p = C.c_void_p()
+        _lib.check(lib.aukit_cuda_host_alloc(n, C.byref(p)))
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        import weakref
+        weakref.finalize(buf, lib.aukit_cuda_host_free, C.c_void_p(p.value))
+        return arr
+
+    def describe(self, nbytes, bitDepth=16, dataType="signed", channels=2, sampleRate=44100, targetRate=48000,
+                 interpolation=None, mono=True, bigEndian=False) -> PipelineDesc:
+        interpolation = interpolation or defaultInterpolation
+        if interpolation not in _INTERPS:
+            raise AukitError("bad argument #2 (invalid interpolation type)")
+        if dataType not in _DATATYPES:
+            raise AukitError("bad argument #3 (invalid data type)")
+        if bitDepth not in (8, 16, 24, 32):
+            raise AukitError("bad argument #2 (invalid bit depth)")
+        B = bitDepth // 8
+        if nbytes % (B * channels):
+            raise AukitError("bad argument #1 (uneven amount of data per channel)")
+        frames = nbytes // (B * channels)
+        n_out = int(self.ctx.lib.aukit_resample_out_len(frames, float(sampleRate), float(targetRate)))
+        return PipelineDesc(bitDepth, _DATATYPES[dataType], channels, int(bool(bigEndian)), float(sampleRate),
+                            float(targetRate), _INTERPS[interpolation], int(bool(mono)), frames, 0, frames, 0, n_out)
+
+    def submit(self, data: np.ndarray, out: np.ndarray, peakAmplitude=0.8, desc: Optional[PipelineDesc] = None, **fmt):
+        """Enqueue one clip: `data` packed interleaved PCM bytes (uint8 array), `out` float32
+        [1 or channels, n_out].  Both must stay alive and untouched until drain()."""
+        d = desc or self.describe(data.nbytes, **fmt)
+        self._keep.append((data, out, d))
+        _lib.check(self.ctx.lib.aukit_cuda_preloader_submit(self.handle, C.byref(d), C.c_void_p(data.ctypes.data), data.nbytes,
+                                                            float(peakAmplitude), C.c_void_p(out.ctypes.data)))
+        return d
+
+    def begin(self, data: np.ndarray, desc: PipelineDesc) -> int:
+        k = C.c_int(-1)
+        self._keep.append((data, desc))
+        _lib.check(self.ctx.lib.aukit_cuda_preloader_begin(self.handle, C.byref(desc), C.c_void_p(data.ctypes.data), data.nbytes,
+                                                           C.byref(k)))
+        return k.value
+
+    def peak_ptr(self, slot: int) -> int:
+        return int(self.ctx.lib.aukit_cuda_preloader_peak_ptr(self.handle, slot) or 0)
+
+    @property
+    def stream(self) -> int:
+        return int(self.ctx.lib.aukit_cuda_preloader_stream(self.handle) or 0)
+
+    def finish(self, slot: int, out: np.ndarray, peakAmplitude=0.8):
+        self._keep.append(out)
+        _lib.check(self.ctx.lib.aukit_cuda_preloader_finish(self.handle, slot, float(peakAmplitude), C.c_void_p(out.ctypes.data)))
+
+    def drain(self):
+        try:
+            _lib.check(self.ctx.lib.aukit_cuda_preloader_drain(self.handle))
+        finally:
+            self._keep.clear()
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.aukit_cuda_preloader_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -615,3 +615,144 @@ extern "C" int aukit_cuda_pipeline_host(aukit_ctx *ctx, const aukit_pipeline_des
     if (!rc) rc = aukit_cuda_synchronize(ctx);
     return rc;
 }
+
+// ------------------------------------------------------------------ pipelined preloader
+struct aukit_preloader {
+    aukit_ctx *ctx;
+    int slots, next;
+    size_t max_in, max_out;                 // bytes / samples per slot
+    cudaStream_t s_in, s_run, s_out;
+    struct slot_t {
+        void *d_in;
+        float *d_out, *d_peak;
+        cudaEvent_t in_done, in_free, run_done, out_done;
+        aukit_pipeline_desc desc;
+        size_t stride;
+        bool busy;
+    } *slot;
+};
+
+extern "C" int aukit_cuda_host_alloc(size_t nbytes, void **out) {
+    if (!out) return aukit_fail("aukit_cuda: null argument");
+    return aukit_cuda_check(cudaMallocHost(out, nbytes ? nbytes : 1), "cudaMallocHost");
+}
+extern "C" void aukit_cuda_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int aukit_cuda_preloader_create(aukit_ctx *ctx, size_t max_in_bytes, size_t max_out_samples, int slots,
+                                           aukit_preloader **out) {
+    if (!ctx || !out) return aukit_fail("aukit_cuda: null argument");
+    if (slots < 1 || slots > 8) return aukit_fail("aukit_cuda: preloader slots must be 1..8");
+    aukit_preloader *pl = new aukit_preloader();
+    pl->ctx = ctx; pl->slots = slots; pl->next = 0;
+    pl->max_in = (max_in_bytes + 255) & ~(size_t)255;
+    pl->max_out = aukit_round_stride(max_out_samples ? max_out_samples : 1);
+    pl->slot = new aukit_preloader::slot_t[slots]();
+    int rc = 0;
+    rc |= aukit_cuda_check(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking), "stream");
+    rc |= aukit_cuda_check(cudaStreamCreateWithFlags(&pl->s_run, cudaStreamNonBlocking), "stream");
+    rc |= aukit_cuda_check(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking), "stream");
+    for (int i = 0; i < slots && !rc; i++) {
+        auto &s = pl->slot[i];
+        rc |= aukit_cuda_check(cudaMalloc(&s.d_in, pl->max_in + 256), "cudaMalloc");
+        rc |= aukit_cuda_check(cudaMalloc(&s.d_out, pl->max_out * sizeof(float)), "cudaMalloc");
+        rc |= aukit_cuda_check(cudaMalloc(&s.d_peak, 256), "cudaMalloc");
+        for (cudaEvent_t *e : {&s.in_done, &s.in_free, &s.run_done, &s.out_done})
+            rc |= aukit_cuda_check(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "event");
+    }
+    if (rc) { aukit_cuda_preloader_destroy(pl); return -1; }
+    *out = pl;
+    return 0;
+}
+
+extern "C" void aukit_cuda_preloader_destroy(aukit_preloader *pl) {
+    if (!pl) return;
+    cudaStreamSynchronize(pl->s_in); cudaStreamSynchronize(pl->s_run); cudaStreamSynchronize(pl->s_out);
+    for (int i = 0; i < pl->slots; i++) {
+        auto &s = pl->slot[i];
+        cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_peak);
+        for (cudaEvent_t e : {s.in_done, s.in_free, s.run_done, s.out_done}) if (e) cudaEventDestroy(e);
+    }
+    cudaStreamDestroy(pl->s_in); cudaStreamDestroy(pl->s_run); cudaStreamDestroy(pl->s_out);
+    delete[] pl->slot;
+    delete pl;
+}
+
+extern "C" float *aukit_cuda_preloader_peak_ptr(aukit_preloader *pl, int slot) {
+    return (pl && slot >= 0 && slot < pl->slots) ? pl->slot[slot].d_peak : nullptr;
+}
+extern "C" void *aukit_cuda_preloader_stream(aukit_preloader *pl) { return pl ? (void *)pl->s_run : nullptr; }
+
+// the passes are enqueued through the context's entry points: point it at the preloader's stream meanwhile
+struct stream_swap {
+    aukit_ctx *c; cudaStream_t old;
+    stream_swap(aukit_ctx *ctx, cudaStream_t s) : c(ctx), old(ctx->stream) { ctx->stream = s; }
+    ~stream_swap() { c->stream = old; }
+};
+
+extern "C" int aukit_cuda_preloader_begin(aukit_preloader *pl, const aukit_pipeline_desc *p, const void *h_in, size_t nbytes,
+                                          int *slot_out) {
+    if (!pl || !p || !slot_out) return aukit_fail("aukit_cuda: null argument");
+    const size_t need = p->in_avail * (size_t)p->channels * (size_t)(p->bitDepth / 8);
+    if (nbytes < need) return aukit_fail("aukit_cuda: host buffer smaller than in_avail frames");
+    if (need > pl->max_in) return aukit_fail("aukit_cuda: clip larger than the preloader's input slots");
+    const int out_ch = p->mono ? 1 : p->channels;
+    const size_t stride = aukit_round_stride(p->n_out ? p->n_out : 1);
+    if (stride * (size_t)out_ch > pl->max_out) return aukit_fail("aukit_cuda: clip larger than the preloader's output slots");
+    const int k = pl->next;
+    auto &s = pl->slot[k];
+    if (s.busy) {                                   // begun but never finished
+        return aukit_fail("aukit_cuda: preloader slot %d is still between begin and finish", k);
+    }
+    pl->next = (k + 1) % pl->slots;
+    s.desc = *p; s.stride = stride; s.busy = true;
+    // upload: the slot's input buffer is free once the apply pass that last read it is done
+    AUKIT_CUDA_TRY(cudaStreamWaitEvent(pl->s_in, s.in_free, 0));
+    if (need) AUKIT_CUDA_TRY(cudaMemcpyAsync(s.d_in, h_in, need, cudaMemcpyHostToDevice, pl->s_in));
+    AUKIT_CUDA_TRY(cudaEventRecord(s.in_done, pl->s_in));
+    // peak pass
+    AUKIT_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, s.in_done, 0));
+    AUKIT_CUDA_TRY(cudaMemsetAsync(s.d_peak, 0, sizeof(float), pl->s_run));
+    stream_swap sw(pl->ctx, pl->s_run);
+    if (aukit_cuda_dev_pipeline_peak(pl->ctx, &s.desc, s.d_in, s.d_peak)) return -1;
+    *slot_out = k;
+    return 0;
+}
+
+extern "C" int aukit_cuda_preloader_finish(aukit_preloader *pl, int k, double peakAmplitude, float *h_out) {
+    if (!pl || !h_out) return aukit_fail("aukit_cuda: null argument");
+    if (k < 0 || k >= pl->slots || !pl->slot[k].busy) return aukit_fail("aukit_cuda: preloader slot %d was not begun", k);
+    auto &s = pl->slot[k];
+    const aukit_pipeline_desc *p = &s.desc;
+    const int out_ch = p->mono ? 1 : p->channels;
+    // the slot's output buffer is free once its previous download is done
+    AUKIT_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, s.out_done, 0));
+    {
+        stream_swap sw(pl->ctx, pl->s_run);
+        if (aukit_cuda_dev_pipeline_apply(pl->ctx, p, s.d_in, peakAmplitude, s.d_peak, s.d_out, s.stride)) { s.busy = false; return -1; }
+    }
+    AUKIT_CUDA_TRY(cudaEventRecord(s.run_done, pl->s_run));
+    AUKIT_CUDA_TRY(cudaEventRecord(s.in_free, pl->s_run));
+    AUKIT_CUDA_TRY(cudaStreamWaitEvent(pl->s_out, s.run_done, 0));
+    if (p->n_out)
+        AUKIT_CUDA_TRY(cudaMemcpy2DAsync(h_out, p->n_out * sizeof(float), s.d_out, s.stride * sizeof(float),
+                                         p->n_out * sizeof(float), (size_t)out_ch, cudaMemcpyDeviceToHost, pl->s_out));
+    AUKIT_CUDA_TRY(cudaEventRecord(s.out_done, pl->s_out));
+    s.busy = false;
+    return 0;
+}
+
+extern "C" int aukit_cuda_preloader_submit(aukit_preloader *pl, const aukit_pipeline_desc *p, const void *h_in, size_t nbytes,
+                                           double peakAmplitude, float *h_out) {
+    int k = -1;
+    if (aukit_cuda_preloader_begin(pl, p, h_in, nbytes, &k)) return -1;
+    return aukit_cuda_preloader_finish(pl, k, peakAmplitude, h_out);
+}
+
+extern "C" int aukit_cuda_preloader_drain(aukit_preloader *pl) {
+    if (!pl) return aukit_fail("aukit_cuda: null argument");
+    AUKIT_CUDA_TRY(cudaStreamSynchronize(pl->s_in));
+    AUKIT_CUDA_TRY(cudaStreamSynchronize(pl->s_run));
+    AUKIT_CUDA_TRY(cudaStreamSynchronize(pl->s_out));
+    stream_swap sw(pl->ctx, pl->s_run);
+    return aukit_cuda_synchronize(pl->ctx);          // surfaces device-side status bits
+}

@@ -112,3 +112,45 @@ class ShardedPreload:
         out = self.run_device(d_in)
         h_out.copy_(out[:, : self.shard.n_out], non_blocking=True)
         return h_out
+
+    # ---- pipelined host path: aukit_cuda_preloader_* (clip i's D2H overlaps clip i+1's H2D)
+    def _preloader(self):
+        if getattr(self, "_pl", None) is None:
+            h = C.c_void_p()
+            _lib.check(self.lib.aukit_cuda_preloader_create(self.ctx.handle, self.in_bytes, self.stride * self.out_channels, 2,
+                                                            C.byref(h)))
+            self._pl = h
+            self._pl_stream = self.torch.cuda.ExternalStream(int(self.lib.aukit_cuda_preloader_stream(h)))
+            self._pl_peaks = {}
+        return self._pl
+
+    def _peak_tensor(self, slot: int):
+        t = self._pl_peaks.get(slot)
+        if t is None:
+            ptr = int(self.lib.aukit_cuda_preloader_peak_ptr(self._pl, slot))
+
+            class _Raw:                                    # one float32 in the preloader's slot
+                __cuda_array_interface__ = {"shape": (1,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+            t = self._pl_peaks[slot] = self.torch.as_tensor(_Raw(), device="cuda")
+        return t
+
+    def submit_host(self, h_in, h_out):
+        """Asynchronous run_host: returns once the copies and passes are enqueued; call drain() before
+        reading h_out or reusing h_in.  h_in / h_out: pinned torch tensors (uint8 bytes / float32)."""
+        pl = self._preloader()
+        k = C.c_int(-1)
+        _lib.check(self.lib.aukit_cuda_preloader_begin(pl, C.byref(self.desc), h_in.data_ptr(), h_in.numel(), C.byref(k)))
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            with self.torch.cuda.stream(self._pl_stream):
+                allreduce_max_(self._peak_tensor(k.value))
+        _lib.check(self.lib.aukit_cuda_preloader_finish(pl, k.value, self.peak, h_out.data_ptr()))
+
+    def drain(self):
+        if getattr(self, "_pl", None) is not None:
+            _lib.check(self.lib.aukit_cuda_preloader_drain(self._pl))
+
+    def close(self):
+        if getattr(self, "_pl", None) is not None:
+            self.lib.aukit_cuda_preloader_destroy(self._pl)
+            self._pl = None

@@ -196,6 +196,32 @@ int aukit_cuda_dev_pipeline_apply(aukit_ctx *ctx, const aukit_pipeline_desc *p, 
 int aukit_cuda_pipeline_host(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *h_in,
                              size_t nbytes, double peakAmplitude, float *h_out);
 
+/* Pipelined host-buffer preloader: the same end-to-end call, double buffered.  PCIe is full duplex but
+ * one clip cannot use it (the normalisation peak needs the whole upload before the first output can
+ * leave), so the preloader overlaps clip i's download with clip i+1's upload: H2D on one stream, the two
+ * passes on a second, D2H on a third, `slots` device buffers in rotation.  Replaces a loop of
+ * aukit.wav / Audio:resample / Audio:mono / effects.normalize calls over a playlist (A:1373, A:653,
+ * A:678, A:3434).  Host buffers should be pinned (aukit_cuda_host_alloc) for the copies to be async.
+ *   submit  = begin + finish;  begin/finish are split so that a multi-GPU caller can all-reduce the
+ *   slot's peak (aukit_cuda_preloader_peak_ptr, on aukit_cuda_preloader_stream) between the passes.
+ *   drain   = wait for every submitted clip and surface device-side errors. */
+typedef struct aukit_preloader aukit_preloader;
+/* max_out_samples: output channels x frames of the largest clip (rows are padded to 32 frames). */
+int aukit_cuda_preloader_create(aukit_ctx *ctx, size_t max_in_bytes, size_t max_out_samples, int slots,
+                                aukit_preloader **out);
+void aukit_cuda_preloader_destroy(aukit_preloader *pl);
+int aukit_cuda_preloader_begin(aukit_preloader *pl, const aukit_pipeline_desc *p, const void *h_in,
+                               size_t nbytes, int *slot);
+float *aukit_cuda_preloader_peak_ptr(aukit_preloader *pl, int slot);
+void *aukit_cuda_preloader_stream(aukit_preloader *pl);
+int aukit_cuda_preloader_finish(aukit_preloader *pl, int slot, double peakAmplitude, float *h_out);
+int aukit_cuda_preloader_submit(aukit_preloader *pl, const aukit_pipeline_desc *p, const void *h_in,
+                                size_t nbytes, double peakAmplitude, float *h_out);
+int aukit_cuda_preloader_drain(aukit_preloader *pl);
+/* pinned host memory for the calls above */
+int aukit_cuda_host_alloc(size_t nbytes, void **out);
+void aukit_cuda_host_free(void *p);
+
 /* ------------------------------------------------------------------ pure host helpers */
 /* floor(n_in * (dstRate/srcRate)) in double, the reference's loop bound (A:658-664). */
 uint64_t aukit_resample_out_len(uint64_t n_in, double srcRate, double dstRate);
