@@ -323,6 +323,7 @@ int launch_run(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     const size_t budget = 224 * 1024;
     int nw = (int)((budget - fixed - 256 - 256) / per_warp);
     if (nw > 24) nw = 24;
+    if (const char *e = getenv("AUKIT_RUN_MAXWARPS")) { const int m = atoi(e); if (m >= 2 && m < nw) nw = m; }   // occupancy experiments
     if (nw < 2) return 0;                                         // not worth it: let the caller fall back
     rp.nwarps = nw;
     const size_t smem = fixed + (((size_t)nw * 8 + 127) & ~(size_t)127) + (size_t)nw * per_warp + 128;
