@@ -78,6 +78,8 @@ SIGNATURES = {
     "aukit_cuda_dev_amplify": (_I, [_P, _P, _SZ, _I, _SZ, _D]),
     "aukit_cuda_dev_absmax": (_I, [_P, _P, _SZ, _I, _SZ, _I, _P]),
     "aukit_cuda_dev_scale_clamp": (_I, [_P, _P, _SZ, _I, _SZ, _D, _I, _P]),
+    "aukit_cuda_lowpass": (_I, [_P, _P, _D]),
+    "aukit_cuda_dev_lowpass": (_I, [_P, _P, _SZ, _I, _SZ, _D, _D]),
     "aukit_cuda_dev_pipeline_peak": (_I, [_P, C.POINTER(PipelineDesc), _P, _P]),
     "aukit_cuda_dev_pipeline_apply": (_I, [_P, C.POINTER(PipelineDesc), _P, _D, _P, _P, _SZ]),
     "aukit_cuda_pipeline_host": (_I, [_P, C.POINTER(PipelineDesc), _P, _SZ, _D, _P]),

@@ -226,6 +226,11 @@ static int l_amplify(lua_State *L) {
     return 0;
 }
 
+static int l_lowpass(lua_State *L) {
+    if (aukit_cuda_lowpass(ctx(L), check_audio(L, 1), luaL_checknumber(L, 2))) return fail(L);
+    return 0;
+}
+
 static int l_normalize(lua_State *L) {
     if (aukit_cuda_normalize(ctx(L), check_audio(L, 1), luaL_optnumber(L, 2, 1.0), optbool(L, 3, 0))) return fail(L);
     return 0;
@@ -279,7 +284,7 @@ static int l_gc(lua_State *L) {
 static const luaL_Reg funcs[] = {
     {"pcm", l_pcm}, {"g711", l_g711}, {"adpcm", l_adpcm}, {"ima_adpcm_wav", l_ima_wav}, {"msadpcm", l_msadpcm},
     {"wav", l_wav}, {"new", l_new}, {"resample", l_resample}, {"mono", l_mono}, {"concat", l_concat},
-    {"amplify", l_amplify}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
+    {"amplify", l_amplify}, {"lowpass", l_lowpass}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
     {"frames", l_frames}, {"read", l_read}, {"write", l_write}, {NULL, NULL}};
 
 int luaopen_aukit_cuda(lua_State *L) {

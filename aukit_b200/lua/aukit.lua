@@ -6,7 +6,7 @@
 -- auplay.lua's load -> :resample(48000) -> :mono() -> effects.normalize(mono, 0.8) runs unchanged.
 --
 -- In scope (device-backed): aukit.pcm, aukit.g711, aukit.adpcm, aukit.msadpcm, aukit.wav, aukit.new,
---   Audio:len/channels/resample/mono/concat, aukit.effects.amplify/normalize, aukit.defaultInterpolation.
+--   Audio:len/channels/resample/mono/concat, aukit.effects.amplify/normalize/lowpass, aukit.defaultInterpolation.
 -- Everything else of the reference (players, streams, FLAC/QOA/DFPWM, editing ops, writers) is out of
 -- scope of this accelerated path; load the reference module alongside for those.
 --
@@ -255,6 +255,15 @@ function aukit.effects.amplify(audio, multiplier)
     expect(2, multiplier, "number")
     if multiplier == 1 then return audio end
     cu.amplify(handle(audio), multiplier)
+    invalidate(audio)
+    return audio
+end
+
+--- Applies a low-pass filter to the specified audio. (A:3586; auplay.lua:30)
+function aukit.effects.lowpass(audio, frequency)
+    expectAudio(1, audio)
+    expect(2, frequency, "number")
+    cu.lowpass(handle(audio), frequency)
     invalidate(audio)
     return audio
 end

@@ -119,6 +119,10 @@ def main():
     report("K8 absmax 2ch", ms, n * 2 * 4, n * 2, "samples")
     ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_scale_clamp(ctx.handle, x.data_ptr(), n, 2, n, 1.0, 0, dmax.data_ptr())))
     report("K9 scale_clamp 2ch", ms, n * 2 * 8, n * 2, "samples")
+    # ---- K11 lowpass (8f rank 1): in place, 4 B read + 4 B written per sample
+    for f in (24000.0, 200.0):
+        ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_lowpass(ctx.handle, x.data_ptr(), n, 2, n, f, 48000.0)))
+        report("K11 lowpass 2ch f=%g Hz" % f, ms, n * 2 * 8, n * 2, "samples", "chained-tile scan, fp64 state")
 
 
 if __name__ == "__main__":

@@ -139,6 +139,11 @@ int aukit_cuda_absmax(aukit_ctx *ctx, const aukit_audio *a, int independent, flo
 int aukit_cuda_scale_clamp(aukit_ctx *ctx, aukit_audio *a, double peakAmplitude, int independent,
                            const float *d_max);
 
+/* aukit.effects.lowpass(audio, frequency) A:3586-3598: in-place one-pole IIR per channel,
+ * a = 1 - exp(-(frequency/sampleRate) * 2 pi), d[i] = d[i-1] + a*(d[i] - d[i-1]) for i >= 2 (auplay.lua:30).
+ * Single pass, chained tiles (decoupled look-back), fp64 state. */
+int aukit_cuda_lowpass(aukit_ctx *ctx, aukit_audio *a, double frequency);
+
 /* ------------------------------------------------------------------ device-pointer level */
 /* Same kernels on caller-owned DEVICE buffers (inputs already resident in HBM; what
  * bench.py's `value` times).  Output layout: d_out[c * out_stride + i]. */
@@ -164,6 +169,8 @@ int aukit_cuda_dev_mono(aukit_ctx *ctx, const float *d_in, size_t in_stride, int
                         float *d_out);
 int aukit_cuda_dev_amplify(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,
                            double multiplier);
+int aukit_cuda_dev_lowpass(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,
+                           double frequency, double sampleRate);
 int aukit_cuda_dev_absmax(aukit_ctx *ctx, const float *d, size_t stride, int channels, size_t n,
                           int independent, float *d_max);
 int aukit_cuda_dev_scale_clamp(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,

@@ -68,6 +68,10 @@ def run_case(R, case, blobs):
         a = call(R.fn("msadpcm"), [blobs["in"], float(A["blockAlign"]), float(A["channels"]), float(A["sampleRate"]), cot])[0]
     elif op == "wav":
         a = R.call("wav", blobs["in"], A.get("head", False))[0]
+    elif op == "lowpass":
+        a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
+        r = R.call(("effects", "lowpass"), a, A["frequency"])[0]
+        assert r is a                           # in place (A:3597)
     elif op in ("resample", "mono", "amplify", "normalize", "chain"):
         if op == "chain":
             a = R.call("wav", blobs["in"])[0]
@@ -208,6 +212,16 @@ def main():
     for interp in ("linear", "cubic", "none"):
         add("chain_c1_mini_%s" % interp, "chain", dict(targetRate=48000, interpolation=interp, peak=0.8, independent=None),
             **{"in": wav_pcm(pcm.tobytes(), 2, 44100, 16)})
+
+    # ---- effects.lowpass (appended after the round-1 cases so that their vectors keep their seeds)
+    rng2 = np.random.default_rng(20260102)
+    z = rng2.uniform(-1, 1, (2, 6000))
+    add("lowpass_auplay_nyquist", "lowpass", dict(sampleRate=48000, frequency=24000.0), x=z)        # auplay.lua:30: sampleRate / 2
+    add("lowpass_1khz", "lowpass", dict(sampleRate=48000, frequency=1000.0), x=z)
+    add("lowpass_20hz_long_memory", "lowpass", dict(sampleRate=48000, frequency=20.0), x=z[:1, :5000] + 0.25)
+    add("lowpass_single_sample", "lowpass", dict(sampleRate=8000, frequency=100.0), x=np.array([[0.5]]))
+    add("lowpass_two_samples", "lowpass", dict(sampleRate=8000, frequency=100.0), x=np.array([[0.5, -0.5], [1.0, 0.0]]))
+    add("lowpass_zero_hz", "lowpass", dict(sampleRate=44100, frequency=0.0), x=z[:, :64])           # a = 0: every sample becomes d[1]
 
     # ---- run everything through the reference
     manifest = []

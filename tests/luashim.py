@@ -86,6 +86,11 @@ def make_module(ak):
             raise LuaError(lib.aukit_cuda_last_error())
         return []
 
+    def l_lowpass(a):
+        if lib.aukit_cuda_lowpass(ctx.handle, a[0].audio._h, float(a[1])) != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        return []
+
     def l_normalize(a):
         if lib.aukit_cuda_normalize(ctx.handle, a[0].audio._h, float(num(a[1] if len(a) > 1 else None, 1.0)),
                                     int(bool(a[2] if len(a) > 2 else False))) != 0:
@@ -115,7 +120,7 @@ def make_module(ak):
 
     mod = LuaTable()
     for name, f in {"pcm": l_pcm, "g711": l_g711, "wav": l_wav, "resample": l_resample, "mono": l_mono, "amplify": l_amplify,
-                    "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
+                    "lowpass": l_lowpass, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
                     "channels": lambda a: [float(a[0].audio.channels())],
                     "sample_rate": lambda a: [float(lib.aukit_cuda_audio_sample_rate(a[0].audio._h))]}.items():
         mod.set(name.encode(), LuaFunction(f, "aukit_cuda." + name))

@@ -65,6 +65,8 @@ def oracle_run(O, m, i):
         return list(O.amplify(x, A["multiplier"]))
     if op == "normalize":
         return list(O.normalize(x, 1.0 if A["peak"] is None else A["peak"], bool(A["independent"])))
+    if op == "lowpass":
+        return list(O.lowpass(x, A["frequency"], A["sampleRate"]))
     if op == "chain":
         out, info = O.wav(raw)
         r = O.resample(out, info["sampleRate"], A["targetRate"], A["interpolation"])
@@ -127,6 +129,8 @@ def cuda_run(ak, m, i):
         a = a.mono()
     if op == "amplify":
         assert ak.effects.amplify(a, A["multiplier"]) is a
+    if op == "lowpass":
+        assert ak.effects.lowpass(a, A["frequency"]) is a
     if op in ("normalize", "chain"):
         args = [] if A.get("peak") is None and A.get("independent") is None else [A.get("peak"), A.get("independent")]
         assert ak.effects.normalize(a, *args) is a

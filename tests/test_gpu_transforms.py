@@ -341,3 +341,31 @@ print("ok", err)
     for extra in ({"AUKIT_RUN_APPLY": "0"}, {"AUKIT_DISABLE_RUN": "1"}, {"AUKIT_DISABLE_POLY": "1"}):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **extra), timeout=600)
         assert r.returncode == 0 and "ok" in r.stdout, (extra, r.stdout + r.stderr)
+
+
+@pytest.mark.parametrize("n,ch,freq,rate", [(1_000_003, 2, 24000.0, 48000), (300_001, 3, 200.0, 44100), (2_000_000, 1, 5.0, 48000),
+                                            (4096, 1, 1000.0, 48000), (4097, 2, 1000.0, 48000), (17, 1, 3000.0, 8000),
+                                            (700_000, 1, 0.05, 48000)])
+def test_lowpass_matches_oracle(ak, O, n, ch, freq, rate):
+    """effects.lowpass (A:3586): chained-tile scan vs the sequential reference recurrence, incl. cut-offs
+    whose memory spans hundreds of 4096-sample tiles (5 Hz, 0.05 Hz: the look-back cannot stop early)."""
+    rng = np.random.default_rng(n)
+    x = (rng.uniform(-1, 1, (ch, n)) + 0.3).astype(np.float32)
+    a = ak.Audio.from_numpy(x, rate)
+    assert ak.effects.lowpass(a, freq) is a
+    got = a.numpy()
+    ref = O.lowpass(x.astype(np.float64), freq, rate)
+    assert got.shape == ref.shape
+    assert np.array_equal(got[:, 0], x[:, 0])                              # d[1] is untouched (A:3591)
+    assert float(np.max(np.abs(got - ref))) <= TOL
+
+
+def test_lowpass_after_normalize_like_auplay(ak, O):
+    """auplay.lua:27-30: normalize(0.8) then lowpass(sampleRate / 2) on the mono mixdown."""
+    pcm = tone_s16(50_000, 2, seed=4)
+    a = ak.pcm(pcm.tobytes(), 16, "signed", 2, 44100).resample(48000, "cubic").mono()
+    ak.effects.normalize(a, 0.8)
+    ak.effects.lowpass(a, a.sampleRate / 2)
+    dec = O.pcm(pcm.tobytes(), 16, "signed", 2, True, False)
+    ref = O.lowpass(O.normalize(O.mono(O.resample(dec, 44100, 48000, "cubic")), 0.8, False), 24000.0, 48000.0)
+    assert float(np.max(np.abs(a.numpy() - ref))) <= 2 * TOL
