@@ -10,7 +10,9 @@
 //     consecutive samples and runs the reference's own step on them, first from a zero state (-> S_t);
 //   * S_t are combined by a warp-shuffle scan with the constant ratio (1-a)^16, then across the 8 warps;
 //   * warp 0 publishes the tile aggregate, looks back over the predecessors' aggregates / inclusive states
-//     (32 at a time, stopping early once (1-a)^k has decayed below 2^-80) and publishes the inclusive state;
+//     (32 at a time, one 16-byte {value, flag} load each, stopping early once (1-a)^k has decayed below
+//     2^-80) and publishes the inclusive state;
+//   * the next tile's loads are issued before any of this, so they are in flight meanwhile;
 //   * every thread re-runs its 16 steps from its true incoming state and the tile is written back.
 // Arithmetic is fp64 like the reference's (Lua numbers): in fp32 the rounding error of a low cut-off is
 // amplified by 1/a and would leave the 2^-20 tolerance; the kernel stays HBM-bound either way (6 fp64 ops
@@ -25,30 +27,53 @@ constexpr int LP_THREADS = 256;
 constexpr int LP_PER = 16;                       // consecutive samples per thread
 constexpr int LP_TILE = LP_THREADS * LP_PER;     // 4096
 constexpr int LP_ROW = LP_PER + 4;               // padded row: conflict-free 16-byte accesses both ways
+constexpr int LP_CTAS_PER_SM = 5;                // resident CTAs: tiles in flight hide the look-back's L2 round trip
 
-struct lp_state {                                // per (channel, tile)
-    double agg;                                  // end state of the tile from a zero start
-    double incl;                                 // true end state
-};
+// Per (channel, tile): ONE 16-byte slot that holds either {aggregate, 1} or {inclusive state, 2}; it is
+// written and read with single 128-bit accesses, so a look-back costs one L2 round trip per window.
+struct __align__(16) lp_slot { double v; long long flag; };
 
-__device__ __forceinline__ int ld_acquire(const int *p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ lp_slot ld_slot(const lp_slot *p) {
+    lp_slot r;
+    // one .b128 access: single-copy atomic, so the value and its flag can never be seen torn
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.gpu.global.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}"
+                 : "=l"(*reinterpret_cast<long long *>(&r.v)), "=l"(r.flag) : "l"(p) : "memory");
+    return r;
 }
-__device__ __forceinline__ void st_release(int *p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_slot(lp_slot *p, double v, long long flag) {
+    asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.gpu.global.b128 [%0], q;\n\t}"
+                 ::"l"(p), "l"(__double_as_longlong(v)), "l"(flag) : "memory");
 }
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 
-__global__ void __launch_bounds__(LP_THREADS)
+// Asynchronous global -> shared copy of one tile into its padded layout (16 bytes per cp.async, no
+// registers held while the loads are in flight); ragged tails are filled with plain loads and zeros.
+__device__ __forceinline__ void lp_fetch_tile(float *tile, const float *base, int cnt, int t) {
+#pragma unroll
+    for (int k = 0; k < LP_PER / 4; k++) {
+        const int i4 = (k * LP_THREADS + t) * 4;                       // first sample of this float4
+        float *dst = &tile[(i4 >> 4) * LP_ROW + (i4 & 15)];
+        if (i4 + 3 < cnt) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(base + i4) : "memory");
+        } else {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i4 < cnt) v.x = base[i4];
+            if (i4 + 1 < cnt) v.y = base[i4 + 1];
+            if (i4 + 2 < cnt) v.z = base[i4 + 2];
+            *reinterpret_cast<float4 *>(dst) = v;
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(LP_THREADS, LP_CTAS_PER_SM)
 lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, double a, double b,
-               lp_state *st, int *flags, unsigned long long *ticket, unsigned long long tiles_per_ch) {
-    __shared__ __align__(16) float tile[LP_THREADS * LP_ROW];
+               lp_slot *slots, unsigned long long *ticket, unsigned long long tiles_per_ch) {
+    __shared__ __align__(16) float tiles[2][LP_THREADS * LP_ROW];      // double buffered: see the loop
     __shared__ double pt_pow[LP_THREADS];        // ((1-a)^16)^t
     __shared__ double warp_tot[LP_THREADS / 32];
     __shared__ double s_carry;
-    __shared__ unsigned long long s_ticket;
+    __shared__ unsigned long long s_ticket[2];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const double pt = pow(b, (double)LP_PER);
     pt_pow[t] = pow(pt, (double)t);
@@ -56,42 +81,44 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
     const double pl = pow(p_tile, (double)lane); // look-back weight of the lane-th predecessor
     const double p_tile32 = pow(p_tile, 32.0);
     const unsigned long long total = tiles_per_ch * (unsigned long long)channels;
-    for (;;) {
+    auto tile_base = [&](unsigned long long id, int &cnt) -> float * {
+        const unsigned long long ch = id / tiles_per_ch, tl = id % tiles_per_ch;
+        const size_t left = n - (size_t)tl * LP_TILE;
+        cnt = left < (size_t)LP_TILE ? (int)left : LP_TILE;
+        return data + (size_t)ch * stride + (size_t)tl * LP_TILE;
+    };
+    // prologue: claim the first tile and start loading it
+    if (t == 0) s_ticket[0] = atomicAdd(ticket, 1ull);
+    __syncthreads();
+    unsigned long long id = s_ticket[0];
+    int cnt = 0;
+    float *base = nullptr;
+    if (id < total) { base = tile_base(id, cnt); lp_fetch_tile(tiles[0], base, cnt, t); }
+    for (int it = 0; id < total; it++) {
+        float *tile = tiles[it & 1];
+        // ---- this tile was fetched during the previous iteration; claim the next one
+        if (t == 0) s_ticket[(it + 1) & 1] = atomicAdd(ticket, 1ull);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        if (t == 0) s_ticket = atomicAdd(ticket, 1ull);
-        __syncthreads();
-        const unsigned long long id = s_ticket;
-        if (id >= total) break;
+        // ---- next tile's loads are in flight while this one is processed (the other buffer was last read
+        // before the barrier above)
+        const unsigned long long next_id = s_ticket[(it + 1) & 1];
+        int next_cnt = 0;
+        float *next_base = nullptr;
+        if (next_id < total) { next_base = tile_base(next_id, next_cnt); lp_fetch_tile(tiles[(it + 1) & 1], next_base, next_cnt, t); }
         const int ch = (int)(id / tiles_per_ch);
         const unsigned long long tl = id % tiles_per_ch;
-        float *base = data + (size_t)ch * stride + (size_t)tl * LP_TILE;
-        const size_t left = n - (size_t)tl * LP_TILE;
-        const int cnt = left < (size_t)LP_TILE ? (int)left : LP_TILE;
-        // ---- stage the tile (rows are 16-byte aligned: stride % 4 == 0 is checked by the host)
-#pragma unroll
-        for (int k = 0; k < LP_PER / 4; k++) {
-            const int i4 = (k * LP_THREADS + t) * 4;                   // first sample of this float4
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i4 + 3 < cnt) v = *reinterpret_cast<const float4 *>(base + i4);
-            else {
-                if (i4 < cnt) v.x = base[i4];
-                if (i4 + 1 < cnt) v.y = base[i4 + 1];
-                if (i4 + 2 < cnt) v.z = base[i4 + 2];
-            }
-            *reinterpret_cast<float4 *>(&tile[(i4 >> 4) * LP_ROW + (i4 & 15)]) = v;
-        }
-        __syncthreads();
-        float x[LP_PER];
-#pragma unroll
-        for (int k = 0; k < LP_PER / 4; k++) {
-            const float4 v = *reinterpret_cast<const float4 *>(&tile[t * LP_ROW + 4 * k]);
-            x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
-        }
         // ---- zero-start run of this thread's samples (the reference's step, A:3593-3594).  Samples past the
         // end of the channel are zeros: they only decay the state, which nothing reads afterwards.
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < LP_PER; k++) s = s + a * ((double)x[k] - s);
+        for (int k = 0; k < LP_PER / 4; k++) {
+            const float4 v = *reinterpret_cast<const float4 *>(&tile[t * LP_ROW + 4 * k]);
+            s = s + a * ((double)v.x - s);
+            s = s + a * ((double)v.y - s);
+            s = s + a * ((double)v.z - s);
+            s = s + a * ((double)v.w - s);
+        }
         // ---- inclusive scan over the block with ratio pt per thread
         double inc = s;
         double r = pt;
@@ -105,11 +132,9 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
         __syncthreads();
         double wprev = 0.0;                                            // state entering this warp (zero tile carry)
         for (int w = 0; w < warp; w++) wprev = fma(p_warp, wprev, warp_tot[w]);
-        // exclusive prefix of this thread = inclusive prefix of thread t-1
-        double exc = shfl_up_d(inc, 1);
+        double exc = shfl_up_d(inc, 1);                                // inclusive prefix of thread t-1
         if (lane == 0) exc = 0.0;
-        // state entering thread t (zero tile carry) = pt^lane * wprev + exc
-        const double enter0 = fma(pt_pow[lane], wprev, exc);
+        const double enter0 = fma(pt_pow[lane], wprev, exc);           // state entering thread t with a zero tile carry
         // ---- tile aggregate + look-back (warp 0)
         if (warp == 0) {
             double agg = 0.0;
@@ -119,29 +144,25 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
                 // A:3591: d[1] is untouched, which is what a state equal to d[1] gives (l + a*(l - l) = l)
                 carry = (double)tile[0];
             } else {
-                if (lane == 0) {
-                    st[id].agg = agg;
-                    st_release(&flags[id], 1);
-                }
+                if (lane == 0) st_slot(&slots[id], agg, 1);
                 double acc = 0.0, scale = 1.0;
                 long long back = (long long)tl - 1;                    // nearest predecessor tile of this channel
-                carry = 0.0;
                 for (;;) {
                     const long long j = back - lane;
-                    int f = 2;
-                    if (j >= 0) {
-                        const int *fp = &flags[(unsigned long long)ch * tiles_per_ch + (unsigned long long)j];
-                        do { f = ld_acquire(fp); } while (f == 0);
+                    lp_slot sv;
+                    sv.v = 0.0; sv.flag = 2;
+                    // only poll predecessors whose weight can still matter: with (1-a)^4096 tiny (any cut-off above
+                    // a few Hz) that is the nearest one or two, and a tile then waits for those alone instead of
+                    // for the slowest of 32 (which locks all CTAs into step; measured 2.4x slower)
+                    const bool live = j >= 0 && pl * scale >= 8.3e-25;
+                    if (live) {
+                        const lp_slot *sp = &slots[(unsigned long long)ch * tiles_per_ch + (unsigned long long)j];
+                        do { sv = ld_slot(sp); } while (sv.flag == 0);
                     }
-                    const unsigned incl_mask = __ballot_sync(0xffffffffu, j >= 0 && f == 2);
-                    const unsigned none_mask = __ballot_sync(0xffffffffu, j < 0);
-                    // first lane holding an inclusive state, or the first lane before tile 0
-                    const int stop = __ffs(incl_mask | none_mask) - 1;    // -1: neither in this window
-                    double term = 0.0;
-                    if (j >= 0 && (stop < 0 || lane <= stop)) {
-                        const lp_state sv = st[(unsigned long long)ch * tiles_per_ch + (unsigned long long)j];
-                        term = pl * ((stop >= 0 && lane == stop && f == 2) ? sv.incl : sv.agg);
-                    }
+                    // first lane holding an inclusive state (tile 0 always does), or the first lane before tile 0
+                    const unsigned stop_mask = __ballot_sync(0xffffffffu, sv.flag == 2);
+                    const int stop = __ffs(stop_mask) - 1;             // -1: only aggregates in this window
+                    double term = (live && (stop < 0 || lane <= stop)) ? pl * sv.v : 0.0;
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) term += __shfl_xor_sync(0xffffffffu, term, d);
                     acc = fma(scale, term, acc);
@@ -153,24 +174,22 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
                 carry = acc;
             }
             if (lane == 0) {
-                st[id].incl = fma(p_tile, carry, agg);
-                st_release(&flags[id], 2);
+                st_slot(&slots[id], fma(p_tile, carry, agg), 2);
                 s_carry = carry;
             }
         }
         __syncthreads();
-        // ---- true run from the incoming state, written back through shared memory
-        // state entering thread t = pt^t * (tile carry) + (state entering t with a zero tile carry)
+        // ---- true run: state entering thread t = pt^t * (tile carry) + (state entering t with a zero tile carry)
         double y = fma(pt_pow[t], s_carry, enter0);
-        float o[LP_PER];
 #pragma unroll
-        for (int k = 0; k < LP_PER; k++) {
-            y = y + a * ((double)x[k] - y);
-            o[k] = (float)y;
+        for (int k = 0; k < LP_PER / 4; k++) {
+            float4 v = *reinterpret_cast<const float4 *>(&tile[t * LP_ROW + 4 * k]);
+            y = y + a * ((double)v.x - y); v.x = (float)y;
+            y = y + a * ((double)v.y - y); v.y = (float)y;
+            y = y + a * ((double)v.z - y); v.z = (float)y;
+            y = y + a * ((double)v.w - y); v.w = (float)y;
+            *reinterpret_cast<float4 *>(&tile[t * LP_ROW + 4 * k]) = v;
         }
-#pragma unroll
-        for (int k = 0; k < LP_PER / 4; k++)
-            *reinterpret_cast<float4 *>(&tile[t * LP_ROW + 4 * k]) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < LP_PER / 4; k++) {
@@ -183,6 +202,7 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
                 if (i4 + 2 < cnt) base[i4 + 2] = v.z;
             }
         }
+        id = next_id; base = next_base; cnt = next_cnt;
     }
 }
 
@@ -197,19 +217,19 @@ extern "C" int aukit_cuda_dev_lowpass(aukit_ctx *ctx, float *d, size_t stride, i
     const double a = 1.0 - exp(-(frequency / sampleRate) * 2.0 * 3.14159265358979323846);      // A:3589
     const double b = 1.0 - a;
     const unsigned long long tiles = (n + LP_TILE - 1) / LP_TILE, total = tiles * (unsigned long long)channels;
-    // scratch: states, flags, ticket
+    // scratch: one 16-byte slot per (channel, tile) + the ticket counter
     void *scratch = nullptr;
-    const size_t st_bytes = (size_t)total * sizeof(lp_state), fl_bytes = ((size_t)total * sizeof(int) + 15) & ~(size_t)15;
-    if (aukit_dev_alloc(ctx, st_bytes + fl_bytes + 16, &scratch)) return -1;
-    lp_state *st = static_cast<lp_state *>(scratch);
-    int *flags = reinterpret_cast<int *>(static_cast<char *>(scratch) + st_bytes);
-    unsigned long long *ticket = reinterpret_cast<unsigned long long *>(static_cast<char *>(scratch) + st_bytes + fl_bytes);
-    int rc = aukit_cuda_check(cudaMemsetAsync(flags, 0, fl_bytes + 16, ctx->stream), "memset");
+    const size_t slot_bytes = (size_t)total * sizeof(lp_slot);
+    if (aukit_dev_alloc(ctx, slot_bytes + 16, &scratch)) return -1;
+    lp_slot *slots = static_cast<lp_slot *>(scratch);
+    unsigned long long *ticket = reinterpret_cast<unsigned long long *>(static_cast<char *>(scratch) + slot_bytes);
+    int rc = aukit_cuda_check(cudaMemsetAsync(scratch, 0, slot_bytes + 16, ctx->stream), "memset");
     if (!rc) {
         unsigned long long g = total;
-        const unsigned long long cap = (unsigned long long)ctx->num_sms * 8;
+        const unsigned long long cap = (unsigned long long)ctx->num_sms * LP_CTAS_PER_SM;
         if (g > cap) g = cap;
-        lowpass_kernel<<<(unsigned)g, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, n, a, b, st, flags, ticket, tiles);
+        cudaFuncSetAttribute(lowpass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        lowpass_kernel<<<(unsigned)g, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, n, a, b, slots, ticket, tiles);
         ctx->launches++;
         rc = aukit_cuda_check(cudaGetLastError(), "lowpass_kernel launch");
     }
