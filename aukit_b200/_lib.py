@@ -79,6 +79,10 @@ SIGNATURES = {
     "aukit_cuda_dev_absmax": (_I, [_P, _P, _SZ, _I, _SZ, _I, _P]),
     "aukit_cuda_dev_scale_clamp": (_I, [_P, _P, _SZ, _I, _SZ, _D, _I, _P]),
     "aukit_cuda_lowpass": (_I, [_P, _P, _D]),
+    "aukit_cuda_audio_pcm": (_I, [_P, _P, _I, _I, _I, _P]),
+    "aukit_cuda_audio_pcm_bytes": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "aukit_cuda_dev_encode_pcm": (_I, [_P, _P, _SZ, _I, _SZ, _I, _I, _I, _P]),
+    "aukit_cuda_dev_encode_pcm_bytes": (_I, [_P, _P, _SZ, _I, _SZ, _I, _I, _I, _I, _P]),
     "aukit_cuda_dev_lowpass": (_I, [_P, _P, _SZ, _I, _SZ, _D, _D]),
     "aukit_cuda_dev_pipeline_peak": (_I, [_P, C.POINTER(PipelineDesc), _P, _P]),
     "aukit_cuda_dev_pipeline_apply": (_I, [_P, C.POINTER(PipelineDesc), _P, _D, _P, _P, _SZ]),

@@ -245,6 +245,37 @@ class Audio:
                                                            C.c_void_p(out.ctypes.data)))
         return out
 
+    def pcm(self, bitDepth=None, dataType=None, interleaved=None) -> np.ndarray:          # A:901
+        """Audio:pcm: the samples as un-rounded PCM values (float64, flat: interleaved or channel-major)."""
+        bitDepth = _expect(1, bitDepth, float, type(None)) or 8
+        dataType = _expect(2, dataType, str, type(None)) or "signed"
+        _expect(3, interleaved, bool, type(None))
+        if interleaved is None:
+            interleaved = True
+        if bitDepth not in (8, 16, 24, 32):
+            raise AukitError("bad argument #2 (invalid bit depth)")
+        if dataType not in _DATATYPES:
+            raise AukitError("bad argument #3 (invalid data type)")
+        if dataType == "float" and bitDepth != 32:
+            raise AukitError("bad argument #2 (float audio must have 32-bit depth)")
+        out = np.empty(self.frames * self.channels(), dtype=np.float64)
+        _lib.check(self._ctx.lib.aukit_cuda_audio_pcm(self._ctx.handle, self._h, int(bitDepth), _DATATYPES[dataType],
+                                                      int(interleaved), C.c_void_p(out.ctypes.data)))
+        return out
+
+    def pcm_bytes(self, bitDepth=16, dataType="signed", interleaved=True, rounding="truncate") -> bytes:
+        """The packed little-endian samples Audio:wav writes (A:981-985); `rounding` is the host
+        string.pack's: "truncate" (Cobalt), "floor" or "nearest"."""
+        if bitDepth not in (8, 16, 24, 32):
+            raise AukitError("bad argument #2 (invalid bit depth)")
+        if dataType not in _DATATYPES:
+            raise AukitError("bad argument #3 (invalid data type)")
+        out = np.empty(self.frames * self.channels() * (bitDepth // 8), dtype=np.uint8)
+        _lib.check(self._ctx.lib.aukit_cuda_audio_pcm_bytes(self._ctx.handle, self._h, int(bitDepth), _DATATYPES[dataType],
+                                                            int(bool(interleaved)), {"truncate": 0, "floor": 1, "nearest": 2}[rounding],
+                                                            C.c_void_p(out.ctypes.data)))
+        return out.tobytes()
+
     def numpy(self) -> np.ndarray:
         """[channels, frames] float32 copy on the host (channel 1's length, like #data[1])."""
         n = self.frames

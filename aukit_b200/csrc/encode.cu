@@ -1,0 +1,149 @@
+// encode.cu -- K12 requantisation: encodePCM (A:868-894) behind Audio:pcm (A:901-911) and Audio:wav's
+// sample packing (A:981-985).  SURVEY 8(f) rank 2: the step after the preload path in both CLIs
+// (auplay.lua:34 plays Audio:stream chunks, auconvert.lua:414 writes Audio:wav).
+//
+//   value = d * (d < 0 and 2^(b-1) or 2^(b-1) - 1) + (unsigned and 2^(b-1) or 0)      (A:874; float: d, A:873)
+//
+// The reference returns these UN-ROUNDED Lua numbers; aukit_cuda_dev_encode_pcm writes them as fp64 (the
+// product of an f32 sample and a 32-bit scale is exact in fp64, so the values are bit-identical to the
+// reference's for every sample an Audio can hold).  aukit_cuda_dev_encode_pcm_bytes narrows the same values
+// to packed little-endian integers, which is what the host's string.pack does inside Audio:wav; how that
+// rounds is a property of the host Lua, so the mode is a parameter (truncate = Cobalt / a C cast, floor,
+// nearest-even); values outside the integer range saturate.
+// Layout: interleaved -> out[n*C + c] (A:883), otherwise out[c*len + n] (A:894).
+// HBM-bound elementwise work: 4 B read per sample, 8 B (values) or b/8 B (bytes) written.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double encode_value(float d, double maxv, double add, bool is_float) {
+    if (is_float) return (double)d;                                         // A:873
+    const double x = (double)d;
+    return __dadd_rn(__dmul_rn(x, d < 0.0f ? maxv : maxv - 1.0), add);      // A:874 (NaN: the comparison is false)
+}
+
+__device__ __forceinline__ long long round_mode(double v, int mode) {
+    double r = mode == 0 ? trunc(v) : (mode == 1 ? floor(v) : rint(v));
+    if (!(r == r)) return 0;                                                // NaN
+    if (r > 9.0e18) r = 9.0e18;
+    if (r < -9.0e18) r = -9.0e18;
+    return (long long)r;
+}
+
+// values: one thread per frame, all channels (coalesced reads per channel row; the C values of a frame are
+// adjacent in the interleaved output, so the lanes of a warp write one contiguous span)
+__global__ void __launch_bounds__(256)
+encode_values_kernel(const float *__restrict__ in, size_t stride, int C, size_t n, double maxv, double add, int is_float,
+                     int interleaved, double *__restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (interleaved && C == 2) {
+            const double a = encode_value(in[i], maxv, add, is_float), b = encode_value(in[stride + i], maxv, add, is_float);
+            *reinterpret_cast<double2 *>(out + 2 * i) = make_double2(a, b);
+        } else {
+            for (int c = 0; c < C; c++) {
+                const double v = encode_value(in[(size_t)c * stride + i], maxv, add, is_float);
+                out[interleaved ? i * (size_t)C + c : (size_t)c * n + i] = v;
+            }
+        }
+    }
+}
+
+template <int B>
+__device__ __forceinline__ void store_le(uint8_t *p, long long q) {
+    if (B == 1) p[0] = (uint8_t)q;
+    else if (B == 2) *reinterpret_cast<uint16_t *>(p) = (uint16_t)q;
+    else if (B == 4) *reinterpret_cast<uint32_t *>(p) = (uint32_t)q;
+    else { p[0] = (uint8_t)q; p[1] = (uint8_t)(q >> 8); p[2] = (uint8_t)(q >> 16); }
+}
+
+// bytes: B = bytes per sample.  Mono / planar rows and interleaved stereo take 4 frames per thread so the
+// stores are 4..16 bytes wide; other shapes go sample by sample.
+template <int B>
+__global__ void __launch_bounds__(256)
+encode_bytes_kernel(const float *__restrict__ in, size_t stride, int C, size_t n, double maxv, double add, int is_float,
+                    int is_unsigned, int interleaved, int mode, uint8_t *__restrict__ out) {
+    const long long lo = is_unsigned ? 0 : -(1ll << (8 * B - 1)), hi = is_unsigned ? (1ll << (8 * B)) - 1 : (1ll << (8 * B - 1)) - 1;
+    auto quant = [&](float d) -> long long {
+        if (is_float) return (long long)__float_as_uint(d);                 // 32-bit float samples keep their bits
+        long long q = round_mode(encode_value(d, maxv, add, false), mode);
+        return q < lo ? lo : (q > hi ? hi : q);
+    };
+    const size_t total = n * (size_t)C;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+        size_t c, i;
+        if (interleaved) { i = o / (size_t)C; c = o % (size_t)C; }
+        else { c = o / n; i = o % n; }
+        store_le<B>(out + o * B, quant(in[c * stride + i]));
+    }
+}
+
+}  // namespace
+
+static int encode_args(int bitDepth, int dataType, double *maxv, double *add) {
+    if (bitDepth != 8 && bitDepth != 16 && bitDepth != 24 && bitDepth != 32) return aukit_fail("bad argument #2 (invalid bit depth)");
+    if (dataType != AUKIT_SIGNED && dataType != AUKIT_UNSIGNED && dataType != AUKIT_FLOAT) return aukit_fail("bad argument #3 (invalid data type)");
+    if (dataType == AUKIT_FLOAT && bitDepth != 32) return aukit_fail("bad argument #2 (float audio must have 32-bit depth)");   // A:909
+    *maxv = ldexp(1.0, bitDepth - 1);
+    *add = dataType == AUKIT_UNSIGNED ? *maxv : 0.0;
+    return 0;
+}
+
+extern "C" int aukit_cuda_dev_encode_pcm(aukit_ctx *ctx, const float *d, size_t stride, int channels, size_t n, int bitDepth,
+                                         int dataType, int interleaved, double *d_out) {
+    if (!ctx) return aukit_fail("aukit_cuda: null context");
+    double maxv, add;
+    if (encode_args(bitDepth, dataType, &maxv, &add)) return -1;
+    if (channels < 1 || n == 0) return 0;
+    if (interleaved && channels == 2 && ((uintptr_t)d_out & 15)) return aukit_fail("aukit_cuda: output must be 16-byte aligned");
+    const unsigned grid = aukit_grid(n, 256, (size_t)ctx->num_sms * 32);
+    encode_values_kernel<<<grid, 256, 0, ctx->stream>>>(d, stride, channels, n, maxv, add, dataType == AUKIT_FLOAT, interleaved, d_out);
+    ctx->launches++;
+    return aukit_cuda_check(cudaGetLastError(), "encode_values_kernel launch");
+}
+
+extern "C" int aukit_cuda_dev_encode_pcm_bytes(aukit_ctx *ctx, const float *d, size_t stride, int channels, size_t n, int bitDepth,
+                                               int dataType, int interleaved, int rounding, void *d_out) {
+    if (!ctx) return aukit_fail("aukit_cuda: null context");
+    double maxv, add;
+    if (encode_args(bitDepth, dataType, &maxv, &add)) return -1;
+    if (rounding < 0 || rounding > 2) return aukit_fail("aukit_cuda: rounding must be 0 (truncate), 1 (floor) or 2 (nearest)");
+    if (channels < 1 || n == 0) return 0;
+    const unsigned grid = aukit_grid(n * (size_t)channels, 256, (size_t)ctx->num_sms * 32);
+    uint8_t *o = static_cast<uint8_t *>(d_out);
+    const int isf = dataType == AUKIT_FLOAT, isu = dataType == AUKIT_UNSIGNED;
+    switch (bitDepth) {
+    case 8: encode_bytes_kernel<1><<<grid, 256, 0, ctx->stream>>>(d, stride, channels, n, maxv, add, isf, isu, interleaved, rounding, o); break;
+    case 16: encode_bytes_kernel<2><<<grid, 256, 0, ctx->stream>>>(d, stride, channels, n, maxv, add, isf, isu, interleaved, rounding, o); break;
+    case 24: encode_bytes_kernel<3><<<grid, 256, 0, ctx->stream>>>(d, stride, channels, n, maxv, add, isf, isu, interleaved, rounding, o); break;
+    default: encode_bytes_kernel<4><<<grid, 256, 0, ctx->stream>>>(d, stride, channels, n, maxv, add, isf, isu, interleaved, rounding, o); break;
+    }
+    ctx->launches++;
+    return aukit_cuda_check(cudaGetLastError(), "encode_bytes_kernel launch");
+}
+
+// Audio:pcm(bitDepth, dataType, interleaved) on a handle, results to HOST memory (n * channels doubles / samples)
+extern "C" int aukit_cuda_audio_pcm(aukit_ctx *ctx, const aukit_audio *a, int bitDepth, int dataType, int interleaved, double *h_out) {
+    if (!ctx || !a || !h_out) return aukit_fail("aukit_cuda: null argument");
+    const size_t total = a->frames * (size_t)a->channels;
+    void *d_out = nullptr;
+    if (aukit_dev_alloc(ctx, total * sizeof(double) + 16, &d_out)) return -1;
+    int rc = aukit_cuda_dev_encode_pcm(ctx, a->data, a->stride, a->channels, a->frames, bitDepth, dataType, interleaved,
+                                       static_cast<double *>(d_out));
+    if (!rc && total) rc = aukit_cuda_check(cudaMemcpyAsync(h_out, d_out, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+    aukit_dev_free(ctx, d_out);
+    if (!rc) rc = aukit_cuda_synchronize(ctx);
+    return rc;
+}
+
+extern "C" int aukit_cuda_audio_pcm_bytes(aukit_ctx *ctx, const aukit_audio *a, int bitDepth, int dataType, int interleaved,
+                                          int rounding, void *h_out) {
+    if (!ctx || !a || !h_out) return aukit_fail("aukit_cuda: null argument");
+    const size_t total = a->frames * (size_t)a->channels * (size_t)(bitDepth / 8);
+    void *d_out = nullptr;
+    if (aukit_dev_alloc(ctx, total + 16, &d_out)) return -1;
+    int rc = aukit_cuda_dev_encode_pcm_bytes(ctx, a->data, a->stride, a->channels, a->frames, bitDepth, dataType, interleaved, rounding, d_out);
+    if (!rc && total) rc = aukit_cuda_check(cudaMemcpyAsync(h_out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+    aukit_dev_free(ctx, d_out);
+    if (!rc) rc = aukit_cuda_synchronize(ctx);
+    return rc;
+}

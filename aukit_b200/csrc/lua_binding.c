@@ -261,6 +261,22 @@ static int l_read(lua_State *L) {
     return 1;
 }
 
+/* cu.pcm_out(audio, bitDepth, dataType, interleaved) -> {numbers}: Audio:pcm (A:901), un-rounded values */
+static int l_pcm_out(lua_State *L) {
+    aukit_audio *a = check_audio(L, 1);
+    const size_t total = aukit_cuda_audio_frames(a) * (size_t)aukit_cuda_audio_channels(a);
+    double *buf = (double *)malloc(sizeof(double) * (total ? total : 1));
+    if (!buf) return luaL_error(L, "out of memory");
+    if (aukit_cuda_audio_pcm(ctx(L), a, (int)luaL_checkinteger(L, 2), (int)luaL_checkinteger(L, 3), optbool(L, 4, 1), buf)) {
+        free(buf);
+        return fail(L);
+    }
+    lua_createtable(L, (int)total, 0);
+    for (size_t i = 0; i < total; i++) { lua_pushnumber(L, buf[i]); lua_rawseti(L, -2, (int)i + 1); }
+    free(buf);
+    return 1;
+}
+
 /* cu.write(audio, channel, first, {numbers}) -- audio.data[c][i] = v */
 static int l_write(lua_State *L) {
     aukit_audio *a = check_audio(L, 1);
@@ -284,7 +300,7 @@ static int l_gc(lua_State *L) {
 static const luaL_Reg funcs[] = {
     {"pcm", l_pcm}, {"g711", l_g711}, {"adpcm", l_adpcm}, {"ima_adpcm_wav", l_ima_wav}, {"msadpcm", l_msadpcm},
     {"wav", l_wav}, {"new", l_new}, {"resample", l_resample}, {"mono", l_mono}, {"concat", l_concat},
-    {"amplify", l_amplify}, {"lowpass", l_lowpass}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
+    {"amplify", l_amplify}, {"lowpass", l_lowpass}, {"pcm_out", l_pcm_out}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
     {"frames", l_frames}, {"read", l_read}, {"write", l_write}, {NULL, NULL}};
 
 int luaopen_aukit_cuda(lua_State *L) {

@@ -6,7 +6,7 @@
 -- auplay.lua's load -> :resample(48000) -> :mono() -> effects.normalize(mono, 0.8) runs unchanged.
 --
 -- In scope (device-backed): aukit.pcm, aukit.g711, aukit.adpcm, aukit.msadpcm, aukit.wav, aukit.new,
---   Audio:len/channels/resample/mono/concat, aukit.effects.amplify/normalize/lowpass, aukit.defaultInterpolation.
+--   Audio:len/channels/resample/mono/concat/pcm, aukit.effects.amplify/normalize/lowpass, aukit.defaultInterpolation.
 -- Everything else of the reference (players, streams, FLAC/QOA/DFPWM, editing ops, writers) is out of
 -- scope of this accelerated path; load the reference module alongside for those.
 --
@@ -112,6 +112,18 @@ function Audio:mono()
     local out = wrap(cu.mono(handle(self)), copy(self.metadata), copy(self.info))
     out.sampleRate = self.sampleRate
     return out
+end
+
+--- Converts the audio data to raw PCM samples: un-rounded numbers, like the reference. (A:901)
+function Audio:pcm(bitDepth, dataType, interleaved)
+    bitDepth = expect(1, bitDepth, "number", "nil") or 8
+    dataType = expect(2, dataType, "string", "nil") or "signed"
+    expect(3, interleaved, "boolean", "nil")
+    if interleaved == nil then interleaved = true end
+    if bitDepth ~= 8 and bitDepth ~= 16 and bitDepth ~= 24 and bitDepth ~= 32 then error("bad argument #2 (invalid bit depth)", 2) end
+    if dataType ~= "signed" and dataType ~= "unsigned" and dataType ~= "float" then error("bad argument #3 (invalid data type)", 2) end
+    if dataType == "float" and bitDepth ~= 32 then error("bad argument #2 (float audio must have 32-bit depth)", 2) end
+    return cu.pcm_out(handle(self), bitDepth, DATATYPE[dataType], interleaved)
 end
 
 --- Concatenates this audio object with others, resampling where rates differ. (A:696)

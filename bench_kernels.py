@@ -119,6 +119,16 @@ def main():
     report("K8 absmax 2ch", ms, n * 2 * 4, n * 2, "samples")
     ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_scale_clamp(ctx.handle, x.data_ptr(), n, 2, n, 1.0, 0, dmax.data_ptr())))
     report("K9 scale_clamp 2ch", ms, n * 2 * 8, n * 2, "samples")
+    # ---- K12 requantisation (8f rank 2): Audio:pcm values (fp64 out) and packed s16 / u8 bytes
+    ev = torch.empty(n * 2, dtype=torch.float64, device="cuda")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_encode_pcm(ctx.handle, x.data_ptr(), n, 2, n, 16, 0, 1, ev.data_ptr())))
+    report("K12 encode_pcm values s16 stereo interleaved", ms, n * 2 * 12, n * 2, "samples", "4 B read + 8 B (fp64, un-rounded) written")
+    eb = torch.empty(n * 2 * 2, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_encode_pcm_bytes(ctx.handle, x.data_ptr(), n, 2, n, 16, 0, 1, 0, eb.data_ptr())))
+    report("K12 encode_pcm bytes s16 stereo interleaved", ms, n * 2 * 6, n * 2, "samples")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_encode_pcm_bytes(ctx.handle, x.data_ptr(), n, 1, n, 8, 0, 1, 1, eb.data_ptr())))
+    report("K12 encode_pcm bytes s8 mono (speaker format)", ms, n * 5, n, "samples")
+    del ev, eb
     # ---- K11 lowpass (8f rank 1): in place, 4 B read + 4 B written per sample
     for f in (24000.0, 200.0):
         ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_lowpass(ctx.handle, x.data_ptr(), n, 2, n, f, 48000.0)))

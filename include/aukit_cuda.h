@@ -144,6 +144,17 @@ int aukit_cuda_scale_clamp(aukit_ctx *ctx, aukit_audio *a, double peakAmplitude,
  * Single pass, chained tiles (decoupled look-back), fp64 state. */
 int aukit_cuda_lowpass(aukit_ctx *ctx, aukit_audio *a, double frequency);
 
+/* Audio:pcm(bitDepth, dataType, interleaved) A:901-911 -> encodePCM A:868-894: every sample as
+ * d * (d < 0 ? 2^(b-1) : 2^(b-1)-1) + (unsigned ? 2^(b-1) : 0), UN-ROUNDED like the reference's Lua
+ * numbers, written as doubles to h_out[frames*channels] (interleaved: [n*C + c], else [c*frames + n]). */
+int aukit_cuda_audio_pcm(aukit_ctx *ctx, const aukit_audio *a, int bitDepth, int dataType,
+                         int interleaved, double *h_out);
+/* The same values as packed little-endian integers of bitDepth/8 bytes (Audio:wav's sample packing,
+ * A:981-985; float = the f32 bits).  rounding: 0 truncate (Cobalt / C cast), 1 floor, 2 nearest-even --
+ * the reference leaves this to the host's string.pack.  Out-of-range values saturate. */
+int aukit_cuda_audio_pcm_bytes(aukit_ctx *ctx, const aukit_audio *a, int bitDepth, int dataType,
+                               int interleaved, int rounding, void *h_out);
+
 /* ------------------------------------------------------------------ device-pointer level */
 /* Same kernels on caller-owned DEVICE buffers (inputs already resident in HBM; what
  * bench.py's `value` times).  Output layout: d_out[c * out_stride + i]. */
@@ -171,6 +182,11 @@ int aukit_cuda_dev_amplify(aukit_ctx *ctx, float *d, size_t stride, int channels
                            double multiplier);
 int aukit_cuda_dev_lowpass(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,
                            double frequency, double sampleRate);
+int aukit_cuda_dev_encode_pcm(aukit_ctx *ctx, const float *d, size_t stride, int channels, size_t n,
+                              int bitDepth, int dataType, int interleaved, double *d_out);
+int aukit_cuda_dev_encode_pcm_bytes(aukit_ctx *ctx, const float *d, size_t stride, int channels,
+                                    size_t n, int bitDepth, int dataType, int interleaved,
+                                    int rounding, void *d_out);
 int aukit_cuda_dev_absmax(aukit_ctx *ctx, const float *d, size_t stride, int channels, size_t n,
                           int independent, float *d_max);
 int aukit_cuda_dev_scale_clamp(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,

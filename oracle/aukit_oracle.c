@@ -511,6 +511,26 @@ double auko_encode_pcm(double d, int bitDepth, int dataType) {               /* 
     return d * (d < 0 ? maxValue : maxValue - 1) + add;
 }
 
+/* Audio:pcm(bitDepth, dataType, interleaved), A:901-911 -> encodePCM(info, 1), A:868-894.
+ * out holds channels*n numbers: interleaved data[(n-1)*nc+c] (A:883), else data[(c-1)*len+n] (A:894). */
+int auko_audio_pcm(const double *d, size_t stride, int channels, size_t n, int bitDepth, int dataType,
+                   int interleaved, double *out) {
+    g_err[0] = 0;
+    if (bitDepth != 8 && bitDepth != 16 && bitDepth != 24 && bitDepth != 32)
+        return fail("bad argument #2 (invalid bit depth)");                                  /* A:907 */
+    if (dataType != AUKO_SIGNED && dataType != AUKO_UNSIGNED && dataType != AUKO_FLOAT)
+        return fail("bad argument #3 (invalid data type)");                                  /* A:908 */
+    if (dataType == AUKO_FLOAT && bitDepth != 32)
+        return fail("bad argument #2 (float audio must have 32-bit depth)");                 /* A:909 */
+    for (int c = 0; c < channels; c++)
+        for (size_t i = 0; i < n; i++) {
+            double v = auko_encode_pcm(d[(size_t)c * stride + i], bitDepth, dataType);
+            if (interleaved) out[i * (size_t)channels + (size_t)c] = v;
+            else out[(size_t)c * n + i] = v;
+        }
+    return 0;
+}
+
 int auko_lowpass(double *d, size_t stride, int channels, size_t n, double frequency,
                  double sampleRate) {                                        /* A:3586-3598 */
     g_err[0] = 0;

@@ -95,6 +95,9 @@ int auko_normalize(double *d, size_t stride, int channels, size_t n, double peak
 
 /* encodePCM's per-sample formula (A:874): d*(d<0 and max or max-1)+add, un-rounded. */
 double auko_encode_pcm(double d, int bitDepth, int dataType);
+/* Audio:pcm (A:901-911): all samples through encodePCM into a flat array (interleaved or channel-major). */
+int auko_audio_pcm(const double *d, size_t stride, int channels, size_t n, int bitDepth, int dataType,
+                   int interleaved, double *out);
 
 /* effects.lowpass (A:3586-3598), in place. */
 int auko_lowpass(double *d, size_t stride, int channels, size_t n, double frequency,

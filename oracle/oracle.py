@@ -65,6 +65,7 @@ def lib():
         L.auko_normalize.argtypes = [dp, sz, C.c_int, sz, C.c_double, C.c_int]
         L.auko_encode_pcm.argtypes = [C.c_double, C.c_int, C.c_int]
         L.auko_encode_pcm.restype = C.c_double
+        L.auko_audio_pcm.argtypes = [dp, sz, C.c_int, sz, C.c_int, C.c_int, C.c_int, dp]
         L.auko_lowpass.argtypes = [dp, sz, C.c_int, sz, C.c_double, C.c_double]
         L.auko_wav_parse.argtypes = [u8p, sz, C.c_void_p]
         L.auko_chain_s16.argtypes = [u8p, sz, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.POINTER(sz)]
@@ -200,6 +201,16 @@ def lowpass(x: np.ndarray, frequency, sampleRate):
     ch, n = x.shape
     _check(lib().auko_lowpass(_ptr(x), n, ch, n, float(frequency), float(sampleRate)))
     return x
+
+
+def audio_pcm(x: np.ndarray, bitDepth=8, dataType="signed", interleaved=True) -> np.ndarray:
+    """Audio:pcm (A:901): flat float64 array of un-rounded encoded values."""
+    x = np.array(np.atleast_2d(x), dtype=np.float64, order="C")
+    ch, n = x.shape
+    out = np.zeros(max(1, ch * n), dtype=np.float64)
+    dt = DATATYPES.get(dataType, 99) if isinstance(dataType, str) else dataType
+    _check(lib().auko_audio_pcm(_ptr(x), n, ch, n, int(bitDepth), dt, int(bool(interleaved)), _ptr(out)))
+    return out[: ch * n]
 
 
 def encode_pcm(d: float, bitDepth=8, dataType="signed") -> float:

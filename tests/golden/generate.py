@@ -68,6 +68,12 @@ def run_case(R, case, blobs):
         a = call(R.fn("msadpcm"), [blobs["in"], float(A["blockAlign"]), float(A["channels"]), float(A["sampleRate"]), cot])[0]
     elif op == "wav":
         a = R.call("wav", blobs["in"], A.get("head", False))[0]
+    elif op == "pcm_out":
+        a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
+        t = R.method(a, "pcm", A.get("bitDepth"), A.get("dataType"), A.get("interleaved"))[0]
+        out = R.call("new", 0, 1, A["sampleRate"])[0]          # carrier: one "channel" holding the flat result
+        out.get(b"data").arr[0].arr = list(t.arr)
+        return out
     elif op == "lowpass":
         a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
         r = R.call(("effects", "lowpass"), a, A["frequency"])[0]
@@ -222,6 +228,20 @@ def main():
     add("lowpass_single_sample", "lowpass", dict(sampleRate=8000, frequency=100.0), x=np.array([[0.5]]))
     add("lowpass_two_samples", "lowpass", dict(sampleRate=8000, frequency=100.0), x=np.array([[0.5, -0.5], [1.0, 0.0]]))
     add("lowpass_zero_hz", "lowpass", dict(sampleRate=44100, frequency=0.0), x=z[:, :64])           # a = 0: every sample becomes d[1]
+
+    # ---- Audio:pcm / encodePCM: un-rounded values; inputs are f32-representable
+    w = np.concatenate([np.array([-1.0, -0.5, 0.0, 0.5, 1.0, 0.999969482421875, -3.0517578125e-05, 1.5, -1.25]),
+                        rng2.uniform(-1, 1, 291)]).astype(np.float32).astype(np.float64)
+    w2 = np.stack([w, w[::-1]])
+    for bits, dt in ((8, "signed"), (8, "unsigned"), (16, "signed"), (16, "unsigned"), (24, "signed"), (32, "signed"),
+                     (32, "unsigned"), (32, "float")):
+        add("pcmout_%d_%s_il" % (bits, dt), "pcm_out", dict(sampleRate=48000, bitDepth=bits, dataType=dt, interleaved=True), x=w2)
+    add("pcmout_defaults", "pcm_out", dict(sampleRate=48000, bitDepth=None, dataType=None, interleaved=None), x=w2)
+    add("pcmout_16_planar", "pcm_out", dict(sampleRate=48000, bitDepth=16, dataType="signed", interleaved=False), x=w2)
+    add("pcmout_mono_24u", "pcm_out", dict(sampleRate=48000, bitDepth=24, dataType="unsigned", interleaved=True), x=w2[:1])
+    add("pcmout_bad_depth", "pcm_out", dict(sampleRate=48000, bitDepth=12, dataType="signed", interleaved=True), x=w2)
+    add("pcmout_bad_type", "pcm_out", dict(sampleRate=48000, bitDepth=16, dataType="int", interleaved=True), x=w2)
+    add("pcmout_float16", "pcm_out", dict(sampleRate=48000, bitDepth=16, dataType="float", interleaved=True), x=w2)
 
     # ---- run everything through the reference
     manifest = []

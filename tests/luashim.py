@@ -91,6 +91,16 @@ def make_module(ak):
             raise LuaError(lib.aukit_cuda_last_error())
         return []
 
+    def l_pcm_out(a):
+        au = a[0].audio
+        out = np.empty(au.frames * au.channels(), dtype=np.float64)
+        il = True if len(a) < 4 or a[3] is None else bool(a[3])
+        if lib.aukit_cuda_audio_pcm(ctx.handle, au._h, int(a[1]), int(a[2]), int(il), C.c_void_p(out.ctypes.data)) != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        t = LuaTable()
+        t.arr = [float(v) for v in out]
+        return [t]
+
     def l_normalize(a):
         if lib.aukit_cuda_normalize(ctx.handle, a[0].audio._h, float(num(a[1] if len(a) > 1 else None, 1.0)),
                                     int(bool(a[2] if len(a) > 2 else False))) != 0:
@@ -120,7 +130,7 @@ def make_module(ak):
 
     mod = LuaTable()
     for name, f in {"pcm": l_pcm, "g711": l_g711, "wav": l_wav, "resample": l_resample, "mono": l_mono, "amplify": l_amplify,
-                    "lowpass": l_lowpass, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
+                    "lowpass": l_lowpass, "pcm_out": l_pcm_out, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
                     "channels": lambda a: [float(a[0].audio.channels())],
                     "sample_rate": lambda a: [float(lib.aukit_cuda_audio_sample_rate(a[0].audio._h))]}.items():
         mod.set(name.encode(), LuaFunction(f, "aukit_cuda." + name))

@@ -67,6 +67,9 @@ def oracle_run(O, m, i):
         return list(O.normalize(x, 1.0 if A["peak"] is None else A["peak"], bool(A["independent"])))
     if op == "lowpass":
         return list(O.lowpass(x, A["frequency"], A["sampleRate"]))
+    if op == "pcm_out":
+        return [O.audio_pcm(x, 8 if A["bitDepth"] is None else A["bitDepth"], A["dataType"] or "signed",
+                            True if A["interleaved"] is None else A["interleaved"])]
     if op == "chain":
         out, info = O.wav(raw)
         r = O.resample(out, info["sampleRate"], A["targetRate"], A["interpolation"])
@@ -122,6 +125,8 @@ def cuda_run(ak, m, i):
         return ak.msadpcm(raw, A["blockAlign"], A["channels"], A["sampleRate"], A.get("coefficients"))
     if op == "wav":
         return ak.wav(raw, bool(A.get("head")))
+    if op == "pcm_out":
+        return ak.Audio.from_numpy(x.astype(np.float32), A["sampleRate"]).pcm(A["bitDepth"], A["dataType"], A["interleaved"])
     a = ak.wav(raw) if op == "chain" else ak.Audio.from_numpy(x.astype(np.float32), A["sampleRate"])
     if op in ("resample", "chain"):
         a = a.resample(A["targetRate"], A.get("interpolation"))
@@ -150,6 +155,10 @@ def test_cuda_matches_reference(ak, i):
         return
     a = cuda_run(ak, m, i)
     exp = expected(i, m)
+    if m["op"] == "pcm_out":
+        # the inputs are f32-representable, so the fp64 products are the reference's own numbers
+        assert a.dtype == np.float64 and same_f64(a, exp[0])
+        return
     assert a.channels() == m["channels"]
     assert float(a.sampleRate) == float(m["sampleRate"])
     decode = m["op"] in ("pcm", "g711", "adpcm", "msadpcm", "wav")

@@ -369,3 +369,45 @@ def test_lowpass_after_normalize_like_auplay(ak, O):
     dec = O.pcm(pcm.tobytes(), 16, "signed", 2, True, False)
     ref = O.lowpass(O.normalize(O.mono(O.resample(dec, 44100, 48000, "cubic")), 0.8, False), 24000.0, 48000.0)
     assert float(np.max(np.abs(a.numpy() - ref))) <= 2 * TOL
+
+
+@pytest.mark.parametrize("bits,dtype", [(8, "signed"), (8, "unsigned"), (16, "signed"), (24, "signed"), (24, "unsigned"),
+                                        (32, "signed"), (32, "unsigned"), (32, "float")])
+@pytest.mark.parametrize("ch,interleaved", [(1, True), (2, True), (2, False), (3, True)])
+def test_audio_pcm_values_bit_exact_and_bytes(ak, O, bits, dtype, ch, interleaved):
+    """Audio:pcm (A:901) / encodePCM (A:868): the un-rounded values are bit-identical to the oracle's doubles
+    (f32 sample x 32-bit scale is exact in fp64); the packed bytes follow the stated rounding mode."""
+    n = 100_003
+    rng = np.random.default_rng(bits * 10 + ch)
+    x = rng.uniform(-1, 1, (ch, n)).astype(np.float32)
+    x[:, :5] = np.array([-1.0, 1.0, 0.0, -0.0, 0.5], dtype=np.float32)
+    a = ak.Audio.from_numpy(x, 48000)
+    got = a.pcm(bits, dtype, interleaved)
+    ref = O.audio_pcm(x.astype(np.float64), bits, dtype, interleaved)
+    assert got.dtype == np.float64 and np.array_equal(got, ref) and np.array_equal(np.signbit(got), np.signbit(ref))
+    B = bits // 8
+    for mode, fn in (("truncate", np.trunc), ("floor", np.floor), ("nearest", np.rint)):
+        raw = np.frombuffer(a.pcm_bytes(bits, dtype, interleaved, mode), dtype=np.uint8).reshape(-1, B)
+        if dtype == "float":
+            order = x.T.reshape(-1) if interleaved else x.reshape(-1)
+            assert np.array_equal(raw.reshape(-1).view("<f4"), order)
+            continue
+        q = fn(ref).astype(np.int64)
+        lo, hi = (0, 2 ** bits - 1) if dtype == "unsigned" else (-2 ** (bits - 1), 2 ** (bits - 1) - 1)
+        q = np.clip(q, lo, hi)
+        want = np.zeros((q.size, B), dtype=np.uint8)
+        for k in range(B):
+            want[:, k] = (q >> (8 * k)) & 0xFF
+        assert np.array_equal(raw, want), mode
+
+
+def test_audio_pcm_requantisation_within_one_lsb_of_reference_chain(ak, O):
+    """north_star's statement for the whole path: after requantisation to 8-bit signed (what speaker.playAudio
+    takes, auplay.lua:34) the CUDA chain is within 1 LSB of the reference chain."""
+    pcm = tone_s16(60_000, 2, seed=6)
+    a = ak.pcm(pcm.tobytes(), 16, "signed", 2, 44100).resample(48000, "cubic").mono()
+    ak.effects.normalize(a, 0.8)
+    got = np.floor(a.pcm(8, "signed", True))
+    ref = np.floor(O.audio_pcm(O.chain_s16(pcm.tobytes(), 2, 44100, 48000, "cubic", 0.8), 8, "signed", True))
+    assert np.max(np.abs(got - ref)) <= 1
+    assert np.mean(got != ref) < 1e-3
