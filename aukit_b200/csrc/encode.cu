@@ -56,8 +56,58 @@ __device__ __forceinline__ void store_le(uint8_t *p, long long q) {
     else { p[0] = (uint8_t)q; p[1] = (uint8_t)(q >> 8); p[2] = (uint8_t)(q >> 16); }
 }
 
-// bytes: B = bytes per sample.  Mono / planar rows and interleaved stereo take 4 frames per thread so the
-// stores are 4..16 bytes wide; other shapes go sample by sample.
+// bytes, fast shapes: 4 consecutive OUTPUT samples per thread, stored as one 4*B-byte word group.
+//   ROWS  (mono, or planar with frames % 4 == 0): the 4 samples are 4 consecutive frames of one input row;
+//   !ROWS (interleaved stereo): 2 frames x 2 channels.
+template <int B, bool ROWS>
+__global__ void __launch_bounds__(256)
+encode_bytes_vec_kernel(const float *__restrict__ in, size_t stride, size_t n, size_t nrows, double maxv, double add, int is_float,
+                        int is_unsigned, int mode, uint8_t *__restrict__ out) {
+    const long long lo = is_unsigned ? 0 : -(1ll << (8 * B - 1)), hi = is_unsigned ? (1ll << (8 * B)) - 1 : (1ll << (8 * B - 1)) - 1;
+    auto quant = [&](float d) -> uint32_t {
+        if (is_float) return __float_as_uint(d);
+        long long q = round_mode(encode_value(d, maxv, add, false), mode);
+        q = q < lo ? lo : (q > hi ? hi : q);
+        return (uint32_t)q & (B == 4 ? 0xFFFFFFFFu : ((1u << (8 * (B & 3))) - 1u));
+    };
+    const size_t groups_per_row = ROWS ? (n + 3) / 4 : (n + 1) / 2;     // !ROWS: one "row" of frame pairs
+    const size_t total = groups_per_row * (ROWS ? nrows : 1);
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        float v[4];
+        size_t obase;                                                   // first output sample index
+        int valid = 4;
+        if (ROWS) {
+            const size_t r = g / groups_per_row, i = (g % groups_per_row) * 4;
+            const float *src = in + r * stride + i;
+            if (i + 4 <= n) { const float4 f = *reinterpret_cast<const float4 *>(src); v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w; }
+            else { valid = (int)(n - i); for (int k = 0; k < 4; k++) v[k] = k < valid ? src[k] : 0.f; }
+            obase = r * n + i;
+        } else {
+            const size_t i = g * 2;
+            if (i + 2 <= n) {
+                const float2 a = *reinterpret_cast<const float2 *>(in + i), b = *reinterpret_cast<const float2 *>(in + stride + i);
+                v[0] = a.x; v[1] = b.x; v[2] = a.y; v[3] = b.y;
+            } else { v[0] = in[i]; v[1] = in[stride + i]; v[2] = v[3] = 0.f; valid = 2; }
+            obase = i * 2;
+        }
+        const uint32_t q0 = quant(v[0]), q1 = quant(v[1]), q2 = quant(v[2]), q3 = quant(v[3]);
+        uint8_t *dst = out + obase * B;
+        if (valid == 4 && ((uintptr_t)dst % (4 * (B == 3 ? 1 : B))) == 0) {
+            if (B == 1) *reinterpret_cast<uint32_t *>(dst) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+            else if (B == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(q0 | (q1 << 16), q2 | (q3 << 16));
+            else if (B == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(q0, q1, q2, q3);
+            else {                                                      // 12 bytes = three words
+                uint32_t *w = reinterpret_cast<uint32_t *>(dst);
+                w[0] = q0 | (q1 << 24); w[1] = (q1 >> 8) | (q2 << 16); w[2] = (q2 >> 16) | (q3 << 8);
+            }
+        } else {
+            const uint32_t q[4] = {q0, q1, q2, q3};
+            for (int k = 0; k < valid; k++) store_le<B>(dst + k * B, (long long)q[k]);
+        }
+    }
+}
+
+// bytes, any shape: sample by sample
 template <int B>
 __global__ void __launch_bounds__(256)
 encode_bytes_kernel(const float *__restrict__ in, size_t stride, int C, size_t n, double maxv, double add, int is_float,
@@ -108,9 +158,29 @@ extern "C" int aukit_cuda_dev_encode_pcm_bytes(aukit_ctx *ctx, const float *d, s
     if (encode_args(bitDepth, dataType, &maxv, &add)) return -1;
     if (rounding < 0 || rounding > 2) return aukit_fail("aukit_cuda: rounding must be 0 (truncate), 1 (floor) or 2 (nearest)");
     if (channels < 1 || n == 0) return 0;
-    const unsigned grid = aukit_grid(n * (size_t)channels, 256, (size_t)ctx->num_sms * 32);
     uint8_t *o = static_cast<uint8_t *>(d_out);
     const int isf = dataType == AUKIT_FLOAT, isu = dataType == AUKIT_UNSIGNED;
+    // fast shapes (see encode_bytes_vec_kernel); rows must keep the 16-byte input alignment
+    const bool in_ok = ((uintptr_t)d % 16 == 0) && (channels == 1 || stride % 4 == 0);
+    const bool rows = in_ok && (channels == 1 || (!interleaved && n % 4 == 0));
+    const bool pairs = in_ok && interleaved && channels == 2;
+    if (rows || pairs) {
+        const size_t groups = rows ? (n + 3) / 4 * (size_t)channels : (n + 1) / 2;
+        const unsigned vg = aukit_grid(groups, 256, (size_t)ctx->num_sms * 32);
+#define AUKIT_ENC_VEC(BB)                                                                                                \
+    if (rows) encode_bytes_vec_kernel<BB, true><<<vg, 256, 0, ctx->stream>>>(d, stride, n, (size_t)channels, maxv, add, isf, isu, rounding, o); \
+    else encode_bytes_vec_kernel<BB, false><<<vg, 256, 0, ctx->stream>>>(d, stride, n, 1, maxv, add, isf, isu, rounding, o)
+        switch (bitDepth) {
+        case 8: AUKIT_ENC_VEC(1); break;
+        case 16: AUKIT_ENC_VEC(2); break;
+        case 24: AUKIT_ENC_VEC(3); break;
+        default: AUKIT_ENC_VEC(4); break;
+        }
+#undef AUKIT_ENC_VEC
+        ctx->launches++;
+        return aukit_cuda_check(cudaGetLastError(), "encode_bytes_vec_kernel launch");
+    }
+    const unsigned grid = aukit_grid(n * (size_t)channels, 256, (size_t)ctx->num_sms * 32);
     switch (bitDepth) {
     case 8: encode_bytes_kernel<1><<<grid, 256, 0, ctx->stream>>>(d, stride, channels, n, maxv, add, isf, isu, interleaved, rounding, o); break;
     case 16: encode_bytes_kernel<2><<<grid, 256, 0, ctx->stream>>>(d, stride, channels, n, maxv, add, isf, isu, interleaved, rounding, o); break;
