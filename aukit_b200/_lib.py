@@ -24,6 +24,17 @@ class WavInfo(C.Structure):
                 ("ntags", C.c_int), ("tags", WavTag * 64)]
 
 
+class _ContainerMeta(C.Structure):
+    _fields_ = [("key", C.c_char * 12), ("off", C.c_size_t), ("len", C.c_size_t)]
+
+
+class ContainerInfo(C.Structure):
+    """aukit_container_info (include/aukit_cuda.h)."""
+    _fields_ = [("codec", C.c_int), ("bitDepth", C.c_int), ("dataType", C.c_int), ("bigEndian", C.c_int), ("ulaw", C.c_int),
+                ("channels", C.c_int), ("sampleRate", C.c_double), ("data_off", C.c_size_t), ("data_len", C.c_size_t),
+                ("nmeta", C.c_int), ("meta", _ContainerMeta * 16)]
+
+
 class PipelineDesc(C.Structure):
     _fields_ = [("bitDepth", C.c_int), ("dataType", C.c_int), ("channels", C.c_int), ("bigEndian", C.c_int),
                 ("srcRate", C.c_double), ("dstRate", C.c_double), ("interpolation", C.c_int), ("mono", C.c_int),
@@ -78,6 +89,10 @@ SIGNATURES = {
     "aukit_cuda_dev_amplify": (_I, [_P, _P, _SZ, _I, _SZ, _D]),
     "aukit_cuda_dev_absmax": (_I, [_P, _P, _SZ, _I, _SZ, _I, _P]),
     "aukit_cuda_dev_scale_clamp": (_I, [_P, _P, _SZ, _I, _SZ, _D, _I, _P]),
+    "aukit_cuda_au_parse": (_I, [_P, _SZ, C.POINTER(ContainerInfo)]),
+    "aukit_cuda_aiff_parse": (_I, [_P, _SZ, C.POINTER(ContainerInfo)]),
+    "aukit_cuda_au": (_I, [_P, _P, _SZ, C.POINTER(ContainerInfo), C.POINTER(_P)]),
+    "aukit_cuda_aiff": (_I, [_P, _P, _SZ, _I, C.POINTER(ContainerInfo), C.POINTER(_P)]),
     "aukit_cuda_lowpass": (_I, [_P, _P, _D]),
     "aukit_cuda_audio_pcm": (_I, [_P, _P, _I, _I, _I, _P]),
     "aukit_cuda_audio_pcm_bytes": (_I, [_P, _P, _I, _I, _I, _I, _P]),

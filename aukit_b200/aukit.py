@@ -30,7 +30,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import AukitError, PipelineDesc, WavInfo
+from ._lib import AukitError, ContainerInfo, PipelineDesc, WavInfo
 
 _VERSION = "1.10.0-b200"
 defaultInterpolation = "linear"                                           # A:99
@@ -463,6 +463,37 @@ def wav(data, head=False, dialect=DIALECT_LITERAL, ctx: Optional[Context] = None
     _lib.check(ctx.lib.aukit_cuda_wav(ctx.handle, p, n, int(bool(head)), dialect, C.byref(info), C.byref(out)))
     d = _info_dict(info, keep)
     return Audio(ctx, out, d["metadata"], {"dataType": d["dataType"], "bitDepth": d["bitDepth"]})   # A:1553-1554
+
+
+def _container_audio(ctx, out, ci: ContainerInfo, raw: bytes, meta_override: bool) -> Audio:
+    if ci.codec:                                   # aukit.g711: bitDepth/dataType live in `metadata` (A:1383)
+        metadata, info = {"bitDepth": 14 if ci.ulaw else 13, "dataType": "signed"}, {}
+    else:                                          # aukit.pcm: in `info` (A:1171)
+        metadata, info = {}, {"bitDepth": ci.bitDepth, "dataType": ["signed", "unsigned", "float"][ci.dataType]}
+    if meta_override:                              # aiff: obj.metadata = meta (A:1617)
+        metadata = {ci.meta[i].key.decode(): raw[ci.meta[i].off: ci.meta[i].off + ci.meta[i].len] for i in range(ci.nmeta)}
+    return Audio(ctx, out, metadata, info)
+
+
+def au(data, ctx: Optional[Context] = None) -> Audio:                       # A:1634
+    ctx = ctx or context()
+    b = _as_bytes(data)
+    p, n, keep = _buf(b)
+    ci, out = ContainerInfo(), C.c_void_p()
+    _lib.check(ctx.lib.aukit_cuda_au(ctx.handle, p, n, C.byref(ci), C.byref(out)))
+    return _container_audio(ctx, out, ci, bytes(b), False)
+
+
+def aiff(data, head=False, ctx: Optional[Context] = None) -> Audio:         # A:1580
+    ctx = ctx or context()
+    b = _as_bytes(data)
+    p, n, keep = _buf(b)
+    ci, out = ContainerInfo(), C.c_void_p()
+    _lib.check(ctx.lib.aukit_cuda_aiff(ctx.handle, p, n, int(bool(head)), C.byref(ci), C.byref(out)))
+    a = _container_audio(ctx, out, ci, bytes(b), True)
+    if head:
+        a.info = {}                                # aukit.new leaves info empty (A:1610)
+    return a
 
 
 # ------------------------------------------------------------------ effects (in place)

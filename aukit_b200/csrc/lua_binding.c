@@ -188,6 +188,44 @@ static int l_wav(lua_State *L) {
     return 2;
 }
 
+/* cu.au(data) / cu.aiff(data, head) -> audio, {codec, bitDepth, dataType, ulaw, meta = {{key, value}, ...}} */
+static int push_container(lua_State *L, aukit_audio *a, const aukit_container_info *ci, const char *d) {
+    static const char *dt_names[] = {"signed", "unsigned", "float"};
+    push_audio(L, a);
+    lua_createtable(L, 0, 6);
+    lua_pushstring(L, ci->codec == AUKIT_CODEC_G711 ? "g711" : "pcm"); lua_setfield(L, -2, "codec");
+    lua_pushinteger(L, ci->bitDepth); lua_setfield(L, -2, "bitDepth");
+    lua_pushstring(L, dt_names[ci->dataType]); lua_setfield(L, -2, "dataType");
+    lua_pushboolean(L, ci->ulaw); lua_setfield(L, -2, "ulaw");
+    lua_createtable(L, ci->nmeta, 0);
+    for (int i = 0; i < ci->nmeta; i++) {
+        lua_createtable(L, 2, 0);
+        lua_pushstring(L, ci->meta[i].key); lua_rawseti(L, -2, 1);
+        lua_pushlstring(L, d + ci->meta[i].off, ci->meta[i].len); lua_rawseti(L, -2, 2);
+        lua_rawseti(L, -2, i + 1);
+    }
+    lua_setfield(L, -2, "meta");
+    return 2;
+}
+
+static int l_au(lua_State *L) {
+    size_t n;
+    const char *d = luaL_checklstring(L, 1, &n);
+    aukit_container_info ci;
+    aukit_audio *a = NULL;
+    if (aukit_cuda_au(ctx(L), d, n, &ci, &a)) return fail(L);
+    return push_container(L, a, &ci, d);
+}
+
+static int l_aiff(lua_State *L) {
+    size_t n;
+    const char *d = luaL_checklstring(L, 1, &n);
+    aukit_container_info ci;
+    aukit_audio *a = NULL;
+    if (aukit_cuda_aiff(ctx(L), d, n, optbool(L, 2, 0), &ci, &a)) return fail(L);
+    return push_container(L, a, &ci, d);
+}
+
 /* cu.new(channels, frames, sampleRate) */
 static int l_new(lua_State *L) {
     aukit_audio *a = NULL;
@@ -300,7 +338,7 @@ static int l_gc(lua_State *L) {
 static const luaL_Reg funcs[] = {
     {"pcm", l_pcm}, {"g711", l_g711}, {"adpcm", l_adpcm}, {"ima_adpcm_wav", l_ima_wav}, {"msadpcm", l_msadpcm},
     {"wav", l_wav}, {"new", l_new}, {"resample", l_resample}, {"mono", l_mono}, {"concat", l_concat},
-    {"amplify", l_amplify}, {"lowpass", l_lowpass}, {"pcm_out", l_pcm_out}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
+    {"au", l_au}, {"aiff", l_aiff}, {"amplify", l_amplify}, {"lowpass", l_lowpass}, {"pcm_out", l_pcm_out}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
     {"frames", l_frames}, {"read", l_read}, {"write", l_write}, {NULL, NULL}};
 
 int luaopen_aukit_cuda(lua_State *L) {

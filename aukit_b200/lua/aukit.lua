@@ -258,6 +258,33 @@ function aukit.wav(data, head)
     return out
 end
 
+local function container(h, info, aiffMeta)
+    local metadata, inf
+    if info.codec == "g711" then metadata, inf = {bitDepth = info.ulaw and 14 or 13, dataType = "signed"}, {}    -- A:1383
+    else metadata, inf = {}, {bitDepth = info.bitDepth, dataType = info.dataType} end                          -- A:1171
+    if aiffMeta then
+        metadata = {}
+        for _, kv in ipairs(info.meta) do metadata[kv[1]] = kv[2] end                                           -- A:1617-1630
+    end
+    return wrap(h, metadata, inf)
+end
+
+--- Creates a new audio object from an AU file. (A:1634)
+function aukit.au(data)
+    expect(1, data, "string")
+    local h, info = cu.au(data)
+    return container(h, info, false)
+end
+
+--- Creates a new audio object from an AIFF or AIFC file. (A:1580)
+function aukit.aiff(data, head)
+    expect(1, data, "string")
+    local h, info = cu.aiff(data, head and true or false)
+    local out = container(h, info, true)
+    if head then out.info = {} end
+    return out
+end
+
 -- ---------------------------------------------------------------------------------------------
 -- effects: mutate the argument and return it (A:3368, A:3458; auplay.lua:27 relies on it)
 

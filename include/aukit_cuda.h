@@ -117,6 +117,26 @@ int aukit_cuda_wav_parse(const void *h_data, size_t nbytes, aukit_wav_info *info
 int aukit_cuda_wav(aukit_ctx *ctx, const void *h_data, size_t nbytes, int head_only, int dialect,
                    aukit_wav_info *info_out, aukit_audio **out);
 
+/* aukit.au(data) A:1634-1647 and aukit.aiff(data, head) A:1580-1631: header walk on the host, payload
+ * through aukit_cuda_pcm (bigEndian as flagged) or aukit_cuda_g711, as the reference dispatches.  The
+ * reference's own index arithmetic is kept (see csrc/containers.cu). */
+enum { AUKIT_CODEC_PCM = 0, AUKIT_CODEC_G711 = 1 };
+typedef struct {
+    int codec;                  /* AUKIT_CODEC_* */
+    int bitDepth, dataType, bigEndian, ulaw;
+    int channels;
+    double sampleRate;
+    size_t data_off, data_len;  /* payload bytes inside the file */
+    int nmeta;                  /* aiff NAME/AUTH/"(c) "/ANNO -> title/artist/copyright/comment, file order */
+    struct { char key[12]; size_t off, len; } meta[16];
+} aukit_container_info;
+int aukit_cuda_au_parse(const void *h_data, size_t nbytes, aukit_container_info *info);   /* host only */
+int aukit_cuda_aiff_parse(const void *h_data, size_t nbytes, aukit_container_info *info); /* host only */
+int aukit_cuda_au(aukit_ctx *ctx, const void *h_data, size_t nbytes, aukit_container_info *info_out,
+                  aukit_audio **out);
+int aukit_cuda_aiff(aukit_ctx *ctx, const void *h_data, size_t nbytes, int head_only,
+                    aukit_container_info *info_out, aukit_audio **out);
+
 /* ------------------------------------------------------------------ transforms (new Audio) */
 /* Audio:resample(sampleRate, interpolation) A:653 */
 int aukit_cuda_resample(aukit_ctx *ctx, const aukit_audio *in, double sampleRate, int interpolation,

@@ -671,3 +671,119 @@ double *auko_chain_s16(const uint8_t *data, size_t nbytes, int channels, double 
     if (n_out) *n_out = nl;
     return mono;
 }
+
+/* ---------------------------------------------------------------- aukit.au, A:1634-1647 */
+static uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+/* str_sub(s, i, j) with 1-based i >= 0 and a signed j (nil = -1): the 0-based [*off, *off + *len) it selects */
+static void lua_sub(size_t n, long long i, long long j, size_t *off, size_t *len) {
+    if (i < 1) i = 1;
+    if (j < 0) j = (long long)n + j + 1;
+    if (j > (long long)n) j = (long long)n;
+    if (i > j) { *off = 0; *len = 0; return; }
+    *off = (size_t)(i - 1);
+    *len = (size_t)(j - i + 1);
+}
+
+int auko_au_parse(const uint8_t *data, size_t nbytes, auko_container_info *info) {
+    g_err[0] = 0;
+    memset(info, 0, sizeof *info);
+    if (nbytes < 24) return fail("bad argument #2 to 'unpack' (data string too short)");                 /* str_unpack(">c4IIIII") */
+    if (memcmp(data, ".snd", 4)) return fail("invalid AU file");            /* A:1637 */
+    const uint32_t offset = be32(data + 4), size = be32(data + 8), encoding = be32(data + 12);
+    info->sampleRate = (double)be32(data + 16);
+    info->channels = (int)be32(data + 20);
+    /* str_sub(data, offset, size ~= 0xFFFFFFFF and offset + size - 1 or nil): offset is used as a 1-based index */
+    lua_sub(nbytes, (long long)offset, size != 0xFFFFFFFFu ? (long long)offset + (long long)size - 1 : -1,
+            &info->data_off, &info->data_len);
+    info->bigEndian = 1;
+    switch (encoding) {                                                      /* A:1638-1645 */
+    case 1: info->codec = 1; info->ulaw = 1; break;
+    case 2: info->bitDepth = 8; info->dataType = AUKO_SIGNED; break;
+    case 3: info->bitDepth = 16; info->dataType = AUKO_SIGNED; break;
+    case 4: info->bitDepth = 24; info->dataType = AUKO_SIGNED; break;
+    case 5: info->bitDepth = 32; info->dataType = AUKO_SIGNED; break;
+    case 6: info->bitDepth = 32; info->dataType = AUKO_FLOAT; break;
+    case 27: info->codec = 1; info->ulaw = 0; break;
+    default: return fail("unsupported encoding type %u", (unsigned)encoding); /* A:1646 */
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- aukit.aiff, A:1580-1631 */
+int auko_aiff_parse(const uint8_t *data, size_t nbytes, auko_container_info *info) {
+    g_err[0] = 0;
+    memset(info, 0, sizeof *info);
+    if (nbytes < 4) return fail("bad argument #2 to 'unpack' (data string too short)");
+    if (memcmp(data, "FORM", 4)) return fail("bad argument #1 (not an AIFF file)");   /* A:1585 */
+    size_t pos = 8;                                                          /* 0-based; A:1586 skips the size */
+    if (pos + 4 > nbytes) return fail("bad argument #2 to 'unpack' (data string too short)");
+    int isAIFC = 0;
+    if (!memcmp(data + pos, "AIFC", 4)) isAIFC = 1;
+    else if (memcmp(data + pos, "AIFF", 4)) return fail("bad argument #1 (not an AIFF file)");
+    pos += 4;
+    int have_comm = 0, have_comp = 0;
+    char comp[5] = {0};
+    double length = 0;
+    while (pos < nbytes) {                                                   /* pos <= #data, 1-based */
+        if (pos + 8 > nbytes) return fail("bad argument #2 to 'unpack' (data string too short)");
+        const uint8_t *id = data + pos;
+        const uint32_t size = be32(data + pos + 4);
+        pos += 8;
+        if (!memcmp(id, "COMM", 4)) {                                        /* ">hIhHI7x", A:1597 */
+            if (pos + 18 > nbytes) return fail("bad argument #2 to 'unpack' (data string too short)");
+            info->channels = (int)(int16_t)((data[pos] << 8) | data[pos + 1]);
+            const double frames = (double)be32(data + pos + 2);
+            info->bitDepth = (int)(int16_t)((data[pos + 6] << 8) | data[pos + 7]);
+            int e = (data[pos + 8] << 8) | data[pos + 9];
+            double m = 0;                                                    /* I7 as a Lua number (double) */
+            { unsigned long long mi = 0; for (int k = 0; k < 7; k++) mi = (mi << 8) | data[pos + 10 + k]; m = (double)mi; }
+            pos += 18;
+            if (isAIFC) {                                                    /* ">c4s1", A:1599-1600 */
+                if (pos + 5 > nbytes) return fail("bad argument #2 to 'unpack' (data string too short)");
+                memcpy(comp, data + pos, 4);
+                have_comp = 1;
+                const size_t sl = data[pos + 4];
+                if (pos + 5 + sl > nbytes) return fail("bad argument #2 to 'unpack' (data string too short)");
+                pos += 5 + sl;
+                if (sl % 2 == 0) pos += 1;
+            }
+            length = frames * (double)info->channels * floor((double)info->bitDepth / 8.0);     /* A:1602 */
+            const int sgn = (e & 0x8000) != 0;
+            int ee = ((e & 0x7FFF) - 0x3FFE) % 0x800;                        /* Lua %: floored */
+            if (ee < 0) ee += 0x800;
+            info->sampleRate = ldexp(m * (sgn ? -1.0 : 1.0) / 72057594037927936.0, ee);          /* A:1605 */
+            have_comm = 1;
+        } else if (!memcmp(id, "SSND", 4)) {                                 /* A:1606 */
+            if (pos + 8 > nbytes) return fail("bad argument #2 to 'unpack' (data string too short)");
+            const uint32_t offset = be32(data + pos);
+            pos += 8;
+            if (!have_comm) return fail("attempt to perform arithmetic on a nil value (local 'length')");
+            /* str_sub(data, pos + offset, pos + offset + length - 1), pos 1-based */
+            const double i1 = (double)(pos + 1) + (double)offset, j1 = i1 + length - 1.0;
+            lua_sub(nbytes, (long long)i1, (long long)j1, &info->data_off, &info->data_len);
+            info->bigEndian = 1;
+            info->dataType = AUKO_SIGNED;
+            if (!have_comp || !memcmp(comp, "NONE", 4)) { /* pcm big-endian, A:1612 */ }
+            else if (!memcmp(comp, "sowt", 4)) info->bigEndian = 0;
+            else if (!memcmp(comp, "fl32", 4) || !memcmp(comp, "FL32", 4)) { info->bitDepth = 32; info->dataType = AUKO_FLOAT; }
+            else if (!memcmp(comp, "alaw", 4) || !memcmp(comp, "ALAW", 4)) { info->codec = 1; info->ulaw = 0; }
+            else if (!memcmp(comp, "ulaw", 4) || !memcmp(comp, "ULAW", 4)) { info->codec = 1; info->ulaw = 1; }
+            else return fail("Unsupported compression scheme %.4s", comp);   /* A:1616 */
+            return 0;
+        } else {
+            const char *key = !memcmp(id, "NAME", 4) ? "title" : !memcmp(id, "AUTH", 4) ? "artist"
+                            : !memcmp(id, "(c) ", 4) ? "copyright" : !memcmp(id, "ANNO", 4) ? "comment" : NULL;
+            if (key && info->nmeta < 16) {                                   /* A:1619-1630: str_sub(data, pos, pos+size-1) */
+                size_t off, len;
+                lua_sub(nbytes, (long long)pos + 1, (long long)pos + (long long)size, &off, &len);
+                strcpy(info->meta[info->nmeta].key, key);
+                info->meta[info->nmeta].off = off;
+                info->meta[info->nmeta].len = len;
+                info->nmeta++;
+            }
+            pos += size;
+        }
+    }
+    return fail("invalid AIFF file");                                        /* A:1632 */
+}

@@ -118,6 +118,20 @@ typedef struct {
 } auko_wav_info;
 int auko_wav_parse(const uint8_t *data, size_t nbytes, auko_wav_info *info);
 
+/* aukit.au (A:1634-1647) and aukit.aiff (A:1580-1631): header parse only; the payload then goes through
+ * auko_pcm (bigEndian as flagged) or auko_g711, exactly as the reference dispatches. */
+typedef struct {
+    int codec;             /* 0 = aukit.pcm, 1 = aukit.g711 */
+    int bitDepth, dataType, bigEndian, ulaw;
+    int channels;
+    double sampleRate;
+    size_t data_off, data_len; /* payload bytes (clipped to the file like str_sub) */
+    int nmeta;             /* aiff: NAME/AUTH/"(c) "/ANNO -> title/artist/copyright/comment, file order */
+    struct { char key[12]; size_t off, len; } meta[16];
+} auko_container_info;
+int auko_au_parse(const uint8_t *data, size_t nbytes, auko_container_info *info);
+int auko_aiff_parse(const uint8_t *data, size_t nbytes, auko_container_info *info);
+
 /* Whole auplay-style chain on one buffer, used for the CPU baseline timing:
  * s16le interleaved PCM -> resample -> mono -> normalize. Returns malloc'd mono doubles. */
 double *auko_chain_s16(const uint8_t *data, size_t nbytes, int channels, double srcRate,

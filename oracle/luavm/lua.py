@@ -2215,6 +2215,8 @@ def make_math():
            "exp": safe(math.exp, "exp"), "log": safe(lambda x, b=None: math.log(x) if b is None else math.log(x, b), "log"),
            "pow": safe(math.pow, "pow"), "fmod": safe(math.fmod, "fmod"), "atan": safe(math.atan, "atan"),
            "atan2": safe(math.atan2, "atan2"), "asin": safe(math.asin, "asin"), "acos": safe(math.acos, "acos"),
+           "ldexp": safe(lambda m, e: math.ldexp(m, int(e)), "ldexp"),
+           "frexp": lambda a: (lambda r: [float(r[0]), float(r[1])])(math.frexp(_checknum(a, 0, "frexp"))),
            "random": lambda a: [0.5], "randomseed": lambda a: [],
            "modf": lambda a: (lambda x: [float(math.trunc(x)), x - math.trunc(x)])(_checknum(a, 0, "modf"))}
     for k, f in fns.items():

@@ -66,6 +66,8 @@ def lib():
         L.auko_encode_pcm.argtypes = [C.c_double, C.c_int, C.c_int]
         L.auko_encode_pcm.restype = C.c_double
         L.auko_audio_pcm.argtypes = [dp, sz, C.c_int, sz, C.c_int, C.c_int, C.c_int, dp]
+        L.auko_au_parse.argtypes = [u8p, sz, C.c_void_p]
+        L.auko_aiff_parse.argtypes = [u8p, sz, C.c_void_p]
         L.auko_lowpass.argtypes = [dp, sz, C.c_int, sz, C.c_double, C.c_double]
         L.auko_wav_parse.argtypes = [u8p, sz, C.c_void_p]
         L.auko_chain_s16.argtypes = [u8p, sz, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.POINTER(sz)]
@@ -266,6 +268,45 @@ def wav(data, dialect=LITERAL):
     else:
         x = pcm(payload, info["bitDepth"], dt, info["channels"], True, False)
     return x, info
+
+
+class _Meta(C.Structure):
+    _fields_ = [("key", C.c_char * 12), ("off", C.c_size_t), ("len", C.c_size_t)]
+
+
+class _ContainerInfo(C.Structure):
+    _fields_ = [("codec", C.c_int), ("bitDepth", C.c_int), ("dataType", C.c_int), ("bigEndian", C.c_int), ("ulaw", C.c_int),
+                ("channels", C.c_int), ("sampleRate", C.c_double), ("data_off", C.c_size_t), ("data_len", C.c_size_t),
+                ("nmeta", C.c_int), ("meta", _Meta * 16)]
+
+
+def _container(parse, data, head=False):
+    b = _bytes(data)
+    ci = _ContainerInfo()
+    _check(parse(_ptr(b), b.size, C.byref(ci)))
+    raw = b.tobytes()
+    info = {"codec": "g711" if ci.codec else "pcm", "bitDepth": ci.bitDepth, "dataType": ["signed", "unsigned", "float"][ci.dataType],
+            "bigEndian": bool(ci.bigEndian), "ulaw": bool(ci.ulaw), "channels": ci.channels, "sampleRate": ci.sampleRate,
+            "data_off": ci.data_off, "data_len": ci.data_len,
+            "metadata": {ci.meta[i].key.decode(): raw[ci.meta[i].off: ci.meta[i].off + ci.meta[i].len] for i in range(ci.nmeta)}}
+    if head:
+        return [np.zeros(0)] * max(ci.channels, 0), info
+    payload = b[ci.data_off: ci.data_off + ci.data_len]
+    if ci.codec:
+        x = g711(payload, bool(ci.ulaw), ci.channels)
+    else:
+        x = pcm(payload, ci.bitDepth, info["dataType"], ci.channels, True, bool(ci.bigEndian))
+    return x, info
+
+
+def au(data):
+    """aukit.au (A:1634-1647): (samples, info)."""
+    return _container(lib().auko_au_parse, data)
+
+
+def aiff(data, head=False):
+    """aukit.aiff (A:1580-1631): (samples, info)."""
+    return _container(lib().auko_aiff_parse, data, head)
 
 
 def chain_s16(data, channels, srcRate, dstRate, interpolation="cubic", peak=1.0) -> np.ndarray:

@@ -68,6 +68,10 @@ def run_case(R, case, blobs):
         a = call(R.fn("msadpcm"), [blobs["in"], float(A["blockAlign"]), float(A["channels"]), float(A["sampleRate"]), cot])[0]
     elif op == "wav":
         a = R.call("wav", blobs["in"], A.get("head", False))[0]
+    elif op == "au":
+        a = R.call("au", blobs["in"])[0]
+    elif op == "aiff":
+        a = R.call("aiff", blobs["in"], A.get("head", False))[0]
     elif op == "pcm_out":
         a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
         t = R.method(a, "pcm", A.get("bitDepth"), A.get("dataType"), A.get("interleaved"))[0]
@@ -242,6 +246,57 @@ def main():
     add("pcmout_bad_depth", "pcm_out", dict(sampleRate=48000, bitDepth=12, dataType="signed", interleaved=True), x=w2)
     add("pcmout_bad_type", "pcm_out", dict(sampleRate=48000, bitDepth=16, dataType="int", interleaved=True), x=w2)
     add("pcmout_float16", "pcm_out", dict(sampleRate=48000, bitDepth=16, dataType="float", interleaved=True), x=w2)
+
+    # ---- aukit.au / aukit.aiff containers
+    def au_file(enc, ch, rate, payload, size=None, offset=24, extra=b""):
+        return b".snd" + struct.pack(">IIIII", offset, len(payload) if size is None else size, enc, rate, ch) + extra + payload
+
+    pay = rng2.integers(0, 256, 960, dtype=np.uint8).tobytes()
+    fpay = rng2.standard_normal(240).astype(">f4").tobytes()
+    for enc, name in ((1, "ulaw"), (2, "s8"), (3, "s16"), (5, "s32"), (27, "alaw")):
+        add("au_%s_stereo" % name, "au", **{"in": au_file(enc, 2, 22050, pay)})
+    add("au_s24_mono", "au", **{"in": au_file(4, 1, 8000, pay + b"\0\1\2")})
+    add("au_f32_mono_unknown_size", "au", **{"in": au_file(6, 1, 48000, fpay + b"\0\0\0", size=0xFFFFFFFF)})
+    add("au_s16_annotation", "au", **{"in": au_file(3, 2, 44100, pay, offset=32, extra=b"hello!!\0")})
+    add("au_bad_magic", "au", **{"in": b".sndX"[1:] + bytes(24)})
+    add("au_short", "au", **{"in": b".snd" + bytes(10)})
+    add("au_bad_encoding", "au", **{"in": au_file(23, 1, 8000, pay)})
+
+    def ext80(rate):
+        m, e = np.frexp(float(rate))                     # rate = m * 2^e, 0.5 <= m < 1
+        return struct.pack(">HQ", 0x3FFE + int(e), int(m * 2 ** 64))
+
+    def chunk(tag, body):
+        return tag + struct.pack(">I", len(body)) + body
+
+    def aiff_file(ch, bits, rate, payload, comp=None, texts=(), frames=None, ssnd_off=0):
+        frames = len(payload) // (ch * (bits // 8)) if frames is None else frames
+        comm = struct.pack(">hIh", ch, frames, bits) + ext80(rate)
+        if comp is not None:
+            cname = b"not compressed"
+            comm += comp + bytes([len(cname)]) + cname + (b"\0" if len(cname) % 2 == 0 else b"")
+        body = (b"AIFC" if comp is not None else b"AIFF") + chunk(b"COMM", comm)
+        for tag, text in texts:
+            body += chunk(tag, text)
+        body += chunk(b"SSND", struct.pack(">II", ssnd_off, 0) + bytes(ssnd_off) + payload)
+        return b"FORM" + struct.pack(">I", len(body)) + body
+
+    add("aiff_s16_stereo", "aiff", dict(head=False), **{"in": aiff_file(2, 16, 44100, pay)})
+    add("aiff_s8_mono_meta", "aiff", dict(head=False), **{"in": aiff_file(1, 8, 22050, pay, texts=((b"NAME", b"Song"), (b"AUTH", b"Me"),
+                                                                                                     (b"(c) ", b"2026"), (b"ANNO", b"note")))})
+    add("aiff_s24_3ch", "aiff", dict(head=False), **{"in": aiff_file(3, 24, 48000, pay[:954])})
+    add("aiff_s32_offset", "aiff", dict(head=False), **{"in": aiff_file(2, 32, 96000, pay, ssnd_off=4)})
+    add("aifc_none", "aiff", dict(head=False), **{"in": aiff_file(2, 16, 32000, pay, comp=b"NONE")})
+    add("aifc_sowt", "aiff", dict(head=False), **{"in": aiff_file(2, 16, 44100, pay, comp=b"sowt")})
+    add("aifc_fl32", "aiff", dict(head=False), **{"in": aiff_file(1, 32, 48000, fpay, comp=b"fl32")})
+    add("aifc_ulaw", "aiff", dict(head=False), **{"in": aiff_file(2, 8, 8000, pay, comp=b"ulaw")})
+    add("aifc_alaw_upper", "aiff", dict(head=False), **{"in": aiff_file(1, 8, 8000, pay, comp=b"ALAW")})
+    add("aiff_head_only", "aiff", dict(head=True), **{"in": aiff_file(2, 16, 44100, pay, texts=((b"NAME", b"T"),))})
+    add("aiff_odd_rate", "aiff", dict(head=False), **{"in": aiff_file(1, 16, 11025.5, pay)})
+    add("aiff_short_payload", "aiff", dict(head=False), **{"in": aiff_file(2, 16, 44100, pay, frames=300)})
+    add("aifc_bad_compression", "aiff", dict(head=False), **{"in": aiff_file(2, 16, 44100, pay, comp=b"ima4")})
+    add("aiff_not_aiff", "aiff", dict(head=False), **{"in": b"FORM" + bytes(4) + b"WAVE" + bytes(20)})
+    add("aiff_no_ssnd", "aiff", dict(head=False), **{"in": b"FORM" + bytes(4) + b"AIFF" + chunk(b"COMM", struct.pack(">hIh", 1, 0, 8) + ext80(8000))})
 
     # ---- run everything through the reference
     manifest = []

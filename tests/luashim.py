@@ -75,6 +75,32 @@ def make_module(ak):
         t.set(b"tags", tags)
         return [Handle(ak.Audio(ctx, out)), t]
 
+    def container(fn, a, *extra):
+        data = a[0]
+        p, n = buf(data)
+        ci = ak.ContainerInfo()
+        out = C.c_void_p()
+        if fn(ctx.handle, p, n, *extra, C.byref(ci), C.byref(out)) != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        t = LuaTable()
+        t.set(b"codec", b"g711" if ci.codec else b"pcm")
+        t.set(b"bitDepth", float(ci.bitDepth))
+        t.set(b"dataType", [b"signed", b"unsigned", b"float"][ci.dataType])
+        t.set(b"ulaw", bool(ci.ulaw))
+        meta = LuaTable()
+        for i in range(ci.nmeta):
+            e = LuaTable()
+            e.arr = [ci.meta[i].key, data[ci.meta[i].off: ci.meta[i].off + ci.meta[i].len]]
+            meta.set(i + 1, e)
+        t.set(b"meta", meta)
+        return [Handle(ak.Audio(ctx, out)), t]
+
+    def l_au(a):
+        return container(lib.aukit_cuda_au, a)
+
+    def l_aiff(a):
+        return container(lib.aukit_cuda_aiff, a, int(bool(a[1] if len(a) > 1 else False)))
+
     def l_resample(a):
         return [wrap(lib.aukit_cuda_resample, a[0].audio._h, float(a[1]), int(a[2]))]
 
@@ -130,7 +156,7 @@ def make_module(ak):
 
     mod = LuaTable()
     for name, f in {"pcm": l_pcm, "g711": l_g711, "wav": l_wav, "resample": l_resample, "mono": l_mono, "amplify": l_amplify,
-                    "lowpass": l_lowpass, "pcm_out": l_pcm_out, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
+                    "lowpass": l_lowpass, "pcm_out": l_pcm_out, "au": l_au, "aiff": l_aiff, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
                     "channels": lambda a: [float(a[0].audio.channels())],
                     "sample_rate": lambda a: [float(lib.aukit_cuda_audio_sample_rate(a[0].audio._h))]}.items():
         mod.set(name.encode(), LuaFunction(f, "aukit_cuda." + name))

@@ -56,6 +56,9 @@ def oracle_run(O, m, i):
             return [np.zeros(0)] * info["channels"]
         out, _ = O.wav(raw)
         return list(out)
+    if op in ("au", "aiff"):
+        out, _ = (O.au(raw) if op == "au" else O.aiff(raw, bool(A.get("head"))))
+        return list(out)
     if op == "resample":
         interp = A["interpolation"] or "linear"                   # aukit.defaultInterpolation (A:99)
         return list(O.resample(x, A["sampleRate"], A["targetRate"], interp))
@@ -125,6 +128,10 @@ def cuda_run(ak, m, i):
         return ak.msadpcm(raw, A["blockAlign"], A["channels"], A["sampleRate"], A.get("coefficients"))
     if op == "wav":
         return ak.wav(raw, bool(A.get("head")))
+    if op == "au":
+        return ak.au(raw)
+    if op == "aiff":
+        return ak.aiff(raw, bool(A.get("head")))
     if op == "pcm_out":
         return ak.Audio.from_numpy(x.astype(np.float32), A["sampleRate"]).pcm(A["bitDepth"], A["dataType"], A["interleaved"])
     a = ak.wav(raw) if op == "chain" else ak.Audio.from_numpy(x.astype(np.float32), A["sampleRate"])
@@ -161,7 +168,7 @@ def test_cuda_matches_reference(ak, i):
         return
     assert a.channels() == m["channels"]
     assert float(a.sampleRate) == float(m["sampleRate"])
-    decode = m["op"] in ("pcm", "g711", "adpcm", "msadpcm", "wav")
+    decode = m["op"] in ("pcm", "g711", "adpcm", "msadpcm", "wav", "au", "aiff")
     x = blob(i, "x")
     for c, e in enumerate(exp):
         g = a.data[c]
@@ -175,6 +182,9 @@ def test_cuda_matches_reference(ak, i):
             scale = max(1.0, float(np.max(np.abs(e[fin])))) if fin.any() else 1.0
             err = float(np.max(np.abs(g[fin] - e[fin]))) if fin.any() else 0.0
             assert err <= TOL * scale * (2 if m["op"] != "chain" else 1), (m["name"], float(err))
+    if m["op"] in ("au", "aiff"):
+        got_meta = {k: (v.decode("latin-1") if isinstance(v, bytes) else v) for k, v in a.metadata.items()}
+        assert got_meta == m["metadata"] and a.info == m["info"]
     if m["op"] == "wav" and not m["args"].get("head"):
         want_meta = {k: v for k, v in m["metadata"].items()}
         got_meta = {k: (v.decode("latin-1") if isinstance(v, bytes) else v) for k, v in a.metadata.items()}

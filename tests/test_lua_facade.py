@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from util import TOL
+from util import TOL, tone_s16
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -71,3 +71,27 @@ def test_facade_errors_and_effects_semantics(lua):
         return b == a, c == a, a.data[1][1], a.data[1][2], #a.data[1], a:len(), a:channels()
     ''')
     assert r == [True, True, 1.0, -1.0, 2.0, 2 / 8000.0, 1.0]
+
+
+def test_facade_next_rows_lowpass_pcm_containers(lua, O):
+    """SURVEY 8(f) rows through the Lua facade: auplay.lua:27-34 continues with effects.lowpass and the
+    requantisation of Audio:pcm; aukit.au / aukit.aiff land on the same loaders."""
+    import struct
+    pcm = tone_s16(2000, 1, 8000, seed=8)
+    au = b".snd" + struct.pack(">IIIII", 24, pcm.nbytes, 3, 8000, 1) + pcm.astype(">i2").tobytes()
+    lua.G.set(b"AU_FILE", au)
+    r = lua.run('''
+        local aukit = require "aukit"
+        local a = aukit.au(AU_FILE)
+        local rate, ch, n = a.sampleRate, a:channels(), #a.data[1]
+        aukit.effects.normalize(a, 0.8)
+        local same = aukit.effects.lowpass(a, a.sampleRate / 2) == a
+        local q = a:pcm(8, "signed", true)
+        return rate, ch, n, same, q, a.info.bitDepth, a.info.dataType
+    ''')
+    ref_dec, info = O.au(au)
+    ref = O.audio_pcm(O.lowpass(O.normalize(ref_dec, 0.8, False), 4000.0, 8000.0), 8, "signed", True)
+    assert r[0] == 8000.0 and r[1] == 1.0 and r[2] == ref_dec.shape[1] and r[3] is True
+    got = np.array(r[4].arr)
+    assert got.shape == ref.shape and np.max(np.abs(got - ref)) <= 128 * 2 * TOL
+    assert r[5:] == [16.0, b"signed"]
