@@ -4,6 +4,11 @@
 // kernels of pcm.cu / adpcm.cu / resample.cu / effects.cu / pipeline*.cu; this file owns
 // device memory (stream-ordered allocations from the device's default pool), the H2D / D2H
 // copies of the end-to-end calls, and the integer-only parsing of RIFF headers (A:1456-1574).
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <sched.h>
+#include <ctype.h>
 #include "common.cuh"
 
 #include <math.h>
@@ -632,9 +637,46 @@ struct aukit_preloader {
     } *slot;
 };
 
+// Pinned memory is first touched (and therefore placed) by the allocating thread: run the allocation on
+// the CPUs next to the current device (sysfs local_cpulist of its PCI function) so that on a multi-socket
+// host every GPU's staging buffers sit on its own NUMA node.  Best effort; the affinity is restored.
+static bool gpu_local_cpus(cpu_set_t *set) {
+    int dev = 0;
+    char bus[32] = "";
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    char line[4096] = "";
+    const bool ok = fgets(line, sizeof line, f) != nullptr;
+    fclose(f);
+    if (!ok) return false;
+    CPU_ZERO(set);
+    int n = 0;
+    for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k < 1) continue;
+        if (k == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, set); n++; }
+    }
+    return n > 0;
+}
+
 extern "C" int aukit_cuda_host_alloc(size_t nbytes, void **out) {
     if (!out) return aukit_fail("aukit_cuda: null argument");
-    return aukit_cuda_check(cudaMallocHost(out, nbytes ? nbytes : 1), "cudaMallocHost");
+    cpu_set_t old, near, both;
+    bool moved = false;
+    if (sched_getaffinity(0, sizeof old, &old) == 0 && gpu_local_cpus(&near)) {
+        CPU_AND(&both, &old, &near);
+        if (CPU_COUNT(&both) > 0 && !CPU_EQUAL(&both, &old)) moved = sched_setaffinity(0, sizeof both, &both) == 0;
+    }
+    int rc = aukit_cuda_check(cudaMallocHost(out, nbytes ? nbytes : 1), "cudaMallocHost");
+    if (!rc && nbytes) memset(*out, 0, nbytes);                      // first touch here, on the local node
+    if (moved) sched_setaffinity(0, sizeof old, &old);
+    return rc;
 }
 extern "C" void aukit_cuda_host_free(void *p) { if (p) cudaFreeHost(p); }
 

@@ -168,6 +168,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def pin_near_gpu(torch, local):
+    """Run this rank on the CPUs next to its GPU (sysfs local_cpulist), so that pinned host buffers are first
+    touched on the GPU's own NUMA node -- on a multi-socket host the e2e copies of 8 ranks otherwise all cross
+    one socket.  Best effort (aukit_cuda_host_alloc does the same for the C ABI's own allocations)."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except (OSError, ValueError, AttributeError):
+        pass
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -178,6 +198,7 @@ def run_b200(args):
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
     torch.cuda.set_device(local)
+    pin_near_gpu(torch, local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
