@@ -7,7 +7,7 @@
 // PRMT selectors after unrolling) and writes one float4 per channel per 4 frames.
 // Integer scaling reproduces A:1133 / A:1152 bit-exactly (see common.cuh::s16_to_float and
 // tests/test_scaling_exact.py); 32-bit integer input divides in fp64 because float(s) is
-// inexact there.  G.711 uses a 256-entry shared-memory table built from A:1374-1379.
+// inexact there.  G.711 and 8-bit PCM use exact float bit constructions (sample_formats.cuh::convert8).
 #include "common.cuh"
 #include "sample_formats.cuh"
 
@@ -16,7 +16,7 @@ using namespace aukit_fmt;
 
 template <int B, int KIND>
 __device__ __forceinline__ float conv_lut(uint32_t raw, const float *lut) {
-    if (B == 1) return lut[raw & 0xFFu];
+    if (B == 1) return convert8<KIND>(raw & 0xFFu);
     return convert<B, KIND>(raw, lut);
 }
 
@@ -28,15 +28,8 @@ template <int B, int KIND, bool BE, int C>
 __global__ void __launch_bounds__(256)
 pcm_unpack_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_t frames,
                   size_t out_stride, int channels_rt, size_t planar_row_bytes, int vec_ok) {
-    // 8-bit formats (G.711 and 8-bit PCM) decode through a 256-entry shared table built with the exact
-    // per-sample formula (A:1374-1379 / A:1133 / A:1152); wider formats compute in registers
-    constexpr bool USE_LUT = (B == 1);
-    __shared__ float lut[USE_LUT ? 256 : 1];
-    if (USE_LUT) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x)
-            lut[i] = (KIND == K_ALAW || KIND == K_ULAW) ? g711_value(i, KIND == K_ULAW) : convert<B, KIND>((uint32_t)i, nullptr);
-        __syncthreads();
-    }
+    // every format converts in registers (8-bit ones through convert8: no table)
+    const float *lut = nullptr;
     const uint8_t *src = in + (size_t)blockIdx.y * planar_row_bytes;
     float *dst = out + (size_t)blockIdx.y * out_stride;
     constexpr int CC = C > 0 ? C : 1;
@@ -104,6 +97,101 @@ pcm_unpack_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_
     }
 }
 
+// Narrow frames (4 frames = 4 or 8 bytes: 8-bit mono / stereo, 16-bit mono): a 16-byte load per thread would make
+// every thread store 2-4 consecutive float4 per channel, i.e. warp stores of half-filled sectors 32-64 bytes apart
+// (the scattered-store pattern that capped these formats at ~70 %).  Instead a warp owns 32 * SUB groups of 4 frames
+// and lane l takes groups l, l + 32, ...: every load instruction reads one contiguous 128/256-byte span and every
+// store instruction writes one contiguous 512-byte span per channel.
+template <int B, int KIND, bool BE, int C>
+__global__ void __launch_bounds__(256)
+pcm_unpack_narrow_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_t frames, size_t out_stride,
+                         size_t planar_row_bytes) {
+    constexpr int SB = 4 * C * B;                   // bytes per group of 4 frames: 4, 8 (8/16-bit) or 12, 24 (24-bit)
+    constexpr int SUB = SB <= 8 ? 16 / SB : 1;      // groups per lane
+    static_assert(SB == 4 || SB == 8 || SB == 12 || SB == 24, "narrow frames only");
+    const uint8_t *src = in + (size_t)blockIdx.y * planar_row_bytes;
+    float *dst = out + (size_t)blockIdx.y * out_stride;
+    const size_t ngroups = (frames + 3) / 4;
+    const int lane = threadIdx.x & 31;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t wg = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 * SUB); wg < ngroups; wg += warps * (32 * SUB)) {
+#pragma unroll
+        for (int k = 0; k < SUB; k++) {
+            const size_t g = wg + (size_t)k * 32 + lane;
+            if (g >= ngroups) continue;
+            const size_t f0 = g * 4;
+            if (f0 + 4 <= frames) {
+                uint32_t w[SB / 4 + 1];
+                if (SB % 8 == 0) {
+#pragma unroll
+                    for (int i = 0; i < SB / 8; i++) {
+                        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src + g * SB) + i);
+                        w[2 * i] = v.x; w[2 * i + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < SB / 4; i++) w[i] = __ldg(reinterpret_cast<const uint32_t *>(src + g * SB) + i);
+                }
+                w[SB / 4] = 0;
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    float4 o;
+                    o.x = conv_lut<B, KIND>(extract<B, BE>(w, (0 * C + c) * B), nullptr);
+                    o.y = conv_lut<B, KIND>(extract<B, BE>(w, (1 * C + c) * B), nullptr);
+                    o.z = conv_lut<B, KIND>(extract<B, BE>(w, (2 * C + c) * B), nullptr);
+                    o.w = conv_lut<B, KIND>(extract<B, BE>(w, (3 * C + c) * B), nullptr);
+                    stg_stream(reinterpret_cast<float4 *>(dst + (size_t)c * out_stride + f0), o);
+                }
+            } else {
+                for (int c = 0; c < C; c++)
+                    for (size_t f = f0; f < frames; f++)
+                        dst[(size_t)c * out_stride + f] = conv_lut<B, KIND>(load_raw<B, BE>(src + (f * (size_t)C + c) * B), nullptr);
+            }
+        }
+    }
+}
+
+// Many channels with a frame size that is a multiple of 16 bytes (f32 / s32 with C % 4 == 0, s16 with C % 8 == 0,
+// 8-bit with C % 16 == 0): one thread owns 4 frames x G = 16/B channels -- four 128-bit loads, a 4 x G transpose
+// in registers, G float4 stores.  The per-sample-load path above spent its time in the LSU queue (lg_throttle):
+// 1.25 memory instructions per sample against (4 + G) / (4 G) here.
+template <int B, int KIND, bool BE>
+__global__ void __launch_bounds__(256)
+pcm_unpack_groups_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, size_t frames, size_t out_stride, int nc) {
+    constexpr int G = 16 / B;
+    const int ngroups = nc / G;
+    const size_t nquads = frames / 4, items = nquads * (size_t)ngroups;    // the ragged last frames go sample by sample
+    const size_t fbytes = (size_t)nc * B;
+    for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < items; id += (size_t)gridDim.x * blockDim.x) {
+        const size_t q = id / (size_t)ngroups;
+        const int g = (int)(id % (size_t)ngroups);
+        const uint8_t *p = in + q * 4 * fbytes + (size_t)g * 16;
+        uint32_t w[4][5];
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            const uint4 v = ldg_stream(reinterpret_cast<const uint4 *>(p + f * fbytes));
+            w[f][0] = v.x; w[f][1] = v.y; w[f][2] = v.z; w[f][3] = v.w; w[f][4] = 0;
+        }
+        float *d = out + (size_t)(g * G) * out_stride + q * 4;
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            float4 o;
+            o.x = conv_lut<B, KIND>(extract<B, BE>(w[0], j * B), nullptr);
+            o.y = conv_lut<B, KIND>(extract<B, BE>(w[1], j * B), nullptr);
+            o.z = conv_lut<B, KIND>(extract<B, BE>(w[2], j * B), nullptr);
+            o.w = conv_lut<B, KIND>(extract<B, BE>(w[3], j * B), nullptr);
+            stg_stream(reinterpret_cast<float4 *>(d + (size_t)j * out_stride), o);
+        }
+    }
+    // ragged tail: frames % 4 leftover frames
+    const size_t tail0 = nquads * 4, ntail = (frames - tail0) * (size_t)nc;
+    for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < ntail; id += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = tail0 + id / (size_t)nc;
+        const int c = (int)(id % (size_t)nc);
+        out[(size_t)c * out_stride + f] = conv_lut<B, KIND>(load_raw<B, BE>(in + (f * (size_t)nc + c) * B), nullptr);
+    }
+}
+
 template <int B, int KIND, bool BE>
 int launch_c(aukit_ctx *ctx, const uint8_t *d_in, float *d_out, size_t frames, size_t out_stride,
              int channels, bool interleaved) {
@@ -119,11 +207,30 @@ int launch_c(aukit_ctx *ctx, const uint8_t *d_in, float *d_out, size_t frames, s
         const size_t row_bytes = frames * (size_t)B;
         const int vok = vec_ok && (channels == 1 || row_bytes % 16 == 0);
         dim3 grid(grid_for(frames_per_thread(B, 1)), channels);
+        if constexpr (B <= 3) {
+            if (vok) {
+                dim3 ngrid(grid_for(B == 3 ? 4 : 16), channels);
+                pcm_unpack_narrow_kernel<B, KIND, BE, 1><<<ngrid, threads, 0, ctx->stream>>>(d_in, d_out, frames, out_stride, row_bytes);
+                ctx->launches++;
+                return aukit_cuda_check(cudaGetLastError(), "pcm_unpack_narrow launch");
+            }
+        }
         pcm_unpack_kernel<B, KIND, BE, 1><<<grid, threads, 0, ctx->stream>>>(d_in, d_out, frames, out_stride, 1,
                                                                               row_bytes, vok);
     } else if (channels == 2) {
+        if constexpr (B == 1 || B == 3) {
+            if (vec_ok) {
+                pcm_unpack_narrow_kernel<B, KIND, BE, 2><<<grid_for(B == 3 ? 4 : 8), threads, 0, ctx->stream>>>(d_in, d_out, frames, out_stride, 0);
+                ctx->launches++;
+                return aukit_cuda_check(cudaGetLastError(), "pcm_unpack_narrow launch");
+            }
+        }
         pcm_unpack_kernel<B, KIND, BE, 2><<<grid_for(frames_per_thread(B, 2)), threads, 0, ctx->stream>>>(
             d_in, d_out, frames, out_stride, 2, 0, vec_ok);
+    } else if (B != 3 && vec_ok && ((size_t)channels * B) % 16 == 0) {
+        const size_t items = frames / 4 * (size_t)(channels / (16 / B));
+        pcm_unpack_groups_kernel<B, KIND, BE><<<aukit_grid(items ? items : 1, threads, (size_t)ctx->num_sms * 8 * 16), threads, 0, ctx->stream>>>(
+            d_in, d_out, frames, out_stride, channels);
     } else {
         // vec_ok here = samples are naturally aligned (natural-width loads) and float4 stores are legal
         const int vok = ((uintptr_t)d_in % B == 0 || B == 3) && ((uintptr_t)d_out % 16 == 0) && (out_stride % 4 == 0);

@@ -27,6 +27,35 @@ __device__ __forceinline__ float g711_value(unsigned byte, bool ulaw) {
     return neg ? -v : v;   // m / -0x2000: yields -0.0 for m == 0, like the reference
 }
 
+// 8-bit formats without a table (a 256-entry shared-memory table costs ~2.5 bank-conflict wavefronts per
+// random lookup; ncu showed K1/K2 on 8-bit input stalled on mio_throttle).  All forms are exact:
+//   PCM (A:1133 / A:1152): with u = s + 128 (signed) or the byte itself (unsigned), float bits 0x4B000000 | u
+//     are 2^23 + u, so one FADD gives u - 128; then the same FMA as s16_to_float with 127 * 128 in place of
+//     32767 * 32768 (checked for all 256 values against (float)((double)s / 127)).
+//   G.711 (A:1374-1379): after the XOR, ((2m + 33) << e) / 8192 has float bits 0x3B840000 + ((b & 0x7F) << 19)
+//     -- the exponent and mantissa fields of the code line up with the float's; mu-law subtracts 33/8192
+//     (exact), A-law's e == 0 segment is (4m + 2) / 8192; the sign bit is XORed in, which also yields the
+//     reference's -0.0 for m == 0.
+template <int KIND>
+__device__ __forceinline__ float convert8(uint32_t byte) {
+    if (KIND == K_ULAW || KIND == K_ALAW) {
+        const uint32_t b = byte ^ (KIND == K_ULAW ? 0xFFu : 0x55u);
+        float v = __uint_as_float(0x3B840000u + ((b & 0x7Fu) << 19));
+        uint32_t sign;
+        if (KIND == K_ULAW) {
+            v = __fadd_rn(v, -33.0f / 8192.0f);
+            sign = (b & 0x80u) << 24;
+        } else {
+            if ((b & 0x70u) == 0) v = (float)(4 * (b & 0x0Fu) + 2) * (1.0f / 8192.0f);
+            sign = (~b & 0x80u) << 24;
+        }
+        return __uint_as_float(__float_as_uint(v) ^ sign);
+    }
+    const uint32_t u = KIND == K_SIGNED ? (byte ^ 0x80u) : byte;
+    const float lo = __fmul_rn(__fadd_rn(__uint_as_float(0x4B000000u | u), -8388736.0f), 1.0f / 128.0f);
+    return __fmaf_rn(__saturatef(lo), (1.0f / (127.0f * 128.0f)) * 128.0f, lo);
+}
+
 template <int B, int KIND>
 __device__ __forceinline__ float convert(uint32_t raw, const float *lut) {
     if (KIND == K_FLOAT) return __uint_as_float(raw);

@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warm", type=int, default=3, help="untimed launches before timing (0 for ncu captures)")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -37,7 +38,7 @@ def main():
     stream = torch.cuda.current_stream()
 
     def timed(fn):
-        for _ in range(3):
+        for _ in range(args.warm):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
