@@ -224,6 +224,33 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
                 }
             }
         }
+        if ((CT == 1 || CT == 2) && a.planar_f32 && gA >= in_lo && gA >= 0 && ((uintptr_t)a.in & 15) == 0 &&
+            (CT == 1 || (a.in_stride & 3) == 0)) {
+            // interior tile of planar f32 input (standalone Audio:resample): 128-bit loads per row from a 16-byte
+            // aligned start, interleaved into shared memory; no index clamping needed inside the signal
+            const size_t foff = (size_t)(gA - in_lo);
+            const size_t a0 = foff & ~(size_t)3;
+            const int shf = (int)(foff - a0);
+            const int nvec = (pl.nfr + shf + 3) / 4;
+            const long long last = (long long)a0 + in_lo + (long long)nvec * 4;                 // one past the last frame read
+            if (last <= in_hi && last <= n_total) {
+                fast = true;
+                sh = shf;
+                const float4 *r0 = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(a.in) + a0);
+                if (CT == 1) {
+                    float4 *dst = reinterpret_cast<float4 *>(sm);
+                    for (int v = t; v < nvec; v += blockDim.x) dst[v] = __ldg(r0 + v);
+                } else {
+                    const float4 *r1 = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(a.in) + a.in_stride + a0);
+                    float4 *dst = reinterpret_cast<float4 *>(sm);
+                    for (int v = t; v < nvec; v += blockDim.x) {
+                        const float4 l = __ldg(r0 + v), r = __ldg(r1 + v);
+                        dst[2 * v] = make_float4(l.x, r.x, l.y, r.y);
+                        dst[2 * v + 1] = make_float4(l.z, r.z, l.w, r.w);
+                    }
+                }
+            }
+        }
         if (!fast) stage_dispatch<CT>(a, pl, gA, sm, nfr_cap);
         if (PX == PX_TABLE || PX == PX_MID) {
             // exact hit / near-hit decision for the tile's j == 0 outputs with the reference's own
