@@ -181,6 +181,10 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
     }
     float mult = 0.f;
     if (APPLY && !a.raw_out) mult = (float)(a.peak / (double)a.d_max[0]);   // A:3444
+    // final clamp bounds (A:3455).  max == 0 (silence) makes every product 0 * inf = NaN, which the reference's
+    // clamp lets through (A:228): NaN bounds keep it NaN through fmin/fmax as well.
+    const float fin_hi = (APPLY && !a.raw_out && !(a.d_max[0] > 0.f)) ? __int_as_float(0x7FC00000) : 1.0f;
+    const float fin_lo = -fin_hi;
     const float inv_cn = a.inv_cn;                                      // s / cn (A:687) as a multiply
     float mx = 0.f;
     const unsigned long long out_lo = a.out_first, out_hi = a.out_first + a.n_out;
@@ -189,6 +193,10 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
     const long long in_lo = (long long)a.in_first, in_hi = in_lo + (long long)a.in_avail;
     const bool s16le = !a.planar_f32 && pl.fmt == ((2 << 8) | (K_SIGNED << 4) | 0);
 
+    auto clamp_out = [&](float v) {
+        if (PX != PX_RATIONAL) return clamp_ref(v);
+        return fminf(fmaxf(v, fin_lo), fin_hi);
+    };
     auto clampv = [](float v) {
         if (PX != PX_RATIONAL) return clamp_ref(v);                     // NaN passes through like A:228-232
         return fminf(fmaxf(v, -1.0f), 1.0f);                            // finite inputs: same result, 2 FMNMX
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
                 if (MONO) acc = vl + vr;                                // (0 + L) + R, A:686
                 else if (APPLY) {
                     if (a.raw_out) { outp[0] = vl; outp[a.out_stride] = vr; }
-                    else { outp[0] = clampv(vl * mult); outp[a.out_stride] = clampv(vr * mult); }
+                    else { outp[0] = clamp_out(vl * mult); outp[a.out_stride] = clamp_out(vr * mult); }
                 }
                 else mx = fmaxf(mx, fmaxf(fabsf(vl), fabsf(vr)));
             } else {
@@ -363,13 +371,13 @@ __global__ void __launch_bounds__(512, 3) poly_kernel(pipe_args a, poly_plan pl)
                     const float p3 = (MODE == AUKIT_INTERP_CUBIC) ? f[3] : 0.f;
                     const float v = value(p0, p1, p2, p3);
                     if (MONO) acc += v;
-                    else if (APPLY) outp[(size_t)c * a.out_stride] = a.raw_out ? v : clampv(v * mult);
+                    else if (APPLY) outp[(size_t)c * a.out_stride] = a.raw_out ? v : clamp_out(v * mult);
                     else mx = fmaxf(mx, fabsf(v));
                 }
             }
             if (MONO) {
                 const float mv = acc * inv_cn;                          // s / cn, A:687
-                if (APPLY) outp[0] = clampv(mv * mult);                 // A:3455
+                if (APPLY) outp[0] = clamp_out(mv * mult);              // A:3455
                 else mx = fmaxf(mx, fabsf(mv));
             }
             if (APPLY) outp += pl.Sp;

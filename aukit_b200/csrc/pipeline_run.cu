@@ -126,7 +126,9 @@ __device__ __noinline__ void flush_stage(const float *stage, float *g_tile, int 
 // classes half a period apart (two weight addresses per LDS.128, two script bytes).  Halving the run per lane
 // halves the shared memory per warp, which is what bounds the number of resident warps.
 // CMIN = floor(L / M): every new input frame yields CMIN outputs, some one more (bit flags per 8 frames).
-template <bool APPLY, int CMIN>
+// CLAMP1: keep the final clamp(v * peak/max, -1, 1) of A:3455.  |v| <= max for every output, so for
+// peakAmplitude < 1 - 2^-20 it can never act and the apply pass drops it (two ALU-pipe instructions per output).
+template <bool APPLY, int CMIN, bool CLAMP1>
 __global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int L = rp.L, M = rp.M, LH = L / 2;
@@ -158,6 +160,18 @@ __global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
         W[e] = make_float4((float)(-0.5 * x3 + x2 - 0.5 * x), (float)(1.5 * x3 - 2.5 * x2 + 1.0),
                            (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x), (float)(0.5 * x3 - 0.5 * x2));
     }
+    // Output scale of the apply pass: peak/max (A:3444) * 2^-15 (sample scale) * 1/2 (mono mean, A:687).  It stays a
+    // separate multiply (not folded into the weights) so that these outputs are bit-identical to the polyphase
+    // kernel's, which is what makes a time-sharded run equal a single pass bit for bit.  max == 0 (silence): the
+    // reference computes 0 * inf = NaN for every sample and its clamp lets NaN through; a NaN scale (and NaN clamp
+    // bounds: fmin/fmax of two NaNs stay NaN) reproduces that.
+    float mult = 0.f, one_hi = 1.0f;
+    if (APPLY) {
+        const float mx0 = a.d_max[0];
+        mult = mx0 > 0.f ? (float)(a.peak / (double)mx0) * (1.0f / 65536.0f) : __int_as_float(0x7FC00000);
+        if (!(mx0 > 0.f)) one_hi = mult;
+    }
+    const float one_lo = -one_hi;
     // count(cls, s) = outputs of class cls whose floor position is fbase_cls + s  (s = step index, 0-based)
     auto count_at = [&](int cls, int s) -> int {
         const int eb = cls * LH, ee = eb + LH;
@@ -181,8 +195,6 @@ __global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    float mult = 0.f;
-    if (APPLY) mult = (float)(a.peak / (double)a.d_max[0]) * (1.0f / 65536.0f);   // A:3444; 2^-15 (scale) * 1/2 (mono, A:687)
     float mx = 0.f;
     uint32_t parity = 0;
     const unsigned long long warps_total = (unsigned long long)gridDim.x * rp.nwarps;
@@ -233,7 +245,8 @@ __global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
             vr = fminf(fmaxf(vr, -32768.0f), 32768.0f);
             const float sum = vl + vr;                    // (0 + L) + R, A:686; the /2 is in the final scale
             if (APPLY) {
-                my_stage[(er & (STAGE_RING - 1)) ^ swz] = fminf(fmaxf(sum * mult, -1.0f), 1.0f);   // A:3455
+                const float o = sum * mult;
+                my_stage[(er & (STAGE_RING - 1)) ^ swz] = CLAMP1 ? fminf(fmaxf(o, one_lo), one_hi) : o;   // A:3455
             } else {
                 mx = fmaxf(mx, fabsf(sum));
             }
@@ -328,7 +341,10 @@ int launch_run(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     rp.nwarps = nw;
     const size_t smem = fixed + (((size_t)nw * 8 + 127) & ~(size_t)127) + (size_t)nw * per_warp + 128;
     const int cmin = L / M;
-    auto kern = cmin == 1 ? run_kernel<APPLY, 1> : (cmin == 2 ? run_kernel<APPLY, 2> : run_kernel<APPLY, 4>);
+    // the final clamp to +-1 can only act when peakAmplitude is (about) 1 or more
+    const bool clamp1 = APPLY && !(a.peak < 1.0 - 9.5367431640625e-07);
+    auto kern = cmin == 1 ? run_kernel<APPLY, 1, false> : (cmin == 2 ? run_kernel<APPLY, 2, false> : run_kernel<APPLY, 4, false>);
+    if (clamp1) kern = cmin == 1 ? run_kernel<APPLY, 1, true> : (cmin == 2 ? run_kernel<APPLY, 2, true> : run_kernel<APPLY, 4, true>);
     if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
     unsigned long long g = (rp.ntiles + nw - 1) / nw;
     if (g > (unsigned long long)ctx->num_sms) g = ctx->num_sms;

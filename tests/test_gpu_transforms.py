@@ -411,3 +411,24 @@ def test_audio_pcm_requantisation_within_one_lsb_of_reference_chain(ak, O):
     ref = np.floor(O.audio_pcm(O.chain_s16(pcm.tobytes(), 2, 44100, 48000, "cubic", 0.8), 8, "signed", True))
     assert np.max(np.abs(got - ref)) <= 1
     assert np.mean(got != ref) < 1e-3
+
+
+@pytest.mark.parametrize("peak", [1.0, 1.5, 0.25])
+def test_run_per_lane_kernel_other_peaks(ak, O, peak):
+    """peakAmplitude >= 1 keeps the final clamp of A:3455 (CLAMP1 variant; 1.5 makes it act), < 1 drops it."""
+    n = 1_200_011
+    pcm = np.random.default_rng(int(peak * 100)).integers(-32768, 32768, (n, 2)).astype(np.int16)
+    got = ak.preload(pcm.tobytes(), 16, "signed", 2, 44100, 48000, "cubic", True, peak)[0]
+    ref = O.chain_s16(pcm.tobytes(), 2, 44100, 48000, "cubic", peak)
+    assert got.shape == ref.shape and np.max(np.abs(got - ref)) <= TOL * max(1.0, peak)
+    if peak > 1:
+        assert np.max(got) == 1.0 and np.min(got) == -1.0
+
+
+def test_fused_chain_on_silence_is_all_nan_like_the_reference(ak, O):
+    """max == 0: the reference multiplies every sample by peak / 0 = inf, 0 * inf = NaN, and its clamp lets NaN
+    through (A:228, A:3444-3455) -- also on the interior tiles that the run-per-lane kernel takes."""
+    n = 1_000_000
+    got = ak.preload(bytes(4 * n), 16, "signed", 2, 44100, 48000, "cubic", True, 0.8)[0]
+    ref = O.chain_s16(bytes(4 * 4000), 2, 44100, 48000, "cubic", 0.8)
+    assert np.all(np.isnan(ref)) and np.all(np.isnan(got))
