@@ -36,7 +36,7 @@ _VERSION = "1.10.0-b200"
 defaultInterpolation = "linear"                                           # A:99
 
 _DATATYPES = {"signed": 0, "unsigned": 1, "float": 2}
-_INTERPS = {"none": 0, "linear": 1, "cubic": 2}
+_INTERPS = {"none": 0, "linear": 1, "cubic": 2, "sinc": 3}
 DIALECT_LITERAL, DIALECT_GENERAL = 0, 1
 _WAV_TYPES = ["signed", "unsigned", "float", "alaw", "ulaw", "adpcm", "msadpcm", "dfpwm", None]
 

@@ -507,7 +507,7 @@ static int ragged_error(const aukit_audio *a) {
 extern "C" int aukit_cuda_resample(aukit_ctx *ctx, const aukit_audio *in, double sampleRate, int interpolation,
                                    aukit_audio **out) {
     if (!ctx || !in || !out) return aukit_fail("aukit_cuda: null argument");
-    if (interpolation < 0 || interpolation > 2) return aukit_fail("bad argument #2 (invalid interpolation type)");
+    if (interpolation < 0 || interpolation > 3) return aukit_fail("bad argument #2 (invalid interpolation type)");
     if (ragged_error(in)) return -1;
     const uint64_t n_out = aukit_resample_out_len(in->frames, in->sampleRate, sampleRate);
     aukit_audio *a = nullptr;

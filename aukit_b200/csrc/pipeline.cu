@@ -127,6 +127,7 @@ static int validate(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *d_
     if (p->dataType == AUKIT_FLOAT && p->bitDepth != 32)
         return aukit_fail("bad argument #2 (float audio must have 32-bit depth)");
     if (p->channels < 1) return aukit_fail("aukit_cuda: channels < 1");
+    if (p->interpolation == AUKIT_INTERP_SINC) return aukit_fail("aukit_cuda: sinc interpolation is available through Audio:resample only, not the fused chain");
     if (p->interpolation < 0 || p->interpolation > 2) return aukit_fail("bad argument #2 (invalid interpolation type)");
     const int B = p->bitDepth / 8;
     if ((B == 2 || B == 4) && (uintptr_t)d_in % B) return aukit_fail("aukit_cuda: packed input must be sample-aligned");

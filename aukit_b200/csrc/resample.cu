@@ -67,6 +67,32 @@ __global__ void __launch_bounds__(256) resample_kernel(resample_args a) {
         }
         const long long n = (long long)a.n_total;
         const long long base = f - 1 - (long long)a.in_first;          // offset of p1 in `in`
+        if (MODE == AUKIT_INTERP_SINC) {
+            // A:267-281: sum over k = -10..10 of data[f + k] * sin(pi (fx - k)) / (pi (fx - k)), taps outside the
+            // signal skipped (not clamped).  The 21 weights are evaluated in fp64 like the reference's and shared
+            // by the channels of the frame.
+            float w[21];
+#pragma unroll
+            for (int k = -10; k <= 10; k++) {
+                const double px = 3.14159265358979323846 * (fxd - (double)k);
+                w[k + 10] = (f + k >= 1 && f + k <= n) ? (px == 0.0 ? 1.0f : (float)(sin(px) / px)) : 0.0f;
+            }
+            for (int c = 0; c < a.channels; c++) {
+                const float *ch = a.in + (size_t)c * a.in_stride;
+                float v;
+                if (hit) {
+                    v = ch[base];                                      // copied unclamped, A:667
+                } else {
+                    float sum = 0.f;
+#pragma unroll
+                    for (int k = -10; k <= 10; k++)
+                        if (f + k >= 1 && f + k <= n) sum = __fmaf_rn(ch[base + k], w[k + 10], sum);
+                    v = clamp_ref(sum);
+                }
+                a.out[(size_t)c * a.out_stride + o] = v;
+            }
+            continue;
+        }
         for (int c = 0; c < a.channels; c++) {
             const float *ch = a.in + (size_t)c * a.in_stride;
             const float p1 = ch[base];
@@ -143,13 +169,14 @@ extern "C" double aukit_resample_position(uint64_t i, double srcRate, double dst
 extern "C" int aukit_resample_window(uint64_t n_in_total, double srcRate, double dstRate, int interpolation,
                                      uint64_t out_first, uint64_t n_out, uint64_t *in_first,
                                      uint64_t *in_count) {
-    if (interpolation < 0 || interpolation > 2) return aukit_fail("bad argument #2 (invalid interpolation type)");
+    if (interpolation < 0 || interpolation > 3) return aukit_fail("bad argument #2 (invalid interpolation type)");
     if (n_out == 0 || n_in_total == 0) { *in_first = 0; *in_count = 0; return 0; }
     const double xa = aukit_resample_position(out_first + 1, srcRate, dstRate);
     const double xb = aukit_resample_position(out_first + n_out, srcRate, dstRate);
     // positions are monotone in i; taps span floor(x) + [lo, hi] (1-based)
-    const int lo = interpolation == AUKIT_INTERP_CUBIC ? -1 : 0;
-    const int hi = interpolation == AUKIT_INTERP_CUBIC ? 2 : (interpolation == AUKIT_INTERP_LINEAR ? 1 : 0);
+    const int lo = interpolation == AUKIT_INTERP_SINC ? -10 : (interpolation == AUKIT_INTERP_CUBIC ? -1 : 0);
+    const int hi = interpolation == AUKIT_INTERP_SINC ? 10
+                 : (interpolation == AUKIT_INTERP_CUBIC ? 2 : (interpolation == AUKIT_INTERP_LINEAR ? 1 : 0));
     double fa = floor(xa) + lo, fb = floor(xb) + hi;
     if (fa < 1) fa = 1;
     if (fb > (double)n_in_total) fb = (double)n_in_total;
@@ -164,7 +191,7 @@ extern "C" int aukit_cuda_dev_resample(aukit_ctx *ctx, const float *d_in, size_t
                                        double dstRate, int interpolation, uint64_t out_first, size_t n_out,
                                        float *d_out, size_t out_stride) {
     if (!ctx) return aukit_fail("aukit_cuda: null context");
-    if (interpolation < 0 || interpolation > 2) return aukit_fail("bad argument #2 (invalid interpolation type)");  // A:656
+    if (interpolation < 0 || interpolation > 3) return aukit_fail("bad argument #2 (invalid interpolation type)");  // A:656
     if (channels < 1) return aukit_fail("aukit_cuda: channels < 1");
     if (n_out == 0) return 0;
     const uint64_t total_out = aukit_resample_out_len(n_in_total, srcRate, dstRate);
@@ -181,7 +208,7 @@ extern "C" int aukit_cuda_dev_resample(aukit_ctx *ctx, const float *d_in, size_t
                           (unsigned long long)need_first, (unsigned long long)(need_first + need_count));
     // integer rates with a short period: the polyphase kernels (pipeline_poly.cu) do the same arithmetic with
     // shared-memory tap reuse and loop-invariant weights; everything else takes the per-frame fp64 kernel below
-    {
+    if (interpolation != AUKIT_INTERP_SINC) {
         const int r = aukit_poly_resample_try(ctx, d_in, in_stride, channels, n_in_total, in_first, in_avail, srcRate, dstRate,
                                               interpolation, out_first, n_out, d_out, out_stride);
         if (r != 0) return r < 0 ? -1 : 0;
@@ -198,6 +225,7 @@ extern "C" int aukit_cuda_dev_resample(aukit_ctx *ctx, const float *d_in, size_t
     switch (interpolation) {
     case AUKIT_INTERP_NONE: AUKIT_RS(AUKIT_INTERP_NONE); break;
     case AUKIT_INTERP_LINEAR: AUKIT_RS(AUKIT_INTERP_LINEAR); break;
+    case AUKIT_INTERP_SINC: AUKIT_RS(AUKIT_INTERP_SINC); break;
     default: AUKIT_RS(AUKIT_INTERP_CUBIC); break;
     }
 #undef AUKIT_RS

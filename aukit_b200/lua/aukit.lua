@@ -25,7 +25,7 @@ local Audio = {}
 local Audio_mt
 
 local DATATYPE = {signed = 0, unsigned = 1, float = 2}
-local INTERP = {none = 0, linear = 1, cubic = 2}
+local INTERP = {none = 0, linear = 1, cubic = 2, sinc = 3}
 aukit.DIALECT_LITERAL, aukit.DIALECT_GENERAL = 0, 1
 --- ADPCM block layout: LITERAL reproduces the reference for 1/2 channels (A:1544, A:1331 quirks
 --- included); GENERAL is the standard N-channel layout the reference rejects (A:1349, A:1199).

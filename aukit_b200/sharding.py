@@ -19,7 +19,7 @@ from typing import List, Optional
 from . import _lib
 from ._lib import PipelineDesc
 
-_INTERPS = {"none": 0, "linear": 1, "cubic": 2}
+_INTERPS = {"none": 0, "linear": 1, "cubic": 2, "sinc": 3}
 
 
 @dataclass

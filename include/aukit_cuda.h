@@ -33,7 +33,8 @@ typedef struct aukit_ctx aukit_ctx;     /* one per (host thread, device) */
 typedef struct aukit_audio aukit_audio; /* device-resident aukit.Audio (A:116-123) */
 
 enum { AUKIT_SIGNED = 0, AUKIT_UNSIGNED = 1, AUKIT_FLOAT = 2 };              /* dataType */
-enum { AUKIT_INTERP_NONE = 0, AUKIT_INTERP_LINEAR = 1, AUKIT_INTERP_CUBIC = 2 };
+enum { AUKIT_INTERP_NONE = 0, AUKIT_INTERP_LINEAR = 1, AUKIT_INTERP_CUBIC = 2,
+       AUKIT_INTERP_SINC = 3 /* Audio:resample only (A:267-281, window +-10); not in the fused chain */ };
 /* ADPCM dialect: LITERAL reproduces aukit.wav / aukit.msadpcm for channels 1 and 2 exactly
  * (A:1544 index mask, A:1331 first-header reuse); GENERAL is the standard N-channel block
  * layout (IMA: aukit.stream.adpcm A:2798-2815), the only one defined for channels > 2. */

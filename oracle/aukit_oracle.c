@@ -408,6 +408,19 @@ static int interp_eval(int mode, const double *d, size_t n, double x, double *re
         *res = a + (b - a) * (x - ffx);
         return 0;
     }
+    if (mode == AUKO_INTERP_SINC) {                                          /* A:267-281, sincWindowSize = 10 (A:129) */
+        double fx = x - ffx, sum = 0;
+        for (int k = -10; k <= 10; k++) {
+            double dv = tget(d, n, ffx + k, &nil);
+            if (!nil) {
+                double px = 3.14159265358979323846 * (fx - k);
+                if (px == 0) sum = sum + dv;
+                else sum = sum + dv * sin(px) / px;
+            }
+        }
+        *res = sum;
+        return 0;
+    }
     /* cubic, A:261-266 */
     int n0, n1, n2, n3;
     double p0 = tget(d, n, ffx - 1, &n0), p1 = tget(d, n, ffx, &n1);
@@ -437,7 +450,7 @@ double auko_resample_pos(uint64_t i, double srcRate, double dstRate) {
 int auko_resample(const double *in, size_t in_stride, int channels, size_t n_in, double srcRate,
                   double dstRate, int interp, double *out, size_t out_stride, size_t *n_out) {
     g_err[0] = 0;
-    if (interp < 0 || interp > 2) return fail("bad argument #2 (invalid interpolation type)");
+    if (interp < 0 || interp > 3) return fail("bad argument #2 (invalid interpolation type)");
     double ratio = dstRate / srcRate;
     size_t newlen = auko_resample_len(n_in, srcRate, dstRate);
     if (n_out) *n_out = newlen;

@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 enum { AUKO_SIGNED = 0, AUKO_UNSIGNED = 1, AUKO_FLOAT = 2 };
-enum { AUKO_INTERP_NONE = 0, AUKO_INTERP_LINEAR = 1, AUKO_INTERP_CUBIC = 2 };
+enum { AUKO_INTERP_NONE = 0, AUKO_INTERP_LINEAR = 1, AUKO_INTERP_CUBIC = 2, AUKO_INTERP_SINC = 3 };
 /* ADPCM dialects: LITERAL = what aukit.wav/aukit.msadpcm actually do for channels 1/2
  * (bugs included); GENERAL = the standard N-channel layouts (authority for IMA:
  * aukit.stream.adpcm A:2798-2815), used where the reference itself errors (C > 2). */

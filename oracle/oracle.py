@@ -20,7 +20,7 @@ SIGNED, UNSIGNED, FLOAT = 0, 1, 2
 NONE, LINEAR, CUBIC = 0, 1, 2
 LITERAL, GENERAL = 0, 1
 DATATYPES = {"signed": SIGNED, "unsigned": UNSIGNED, "float": FLOAT}
-INTERPS = {"none": NONE, "linear": LINEAR, "cubic": CUBIC}
+INTERPS = {"none": NONE, "linear": LINEAR, "cubic": CUBIC, "sinc": 3}
 
 
 class OracleError(RuntimeError):

@@ -298,6 +298,13 @@ def main():
     add("aiff_not_aiff", "aiff", dict(head=False), **{"in": b"FORM" + bytes(4) + b"WAVE" + bytes(20)})
     add("aiff_no_ssnd", "aiff", dict(head=False), **{"in": b"FORM" + bytes(4) + b"AIFF" + chunk(b"COMM", struct.pack(">hIh", 1, 0, 8) + ext80(8000))})
 
+    # ---- interpolate.sinc: window +-10, taps outside the signal skipped
+    zs = rng2.uniform(-1, 1, (2, 700))
+    for src, dst in ((44100, 48000), (48000, 44100), (8000, 48000), (96000, 48000), (48000, 48000)):
+        add("resample_sinc_%d_%d" % (src, dst), "resample", dict(sampleRate=src, targetRate=dst, interpolation="sinc"), x=zs)
+    add("resample_sinc_short", "resample", dict(sampleRate=22050, targetRate=48000, interpolation="sinc"), x=zs[:1, :7])
+    add("resample_sinc_loud", "resample", dict(sampleRate=44100, targetRate=48000, interpolation="sinc"), x=zs[:1, :300] * 1.4)
+
     # ---- run everything through the reference
     manifest = []
     for i, case in enumerate(cases):

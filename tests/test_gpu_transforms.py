@@ -432,3 +432,29 @@ def test_fused_chain_on_silence_is_all_nan_like_the_reference(ak, O):
     got = ak.preload(bytes(4 * n), 16, "signed", 2, 44100, 48000, "cubic", True, 0.8)[0]
     ref = O.chain_s16(bytes(4 * 4000), 2, 44100, 48000, "cubic", 0.8)
     assert np.all(np.isnan(ref)) and np.all(np.isnan(got))
+
+
+@pytest.mark.parametrize("src,dst,ch", [(44100, 48000, 2), (48000, 8000, 1), (11025, 48000, 3), (44100, 44100, 1)])
+def test_resample_sinc_matches_oracle_and_shards(ak, O, src, dst, ch):
+    """interpolate.sinc (A:267-281) through Audio:resample, whole and as two output shards that only hold
+    their +-10 frame window (aukit_resample_window)."""
+    lib = ak._lib.load()
+    ctx = ak.context()
+    n = 20_011
+    x = np.random.default_rng(src + dst).uniform(-1, 1, (ch, n)).astype(np.float32)
+    got = ak.Audio.from_numpy(x, src).resample(dst, "sinc").numpy()
+    ref = O.resample(x.astype(np.float64), src, dst, "sinc")
+    assert got.shape == ref.shape and float(np.max(np.abs(got - ref))) <= 2 * TOL
+    n_out = got.shape[1]
+    parts = []
+    for o0, o1 in ((0, n_out // 2), (n_out // 2, n_out)):
+        f, c = C.c_uint64(), C.c_uint64()
+        assert lib.aukit_resample_window(n, float(src), float(dst), 3, o0, o1 - o0, C.byref(f), C.byref(c)) == 0
+        shard_in = ak.Audio.from_numpy(np.ascontiguousarray(x[:, f.value: f.value + c.value]), src)
+        out = ak.Audio.from_numpy(np.zeros((ch, o1 - o0), dtype=np.float32), dst)
+        ak._lib.check(lib.aukit_cuda_dev_resample(ctx.handle, shard_in.data_ptr, shard_in.stride, ch, n, f.value, c.value,
+                                                  float(src), float(dst), 3, o0, o1 - o0, out.data_ptr, out.stride))
+        parts.append(out.numpy())
+    assert f32_equal_bits(np.concatenate(parts, axis=1), got)
+    with pytest.raises(ak.AukitError, match="Audio:resample only"):
+        ak.preload(bytes(4000), 16, "signed", 2, 44100, 48000, "sinc", True, 0.8)
