@@ -93,6 +93,14 @@ SIGNATURES = {
     "aukit_cuda_aiff_parse": (_I, [_P, _SZ, C.POINTER(ContainerInfo)]),
     "aukit_cuda_au": (_I, [_P, _P, _SZ, C.POINTER(ContainerInfo), C.POINTER(_P)]),
     "aukit_cuda_aiff": (_I, [_P, _P, _SZ, _I, C.POINTER(ContainerInfo), C.POINTER(_P)]),
+    "aukit_cuda_invert": (_I, [_P, _P]),
+    "aukit_cuda_fade": (_I, [_P, _P, _D, _D, _D, _D]),
+    "aukit_cuda_delay": (_I, [_P, _P, _D, _D]),
+    "aukit_cuda_center": (_I, [_P, _P]),
+    "aukit_cuda_dev_invert": (_I, [_P, _P, _SZ, _I, _SZ]),
+    "aukit_cuda_dev_fade": (_I, [_P, _P, _SZ, _I, _SZ, _D, _D, _D, _D, _D]),
+    "aukit_cuda_dev_delay": (_I, [_P, _P, _SZ, _I, _SZ, _D, _D, _D]),
+    "aukit_cuda_dev_center": (_I, [_P, _P, _SZ, _I, _SZ, _D]),
     "aukit_cuda_lowpass": (_I, [_P, _P, _D]),
     "aukit_cuda_audio_pcm": (_I, [_P, _P, _I, _I, _I, _P]),
     "aukit_cuda_audio_pcm_bytes": (_I, [_P, _P, _I, _I, _I, _I, _P]),

@@ -506,6 +506,36 @@ class effects:
         return audio
 
     @staticmethod
+    def invert(audio: Audio) -> Audio:                                     # A:3412
+        _expect_audio(1, audio)
+        _lib.check(audio._ctx.lib.aukit_cuda_invert(audio._ctx.handle, audio._h))
+        return audio
+
+    @staticmethod
+    def fade(audio: Audio, startTime, startAmplitude, endTime, endAmplitude) -> Audio:   # A:3392
+        _expect_audio(1, audio)
+        for i, v in enumerate((startTime, startAmplitude, endTime, endAmplitude)):
+            _expect(i + 2, v, float)
+        _lib.check(audio._ctx.lib.aukit_cuda_fade(audio._ctx.handle, audio._h, float(startTime), float(startAmplitude),
+                                                  float(endTime), float(endAmplitude)))
+        return audio
+
+    @staticmethod
+    def delay(audio: Audio, delay, multiplier=None) -> Audio:              # A:3500
+        _expect_audio(1, audio)
+        _expect(2, delay, float)
+        multiplier = _expect(3, multiplier, float, type(None))
+        _lib.check(audio._ctx.lib.aukit_cuda_delay(audio._ctx.handle, audio._h, float(delay),
+                                                   0.5 if multiplier is None else float(multiplier)))
+        return audio
+
+    @staticmethod
+    def center(audio: Audio) -> Audio:                                     # A:3465
+        _expect_audio(1, audio)
+        _lib.check(audio._ctx.lib.aukit_cuda_center(audio._ctx.handle, audio._h))
+        return audio
+
+    @staticmethod
     def lowpass(audio: Audio, frequency) -> Audio:                         # A:3586
         _expect_audio(1, audio)
         _expect(2, frequency, float)

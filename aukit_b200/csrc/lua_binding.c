@@ -264,6 +264,27 @@ static int l_amplify(lua_State *L) {
     return 0;
 }
 
+static int l_invert(lua_State *L) {
+    if (aukit_cuda_invert(ctx(L), check_audio(L, 1))) return fail(L);
+    return 0;
+}
+
+static int l_fade(lua_State *L) {
+    if (aukit_cuda_fade(ctx(L), check_audio(L, 1), luaL_checknumber(L, 2), luaL_checknumber(L, 3), luaL_checknumber(L, 4),
+                        luaL_checknumber(L, 5))) return fail(L);
+    return 0;
+}
+
+static int l_delay(lua_State *L) {
+    if (aukit_cuda_delay(ctx(L), check_audio(L, 1), luaL_checknumber(L, 2), luaL_optnumber(L, 3, 0.5))) return fail(L);
+    return 0;
+}
+
+static int l_center(lua_State *L) {
+    if (aukit_cuda_center(ctx(L), check_audio(L, 1))) return fail(L);
+    return 0;
+}
+
 static int l_lowpass(lua_State *L) {
     if (aukit_cuda_lowpass(ctx(L), check_audio(L, 1), luaL_checknumber(L, 2))) return fail(L);
     return 0;
@@ -338,7 +359,7 @@ static int l_gc(lua_State *L) {
 static const luaL_Reg funcs[] = {
     {"pcm", l_pcm}, {"g711", l_g711}, {"adpcm", l_adpcm}, {"ima_adpcm_wav", l_ima_wav}, {"msadpcm", l_msadpcm},
     {"wav", l_wav}, {"new", l_new}, {"resample", l_resample}, {"mono", l_mono}, {"concat", l_concat},
-    {"au", l_au}, {"aiff", l_aiff}, {"amplify", l_amplify}, {"lowpass", l_lowpass}, {"pcm_out", l_pcm_out}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
+    {"au", l_au}, {"aiff", l_aiff}, {"amplify", l_amplify}, {"invert", l_invert}, {"fade", l_fade}, {"delay", l_delay}, {"center", l_center}, {"lowpass", l_lowpass}, {"pcm_out", l_pcm_out}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
     {"frames", l_frames}, {"read", l_read}, {"write", l_write}, {NULL, NULL}};
 
 int luaopen_aukit_cuda(lua_State *L) {

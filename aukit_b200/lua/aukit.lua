@@ -298,6 +298,45 @@ function aukit.effects.amplify(audio, multiplier)
     return audio
 end
 
+--- Inverts all channels in the specified audio. (A:3412)
+function aukit.effects.invert(audio)
+    expectAudio(1, audio)
+    cu.invert(handle(audio))
+    invalidate(audio)
+    return audio
+end
+
+--- Fades a period of music from one amplitude to another. (A:3392)
+function aukit.effects.fade(audio, startTime, startAmplitude, endTime, endAmplitude)
+    expectAudio(1, audio)
+    expect(2, startTime, "number")
+    expect(3, startAmplitude, "number")
+    expect(4, endTime, "number")
+    expect(5, endAmplitude, "number")
+    if startAmplitude == 1 and endAmplitude == 1 then return audio end
+    cu.fade(handle(audio), startTime, startAmplitude, endTime, endAmplitude)
+    invalidate(audio)
+    return audio
+end
+
+--- Adds a delay to the specified audio. (A:3500)
+function aukit.effects.delay(audio, delay, multiplier)
+    expectAudio(1, audio)
+    expect(2, delay, "number")
+    multiplier = expect(3, multiplier, "number", "nil") or 0.5
+    cu.delay(handle(audio), delay, multiplier)
+    invalidate(audio)
+    return audio
+end
+
+--- Centers the DC offset of each channel. (A:3465)
+function aukit.effects.center(audio)
+    expectAudio(1, audio)
+    cu.center(handle(audio))
+    invalidate(audio)
+    return audio
+end
+
 --- Applies a low-pass filter to the specified audio. (A:3586; auplay.lua:30)
 function aukit.effects.lowpass(audio, frequency)
     expectAudio(1, audio)

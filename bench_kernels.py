@@ -120,6 +120,15 @@ def main():
     report("K8 absmax 2ch", ms, n * 2 * 4, n * 2, "samples")
     ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_scale_clamp(ctx.handle, x.data_ptr(), n, 2, n, 1.0, 0, dmax.data_ptr())))
     report("K9 scale_clamp 2ch", ms, n * 2 * 8, n * 2, "samples")
+    # ---- K13 remaining in-place effects (8f rank 4): 8 B per touched sample
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_invert(ctx.handle, x.data_ptr(), n, 2, n)))
+    report("K13 invert 2ch", ms, n * 2 * 8, n * 2, "samples")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_fade(ctx.handle, x.data_ptr(), n, 2, n, 48000.0, 1.0, 0.5, (n - 1) / 48000.0, 1.0)))
+    report("K13 fade 2ch (whole buffer)", ms, n * 2 * 8, n * 2, "samples")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_center(ctx.handle, x.data_ptr(), n, 2, n, 48000.0)))
+    report("K13 center 2ch (1 s blocks)", ms, n * 2 * 8, n * 2, "samples", "a block's second read (subtract) is L2-resident: 4 B read + 4 B written from HBM")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_delay(ctx.handle, x.data_ptr(), n, 2, n, 48000.0, 0.25, 0.5)))
+    report("K13 delay 2ch", ms, n * 2 * 20, n * 2, "samples", "copy (4+4) + two reads + one write per sample")
     # ---- K12 requantisation (8f rank 2): Audio:pcm values (fp64 out) and packed s16 / u8 bytes
     ev = torch.empty(n * 2, dtype=torch.float64, device="cuda")
     ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_encode_pcm(ctx.handle, x.data_ptr(), n, 2, n, 16, 0, 1, ev.data_ptr())))

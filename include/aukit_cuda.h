@@ -165,6 +165,14 @@ int aukit_cuda_scale_clamp(aukit_ctx *ctx, aukit_audio *a, double peakAmplitude,
  * Single pass, chained tiles (decoupled look-back), fp64 state. */
 int aukit_cuda_lowpass(aukit_ctx *ctx, aukit_audio *a, double frequency);
 
+/* The remaining elementwise in-place effects: effects.invert A:3412, effects.fade A:3392, effects.delay A:3500,
+ * effects.center A:3465 (argument meaning as in the reference; times in seconds). */
+int aukit_cuda_invert(aukit_ctx *ctx, aukit_audio *a);
+int aukit_cuda_fade(aukit_ctx *ctx, aukit_audio *a, double startTime, double startAmplitude,
+                    double endTime, double endAmplitude);
+int aukit_cuda_delay(aukit_ctx *ctx, aukit_audio *a, double delay, double multiplier);
+int aukit_cuda_center(aukit_ctx *ctx, aukit_audio *a);
+
 /* Audio:pcm(bitDepth, dataType, interleaved) A:901-911 -> encodePCM A:868-894: every sample as
  * d * (d < 0 ? 2^(b-1) : 2^(b-1)-1) + (unsigned ? 2^(b-1) : 0), UN-ROUNDED like the reference's Lua
  * numbers, written as doubles to h_out[frames*channels] (interleaved: [n*C + c], else [c*frames + n]). */
@@ -203,6 +211,13 @@ int aukit_cuda_dev_amplify(aukit_ctx *ctx, float *d, size_t stride, int channels
                            double multiplier);
 int aukit_cuda_dev_lowpass(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,
                            double frequency, double sampleRate);
+int aukit_cuda_dev_invert(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n);
+int aukit_cuda_dev_fade(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n, double sampleRate,
+                        double startTime, double startAmplitude, double endTime, double endAmplitude);
+int aukit_cuda_dev_delay(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,
+                         double sampleRate, double delay, double multiplier);
+int aukit_cuda_dev_center(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,
+                          double sampleRate);
 int aukit_cuda_dev_encode_pcm(aukit_ctx *ctx, const float *d, size_t stride, int channels, size_t n,
                               int bitDepth, int dataType, int interleaved, double *d_out);
 int aukit_cuda_dev_encode_pcm_bytes(aukit_ctx *ctx, const float *d, size_t stride, int channels,

@@ -524,6 +524,78 @@ double auko_encode_pcm(double d, int bitDepth, int dataType) {               /* 
     return d * (d < 0 ? maxValue : maxValue - 1) + add;
 }
 
+/* ---------------------------------------------------------------- more in-place effects */
+/* table read with a float key: a non-integer key has no entry */
+static double tgetx(const double *d, size_t n, double idx, int *nil) {
+    if (idx != floor(idx)) { *nil = 1; return 0; }
+    return tget(d, n, idx, nil);
+}
+
+int auko_invert(double *d, size_t stride, int channels, size_t n) {          /* A:3412-3419 */
+    g_err[0] = 0;
+    for (int c = 0; c < channels; c++)
+        for (size_t i = 0; i < n; i++) d[(size_t)c * stride + i] = -d[(size_t)c * stride + i];
+    return 0;
+}
+
+int auko_fade(double *d, size_t stride, int channels, size_t n, double sampleRate, double startTime,
+              double startAmplitude, double endTime, double endAmplitude) {  /* A:3392-3410 */
+    g_err[0] = 0;
+    if (startAmplitude == 1 && endAmplitude == 1) return 0;
+    for (int c = 0; c < channels; c++) {
+        double *ch = d + (size_t)c * stride;
+        double start = startTime * sampleRate;
+        double m = (endAmplitude - startAmplitude) / ((endTime - startTime) * sampleRate);
+        for (double i = start; i <= endTime * sampleRate; i = i + 1) {
+            int nil;
+            double v = tgetx(ch, n, i, &nil);                                 /* non-integer or out-of-range key: nil */
+            if (nil) return fail("attempt to perform arithmetic on a nil value (field '?')");
+            ch[(size_t)i - 1] = clampd(v * (m * (i - start) + startAmplitude), -1, 1);
+        }
+    }
+    return 0;
+}
+
+int auko_delay(double *d, size_t stride, int channels, size_t n, double sampleRate, double delay,
+               double multiplier) {                                          /* A:3500-3513 */
+    g_err[0] = 0;
+    double samples = floor(delay * sampleRate);
+    double *original = (double *)malloc(sizeof(double) * (n ? n : 1));
+    for (int c = 0; c < channels; c++) {
+        double *o = d + (size_t)c * stride;
+        for (size_t i = 0; i < n; i++) original[i] = o[i];
+        for (double i = samples + 1; i <= (double)n; i = i + 1) {
+            int nil1, nil2;
+            double a = tgetx(o, n, i, &nil1), b = tgetx(original, n, i - samples, &nil2);
+            if (nil1 || nil2) { free(original); return fail("attempt to perform arithmetic on a nil value (field '?')"); }
+            o[(size_t)i - 1] = clampd(a + b * multiplier, -1, 1);
+        }
+    }
+    free(original);
+    return 0;
+}
+
+int auko_center(double *d, size_t stride, int channels, size_t n, double sampleRate) {   /* A:3465-3478 */
+    g_err[0] = 0;
+    if (!(sampleRate > 0)) return fail("'for' step must be positive");
+    for (int c = 0; c < channels; c++) {
+        double *ch = d + (size_t)c * stride;
+        for (double i = 0; i <= (double)n - 1; i = i + sampleRate) {
+            double avg = 0;
+            double l = (double)n - i < sampleRate ? (double)n - i : sampleRate;
+            for (double j = 1; j <= l; j = j + 1) {
+                int nil;
+                double v = tgetx(ch, n, i + j, &nil);
+                if (nil) return fail("attempt to perform arithmetic on a nil value (field '?')");
+                avg = avg + v;
+            }
+            avg = avg / l;
+            for (double j = 1; j <= l; j = j + 1) ch[(size_t)(i + j) - 1] = clampd(ch[(size_t)(i + j) - 1] - avg, -1, 1);
+        }
+    }
+    return 0;
+}
+
 /* Audio:pcm(bitDepth, dataType, interleaved), A:901-911 -> encodePCM(info, 1), A:868-894.
  * out holds channels*n numbers: interleaved data[(n-1)*nc+c] (A:883), else data[(c-1)*len+n] (A:894). */
 int auko_audio_pcm(const double *d, size_t stride, int channels, size_t n, int bitDepth, int dataType,

@@ -95,6 +95,12 @@ int auko_normalize(double *d, size_t stride, int channels, size_t n, double peak
 
 /* encodePCM's per-sample formula (A:874): d*(d<0 and max or max-1)+add, un-rounded. */
 double auko_encode_pcm(double d, int bitDepth, int dataType);
+/* effects.invert A:3412, effects.fade A:3392, effects.delay A:3500, effects.center A:3465 (in place) */
+int auko_invert(double *d, size_t stride, int channels, size_t n);
+int auko_fade(double *d, size_t stride, int channels, size_t n, double sampleRate, double startTime,
+              double startAmplitude, double endTime, double endAmplitude);
+int auko_delay(double *d, size_t stride, int channels, size_t n, double sampleRate, double delay, double multiplier);
+int auko_center(double *d, size_t stride, int channels, size_t n, double sampleRate);
 /* Audio:pcm (A:901-911): all samples through encodePCM into a flat array (interleaved or channel-major). */
 int auko_audio_pcm(const double *d, size_t stride, int channels, size_t n, int bitDepth, int dataType,
                    int interleaved, double *out);

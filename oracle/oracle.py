@@ -68,6 +68,10 @@ def lib():
         L.auko_audio_pcm.argtypes = [dp, sz, C.c_int, sz, C.c_int, C.c_int, C.c_int, dp]
         L.auko_au_parse.argtypes = [u8p, sz, C.c_void_p]
         L.auko_aiff_parse.argtypes = [u8p, sz, C.c_void_p]
+        L.auko_invert.argtypes = [dp, sz, C.c_int, sz]
+        L.auko_fade.argtypes = [dp, sz, C.c_int, sz, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.auko_delay.argtypes = [dp, sz, C.c_int, sz, C.c_double, C.c_double, C.c_double]
+        L.auko_center.argtypes = [dp, sz, C.c_int, sz, C.c_double]
         L.auko_lowpass.argtypes = [dp, sz, C.c_int, sz, C.c_double, C.c_double]
         L.auko_wav_parse.argtypes = [u8p, sz, C.c_void_p]
         L.auko_chain_s16.argtypes = [u8p, sz, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.POINTER(sz)]
@@ -203,6 +207,29 @@ def lowpass(x: np.ndarray, frequency, sampleRate):
     ch, n = x.shape
     _check(lib().auko_lowpass(_ptr(x), n, ch, n, float(frequency), float(sampleRate)))
     return x
+
+
+def _inplace(fn, x, *args):
+    x = np.array(np.atleast_2d(x), dtype=np.float64, order="C")
+    ch, n = x.shape
+    _check(fn(_ptr(x), n, ch, n, *[float(a) for a in args]))
+    return x
+
+
+def invert(x):
+    return _inplace(lib().auko_invert, x)
+
+
+def fade(x, sampleRate, startTime, startAmplitude, endTime, endAmplitude):
+    return _inplace(lib().auko_fade, x, sampleRate, startTime, startAmplitude, endTime, endAmplitude)
+
+
+def delay(x, sampleRate, delay, multiplier=0.5):
+    return _inplace(lib().auko_delay, x, sampleRate, delay, multiplier)
+
+
+def center(x, sampleRate):
+    return _inplace(lib().auko_center, x, sampleRate)
 
 
 def audio_pcm(x: np.ndarray, bitDepth=8, dataType="signed", interleaved=True) -> np.ndarray:

@@ -72,6 +72,13 @@ def run_case(R, case, blobs):
         a = R.call("au", blobs["in"])[0]
     elif op == "aiff":
         a = R.call("aiff", blobs["in"], A.get("head", False))[0]
+    elif op in ("invert", "fade", "delay", "center"):
+        a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
+        extra = {"invert": [], "center": [],
+                 "fade": [A.get("startTime"), A.get("startAmplitude"), A.get("endTime"), A.get("endAmplitude")],
+                 "delay": [A.get("delay"), A.get("multiplier")]}[op]
+        r = call(R.fn("effects", op), [a] + [to_lua(v) for v in extra])[0]
+        assert r is a
     elif op == "pcm_out":
         a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
         t = R.method(a, "pcm", A.get("bitDepth"), A.get("dataType"), A.get("interleaved"))[0]
@@ -304,6 +311,23 @@ def main():
         add("resample_sinc_%d_%d" % (src, dst), "resample", dict(sampleRate=src, targetRate=dst, interpolation="sinc"), x=zs)
     add("resample_sinc_short", "resample", dict(sampleRate=22050, targetRate=48000, interpolation="sinc"), x=zs[:1, :7])
     add("resample_sinc_loud", "resample", dict(sampleRate=44100, targetRate=48000, interpolation="sinc"), x=zs[:1, :300] * 1.4)
+
+    # ---- effects.invert / fade / delay / center
+    ze = rng2.uniform(-1, 1, (2, 2500)) + 0.2
+    add("invert_2ch", "invert", dict(sampleRate=1000), x=ze)
+    add("fade_out", "fade", dict(sampleRate=1000, startTime=0.5, startAmplitude=1.0, endTime=2.0, endAmplitude=0.0), x=ze)
+    add("fade_in_boost", "fade", dict(sampleRate=1000, startTime=0.001, startAmplitude=0.0, endTime=1.2345, endAmplitude=1.7), x=ze)
+    add("fade_noop", "fade", dict(sampleRate=1000, startTime=0.5, startAmplitude=1, endTime=2.0, endAmplitude=1), x=ze)
+    add("fade_fractional_start", "fade", dict(sampleRate=1000, startTime=0.0005, startAmplitude=0.5, endTime=1.0, endAmplitude=1.0), x=ze)
+    add("fade_from_zero_time", "fade", dict(sampleRate=1000, startTime=0.0, startAmplitude=0.5, endTime=1.0, endAmplitude=1.0), x=ze)
+    add("fade_past_end", "fade", dict(sampleRate=1000, startTime=1.0, startAmplitude=0.5, endTime=3.0, endAmplitude=1.0), x=ze)
+    add("delay_default", "delay", dict(sampleRate=1000, delay=0.3, multiplier=None), x=ze)
+    add("delay_loud", "delay", dict(sampleRate=1000, delay=0.0105, multiplier=1.5), x=ze)
+    add("delay_longer_than_audio", "delay", dict(sampleRate=1000, delay=5.0, multiplier=0.5), x=ze)
+    add("delay_negative", "delay", dict(sampleRate=1000, delay=-0.1, multiplier=0.5), x=ze)
+    add("center_blocks", "center", dict(sampleRate=1000), x=ze)
+    add("center_one_block", "center", dict(sampleRate=48000), x=ze[:, :300])
+    add("center_fractional_rate", "center", dict(sampleRate=1000.5), x=ze)
 
     # ---- run everything through the reference
     manifest = []

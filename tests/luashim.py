@@ -117,6 +117,14 @@ def make_module(ak):
             raise LuaError(lib.aukit_cuda_last_error())
         return []
 
+    def simple(fn, nargs, defaults=()):
+        def g(a):
+            vals = [float(num(a[i + 1] if len(a) > i + 1 else None, defaults[i] if i < len(defaults) else None)) for i in range(nargs)]
+            if fn(ctx.handle, a[0].audio._h, *vals) != 0:
+                raise LuaError(lib.aukit_cuda_last_error())
+            return []
+        return g
+
     def l_pcm_out(a):
         au = a[0].audio
         out = np.empty(au.frames * au.channels(), dtype=np.float64)
@@ -156,7 +164,9 @@ def make_module(ak):
 
     mod = LuaTable()
     for name, f in {"pcm": l_pcm, "g711": l_g711, "wav": l_wav, "resample": l_resample, "mono": l_mono, "amplify": l_amplify,
-                    "lowpass": l_lowpass, "pcm_out": l_pcm_out, "au": l_au, "aiff": l_aiff, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
+                    "lowpass": l_lowpass, "pcm_out": l_pcm_out, "invert": simple(lib.aukit_cuda_invert, 0),
+                    "fade": simple(lib.aukit_cuda_fade, 4), "delay": simple(lib.aukit_cuda_delay, 2, (None, 0.5)),
+                    "center": simple(lib.aukit_cuda_center, 0), "au": l_au, "aiff": l_aiff, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
                     "channels": lambda a: [float(a[0].audio.channels())],
                     "sample_rate": lambda a: [float(lib.aukit_cuda_audio_sample_rate(a[0].audio._h))]}.items():
         mod.set(name.encode(), LuaFunction(f, "aukit_cuda." + name))

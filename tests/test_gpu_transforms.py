@@ -458,3 +458,25 @@ def test_resample_sinc_matches_oracle_and_shards(ak, O, src, dst, ch):
     assert f32_equal_bits(np.concatenate(parts, axis=1), got)
     with pytest.raises(ak.AukitError, match="Audio:resample only"):
         ak.preload(bytes(4000), 16, "signed", 2, 44100, 48000, "sinc", True, 0.8)
+
+
+def test_more_effects_match_oracle_at_size(ak, O):
+    """effects.invert / fade / delay / center (A:3392-3513) on buffers that span many CTAs and centre blocks."""
+    rate, n = 8000, 1_000_003
+    x = (np.random.default_rng(77).uniform(-1, 1, (2, n)) * 0.9 + 0.05).astype(np.float32)
+    xd = x.astype(np.float64)
+    a = ak.Audio.from_numpy(x, rate)
+    assert ak.effects.invert(a) is a and np.array_equal(a.numpy(), -x)
+    a = ak.Audio.from_numpy(x, rate)
+    ak.effects.fade(a, 1.0, 0.25, 100.0, 1.75)
+    assert float(np.max(np.abs(a.numpy() - O.fade(xd, rate, 1.0, 0.25, 100.0, 1.75)))) <= TOL
+    a = ak.Audio.from_numpy(x, rate)
+    ak.effects.delay(a, 0.37, 0.8)
+    assert float(np.max(np.abs(a.numpy() - O.delay(xd, rate, 0.37, 0.8)))) <= TOL
+    a = ak.Audio.from_numpy(x, rate)
+    ak.effects.center(a)
+    assert float(np.max(np.abs(a.numpy() - O.center(xd, rate)))) <= TOL
+    with pytest.raises(ak.AukitError, match="arithmetic on a nil value"):
+        ak.effects.fade(ak.Audio.from_numpy(x, rate), 0.00001, 0.5, 1.0, 1.0)
+    with pytest.raises(ak.AukitError, match="arithmetic on a nil value"):
+        ak.effects.delay(ak.Audio.from_numpy(x, rate), -1.0)
