@@ -483,7 +483,7 @@ __device__ __forceinline__ void ms_record_nibs(const ms_rec<TC> &r, const uint8_
 
 // requires spb % 4 == 0 and 16-byte aligned output rows; chain layout as ms_adpcm_kernel
 template <int TC, int NQ>
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(128, NQ == 16 ? 6 : 8)               // NQ = 16: shared memory allows 6 CTAs anyway
 ms_adpcm_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, int literal_mono,
                       size_t nblocks, size_t spb, const __grid_constant__ ms_coefs coefs,
                       float *__restrict__ out, size_t stride, int *status) {
@@ -533,14 +533,15 @@ ms_adpcm_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, i
             s1 = gs.s1; s2 = gs.s2; delta = gs.delta;
             return v;
         };
-        ms_rec<TC> rec = ms_load_rec<TC>(blk, 0);
-        ms_rec<TC> rec_next = ms_load_rec<TC>(blk, nquads > 1 ? 1 : 0);
+        // records are fetched four quads ahead of their use (a ring of 4, statically indexed inside the unrolled
+        // period): ncu showed the chain stalled on the record loads with only two in flight
+        ms_rec<TC> ring[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) ring[i] = ms_load_rec<TC>(blk, i < nquads ? i : 0);
         // samples 4j..4j+3 of the block; `first`: the two header samples lead (A:1312-1315)
-        auto quad = [&](int j, bool first) -> float4 {
+        auto quad = [&](int j, bool first, const ms_rec<TC> &rec) -> float4 {
             int nb[4];
             ms_record_nibs<TC>(rec, blk, C, c, cs, j, nb);
-            rec = rec_next;
-            if (j + 2 < nquads) rec_next = ms_load_rec<TC>(blk, j + 2); // two quads in flight while the chain runs
             const bool quick = narrow && delta < (1 << 14) && delta > -(1 << 16);
             float4 v;
             if (first) {
@@ -557,16 +558,29 @@ ms_adpcm_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, i
         size_t col = 0;
         const int nper = nquads / NQ;
         for (int per = 0; per < nper; per++, col += 4 * NQ) {
-            stage_put<NQ>(st, lane, 0, quad(NQ * per, per == 0));
+            if (TC > 0) {
+                // the records of one period span NQ * 2C bytes; every eighth record load opened a new 128-byte line
+                // and waited for DRAM (ncu: a third of all stall samples) -- ask for the next period's lines now
+                const uint8_t *nx = blk + (size_t)(2 * TC) * (size_t)(3 + NQ * (per + 1));
 #pragma unroll
-            for (int q = 1; q < NQ; q++) stage_put<NQ>(st, lane, q, quad(NQ * per + q, false));
+                for (int o = 0; o < NQ * 2 * TC; o += 128)
+                    if (nx + o < blk + blockAlign) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + o));
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const int j = NQ * per + q;
+                const ms_rec<TC> rec = ring[q & 3];
+                if (j + 4 < nquads) ring[q & 3] = ms_load_rec<TC>(blk, j + 4);
+                stage_put<NQ>(st, lane, q, quad(j, q == 0 && per == 0, rec));
+            }
             __syncwarp();
             stage_flush<NQ>(st, out, rowb, col, lane, NQ);
             __syncwarp();
         }
         const int rem = nquads - nper * NQ;
         if (rem) {
-            for (int q = 0; q < rem; q++) stage_put<NQ>(st, lane, q, quad(NQ * nper + q, nper == 0 && q == 0));
+            for (int q = 0; q < rem; q++)
+                stage_put<NQ>(st, lane, q, quad(NQ * nper + q, nper == 0 && q == 0, ms_load_rec<TC>(blk, NQ * nper + q)));
             __syncwarp();
             stage_flush<NQ>(st, out, rowb, col, lane, rem);
             __syncwarp();
