@@ -13,6 +13,7 @@
 //
 // One thread per output frame: the position is computed once and shared by all channels.
 #include "common.cuh"
+#include <stdlib.h>
 #include "pipeline.cuh"
 
 #include <math.h>
@@ -33,7 +34,21 @@ struct resample_args {
     double y;             // RN(1 / ratio)
     int quotient_fma_ok;  // host-proved: fma(fma(-q0, r, n), y, q0) == RN(n / r) over the whole index range
     double base_d;        // (double)(in_first + 1): 1-based index of the first frame held in `in`
+    const float2 *sinc_tab;        // [L][21] {weight, d(weight)/d(fx)} at fx = j / L, or null (sinc only)
+    unsigned long long L, M;       // dst / gcd, src / gcd when sinc_tab is set
 };
+
+// sinc weights of A:273-276 at the L rational phases, in fp64, with their derivative for the first-order
+// correction to the reference's own (rounded) fraction
+__global__ void sinc_table_kernel(float2 *tab, unsigned long long L) {
+    const unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= L * 21) return;
+    const double fx = (double)(e / 21) / (double)L;
+    const double px = 3.14159265358979323846 * (fx - (double)((int)(e % 21) - 10));
+    if (px == 0.0) { tab[e] = make_float2(1.0f, 0.0f); return; }
+    const double sn = sin(px), cs = cos(px);
+    tab[e] = make_float2((float)(sn / px), (float)(3.14159265358979323846 * (cs * px - sn) / (px * px)));
+}
 
 template <int MODE, bool QFMA>
 __global__ void __launch_bounds__(256) resample_kernel(resample_args a) {
@@ -72,10 +87,33 @@ __global__ void __launch_bounds__(256) resample_kernel(resample_args a) {
             // signal skipped (not clamped).  The 21 weights are evaluated in fp64 like the reference's and shared
             // by the channels of the frame.
             float w[21];
+            bool tabled = false;
+            if (a.sinc_tab && !hit) {
+                // rational position n*M/L = F + j/L: when the reference's floor agrees (it can be one lower at an
+                // exact multiple, SURVEY finding 5) the weights come from row j of the table, corrected to first
+                // order for the difference between j/L and the reference's rounded fraction
+                const unsigned long long nm = i0 * a.M, F = nm / a.L, j = nm - F * a.L;
+                // shift = 1: the reference's floor is one below the rational one (only at exact multiples, j == 0):
+                // its fraction is then just under 1, i.e. phase 0 seen from one tap earlier
+                const int shift = (int)((long long)F + 1 - f);
+                if (shift == 0 || (shift == 1 && j == 0)) {
+                    tabled = true;
+                    const float dfx = (float)(fxd - ((double)j / (double)a.L + (double)shift));
+                    const float2 *row = a.sinc_tab + j * 21;
 #pragma unroll
-            for (int k = -10; k <= 10; k++) {
-                const double px = 3.14159265358979323846 * (fxd - (double)k);
-                w[k + 10] = (f + k >= 1 && f + k <= n) ? (px == 0.0 ? 1.0f : (float)(sin(px) / px)) : 0.0f;
+                    for (int k = 0; k < 21; k++) {
+                        float2 t = make_float2(0.f, 0.f);
+                        if (k - shift >= 0) t = __ldg(row + (k - shift));
+                        w[k] = (f + k - 10 >= 1 && f + k - 10 <= n) ? __fmaf_rn(dfx, t.y, t.x) : 0.0f;
+                    }
+                }
+            }
+            if (!tabled) {
+#pragma unroll
+                for (int k = -10; k <= 10; k++) {
+                    const double px = 3.14159265358979323846 * (fxd - (double)k);
+                    w[k + 10] = (f + k >= 1 && f + k <= n) ? (px == 0.0 ? 1.0f : (float)(sin(px) / px)) : 0.0f;
+                }
             }
             for (int c = 0; c < a.channels; c++) {
                 const float *ch = a.in + (size_t)c * a.in_stride;
@@ -217,6 +255,22 @@ extern "C" int aukit_cuda_dev_resample(aukit_ctx *ctx, const float *d_in, size_t
     a.y = 1.0 / a.ratio;
     a.quotient_fma_ok = aukit_quotient_fma_is_exact(a.ratio, 44) ? 1 : 0;
     a.base_d = (double)(in_first + 1);
+    a.sinc_tab = nullptr; a.L = a.M = 0;
+    void *tab = nullptr;
+    if (interpolation == AUKIT_INTERP_SINC && srcRate == floor(srcRate) && dstRate == floor(dstRate) && srcRate >= 1 &&
+        dstRate >= 1 && srcRate < 2147483648.0 && dstRate < 2147483648.0 && !getenv("AUKIT_DISABLE_SINC_TABLE")) {
+        unsigned long long x = (unsigned long long)srcRate, y = (unsigned long long)dstRate;
+        while (y) { const unsigned long long t = x % y; x = y; y = t; }
+        const unsigned long long L = (unsigned long long)dstRate / x, M = (unsigned long long)srcRate / x;
+        // n * M must stay in 64 bits and the rational fraction within the correction's reach of the reference's
+        if (L <= 4096 && (double)(out_first + n_out) * (double)M < 9.0e18 && (double)(out_first + n_out) / a.ratio < 268435456.0) {
+            if (aukit_dev_alloc(ctx, (size_t)L * 21 * sizeof(float2), &tab)) return -1;
+            sinc_table_kernel<<<(unsigned)((L * 21 + 255) / 256), 256, 0, ctx->stream>>>(static_cast<float2 *>(tab), L);
+            ctx->launches++;
+            a.sinc_tab = static_cast<const float2 *>(tab);
+            a.L = L; a.M = M;
+        }
+    }
     const int threads = 256;
     const unsigned grid = aukit_grid(n_out, threads, (size_t)ctx->num_sms * 8 * 8);
 #define AUKIT_RS(MODE) \
@@ -230,5 +284,6 @@ extern "C" int aukit_cuda_dev_resample(aukit_ctx *ctx, const float *d_in, size_t
     }
 #undef AUKIT_RS
     ctx->launches++;
+    if (tab) aukit_dev_free(ctx, tab);
     return aukit_cuda_check(cudaGetLastError(), "resample_kernel launch");
 }
