@@ -102,6 +102,8 @@ SIGNATURES = {
     "aukit_cuda_dev_delay": (_I, [_P, _P, _SZ, _I, _SZ, _D, _D, _D]),
     "aukit_cuda_dev_center": (_I, [_P, _P, _SZ, _I, _SZ, _D]),
     "aukit_cuda_lowpass": (_I, [_P, _P, _D]),
+    "aukit_cuda_highpass": (_I, [_P, _P, _D]),
+    "aukit_cuda_dev_highpass": (_I, [_P, _P, _SZ, _I, _SZ, _D, _D]),
     "aukit_cuda_audio_pcm": (_I, [_P, _P, _I, _I, _I, _P]),
     "aukit_cuda_audio_pcm_bytes": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "aukit_cuda_dev_encode_pcm": (_I, [_P, _P, _SZ, _I, _SZ, _I, _I, _I, _P]),

@@ -543,6 +543,13 @@ class effects:
         return audio
 
     @staticmethod
+    def highpass(audio: Audio, frequency) -> Audio:                        # A:3605
+        _expect_audio(1, audio)
+        _expect(2, frequency, float)
+        _lib.check(audio._ctx.lib.aukit_cuda_highpass(audio._ctx.handle, audio._h, float(frequency)))
+        return audio
+
+    @staticmethod
     def normalize(audio: Audio, peakAmplitude=None, independent=None) -> Audio:   # A:3431
         _expect_audio(1, audio)
         peakAmplitude = _expect(2, peakAmplitude, float, type(None))

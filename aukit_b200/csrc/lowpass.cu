@@ -66,9 +66,13 @@ __device__ __forceinline__ void lp_fetch_tile(float *tile, const float *base, in
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// HIGH = false: effects.lowpass, y = y + a (x - y), per-step ratio b = 1 - a.
+// HIGH = true:  effects.highpass (A:3605-3618), y = a ((y + x) - x_prev), per-step ratio b = a, y[1] = x[1]; the
+//               previous INPUT sample across a tile boundary comes from `xb` (saved before anything is overwritten).
+template <bool HIGH>
 __global__ void __launch_bounds__(LP_THREADS, LP_CTAS_PER_SM)
 lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, double a, double b,
-               lp_slot *slots, unsigned long long *ticket, unsigned long long tiles_per_ch) {
+               lp_slot *slots, unsigned long long *ticket, unsigned long long tiles_per_ch, const float *__restrict__ xb) {
     __shared__ __align__(16) float tiles[2][LP_THREADS * LP_ROW];      // double buffered: see the loop
     __shared__ double pt_pow[LP_THREADS];        // ((1-a)^16)^t
     __shared__ double warp_tot[LP_THREADS / 32];
@@ -108,16 +112,29 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
         if (next_id < total) { next_base = tile_base(next_id, next_cnt); lp_fetch_tile(tiles[(it + 1) & 1], next_base, next_cnt, t); }
         const int ch = (int)(id / tiles_per_ch);
         const unsigned long long tl = id % tiles_per_ch;
-        // ---- zero-start run of this thread's samples (the reference's step, A:3593-3594).  Samples past the
-        // end of the channel are zeros: they only decay the state, which nothing reads afterwards.
-        double s = 0.0;
+        // one step of the reference's loop (A:3593-3594 / A:3613-3615); `first` = the channel's first sample,
+        // which both effects leave as it is
+        auto step = [&](double y, float x, double &xp, bool first) -> double {
+            if (!HIGH) return y + a * ((double)x - y);
+            const double xd = (double)x;
+            const double r = first ? xd : a * ((y + xd) - xp);
+            xp = xd;
+            return r;
+        };
+        // input sample just before this thread's first one (highpass only); read now, the rows are overwritten later
+        double xprev0 = 0.0;
+        if (HIGH) xprev0 = t > 0 ? (double)tile[(t - 1) * LP_ROW + LP_PER - 1] : (tl > 0 ? (double)xb[id] : 0.0);
+        const bool chan_first = HIGH && tl == 0 && t == 0;
+        // ---- zero-start run of this thread's samples.  Samples past the end of the channel are zeros: they
+        // only decay the state, which nothing reads afterwards.
+        double s = 0.0, xp = xprev0;
 #pragma unroll
         for (int k = 0; k < LP_PER / 4; k++) {
             const float4 v = *reinterpret_cast<const float4 *>(&tile[t * LP_ROW + 4 * k]);
-            s = s + a * ((double)v.x - s);
-            s = s + a * ((double)v.y - s);
-            s = s + a * ((double)v.z - s);
-            s = s + a * ((double)v.w - s);
+            s = step(s, v.x, xp, chan_first && k == 0);
+            s = step(s, v.y, xp, false);
+            s = step(s, v.z, xp, false);
+            s = step(s, v.w, xp, false);
         }
         // ---- inclusive scan over the block with ratio pt per thread
         double inc = s;
@@ -141,8 +158,9 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
             for (int w = 0; w < LP_THREADS / 32; w++) agg = fma(p_warp, agg, warp_tot[w]);
             double carry;
             if (tl == 0) {
-                // A:3591: d[1] is untouched, which is what a state equal to d[1] gives (l + a*(l - l) = l)
-                carry = (double)tile[0];
+                // A:3591: d[1] is untouched, which is what a state equal to d[1] gives (l + a*(l - l) = l);
+                // highpass handles its first sample inside step(), so nothing enters the first tile
+                carry = HIGH ? 0.0 : (double)tile[0];
             } else {
                 if (lane == 0) st_slot(&slots[id], agg, 1);
                 double acc = 0.0, scale = 1.0;
@@ -181,13 +199,14 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
         __syncthreads();
         // ---- true run: state entering thread t = pt^t * (tile carry) + (state entering t with a zero tile carry)
         double y = fma(pt_pow[t], s_carry, enter0);
+        xp = xprev0;
 #pragma unroll
         for (int k = 0; k < LP_PER / 4; k++) {
             float4 v = *reinterpret_cast<const float4 *>(&tile[t * LP_ROW + 4 * k]);
-            y = y + a * ((double)v.x - y); v.x = (float)y;
-            y = y + a * ((double)v.y - y); v.y = (float)y;
-            y = y + a * ((double)v.z - y); v.z = (float)y;
-            y = y + a * ((double)v.w - y); v.w = (float)y;
+            y = step(y, v.x, xp, chan_first && k == 0); v.x = (float)y;
+            y = step(y, v.y, xp, false); v.y = (float)y;
+            y = step(y, v.z, xp, false); v.z = (float)y;
+            y = step(y, v.w, xp, false); v.w = (float)y;
             *reinterpret_cast<float4 *>(&tile[t * LP_ROW + 4 * k]) = v;
         }
         __syncthreads();
@@ -208,28 +227,42 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
 
 }  // namespace
 
-extern "C" int aukit_cuda_dev_lowpass(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n, double frequency,
-                                      double sampleRate) {
-    if (!ctx) return aukit_fail("aukit_cuda: null context");
-    if (channels < 1 || n < 2) return 0;                                // for i = 2, #d: nothing to do
-    if (((uintptr_t)d & 15) != 0 || (channels > 1 && stride % 4 != 0))
-        return aukit_fail("aukit_cuda: lowpass needs 16-byte aligned channel rows");
-    const double a = 1.0 - exp(-(frequency / sampleRate) * 2.0 * 3.14159265358979323846);      // A:3589
-    const double b = 1.0 - a;
+// x[tile * 4096 - 1] of every tile after the first, per channel: the highpass step needs the previous INPUT sample
+// and by the time a tile runs its predecessor may already have been overwritten in place
+__global__ void lp_save_boundaries(const float *__restrict__ data, size_t stride, unsigned long long tiles_per_ch,
+                                   unsigned long long total, float *__restrict__ xb) {
+    const unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    const unsigned long long ch = id / tiles_per_ch, tl = id % tiles_per_ch;
+    xb[id] = tl ? data[(size_t)ch * stride + (size_t)tl * LP_TILE - 1] : 0.0f;
+}
+
+static int lp_run(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n, double a, double ratio, bool high) {
     const unsigned long long tiles = (n + LP_TILE - 1) / LP_TILE, total = tiles * (unsigned long long)channels;
-    // scratch: one 16-byte slot per (channel, tile) + the ticket counter
+    // scratch: one 16-byte slot per (channel, tile) + the ticket counter (+ the boundary samples for highpass)
     void *scratch = nullptr;
     const size_t slot_bytes = (size_t)total * sizeof(lp_slot);
-    if (aukit_dev_alloc(ctx, slot_bytes + 16, &scratch)) return -1;
+    const size_t xb_bytes = high ? (((size_t)total * sizeof(float) + 15) & ~(size_t)15) : 0;
+    if (aukit_dev_alloc(ctx, slot_bytes + 16 + xb_bytes, &scratch)) return -1;
     lp_slot *slots = static_cast<lp_slot *>(scratch);
     unsigned long long *ticket = reinterpret_cast<unsigned long long *>(static_cast<char *>(scratch) + slot_bytes);
+    float *xb = high ? reinterpret_cast<float *>(static_cast<char *>(scratch) + slot_bytes + 16) : nullptr;
     int rc = aukit_cuda_check(cudaMemsetAsync(scratch, 0, slot_bytes + 16, ctx->stream), "memset");
+    if (!rc && high) {
+        lp_save_boundaries<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d, stride, tiles, total, xb);
+        ctx->launches++;
+    }
     if (!rc) {
         unsigned long long g = total;
         const unsigned long long cap = (unsigned long long)ctx->num_sms * LP_CTAS_PER_SM;
         if (g > cap) g = cap;
-        cudaFuncSetAttribute(lowpass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        lowpass_kernel<<<(unsigned)g, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, n, a, b, slots, ticket, tiles);
+        if (high) {
+            cudaFuncSetAttribute(lowpass_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            lowpass_kernel<true><<<(unsigned)g, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb);
+        } else {
+            cudaFuncSetAttribute(lowpass_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            lowpass_kernel<false><<<(unsigned)g, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb);
+        }
         ctx->launches++;
         rc = aukit_cuda_check(cudaGetLastError(), "lowpass_kernel launch");
     }
@@ -237,7 +270,32 @@ extern "C" int aukit_cuda_dev_lowpass(aukit_ctx *ctx, float *d, size_t stride, i
     return rc;
 }
 
+extern "C" int aukit_cuda_dev_lowpass(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n, double frequency,
+                                      double sampleRate) {
+    if (!ctx) return aukit_fail("aukit_cuda: null context");
+    if (channels < 1 || n < 2) return 0;                                // for i = 2, #d: nothing to do
+    if (((uintptr_t)d & 15) != 0 || (channels > 1 && stride % 4 != 0))
+        return aukit_fail("aukit_cuda: lowpass needs 16-byte aligned channel rows");
+    const double a = 1.0 - exp(-(frequency / sampleRate) * 2.0 * 3.14159265358979323846);      // A:3589
+    return lp_run(ctx, d, stride, channels, n, a, 1.0 - a, false);
+}
+
+extern "C" int aukit_cuda_dev_highpass(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n, double frequency,
+                                       double sampleRate) {
+    if (!ctx) return aukit_fail("aukit_cuda: null context");
+    if (channels < 1 || n < 2) return 0;
+    if (((uintptr_t)d & 15) != 0 || (channels > 1 && stride % 4 != 0))
+        return aukit_fail("aukit_cuda: highpass needs 16-byte aligned channel rows");
+    const double a = 1.0 / (2.0 * 3.14159265358979323846 * (frequency / sampleRate) + 1.0);       // A:3608
+    return lp_run(ctx, d, stride, channels, n, a, a, true);
+}
+
 extern "C" int aukit_cuda_lowpass(aukit_ctx *ctx, aukit_audio *au, double frequency) {
     if (!ctx || !au) return aukit_fail("aukit_cuda: null argument");
     return aukit_cuda_dev_lowpass(ctx, au->data, au->stride, au->channels, au->frames, frequency, au->sampleRate);
+}
+
+extern "C" int aukit_cuda_highpass(aukit_ctx *ctx, aukit_audio *au, double frequency) {
+    if (!ctx || !au) return aukit_fail("aukit_cuda: null argument");
+    return aukit_cuda_dev_highpass(ctx, au->data, au->stride, au->channels, au->frames, frequency, au->sampleRate);
 }

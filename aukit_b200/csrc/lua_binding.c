@@ -290,6 +290,11 @@ static int l_lowpass(lua_State *L) {
     return 0;
 }
 
+static int l_highpass(lua_State *L) {
+    if (aukit_cuda_highpass(ctx(L), check_audio(L, 1), luaL_checknumber(L, 2))) return fail(L);
+    return 0;
+}
+
 static int l_normalize(lua_State *L) {
     if (aukit_cuda_normalize(ctx(L), check_audio(L, 1), luaL_optnumber(L, 2, 1.0), optbool(L, 3, 0))) return fail(L);
     return 0;
@@ -359,7 +364,7 @@ static int l_gc(lua_State *L) {
 static const luaL_Reg funcs[] = {
     {"pcm", l_pcm}, {"g711", l_g711}, {"adpcm", l_adpcm}, {"ima_adpcm_wav", l_ima_wav}, {"msadpcm", l_msadpcm},
     {"wav", l_wav}, {"new", l_new}, {"resample", l_resample}, {"mono", l_mono}, {"concat", l_concat},
-    {"au", l_au}, {"aiff", l_aiff}, {"amplify", l_amplify}, {"invert", l_invert}, {"fade", l_fade}, {"delay", l_delay}, {"center", l_center}, {"lowpass", l_lowpass}, {"pcm_out", l_pcm_out}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
+    {"au", l_au}, {"aiff", l_aiff}, {"amplify", l_amplify}, {"invert", l_invert}, {"fade", l_fade}, {"delay", l_delay}, {"center", l_center}, {"lowpass", l_lowpass}, {"highpass", l_highpass}, {"pcm_out", l_pcm_out}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
     {"frames", l_frames}, {"read", l_read}, {"write", l_write}, {NULL, NULL}};
 
 int luaopen_aukit_cuda(lua_State *L) {

@@ -346,6 +346,15 @@ function aukit.effects.lowpass(audio, frequency)
     return audio
 end
 
+--- Applies a high-pass filter to the specified audio. (A:3605)
+function aukit.effects.highpass(audio, frequency)
+    expectAudio(1, audio)
+    expect(2, frequency, "number")
+    cu.highpass(handle(audio), frequency)
+    invalidate(audio)
+    return audio
+end
+
 --- Normalizes audio to the specified peak amplitude. (A:3431)
 function aukit.effects.normalize(audio, peakAmplitude, independent)
     expectAudio(1, audio)

@@ -143,6 +143,8 @@ def main():
     for f in (24000.0, 200.0):
         ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_lowpass(ctx.handle, x.data_ptr(), n, 2, n, f, 48000.0)))
         report("K11 lowpass 2ch f=%g Hz" % f, ms, n * 2 * 8, n * 2, "samples", "chained-tile scan, fp64 state")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_highpass(ctx.handle, x.data_ptr(), n, 2, n, 200.0, 48000.0)))
+    report("K11 highpass 2ch f=200 Hz", ms, n * 2 * 8, n * 2, "samples", "same scan, ratio a, saved tile-boundary inputs")
 
 
 if __name__ == "__main__":

@@ -164,6 +164,9 @@ int aukit_cuda_scale_clamp(aukit_ctx *ctx, aukit_audio *a, double peakAmplitude,
  * a = 1 - exp(-(frequency/sampleRate) * 2 pi), d[i] = d[i-1] + a*(d[i] - d[i-1]) for i >= 2 (auplay.lua:30).
  * Single pass, chained tiles (decoupled look-back), fp64 state. */
 int aukit_cuda_lowpass(aukit_ctx *ctx, aukit_audio *a, double frequency);
+/* aukit.effects.highpass(audio, frequency) A:3605-3618: a = 1 / (2 pi frequency/sampleRate + 1),
+ * d[i] = a * (d[i-1] + x[i] - x[i-1]) for i >= 2; the same chained-tile scan with ratio a. */
+int aukit_cuda_highpass(aukit_ctx *ctx, aukit_audio *a, double frequency);
 
 /* The remaining elementwise in-place effects: effects.invert A:3412, effects.fade A:3392, effects.delay A:3500,
  * effects.center A:3465 (argument meaning as in the reference; times in seconds). */
@@ -223,6 +226,8 @@ int aukit_cuda_dev_encode_pcm(aukit_ctx *ctx, const float *d, size_t stride, int
 int aukit_cuda_dev_encode_pcm_bytes(aukit_ctx *ctx, const float *d, size_t stride, int channels,
                                     size_t n, int bitDepth, int dataType, int interleaved,
                                     int rounding, void *d_out);
+int aukit_cuda_dev_highpass(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,
+                            double frequency, double sampleRate);
 int aukit_cuda_dev_absmax(aukit_ctx *ctx, const float *d, size_t stride, int channels, size_t n,
                           int independent, float *d_max);
 int aukit_cuda_dev_scale_clamp(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n,

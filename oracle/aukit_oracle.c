@@ -630,6 +630,23 @@ int auko_lowpass(double *d, size_t stride, int channels, size_t n, double freque
     return 0;
 }
 
+int auko_highpass(double *d, size_t stride, int channels, size_t n, double frequency,
+                  double sampleRate) {                                       /* A:3605-3618 */
+    g_err[0] = 0;
+    double a = 1 / (2 * 3.14159265358979323846 * (frequency / sampleRate) + 1);
+    for (int c = 0; c < channels; c++) {
+        double *ch = d + (size_t)c * stride;
+        if (n == 0) continue;
+        double lx = ch[0];
+        for (size_t i = 1; i < n; i++) {
+            double llx = ch[i];
+            ch[i] = a * (ch[i - 1] + llx - lx);
+            lx = llx;
+        }
+    }
+    return 0;
+}
+
 /* ---------------------------------------------------------------- aukit.wav, A:1456-1574 */
 static const uint8_t guid_tail[12] = {0x00, 0x00, 0x10, 0x00, 0x80, 0x00,
                                       0x00, 0xaa, 0x00, 0x38, 0x9b, 0x71};   /* A:133-139 */

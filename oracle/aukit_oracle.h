@@ -106,6 +106,7 @@ int auko_audio_pcm(const double *d, size_t stride, int channels, size_t n, int b
                    int interleaved, double *out);
 
 /* effects.lowpass (A:3586-3598), in place. */
+int auko_highpass(double *d, size_t stride, int channels, size_t n, double frequency, double sampleRate);
 int auko_lowpass(double *d, size_t stride, int channels, size_t n, double frequency,
                  double sampleRate);
 

@@ -72,6 +72,7 @@ def lib():
         L.auko_fade.argtypes = [dp, sz, C.c_int, sz, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
         L.auko_delay.argtypes = [dp, sz, C.c_int, sz, C.c_double, C.c_double, C.c_double]
         L.auko_center.argtypes = [dp, sz, C.c_int, sz, C.c_double]
+        L.auko_highpass.argtypes = [dp, sz, C.c_int, sz, C.c_double, C.c_double]
         L.auko_lowpass.argtypes = [dp, sz, C.c_int, sz, C.c_double, C.c_double]
         L.auko_wav_parse.argtypes = [u8p, sz, C.c_void_p]
         L.auko_chain_s16.argtypes = [u8p, sz, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.POINTER(sz)]
@@ -230,6 +231,10 @@ def delay(x, sampleRate, delay, multiplier=0.5):
 
 def center(x, sampleRate):
     return _inplace(lib().auko_center, x, sampleRate)
+
+
+def highpass(x, frequency, sampleRate):
+    return _inplace(lib().auko_highpass, x, frequency, sampleRate)
 
 
 def audio_pcm(x: np.ndarray, bitDepth=8, dataType="signed", interleaved=True) -> np.ndarray:

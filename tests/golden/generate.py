@@ -85,9 +85,9 @@ def run_case(R, case, blobs):
         out = R.call("new", 0, 1, A["sampleRate"])[0]          # carrier: one "channel" holding the flat result
         out.get(b"data").arr[0].arr = list(t.arr)
         return out
-    elif op == "lowpass":
+    elif op in ("lowpass", "highpass"):
         a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
-        r = R.call(("effects", "lowpass"), a, A["frequency"])[0]
+        r = R.call(("effects", op), a, A["frequency"])[0]
         assert r is a                           # in place (A:3597)
     elif op in ("resample", "mono", "amplify", "normalize", "chain"):
         if op == "chain":
@@ -328,6 +328,12 @@ def main():
     add("center_blocks", "center", dict(sampleRate=1000), x=ze)
     add("center_one_block", "center", dict(sampleRate=48000), x=ze[:, :300])
     add("center_fractional_rate", "center", dict(sampleRate=1000.5), x=ze)
+
+    # ---- effects.highpass (same scan as lowpass)
+    add("highpass_200hz", "highpass", dict(sampleRate=48000, frequency=200.0), x=ze + 0.3)
+    add("highpass_10khz", "highpass", dict(sampleRate=44100, frequency=10000.0), x=ze)
+    add("highpass_zero_hz", "highpass", dict(sampleRate=8000, frequency=0.0), x=ze[:1, :100])
+    add("highpass_two_samples", "highpass", dict(sampleRate=8000, frequency=100.0), x=np.array([[0.5, -0.5]]))
 
     # ---- run everything through the reference
     manifest = []

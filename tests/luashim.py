@@ -166,7 +166,7 @@ def make_module(ak):
     for name, f in {"pcm": l_pcm, "g711": l_g711, "wav": l_wav, "resample": l_resample, "mono": l_mono, "amplify": l_amplify,
                     "lowpass": l_lowpass, "pcm_out": l_pcm_out, "invert": simple(lib.aukit_cuda_invert, 0),
                     "fade": simple(lib.aukit_cuda_fade, 4), "delay": simple(lib.aukit_cuda_delay, 2, (None, 0.5)),
-                    "center": simple(lib.aukit_cuda_center, 0), "au": l_au, "aiff": l_aiff, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
+                    "center": simple(lib.aukit_cuda_center, 0), "highpass": simple(lib.aukit_cuda_highpass, 1), "au": l_au, "aiff": l_aiff, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
                     "channels": lambda a: [float(a[0].audio.channels())],
                     "sample_rate": lambda a: [float(lib.aukit_cuda_audio_sample_rate(a[0].audio._h))]}.items():
         mod.set(name.encode(), LuaFunction(f, "aukit_cuda." + name))

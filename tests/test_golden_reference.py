@@ -71,6 +71,8 @@ def oracle_run(O, m, i):
         return list(O.normalize(x, 1.0 if A["peak"] is None else A["peak"], bool(A["independent"])))
     if op == "lowpass":
         return list(O.lowpass(x, A["frequency"], A["sampleRate"]))
+    if op == "highpass":
+        return list(O.highpass(x, A["frequency"], A["sampleRate"]))
     if op == "invert":
         return list(O.invert(x))
     if op == "fade":
@@ -152,6 +154,8 @@ def cuda_run(ak, m, i):
         assert ak.effects.amplify(a, A["multiplier"]) is a
     if op == "lowpass":
         assert ak.effects.lowpass(a, A["frequency"]) is a
+    if op == "highpass":
+        assert ak.effects.highpass(a, A["frequency"]) is a
     if op == "invert":
         assert ak.effects.invert(a) is a
     if op == "fade":

@@ -480,3 +480,17 @@ def test_more_effects_match_oracle_at_size(ak, O):
         ak.effects.fade(ak.Audio.from_numpy(x, rate), 0.00001, 0.5, 1.0, 1.0)
     with pytest.raises(ak.AukitError, match="arithmetic on a nil value"):
         ak.effects.delay(ak.Audio.from_numpy(x, rate), -1.0)
+
+
+@pytest.mark.parametrize("n,ch,freq,rate", [(1_000_003, 2, 200.0, 48000), (300_001, 3, 8000.0, 44100), (2_000_000, 1, 0.5, 48000),
+                                            (4097, 2, 1000.0, 48000), (5, 1, 3000.0, 8000)])
+def test_highpass_matches_oracle(ak, O, n, ch, freq, rate):
+    """effects.highpass (A:3605): the lowpass scan with ratio a and input a (x[i] - x[i-1]); 0.5 Hz keeps the
+    state alive across hundreds of tiles, and the tile boundaries need the saved original x[i-1]."""
+    x = (np.random.default_rng(n + 1).uniform(-1, 1, (ch, n)) + 0.3).astype(np.float32)
+    a = ak.Audio.from_numpy(x, rate)
+    assert ak.effects.highpass(a, freq) is a
+    got = a.numpy()
+    ref = O.highpass(x.astype(np.float64), freq, rate)
+    assert np.array_equal(got[:, 0], x[:, 0])
+    assert float(np.max(np.abs(got - ref))) <= 2 * TOL
