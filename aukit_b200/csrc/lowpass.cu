@@ -5,15 +5,15 @@
 // The recurrence y[i] = (1-a) y[i-1] + a x[i] is linear, so a tile's effect on the state is the pair
 // (P, S) = ((1-a)^len, end state from a zero start) and tiles combine associatively.  One pass over
 // HBM (4 B read + 4 B written per sample), single kernel, chained with a decoupled look-back:
-//   * a CTA claims tiles of 4096 samples in order (atomic ticket => every predecessor is running or done);
-//   * the tile is staged through shared memory (coalesced 16-byte accesses both ways); thread t owns 16
+//   * a CTA claims tiles of 8192 samples in order (atomic ticket => every predecessor is running or done);
+//   * the tile is staged through shared memory (coalesced 16-byte accesses both ways); thread t owns 32
 //     consecutive samples and runs the reference's own step on them, first from a zero state (-> S_t);
-//   * S_t are combined by a warp-shuffle scan with the constant ratio (1-a)^16, then across the 8 warps;
+//   * S_t are combined by a warp-shuffle scan with the constant ratio (1-a)^32, then across the 8 warps;
 //   * warp 0 publishes the tile aggregate, looks back over the predecessors' aggregates / inclusive states
 //     (32 at a time, one 16-byte {value, flag} load each, stopping early once (1-a)^k has decayed below
 //     2^-80) and publishes the inclusive state;
 //   * the next tile's loads are issued before any of this, so they are in flight meanwhile;
-//   * every thread re-runs its 16 steps from its true incoming state and the tile is written back.
+//   * every thread re-runs its 32 steps from its true incoming state and the tile is written back.
 // Arithmetic is fp64 like the reference's (Lua numbers): in fp32 the rounding error of a low cut-off is
 // amplified by 1/a and would leave the 2^-20 tolerance; the kernel stays HBM-bound either way (6 fp64 ops
 // per sample).  Samples are narrowed to f32 only when stored.
@@ -24,10 +24,11 @@
 namespace {
 
 constexpr int LP_THREADS = 256;
-constexpr int LP_PER = 16;                       // consecutive samples per thread
-constexpr int LP_TILE = LP_THREADS * LP_PER;     // 4096
+constexpr int LP_PER = 32;                       // consecutive samples per thread
+constexpr int LP_TILE = LP_THREADS * LP_PER;     // 8192
 constexpr int LP_ROW = LP_PER + 4;               // padded row: conflict-free 16-byte accesses both ways
-constexpr int LP_CTAS_PER_SM = 5;                // resident CTAs: tiles in flight hide the look-back's L2 round trip
+constexpr size_t LP_SMEM = 2 * (size_t)LP_THREADS * LP_ROW * sizeof(float);
+constexpr int LP_CTAS_PER_SM = 3;                // resident CTAs: tiles in flight hide the look-back's L2 round trip
 
 // Per (channel, tile): ONE 16-byte slot that holds either {aggregate, 1} or {inclusive state, 2}; it is
 // written and read with single 128-bit accesses, so a look-back costs one L2 round trip per window.
@@ -52,7 +53,7 @@ __device__ __forceinline__ void lp_fetch_tile(float *tile, const float *base, in
 #pragma unroll
     for (int k = 0; k < LP_PER / 4; k++) {
         const int i4 = (k * LP_THREADS + t) * 4;                       // first sample of this float4
-        float *dst = &tile[(i4 >> 4) * LP_ROW + (i4 & 15)];
+        float *dst = &tile[(i4 / LP_PER) * LP_ROW + (i4 % LP_PER)];
         if (i4 + 3 < cnt) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(base + i4) : "memory");
         } else {
@@ -73,8 +74,9 @@ template <bool HIGH>
 __global__ void __launch_bounds__(LP_THREADS, LP_CTAS_PER_SM)
 lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, double a, double b,
                lp_slot *slots, unsigned long long *ticket, unsigned long long tiles_per_ch, const float *__restrict__ xb) {
-    __shared__ __align__(16) float tiles[2][LP_THREADS * LP_ROW];      // double buffered: see the loop
-    __shared__ double pt_pow[LP_THREADS];        // ((1-a)^16)^t
+    extern __shared__ __align__(16) float lp_dyn[];                     // two tile buffers (double buffered: see the loop)
+    float *const tiles[2] = {lp_dyn, lp_dyn + LP_THREADS * LP_ROW};
+    __shared__ double pt_pow[LP_THREADS];        // (ratio^LP_PER)^t
     __shared__ double warp_tot[LP_THREADS / 32];
     __shared__ double s_carry;
     __shared__ unsigned long long s_ticket[2];
@@ -213,7 +215,7 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
 #pragma unroll
         for (int k = 0; k < LP_PER / 4; k++) {
             const int i4 = (k * LP_THREADS + t) * 4;
-            const float4 v = *reinterpret_cast<const float4 *>(&tile[(i4 >> 4) * LP_ROW + (i4 & 15)]);
+            const float4 v = *reinterpret_cast<const float4 *>(&tile[(i4 / LP_PER) * LP_ROW + (i4 % LP_PER)]);
             if (i4 + 3 < cnt) stg_stream(reinterpret_cast<float4 *>(base + i4), v);
             else {
                 if (i4 < cnt) base[i4] = v.x;
@@ -227,7 +229,7 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
 
 }  // namespace
 
-// x[tile * 4096 - 1] of every tile after the first, per channel: the highpass step needs the previous INPUT sample
+// x[tile * LP_TILE - 1] of every tile after the first, per channel: the highpass step needs the previous INPUT sample
 // and by the time a tile runs its predecessor may already have been overwritten in place
 __global__ void lp_save_boundaries(const float *__restrict__ data, size_t stride, unsigned long long tiles_per_ch,
                                    unsigned long long total, float *__restrict__ xb) {
@@ -258,10 +260,12 @@ static int lp_run(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t 
         if (g > cap) g = cap;
         if (high) {
             cudaFuncSetAttribute(lowpass_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            lowpass_kernel<true><<<(unsigned)g, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb);
+            cudaFuncSetAttribute(lowpass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP_SMEM);
+            lowpass_kernel<true><<<(unsigned)g, LP_THREADS, LP_SMEM, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb);
         } else {
             cudaFuncSetAttribute(lowpass_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            lowpass_kernel<false><<<(unsigned)g, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb);
+            cudaFuncSetAttribute(lowpass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP_SMEM);
+            lowpass_kernel<false><<<(unsigned)g, LP_THREADS, LP_SMEM, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb);
         }
         ctx->launches++;
         rc = aukit_cuda_check(cudaGetLastError(), "lowpass_kernel launch");

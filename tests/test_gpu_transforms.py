@@ -344,7 +344,7 @@ print("ok", err)
 
 
 @pytest.mark.parametrize("n,ch,freq,rate", [(1_000_003, 2, 24000.0, 48000), (300_001, 3, 200.0, 44100), (2_000_000, 1, 5.0, 48000),
-                                            (4096, 1, 1000.0, 48000), (4097, 2, 1000.0, 48000), (17, 1, 3000.0, 8000),
+                                            (4096, 1, 1000.0, 48000), (4097, 2, 1000.0, 48000), (8192, 1, 1000.0, 48000), (8193, 2, 150.0, 48000), (17, 1, 3000.0, 8000),
                                             (700_000, 1, 0.05, 48000)])
 def test_lowpass_matches_oracle(ak, O, n, ch, freq, rate):
     """effects.lowpass (A:3586): chained-tile scan vs the sequential reference recurrence, incl. cut-offs
