@@ -171,7 +171,7 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
                     const long long j = back - lane;
                     lp_slot sv;
                     sv.v = 0.0; sv.flag = 2;
-                    // only poll predecessors whose weight can still matter: with (1-a)^4096 tiny (any cut-off above
+                    // only poll predecessors whose weight can still matter: with (1-a)^8192 tiny (any cut-off above
                     // a few Hz) that is the nearest one or two, and a tile then waits for those alone instead of
                     // for the slowest of 32 (which locks all CTAs into step; measured 2.4x slower)
                     const bool live = j >= 0 && pl * scale >= 8.3e-25;

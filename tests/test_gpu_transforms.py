@@ -381,6 +381,17 @@ def test_audio_pcm_values_bit_exact_and_bytes(ak, O, bits, dtype, ch, interleave
     rng = np.random.default_rng(bits * 10 + ch)
     x = rng.uniform(-1, 1, (ch, n)).astype(np.float32)
     x[:, :5] = np.array([-1.0, 1.0, 0.0, -0.0, 0.5], dtype=np.float32)
+    if bits <= 24:
+        # adversarial: products that land on or next to integers and exact ties (k, k + 1/2, +- a few ulps)
+        smax = float(2 ** (bits - 1))
+        k = rng.integers(-2 ** (bits - 1), 2 ** (bits - 1), 4000).astype(np.float64)
+        for j, (off, sc) in enumerate(((0.0, smax), (0.5, smax), (0.0, smax - 1), (0.5, smax - 1))):
+            base = ((k[j * 1000:(j + 1) * 1000] + off) / sc).astype(np.float32)
+            for u, tweak in enumerate((0, 1, -1, 2)):
+                seg = np.nextafter(base, np.float32(np.inf if tweak > 0 else -np.inf)) if tweak else base
+                if abs(tweak) == 2:
+                    seg = np.nextafter(seg, np.float32(np.inf))
+                x[0, 100 + (j * 4 + u) * 1000: 100 + (j * 4 + u + 1) * 1000] = np.clip(seg, -1, 1)
     a = ak.Audio.from_numpy(x, 48000)
     got = a.pcm(bits, dtype, interleaved)
     ref = O.audio_pcm(x.astype(np.float64), bits, dtype, interleaved)
