@@ -276,6 +276,49 @@ class Audio:
                                                             C.c_void_p(out.ctypes.data)))
         return out.tobytes()
 
+    def wav(self, bitDepth=None, rounding="floor", dialect=DIALECT_GENERAL) -> bytes:   # A:942-1004
+        """Audio:wav: a RIFF/WAVE file of the samples (8-bit unsigned, otherwise signed PCM).  The reference packs the
+        un-rounded numbers of Audio:pcm with the host's string.pack; `rounding` says how that pack narrows them
+        ("floor", "truncate" = a C cast, "nearest").  Header quirk kept: with metadata the RIFF size field still
+        counts only the header and the samples (A:1001).
+        dialect LITERAL also keeps the chunk arithmetic of A:981-985: values are packed 32768 at a time for
+        i = 1, #data - 32768, 32768, then a tail of #data % 32768 values that starts ONE VALUE EARLY (at index
+        floor(#data / 32768) * 32768) -- so the last value of the file is dropped, a whole final chunk is lost when
+        #data is a multiple of 32768, and fewer than 32768 values raise (the tail's first argument is data[0] = nil)."""
+        import struct
+        bitDepth = _expect(1, bitDepth, float, type(None)) or 16
+        if bitDepth == 1:
+            raise AukitError("aukit_cuda: DFPWM output is outside the accelerated path")
+        if bitDepth not in (8, 16, 24, 32):
+            raise AukitError("bad argument #2 (invalid bit depth)")
+        bitDepth = int(bitDepth)
+        body = self.pcm_bytes(bitDepth, "unsigned" if bitDepth == 8 else "signed", True, rounding)
+        if dialect == DIALECT_LITERAL:
+            B, nvals, cs = bitDepth // 8, self.frames * self.channels(), 32768
+            k, rem = nvals // cs, nvals % cs
+            if k == 0:
+                raise AukitError("bad argument #2 to 'pack' (number expected, got nil)")
+            nloop = len(range(1, nvals - cs + 1, cs))
+            body = body[: nloop * cs * B] + body[(k * cs - 1) * B: (k * cs - 1 + rem) * B]
+        ch, rate = self.channels(), int(np.floor(self.sampleRate))
+        fmt = struct.pack("<HHIIHH", 1, ch, rate, int(self.sampleRate * ch * bitDepth / 8), ch * bitDepth // 8, bitDepth)
+        head = b"RIFF" + struct.pack("<I", len(body) + 36) + b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt
+        if self.metadata:
+            inv = {}
+            for tag, key in _WAV_METADATA.items():
+                inv.setdefault(key, tag)
+            lst = b"INFO"
+            for k, v in self.metadata.items():
+                if k in inv:
+                    if isinstance(v, float) and v == int(v):
+                        v = int(v)
+                    vb = v if isinstance(v, bytes) else str(v).encode("latin-1")
+                    lst += inv[k].encode() + struct.pack("<I", len(vb)) + vb
+                    if len(lst) % 2:
+                        lst += b"\0"
+            head += b"LIST" + struct.pack("<I", len(lst)) + lst
+        return head + b"data" + struct.pack("<I", len(body)) + body
+
     def numpy(self) -> np.ndarray:
         """[channels, frames] float32 copy on the host (channel 1's length, like #data[1])."""
         n = self.frames

@@ -341,6 +341,22 @@ static int l_pcm_out(lua_State *L) {
     return 1;
 }
 
+/* cu.pcm_bytes(audio, bitDepth, dataType, interleaved, rounding) -> string of packed little-endian samples */
+static int l_pcm_bytes(lua_State *L) {
+    aukit_audio *a = check_audio(L, 1);
+    const int bits = (int)luaL_checkinteger(L, 2);
+    const size_t total = aukit_cuda_audio_frames(a) * (size_t)aukit_cuda_audio_channels(a) * (size_t)(bits > 0 ? bits / 8 : 0);
+    char *buf = (char *)malloc(total ? total : 1);
+    if (!buf) return luaL_error(L, "out of memory");
+    if (aukit_cuda_audio_pcm_bytes(ctx(L), a, bits, (int)luaL_checkinteger(L, 3), optbool(L, 4, 1), (int)luaL_optinteger(L, 5, 1), buf)) {
+        free(buf);
+        return fail(L);
+    }
+    lua_pushlstring(L, buf, total);
+    free(buf);
+    return 1;
+}
+
 /* cu.write(audio, channel, first, {numbers}) -- audio.data[c][i] = v */
 static int l_write(lua_State *L) {
     aukit_audio *a = check_audio(L, 1);
@@ -364,7 +380,7 @@ static int l_gc(lua_State *L) {
 static const luaL_Reg funcs[] = {
     {"pcm", l_pcm}, {"g711", l_g711}, {"adpcm", l_adpcm}, {"ima_adpcm_wav", l_ima_wav}, {"msadpcm", l_msadpcm},
     {"wav", l_wav}, {"new", l_new}, {"resample", l_resample}, {"mono", l_mono}, {"concat", l_concat},
-    {"au", l_au}, {"aiff", l_aiff}, {"amplify", l_amplify}, {"invert", l_invert}, {"fade", l_fade}, {"delay", l_delay}, {"center", l_center}, {"lowpass", l_lowpass}, {"highpass", l_highpass}, {"pcm_out", l_pcm_out}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
+    {"au", l_au}, {"aiff", l_aiff}, {"amplify", l_amplify}, {"invert", l_invert}, {"fade", l_fade}, {"delay", l_delay}, {"center", l_center}, {"lowpass", l_lowpass}, {"highpass", l_highpass}, {"pcm_out", l_pcm_out}, {"pcm_bytes", l_pcm_bytes}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
     {"frames", l_frames}, {"read", l_read}, {"write", l_write}, {NULL, NULL}};
 
 int luaopen_aukit_cuda(lua_State *L) {

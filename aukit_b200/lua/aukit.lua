@@ -6,7 +6,7 @@
 -- auplay.lua's load -> :resample(48000) -> :mono() -> effects.normalize(mono, 0.8) runs unchanged.
 --
 -- In scope (device-backed): aukit.pcm, aukit.g711, aukit.adpcm, aukit.msadpcm, aukit.wav, aukit.new,
---   Audio:len/channels/resample/mono/concat/pcm, aukit.effects.amplify/normalize/lowpass, aukit.defaultInterpolation.
+--   Audio:len/channels/resample/mono/concat/pcm/wav, aukit.effects.amplify/normalize/lowpass, aukit.defaultInterpolation.
 -- Everything else of the reference (players, streams, FLAC/QOA/DFPWM, editing ops, writers) is out of
 -- scope of this accelerated path; load the reference module alongside for those.
 --
@@ -124,6 +124,35 @@ function Audio:pcm(bitDepth, dataType, interleaved)
     if dataType ~= "signed" and dataType ~= "unsigned" and dataType ~= "float" then error("bad argument #3 (invalid data type)", 2) end
     if dataType == "float" and bitDepth ~= 32 then error("bad argument #2 (float audio must have 32-bit depth)", 2) end
     return cu.pcm_out(handle(self), bitDepth, DATATYPE[dataType], interleaved)
+end
+
+--- Converts the audio data to a WAV file (PCM depths; DFPWM is outside this module). (A:942)
+-- aukit.packRounding: how the host's string.pack narrows the un-rounded sample values of Audio:pcm
+-- ("floor", "truncate" or "nearest"); the reference leaves this to the Lua it runs on.
+function Audio:wav(bitDepth)
+    bitDepth = expect(1, bitDepth, "number", "nil") or 16
+    if bitDepth == 1 then error("aukit_cuda: DFPWM output is outside the accelerated path", 2)
+    elseif bitDepth ~= 8 and bitDepth ~= 16 and bitDepth ~= 24 and bitDepth ~= 32 then error("bad argument #2 (invalid bit depth)", 2) end
+    local rounding = ({truncate = 0, floor = 1, nearest = 2})[aukit.packRounding or "floor"] or 1
+    local str = cu.pcm_bytes(handle(self), bitDepth, bitDepth == 8 and 1 or 0, true, rounding)
+    local nc = #self.data
+    if self.metadata and next(self.metadata) then
+        local info = {}
+        for k, v in pairs(self.metadata) do
+            for l, w in pairs(wavMetadata) do
+                if w == k then
+                    info[#info+1] = l
+                    info[#info+1] = tostring(v)
+                    break
+                end
+            end
+        end
+        local list = string.pack("!2<c4" .. ("c4s4Xh"):rep(#info / 2), "INFO", table.unpack(info))
+        return string.pack("<c4Ic4c4IHHIIHHc4s4c4I", "RIFF", #str + 36, "WAVE", "fmt ", 16, 1, nc, self.sampleRate,
+            self.sampleRate * nc * bitDepth / 8, nc * bitDepth / 8, bitDepth, "LIST", list, "data", #str) .. str
+    end
+    return string.pack("<c4Ic4c4IHHIIHHc4I", "RIFF", #str + 36, "WAVE", "fmt ", 16, 1, nc, self.sampleRate,
+        self.sampleRate * nc * bitDepth / 8, nc * bitDepth / 8, bitDepth, "data", #str) .. str
 end
 
 --- Concatenates this audio object with others, resampling where rates differ. (A:696)

@@ -1958,6 +1958,8 @@ def str_pack(args):
             if kind == "align":
                 continue
         if kind == "int":
+            if ai >= len(args) or tonum(args[ai]) is None:
+                raise LuaError(("bad argument #%d to 'pack' (number expected, got %s)" % (ai + 1, "no value" if ai >= len(args) else "nil")).encode())
             v = int(math.floor(tonum(args[ai])))
             ai += 1
             out += (v & ((1 << (8 * size)) - 1)).to_bytes(size, "little" if little else "big")

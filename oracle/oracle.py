@@ -247,6 +247,52 @@ def audio_pcm(x: np.ndarray, bitDepth=8, dataType="signed", interleaved=True) ->
     return out[: ch * n]
 
 
+WAV_METADATA = {"IPRD": "album", "INAM": "title", "IART": "artist", "IWRI": "author", "IMUS": "composer", "IPRO": "producer",
+                "IPRT": "trackNumber", "ITRK": "trackNumber", "IFRM": "trackCount", "PRT1": "partNumber", "PRT2": "partCount",
+                "TLEN": "length", "IRTD": "rating", "ICRD": "date", "ITCH": "encodedBy", "ISFT": "encoder", "ISRF": "media",
+                "IGNR": "genre", "ICMT": "comment", "ICOP": "copyright", "ILNG": "language"}      # A:198-220
+
+
+def wav_out(x: np.ndarray, sampleRate, bitDepth=None, metadata=None) -> bytes:
+    """Audio:wav (A:942-1004) for the PCM depths.  string.pack of a non-integral number is the host Lua's business;
+    this restatement floors (what oracle/luavm does) and wraps modulo 2^bits like a two's-complement store."""
+    import struct
+    bitDepth = 16 if bitDepth is None else bitDepth
+    if bitDepth not in (8, 16, 24, 32):
+        raise OracleError("bad argument #2 (invalid bit depth)")                               # A:975
+    x = np.atleast_2d(x)
+    vals = audio_pcm(x, bitDepth, "unsigned" if bitDepth == 8 else "signed", True)              # A:976
+    q = np.floor(vals).astype(np.int64) & ((1 << bitDepth) - 1)
+    B = bitDepth // 8
+    body = np.zeros((q.size, B), dtype=np.uint8)
+    for k in range(B):
+        body[:, k] = (q >> (8 * k)) & 0xFF
+    body = body.tobytes()
+    # A:981-985: 32768 values per pack for i = 1, #data - csize, csize; then #data % csize values from index
+    # floor(#data / csize) * csize (one value early; data[0] = nil when #data < csize)
+    cs, nvals = 32768, int(q.size)
+    k, rem = nvals // cs, nvals % cs
+    if k == 0:
+        raise OracleError("bad argument #2 to 'pack' (number expected, got nil)")
+    nloop = len(range(1, nvals - cs + 1, cs))
+    body = body[: nloop * cs * B] + body[(k * cs - 1) * B: (k * cs - 1 + rem) * B]
+    nc = x.shape[0]
+    fmt = struct.pack("<HHIIHH", 1, nc, int(np.floor(sampleRate)), int(np.floor(sampleRate * nc * bitDepth / 8)), nc * bitDepth // 8, bitDepth)
+    head = b"RIFF" + struct.pack("<I", len(body) + 36) + b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt   # A:1001-1003
+    if metadata:
+        lst = b"INFO"
+        for k, v in metadata.items():
+            tag = next((t for t, w in WAV_METADATA.items() if w == k), None)
+            if tag is None:
+                continue
+            vb = v if isinstance(v, bytes) else str(v).encode("latin-1")
+            lst += tag.encode() + struct.pack("<I", len(vb)) + vb
+            if len(lst) % 2:
+                lst += b"\0"                                                                     # "Xh" in "!2<..."
+        head += b"LIST" + struct.pack("<I", len(lst)) + lst
+    return head + b"data" + struct.pack("<I", len(body)) + body
+
+
 def encode_pcm(d: float, bitDepth=8, dataType="signed") -> float:
     return float(lib().auko_encode_pcm(float(d), bitDepth, DATATYPES[dataType]))
 

@@ -79,6 +79,15 @@ def run_case(R, case, blobs):
                  "delay": [A.get("delay"), A.get("multiplier")]}[op]
         r = call(R.fn("effects", op), [a] + [to_lua(v) for v in extra])[0]
         assert r is a
+    elif op == "wav_out":
+        a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
+        if A.get("metadata"):
+            for k, v in A["metadata"].items():
+                a.get(b"metadata").set(k.encode(), to_lua(v))
+        s = R.method(a, "wav", A.get("bitDepth"))[0]
+        out = R.call("new", 0, 1, A["sampleRate"])[0]          # carrier: the file's bytes as numbers
+        out.get(b"data").arr[0].arr = [float(b) for b in s]
+        return out
     elif op == "pcm_out":
         a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
         t = R.method(a, "pcm", A.get("bitDepth"), A.get("dataType"), A.get("interleaved"))[0]
@@ -334,6 +343,19 @@ def main():
     add("highpass_10khz", "highpass", dict(sampleRate=44100, frequency=10000.0), x=ze)
     add("highpass_zero_hz", "highpass", dict(sampleRate=8000, frequency=0.0), x=ze[:1, :100])
     add("highpass_two_samples", "highpass", dict(sampleRate=8000, frequency=100.0), x=np.array([[0.5, -0.5]]))
+
+    # ---- Audio:wav writer (8f rank 2, second half); luavm's string.pack floors non-integral numbers.  Sizes are
+    # chosen around the writer's 32768-value chunks (A:981-985): below one chunk it raises, above it the tail is shifted
+    # in range only: what string.pack does with a value that does not fit is the host's business (luavm wraps)
+    wl = np.clip(np.tile(w, 130)[:, None].reshape(1, -1)[:, :39000], -1, 1).astype(np.float32).astype(np.float64)    # 39000 values mono
+    wl2 = np.stack([wl[0, :35000], wl[0, 100:35100]])                                               # 70000 values stereo
+    for bits in (8, 16, 24, 32):
+        add("wavout_%d" % bits, "wav_out", dict(sampleRate=22050, bitDepth=bits), x=wl)
+    add("wavout_default_stereo", "wav_out", dict(sampleRate=8000, bitDepth=None), x=wl2)
+    add("wavout_exact_two_chunks", "wav_out", dict(sampleRate=8000, bitDepth=16), x=wl2[:, :32768])
+    add("wavout_metadata", "wav_out", dict(sampleRate=44100, bitDepth=16, metadata={"title": "A song"}), x=wl)
+    add("wavout_short_raises", "wav_out", dict(sampleRate=44100, bitDepth=16), x=w2)
+    add("wavout_bad_depth", "wav_out", dict(sampleRate=44100, bitDepth=12), x=w2[:, :50])
 
     # ---- run everything through the reference
     manifest = []

@@ -135,6 +135,16 @@ def make_module(ak):
         t.arr = [float(v) for v in out]
         return [t]
 
+    def l_pcm_bytes(a):
+        au = a[0].audio
+        bits = int(a[1])
+        out = np.empty(au.frames * au.channels() * (bits // 8), dtype=np.uint8)
+        il = True if len(a) < 4 or a[3] is None else bool(a[3])
+        if lib.aukit_cuda_audio_pcm_bytes(ctx.handle, au._h, bits, int(a[2]), int(il), int(num(a[4] if len(a) > 4 else None, 1)),
+                                          C.c_void_p(out.ctypes.data)) != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        return [out.tobytes()]
+
     def l_normalize(a):
         if lib.aukit_cuda_normalize(ctx.handle, a[0].audio._h, float(num(a[1] if len(a) > 1 else None, 1.0)),
                                     int(bool(a[2] if len(a) > 2 else False))) != 0:
@@ -164,7 +174,7 @@ def make_module(ak):
 
     mod = LuaTable()
     for name, f in {"pcm": l_pcm, "g711": l_g711, "wav": l_wav, "resample": l_resample, "mono": l_mono, "amplify": l_amplify,
-                    "lowpass": l_lowpass, "pcm_out": l_pcm_out, "invert": simple(lib.aukit_cuda_invert, 0),
+                    "lowpass": l_lowpass, "pcm_out": l_pcm_out, "pcm_bytes": l_pcm_bytes, "invert": simple(lib.aukit_cuda_invert, 0),
                     "fade": simple(lib.aukit_cuda_fade, 4), "delay": simple(lib.aukit_cuda_delay, 2, (None, 0.5)),
                     "center": simple(lib.aukit_cuda_center, 0), "highpass": simple(lib.aukit_cuda_highpass, 1), "au": l_au, "aiff": l_aiff, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,
                     "channels": lambda a: [float(a[0].audio.channels())],

@@ -81,6 +81,8 @@ def oracle_run(O, m, i):
         return list(O.delay(x, A["sampleRate"], A["delay"], 0.5 if A["multiplier"] is None else A["multiplier"]))
     if op == "center":
         return list(O.center(x, A["sampleRate"]))
+    if op == "wav_out":
+        return [np.frombuffer(O.wav_out(x, A["sampleRate"], A.get("bitDepth"), A.get("metadata")), dtype=np.uint8).astype(np.float64)]
     if op == "pcm_out":
         return [O.audio_pcm(x, 8 if A["bitDepth"] is None else A["bitDepth"], A["dataType"] or "signed",
                             True if A["interleaved"] is None else A["interleaved"])]
@@ -143,6 +145,10 @@ def cuda_run(ak, m, i):
         return ak.au(raw)
     if op == "aiff":
         return ak.aiff(raw, bool(A.get("head")))
+    if op == "wav_out":
+        a = ak.Audio.from_numpy(x.astype(np.float32), A["sampleRate"])
+        a.metadata = dict(A.get("metadata") or {})
+        return np.frombuffer(a.wav(A.get("bitDepth"), "floor", ak.DIALECT_LITERAL), dtype=np.uint8).astype(np.float64)
     if op == "pcm_out":
         return ak.Audio.from_numpy(x.astype(np.float32), A["sampleRate"]).pcm(A["bitDepth"], A["dataType"], A["interleaved"])
     a = ak.wav(raw) if op == "chain" else ak.Audio.from_numpy(x.astype(np.float32), A["sampleRate"])
@@ -183,6 +189,9 @@ def test_cuda_matches_reference(ak, i):
         return
     a = cuda_run(ak, m, i)
     exp = expected(i, m)
+    if m["op"] == "wav_out":
+        assert np.array_equal(a, exp[0]), "Audio:wav bytes differ from the reference's"
+        return
     if m["op"] == "pcm_out":
         # the inputs are f32-representable, so the fp64 products are the reference's own numbers
         assert a.dtype == np.float64 and same_f64(a, exp[0])

@@ -95,3 +95,22 @@ def test_facade_next_rows_lowpass_pcm_containers(lua, O):
     got = np.array(r[4].arr)
     assert got.shape == ref.shape and np.max(np.abs(got - ref)) <= 128 * 2 * TOL
     assert r[5:] == [16.0, b"signed"]
+
+
+def test_facade_audio_wav_writer(lua, ak):
+    """Audio:wav through the facade (header packed by the host Lua, samples by the GPU): the same bytes as the
+    Python mirror's general dialect, and a file the loader reads back to within one LSB."""
+    pcm = tone_s16(3000, 2, 8000, seed=9)
+    lua.G.set(b"PCM_BYTES", pcm.tobytes())
+    r = lua.run('''
+        local aukit = require "aukit"
+        local a = aukit.pcm(PCM_BYTES, 16, "signed", 2, 8000)
+        a.metadata.title = "T"
+        return a:wav(16)
+    ''')
+    a = ak.pcm(pcm.tobytes(), 16, "signed", 2, 8000)
+    a.metadata = {"title": "T"}
+    assert r[0] == a.wav(16, "floor", ak.DIALECT_GENERAL)
+    back = ak.wav(r[0])
+    assert back.channels() == 2 and back.frames == 3000 and back.metadata == {"title": b"T"} or back.metadata == {"title": "T"}
+    assert np.max(np.abs(back.numpy() - a.numpy())) <= 1.0 / 32767
