@@ -30,6 +30,27 @@ __device__ __forceinline__ long long round_mode(double v, int mode) {
     return (long long)r;
 }
 
+// Rounding without the conversion unit, for results that fit 32 bits (8/16/24-bit output): adding 2^52 + 2^51 in
+// the wanted rounding direction leaves the integer in the low mantissa word.  ncu showed the packed kernels
+// instruction-bound on FRND / F2I (XU pipe) and 64-bit integer clamps; this path is one F2F, one DFMA, one DADD.
+//   floor: round-down add;  nearest-even: round-to-nearest add;  truncate: floor of |v| with the sign put back.
+// The sample is first clamped to [-4, 4] in fp32 (exact for everything in range; outside it the result saturates
+// either way), so the sum stays far below 2^31.  NaN rounds to 0 like round_mode().
+__device__ __forceinline__ int quant_magic(float d, double maxv, double add, int mode, int lo, int hi) {
+    const float dc = fminf(fmaxf(d, -4.0f), 4.0f);
+    const double v = __fma_rn((double)dc, dc < 0.0f ? maxv : maxv - 1.0, add);      // A:874, one rounding like d*s + add
+    constexpr double MAGIC = 6755399441055744.0;                                    // 2^52 + 2^51
+    int q;
+    if (mode == 1) q = __double2loint(__dadd_rd(v, MAGIC));
+    else if (mode == 2) q = __double2loint(__dadd_rn(v, MAGIC));
+    else {
+        const int m = __double2loint(__dadd_rd(fabs(v), MAGIC));
+        q = v < 0.0 ? -m : m;
+    }
+    if (!(d == d)) q = 0;
+    return min(max(q, lo), hi);
+}
+
 // values: one thread per frame, all channels (coalesced reads per channel row; the C values of a frame are
 // adjacent in the interleaved output, so the lanes of a warp write one contiguous span)
 __global__ void __launch_bounds__(256)
@@ -66,9 +87,10 @@ encode_bytes_vec_kernel(const float *__restrict__ in, size_t stride, size_t n, s
     const long long lo = is_unsigned ? 0 : -(1ll << (8 * B - 1)), hi = is_unsigned ? (1ll << (8 * B)) - 1 : (1ll << (8 * B - 1)) - 1;
     auto quant = [&](float d) -> uint32_t {
         if (is_float) return __float_as_uint(d);
+        if (B <= 3) return (uint32_t)quant_magic(d, maxv, add, mode, (int)lo, (int)hi) & ((1u << (8 * (B & 3))) - 1u);
         long long q = round_mode(encode_value(d, maxv, add, false), mode);
         q = q < lo ? lo : (q > hi ? hi : q);
-        return (uint32_t)q & (B == 4 ? 0xFFFFFFFFu : ((1u << (8 * (B & 3))) - 1u));
+        return (uint32_t)q;
     };
     const size_t groups_per_row = ROWS ? (n + 3) / 4 : (n + 1) / 2;     // !ROWS: one "row" of frame pairs
     const size_t total = groups_per_row * (ROWS ? nrows : 1);
