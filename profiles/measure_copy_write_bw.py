@@ -1,3 +1,5 @@
+"""Write-only / copy / read bandwidth of the device through torch (used to decide whether ADPCM decode, 89 % stores,
+is bounded by a lower write-only rate: it is not -- memset reaches 7.5 TB/s against 6.7 TB/s for a copy)."""
 import torch
 x = torch.empty(6 * 1024**3 // 4, dtype=torch.float32, device="cuda")
 y = torch.empty_like(x)
