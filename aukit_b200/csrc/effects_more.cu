@@ -19,7 +19,19 @@ __device__ __forceinline__ void for_each_vec(float *row, size_t n, F f) {
     const size_t nvec = (n - head) / 4, tail0 = head + nvec * 4;
     const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
     float4 *body = reinterpret_cast<float4 *>(row + head);
-    for (size_t t = t0; t < nvec; t += step) {
+    size_t t = t0;
+    for (; t + 3 * step < nvec; t += 4 * step) {                         // four loads in flight per thread
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = body[t + u * step];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const size_t i = head + 4 * (t + u * step);
+            v[u].x = f(v[u].x, i); v[u].y = f(v[u].y, i + 1); v[u].z = f(v[u].z, i + 2); v[u].w = f(v[u].w, i + 3);
+            stg_stream(body + t + u * step, v[u]);
+        }
+    }
+    for (; t < nvec; t += step) {
         float4 v = body[t];
         const size_t i = head + 4 * t;
         v.x = f(v.x, i); v.y = f(v.y, i + 1); v.z = f(v.z, i + 2); v.w = f(v.w, i + 3);
