@@ -56,7 +56,20 @@ __device__ __forceinline__ int quant_magic(float d, double maxv, double add, int
 __global__ void __launch_bounds__(256)
 encode_values_kernel(const float *__restrict__ in, size_t stride, int C, size_t n, double maxv, double add, int is_float,
                      int interleaved, double *__restrict__ out) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    size_t i = t0;
+    if (interleaved && C == 2) {
+        for (; i + 3 * step < n; i += 4 * step) {                        // eight loads in flight per thread
+            float a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { a[u] = in[i + u * step]; b[u] = in[stride + i + u * step]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                *reinterpret_cast<double2 *>(out + 2 * (i + u * step)) =
+                    make_double2(encode_value(a[u], maxv, add, is_float), encode_value(b[u], maxv, add, is_float));
+        }
+    }
+    for (; i < n; i += step) {
         if (interleaved && C == 2) {
             const double a = encode_value(in[i], maxv, add, is_float), b = encode_value(in[stride + i], maxv, add, is_float);
             *reinterpret_cast<double2 *>(out + 2 * i) = make_double2(a, b);
@@ -94,9 +107,8 @@ encode_bytes_vec_kernel(const float *__restrict__ in, size_t stride, size_t n, s
     };
     const size_t groups_per_row = ROWS ? (n + 3) / 4 : (n + 1) / 2;     // !ROWS: one "row" of frame pairs
     const size_t total = groups_per_row * (ROWS ? nrows : 1);
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
-        float v[4];
-        size_t obase;                                                   // first output sample index
+    // one group: load (returns how many of the 4 samples exist), then quantise + store
+    auto load = [&](size_t g, float (&v)[4], size_t &obase) -> int {
         int valid = 4;
         if (ROWS) {
             const size_t r = g / groups_per_row, i = (g % groups_per_row) * 4;
@@ -112,6 +124,9 @@ encode_bytes_vec_kernel(const float *__restrict__ in, size_t stride, size_t n, s
             } else { v[0] = in[i]; v[1] = in[stride + i]; v[2] = v[3] = 0.f; valid = 2; }
             obase = i * 2;
         }
+        return valid;
+    };
+    auto emit = [&](const float (&v)[4], size_t obase, int valid) {
         const uint32_t q0 = quant(v[0]), q1 = quant(v[1]), q2 = quant(v[2]), q3 = quant(v[3]);
         uint8_t *dst = out + obase * B;
         if (valid == 4 && ((uintptr_t)dst % (4 * (B == 3 ? 1 : B))) == 0) {
@@ -126,6 +141,14 @@ encode_bytes_vec_kernel(const float *__restrict__ in, size_t stride, size_t n, s
             const uint32_t q[4] = {q0, q1, q2, q3};
             for (int k = 0; k < valid; k++) store_le<B>(dst + k * B, (long long)q[k]);
         }
+    };
+    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    size_t g = t0;          // (four groups per iteration was tried: more registers, slower)
+    for (; g < total; g += step) {
+        float v[4];
+        size_t ob;
+        const int va = load(g, v, ob);
+        emit(v, ob, va);
     }
 }
 
