@@ -114,7 +114,33 @@ pcm_unpack_narrow_kernel(const uint8_t *__restrict__ in, float *__restrict__ out
     const size_t ngroups = (frames + 3) / 4;
     const int lane = threadIdx.x & 31;
     const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t full_groups = frames / 4;
     for (size_t wg = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 * SUB); wg < ngroups; wg += warps * (32 * SUB)) {
+        if (SUB > 1 && wg + 32 * SUB <= full_groups) {
+            // interior chunk: issue every load of the lane first (SUB independent requests in flight), then convert
+            uint32_t ww[SUB][SB / 4 + 1];
+#pragma unroll
+            for (int k = 0; k < SUB; k++) {
+                const uint8_t *p = src + (wg + (size_t)k * 32 + lane) * SB;
+                if (SB == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p)); ww[k][0] = v.x; ww[k][1] = v.y; }
+                else ww[k][0] = __ldg(reinterpret_cast<const uint32_t *>(p));
+                ww[k][SB / 4] = 0;
+            }
+#pragma unroll
+            for (int k = 0; k < SUB; k++) {
+                const size_t f0 = (wg + (size_t)k * 32 + lane) * 4;
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    float4 o;
+                    o.x = conv_lut<B, KIND>(extract<B, BE>(ww[k], (0 * C + c) * B), nullptr);
+                    o.y = conv_lut<B, KIND>(extract<B, BE>(ww[k], (1 * C + c) * B), nullptr);
+                    o.z = conv_lut<B, KIND>(extract<B, BE>(ww[k], (2 * C + c) * B), nullptr);
+                    o.w = conv_lut<B, KIND>(extract<B, BE>(ww[k], (3 * C + c) * B), nullptr);
+                    stg_stream(reinterpret_cast<float4 *>(dst + (size_t)c * out_stride + f0), o);
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int k = 0; k < SUB; k++) {
             const size_t g = wg + (size_t)k * 32 + lane;
