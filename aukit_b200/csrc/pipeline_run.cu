@@ -92,11 +92,14 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 // One stereo s16 frame -> (L, R) in the SCALED domain v * 2^15: u + max(u, 0) / 32767 is the correctly
 // rounded s * 32768 / 32767, i.e. 2^15 times the exactly rounded sample of A:1133 (same proof as
 // common.cuh::s16_to_float, scaled by a power of two).  The 2^-15 is folded into the final scale.
+// ALU_MAX: max(u, 0) as an FMNMX on the ALU pipe instead (for kernels whose FMA pipe is the busier one).
+template <bool ALU_MAX = false>
 __device__ __forceinline__ f32x2 cvt_frame(uint32_t w) {
     const float ul = (float)(int)(int16_t)(w & 0xFFFFu), ur = (float)((int)w >> 16);
     constexpr float c = 0.5f / 32767.0f;
     // max(u, 0) = (u + |u|) / 2, evaluated as an FADD with an |.| operand (FMA pipe, exact) instead of an
     // FMNMX (ALU pipe, the busier one here); the 1/2 is folded into c
+    if (ALU_MAX) return fma2(pack2(fmaxf(ul, 0.f), fmaxf(ur, 0.f)), pack2(2.0f * c, 2.0f * c), pack2(ul, ur));
     return fma2(pack2(ul + fabsf(ul), ur + fabsf(ur)), pack2(c, c), pack2(ul, ur));
 }
 
@@ -353,6 +356,252 @@ int launch_run(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     return aukit_cuda_check(cudaGetLastError(), "run_kernel launch") ? -1 : 1;
 }
 
+
+// =====================================================================================================
+// Static variant for the canonical 44.1 -> 48 kHz ratio (L = 160, M = 147).
+//
+// What bounds run_kernel above is instruction issue: per input frame a flag test, a divergent
+// branch (the two half-period classes share a warp) with its BSSY/BSYNC pair and pointer bumps, and per output
+// four FMNMX for the per-channel clamp of A:668 -- and because every output sits in its own basic block the
+// compiler reuses the same registers for consecutive outputs, so they cannot overlap.  Here
+//   * a warp is ONE class: warps 2k / 2k+1 share a 32-period input tile and take the first / second half of
+//     every period (lane = period), so the whole half period is warp-uniform and, with L and M template
+//     parameters, a straight line: which frame yields one or two outputs, every weight address, every staging
+//     slot and every flush point is a compile-time constant (no script, no branches, no pointer arithmetic), and
+//     ptxas interleaves neighbouring outputs;
+//   * the clamp of A:668 is checked, not applied: one FMNMX3 per output tracks max(|l|, |r|) of the unclamped
+//     channel values; only if a tile saw a value beyond +-1 (cubic overshoot of a near-full-scale signal) is the
+//     tile redone by the clamping twin of the same code, and the warp stays on the twin from then on.  Where no
+//     clamp acts the two are the same arithmetic, so results stay bit-identical to the polyphase kernel's;
+//   * four outputs leave in one STS.128 into a 16-column staging tile whose XOR swizzle makes both that store
+//     and the transposed LDS.128 of the flush conflict-free.
+constexpr int SPERIODS = 32;          // periods per warp-pair tile (lane = period)
+constexpr int SSTAGE_WORDS = 32 * 16; // staging floats per warp: 32 rows x 16 columns
+
+template <int L, int M, int CLS>
+struct half_geom {
+    static constexpr int LH = L / 2;
+    static constexpr int EB = CLS * LH;                                     // first output of the half (within the period)
+    static constexpr int FBASE = (int)(((long long)EB * M) / L);            // floor position of that output
+    static constexpr int NSTEPS = (int)(((long long)(EB + LH - 1) * M) / L) - FBASE + 1;
+    // outputs of this half whose floor position is FBASE + s
+    static constexpr int count(int s) {
+        const long long f = FBASE + s;
+        long long lo = (f * L + M - 1) / M, hi = ((f + 1) * L + M - 1) / M;
+        if (lo < EB) lo = EB;
+        if (hi > EB + LH) hi = EB + LH;
+        return hi > lo ? (int)(hi - lo) : 0;
+    }
+    static constexpr int before(int s) {
+        int n = 0;
+        for (int k = 0; k < s; k++) n += count(k);
+        return n;
+    }
+};
+
+struct half_ctx {
+    const uint32_t *row;       // this lane's first frame (floor position FBASE - 1 of its period)
+    const float4 *Wc;          // weights of the half's first output
+    float mult, one_lo, one_hi;
+    float *qb0, *qb1, *qb2, *qb3;   // staging address of column quad 0..3 of this lane's row
+    const float *fsrc;         // flush: this lane's 16-byte piece of staging row lane >> 2
+    float *fdst;               // flush: global address of that piece for column 0
+};
+
+// 16 staged columns of all 32 rows -> global: 4 lanes write 64 contiguous bytes of one period's half
+template <int L>
+__device__ __forceinline__ void sflush(const half_ctx &hc, int col0) {
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        const float4 v = *reinterpret_cast<const float4 *>(hc.fsrc + it * 8 * 16);
+        stg_stream(reinterpret_cast<float4 *>(hc.fdst + (size_t)it * 8 * L + col0), v);
+    }
+    __syncwarp();
+}
+
+template <bool APPLY, bool CLAMPCH, bool CLAMP1, int L, int E>
+__device__ __forceinline__ void semit(const half_ctx &hc, f32x2 p0, f32x2 p1, f32x2 p2, f32x2 p3, float (&o)[4], float &mx, float &chk) {
+    const float4 w = hc.Wc[E];
+    f32x2 acc = mul2(p0, pack2(w.x, w.x));
+    acc = fma2(p1, pack2(w.y, w.y), acc);
+    acc = fma2(p2, pack2(w.z, w.z), acc);
+    acc = fma2(p3, pack2(w.w, w.w), acc);
+    float vl, vr;
+    unpack2(acc, vl, vr);
+    if (CLAMPCH) {
+        vl = fminf(fmaxf(vl, -32768.0f), 32768.0f);       // A:668 in the scaled domain
+        vr = fminf(fmaxf(vr, -32768.0f), 32768.0f);
+    } else {
+        chk = fmaxf(chk, fmaxf(fabsf(vl), fabsf(vr)));    // one FMNMX3: did A:668 have anything to do?
+    }
+    const float sum = vl + vr;                            // (0 + L) + R, A:686; the /2 is in the final scale
+    if (APPLY) {
+        const float v = sum * hc.mult;
+        o[E & 3] = CLAMP1 ? fminf(fmaxf(v, hc.one_lo), hc.one_hi) : v;   // A:3455
+        if ((E & 3) == 3) {
+            float *q = ((E >> 2) & 3) == 0 ? hc.qb0 : (((E >> 2) & 3) == 1 ? hc.qb1 : (((E >> 2) & 3) == 2 ? hc.qb2 : hc.qb3));
+            *reinterpret_cast<float4 *>(q) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        if ((E & 15) == 15) sflush<L>(hc, E - 15);
+    } else {
+        mx = fmaxf(mx, fabsf(sum));
+    }
+}
+
+template <bool APPLY, bool CLAMPCH, bool CLAMP1, bool CVTA, int L, int M, int CLS, int S>
+__device__ __forceinline__ void ssteps(const half_ctx &hc, f32x2 (&c)[8], float (&o)[4], float &mx, float &chk) {
+    using G = half_geom<L, M, CLS>;
+    if constexpr (S < G::NSTEPS) {
+        if constexpr (S + 6 <= G::NSTEPS + 2) c[(S + 6) & 7] = cvt_frame<CVTA>(hc.row[S + 6]);
+        constexpr int E0 = G::before(S), N = G::count(S);
+        static_assert(N <= 5, "at most CMIN + 1 outputs per input frame");
+        if constexpr (N > 0) semit<APPLY, CLAMPCH, CLAMP1, L, E0>(hc, c[S & 7], c[(S + 1) & 7], c[(S + 2) & 7], c[(S + 3) & 7], o, mx, chk);
+        if constexpr (N > 1) semit<APPLY, CLAMPCH, CLAMP1, L, E0 + 1>(hc, c[S & 7], c[(S + 1) & 7], c[(S + 2) & 7], c[(S + 3) & 7], o, mx, chk);
+        if constexpr (N > 2) semit<APPLY, CLAMPCH, CLAMP1, L, E0 + 2>(hc, c[S & 7], c[(S + 1) & 7], c[(S + 2) & 7], c[(S + 3) & 7], o, mx, chk);
+        if constexpr (N > 3) semit<APPLY, CLAMPCH, CLAMP1, L, E0 + 3>(hc, c[S & 7], c[(S + 1) & 7], c[(S + 2) & 7], c[(S + 3) & 7], o, mx, chk);
+        if constexpr (N > 4) semit<APPLY, CLAMPCH, CLAMP1, L, E0 + 4>(hc, c[S & 7], c[(S + 1) & 7], c[(S + 2) & 7], c[(S + 3) & 7], o, mx, chk);
+        ssteps<APPLY, CLAMPCH, CLAMP1, CVTA, L, M, CLS, S + 1>(hc, c, o, mx, chk);
+    }
+}
+
+// one half period of one lane, start to end; returns max |l + r| of its outputs, *chk = max |channel value|
+template <bool APPLY, bool CLAMPCH, bool CLAMP1, bool CVTA, int L, int M, int CLS>
+__device__ __forceinline__ float shalf(const half_ctx &hc, float &chk) {
+    using G = half_geom<L, M, CLS>;
+    static_assert(G::before(G::NSTEPS) == L / 2, "every output of the half is produced");
+    static_assert((L / 2) % 16 == 0, "whole flush groups");
+    f32x2 c[8];
+#pragma unroll
+    for (int i = 0; i < 6; i++) c[i] = cvt_frame<CVTA>(hc.row[i]);
+    c[6] = c[7] = 0;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    float mx = 0.f;
+    ssteps<APPLY, CLAMPCH, CLAMP1, CVTA, L, M, CLS, 0>(hc, c, o, mx, chk);
+    return mx;
+}
+// the clamping twin, out of line: it only runs for tiles in which A:668 acts
+template <bool APPLY, bool CLAMP1, bool CVTA, int L, int M, int CLS>
+__device__ __noinline__ float shalf_clamped(const half_ctx &hc) {
+    float chk = 0.f;
+    return shalf<APPLY, true, CLAMP1, CVTA, L, M, CLS>(hc, chk);
+}
+
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <bool APPLY, bool CLAMP1, bool CVTA, int L, int M>
+__global__ void __launch_bounds__(APPLY ? 576 : 704, 1) run_static_kernel(pipe_args a, run_plan rp) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = warp >> 1, cls = warp & 1, npairs = rp.nwarps >> 1;
+    // layout: weights[L] float4 | mbar[npairs] | per pair: raw words | staging of warp 2k, 2k+1
+    float4 *W = reinterpret_cast<float4 *>(smem);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)L * 16);
+    unsigned char *pair_base = reinterpret_cast<unsigned char *>(bars) + (((size_t)npairs * 8 + 127) & ~(size_t)127);
+    const size_t per_pair = (size_t)rp.raw_words * 4 + (APPLY ? 2 * SSTAGE_WORDS * 4 : 0);
+    uint32_t *raw = reinterpret_cast<uint32_t *>(pair_base + (size_t)pair * per_pair);
+    float *stage = reinterpret_cast<float *>(raw + rp.raw_words) + cls * SSTAGE_WORDS;
+
+    for (int e = threadIdx.x; e < L; e += blockDim.x) {     // fp64 weights of A:265 at fraction j/L + delta, narrowed
+        const int j = (int)(((long long)e * M) % L);
+        const double x = (double)j / (double)L + (double)rp.delta;
+        const double x2 = x * x, x3 = x2 * x;
+        W[e] = make_float4((float)(-0.5 * x3 + x2 - 0.5 * x), (float)(1.5 * x3 - 2.5 * x2 + 1.0),
+                           (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x), (float)(0.5 * x3 - 0.5 * x2));
+    }
+    half_ctx hc;
+    hc.mult = 0.f; hc.one_hi = 1.0f;
+    if (APPLY) {                                            // same scale and silence rule as run_kernel
+        const float mx0 = a.d_max[0];
+        hc.mult = mx0 > 0.f ? (float)(a.peak / (double)mx0) * (1.0f / 65536.0f) : __int_as_float(0x7FC00000);
+        if (!(mx0 > 0.f)) hc.one_hi = hc.mult;
+    }
+    hc.one_lo = -hc.one_hi;
+    hc.Wc = W + cls * (L / 2);
+    {
+        float *my_row = stage + lane * 16;
+        const int sq = (lane >> 1) & 3;
+        hc.qb0 = my_row + 4 * (0 ^ sq); hc.qb1 = my_row + 4 * (1 ^ sq);
+        hc.qb2 = my_row + 4 * (2 ^ sq); hc.qb3 = my_row + 4 * (3 ^ sq);
+        const int b = lane >> 2, q = lane & 3;
+        hc.fsrc = stage + b * 16 + 4 * (q ^ ((b >> 1) & 3));
+    }
+    if (cls == 0 && lane == 0) mbar_init(&bars[pair], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    float mx = 0.f;
+    bool slow = false;
+    uint32_t parity = 0;
+    const int fbase = cls ? half_geom<L, M, 1>::FBASE : 0;
+    const unsigned long long pairs_total = (unsigned long long)gridDim.x * npairs;
+    for (unsigned long long tile = rp.tile0 + (unsigned long long)blockIdx.x * npairs + pair; tile < rp.tile0 + rp.ntiles;
+         tile += pairs_total) {
+        const unsigned long long out0 = tile * (unsigned long long)(SPERIODS * L);
+        const long long gA = (long long)(tile * (unsigned long long)(SPERIODS * M)) - 1;    // first input frame needed
+        const size_t boff = (size_t)(gA - (long long)a.in_first) * 4;
+        const size_t a0 = boff & ~(size_t)15;
+        const int sh = (int)((boff - a0) >> 2);
+        const uint32_t bytes = (uint32_t)(((size_t)(SPERIODS * M + 3 + sh) * 4 + 15) & ~(size_t)15);
+        pair_sync(1 + pair);                          // both warps are done with the previous tile's frames
+        if (cls == 0 && lane == 0) {
+            fence_async_smem();
+            mbar_expect_tx(&bars[pair], bytes);
+            bulk_load(raw, a.in + a0, bytes, &bars[pair]);
+        }
+        mbar_wait(&bars[pair], parity);
+        parity ^= 1;
+        hc.row = raw + sh + lane * M + fbase;
+        if (APPLY) hc.fdst = a.out + (size_t)(out0 - a.out_first) + (size_t)(lane >> 2) * L + cls * (L / 2) + 4 * (lane & 3);
+        if (!slow) {
+            float chk = 0.f;
+            const float mt = cls ? shalf<APPLY, false, CLAMP1, CVTA, L, M, 1>(hc, chk) : shalf<APPLY, false, CLAMP1, CVTA, L, M, 0>(hc, chk);
+            if (__any_sync(0xffffffffu, chk > 32768.0f)) slow = true;    // A:668 acted somewhere in the tile: redo it
+            else mx = fmaxf(mx, mt);
+        }
+        if (slow) {
+            const float mt = cls ? shalf_clamped<APPLY, CLAMP1, CVTA, L, M, 1>(hc) : shalf_clamped<APPLY, CLAMP1, CVTA, L, M, 0>(hc);
+            mx = fmaxf(mx, mt);
+        }
+    }
+    if (!APPLY) {
+        __shared__ float wm[32];
+        mx = warp_max(mx) * (1.0f / 65536.0f);         // back from the scaled domain: 2^-15, and /2 for the mono mean
+        if (lane == 0) wm[warp] = mx;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            mx = threadIdx.x < rp.nwarps ? wm[threadIdx.x] : 0.0f;
+            mx = warp_max(mx);
+            if (threadIdx.x == 0) atomic_max_nonneg(a.d_max, mx);
+        }
+    }
+}
+
+template <bool APPLY, int L, int M>
+int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
+    rp.raw_words = ((SPERIODS * M + 3 + 3) + 31) / 32 * 32;       // tile + halo + alignment shift
+    const size_t fixed = (size_t)L * 16;
+    const size_t per_pair = (size_t)rp.raw_words * 4 + (APPLY ? 2 * SSTAGE_WORDS * 4 : 0);
+    const size_t budget = 224 * 1024;
+    int np = (int)((budget - fixed - 256 - 256) / per_pair);
+    if (np > (APPLY ? 9 : 11)) np = APPLY ? 9 : 11;                // launch bounds; named barriers 1..11
+    if (const char *e = getenv("AUKIT_RUN_MAXWARPS")) { const int m = atoi(e) / 2; if (m >= 1 && m < np) np = m; }   // occupancy experiments
+    if (np < 1) return 0;
+    rp.nwarps = 2 * np;
+    const size_t smem = fixed + (((size_t)np * 8 + 127) & ~(size_t)127) + (size_t)np * per_pair + 128;
+    // the final clamp to +-1 can only act when peakAmplitude is (about) 1 or more
+    const bool clamp1 = APPLY && !(a.peak < 1.0 - 9.5367431640625e-07);
+    static const bool cvt_alu = getenv("AUKIT_RUN_CVT_ALU") && getenv("AUKIT_RUN_CVT_ALU")[0] == '1';   // A/B: max(u,0) on the ALU pipe
+    auto kern = clamp1 ? run_static_kernel<APPLY, APPLY, false, L, M> : run_static_kernel<APPLY, false, false, L, M>;
+    if (cvt_alu) kern = clamp1 ? run_static_kernel<APPLY, APPLY, true, L, M> : run_static_kernel<APPLY, false, true, L, M>;
+    if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
+    unsigned long long g = (rp.ntiles + np - 1) / np;
+    if (g > (unsigned long long)ctx->num_sms) g = ctx->num_sms;
+    kern<<<(unsigned)g, rp.nwarps * 32, smem, ctx->stream>>>(a, rp);
+    ctx->launches++;
+    return aukit_cuda_check(cudaGetLastError(), "run_static_kernel launch") ? -1 : 1;
+}
+
 }  // namespace
 
 // Tries the run-per-lane kernel on the interior of [a.out_first, a.out_first + a.n_out).  On success
@@ -372,7 +621,11 @@ int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipel
     if (L / M != 1 && L / M != 2 && L / M != 4) return 0;          // outputs per input frame: CMIN or CMIN + 1
     if (((uintptr_t)a.in & 15) != 0) return 0;
     if (apply && ((((uintptr_t)a.out) & 15) != 0 || (a.out_first & 3) != 0)) return 0;   // 16-byte aligned bulk stores
-    const unsigned long long tile_out = (unsigned long long)PERIODS * L, tile_in = (unsigned long long)PERIODS * M;
+    // AUKIT_RUN_STATIC=0 keeps the canonical ratio on the scripted kernel (A/B measurements)
+    static const bool no_static = getenv("AUKIT_RUN_STATIC") && getenv("AUKIT_RUN_STATIC")[0] == '0';
+    const bool use_static = !no_static && L == 160 && M == 147;
+    const unsigned long long periods = use_static ? SPERIODS : PERIODS;
+    const unsigned long long tile_out = periods * L, tile_in = periods * M;
     // interior warp tiles: fully inside the output range, every tap inside [0, n_total) and inside the shard window
     unsigned long long t_lo = (a.out_first + tile_out - 1) / tile_out;
     if (t_lo == 0) t_lo = 1;                                       // tile 0 needs frame -1 (clamped): poly path
@@ -406,7 +659,8 @@ int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipel
         rp.tile0 = t;
         rp.ntiles = t_end - t;
         rp.delta = delta;
-        rc = apply ? launch_run<true>(ctx, a, rp) : launch_run<false>(ctx, a, rp);
+        if (use_static) rc = apply ? launch_run_static<true, 160, 147>(ctx, a, rp) : launch_run_static<false, 160, 147>(ctx, a, rp);
+        else rc = apply ? launch_run<true>(ctx, a, rp) : launch_run<false>(ctx, a, rp);
         t = t_end;
     }
     if (rc != 1) return rc;

@@ -505,3 +505,43 @@ def test_highpass_matches_oracle(ak, O, n, ch, freq, rate):
     ref = O.highpass(x.astype(np.float64), freq, rate)
     assert np.array_equal(got[:, 0], x[:, 0])
     assert float(np.max(np.abs(got - ref))) <= 2 * TOL
+
+
+def _quiet_with_bursts(n, bursts, seed=77, base=12000):
+    """Moderate-level stereo noise (no cubic overshoot can reach +-1) with full-scale noise in `bursts`."""
+    rng = np.random.default_rng(seed)
+    pcm = rng.integers(-base, base + 1, (n, 2)).astype(np.int16)
+    for lo, hi in bursts:
+        pcm[lo:hi] = rng.integers(-32768, 32768, (hi - lo, 2)).astype(np.int16)
+    return pcm
+
+
+@pytest.mark.parametrize("bursts", [(), ((400_000, 400_700), (1_100_000, 1_100_040)), ((0, 50), (1_499_000, 1_500_007))])
+def test_static_run_kernel_checked_clamp_and_redo(ak, O, bursts, tmp_path):
+    """44.1 -> 48 kHz takes the straight-line kernel, which checks the per-channel clamp of A:668 instead of applying
+    it and redoes a tile with the clamping twin when it acted: a signal where it never acts, one where it acts in a few
+    interior tiles, one where it acts only in the polyphase edges.  Within tolerance of the oracle, and bit-identical
+    to the scripted kernel and to the polyphase-only pipeline (what keeps time shards equal to a single pass)."""
+    import os
+    import subprocess
+    import sys
+    n = 1_500_007
+    pcm = _quiet_with_bursts(n, bursts)
+    got = ak.preload(pcm.tobytes(), 16, "signed", 2, 44100, 48000, "cubic", True, 0.8)[0]
+    ref = O.chain_s16(pcm.tobytes(), 2, 44100, 48000, "cubic", 0.8)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= TOL
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inp, outp = str(tmp_path / "in.npy"), str(tmp_path / "out.npy")
+    np.save(inp, pcm)
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import aukit_b200 as ak
+pcm = np.load(%r)
+np.save(%r, ak.preload(pcm.tobytes(), 16, "signed", 2, 44100, 48000, "cubic", True, 0.8)[0])
+''' % (root, inp, outp)
+    for extra in ({"AUKIT_RUN_STATIC": "0"}, {"AUKIT_DISABLE_RUN": "1"}, {"AUKIT_RUN_CVT_ALU": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **extra), timeout=600)
+        assert r.returncode == 0, (extra, r.stdout + r.stderr)
+        assert f32_equal_bits(np.load(outp), got), extra
