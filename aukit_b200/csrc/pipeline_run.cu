@@ -38,7 +38,7 @@ struct run_plan {
     float delta;                  // drift of the reference's position in this launch's range (frames)
     unsigned long long tile0;     // first warp tile (32*L outputs each) of this launch
     unsigned long long ntiles;
-    int flags;                    // static kernel: bit 0 = prefetch the pair's next tile into L2
+    int nbuf;                     // static kernel: frame buffers in the CTA's ring
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -404,22 +404,28 @@ struct half_geom {
     }
 };
 
-// Loop state of a warp (and of its pair) lives in SHARED memory on purpose, read through volatile accesses where it
-// is used.  Left in registers, ptxas spills exactly these values around the straight-line body (they are only needed
-// between tiles), and with ~210 KB of shared memory carved out the L1 behind local memory is a few KB: every reload
-// was an L2 round trip per tile (ncu: the instructions after them carried 12 % of all stall samples).
+// Loop state of a warp lives in SHARED memory on purpose, read through volatile accesses where it is used.  Left in
+// registers, ptxas spills exactly these values around the straight-line body (they are only needed between tiles),
+// and with ~220 KB of shared memory carved out the L1 behind local memory is a few KB: every reload was an L2 round
+// trip per tile (ncu: the instructions after them carried 12 % of all stall samples).
 struct __align__(16) warp_state {
-    unsigned long long src;    // pair's next tile: global address of its 16-byte aligned bulk copy
     unsigned long long dst;    // APPLY: global address of output 0 of the current tile
-    int k, n;                  // tiles done / tiles of this pair
-    uint32_t bar;              // shared address of the pair's mbarrier
-    uint32_t raw_off, stage_off;   // byte offsets from the dynamic shared memory base: the pair's frames, this warp's staging tile
-    int cls, pair, pad;
+    int i;                     // the warp's current tile of the CTA's sequence (pair, pair + npairs, ...)
+    uint32_t stage_off;        // byte offset of this warp's staging tile from the dynamic shared memory base
+    int cls, slot;             // half-period class; frame buffer holding tile i
+};
+struct __align__(16) slot_state {       // one frame buffer of the CTA's ring
+    unsigned long long full;   // mbarrier: the bulk copy of the buffer's current tile has landed
+    int done;                  // warps that finished with the buffer (two per use)
+    int issued;                // uses whose bulk copy has been issued (guards the parity wait against a two-phase lead)
 };
 struct __align__(16) cta_state {
-    unsigned long long src_step, dst_step;   // bytes between consecutive tiles of a pair (input / output)
-    uint32_t bytes;                          // size of one bulk copy
-    int prefetch, sh;                        // sh: frames between the 16-byte aligned copy and the tile's first frame
+    unsigned long long src0, src_step;   // global address of the CTA's first bulk copy; bytes between consecutive tiles
+    unsigned long long dst0, dst_step;   // the same for the outputs (bytes)
+    uint32_t bytes;                      // size of one bulk copy
+    int sh;                              // frames between the 16-byte aligned copy and the tile's first frame
+    int n, nbuf, npairs;                 // tiles of this CTA; frame buffers; warp pairs
+    uint32_t bufs_off, buf_bytes;        // ring: offset from the dynamic shared memory base, pitch
     float mult, one_hi;
 };
 
@@ -516,21 +522,25 @@ __device__ __forceinline__ void mbar_wait32(uint32_t bar, uint32_t parity) {
         ::"r"(bar), "r"(parity) : "memory");
 }
 
+constexpr int SMAX_BUFS = 12;
+
 template <bool APPLY, bool CLAMP1, bool CVTA, int L, int M>
-__global__ void __launch_bounds__(APPLY ? 576 : 704, 1) run_static_kernel(pipe_args a, run_plan rp) {
+__global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_args a, run_plan rp) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ warp_state wst[24];
+    __shared__ slot_state sst[SMAX_BUFS];
     __shared__ cta_state cst;
-    const int warp = threadIdx.x >> 5;
+    // The CTA walks tiles  tile0 + blockIdx.x + i * gridDim.x,  i = 0 .. n-1.  Tile i lives in frame buffer i % nbuf and
+    // is consumed by warp pair i % npairs (warp 2p: first halves of its 32 periods, warp 2p+1: second halves).  With
+    // nbuf = npairs + 2 or 3 a pair's next tile was requested a whole tile time earlier: whichever of a buffer's two
+    // warps finishes LAST issues the bulk copy of tile i + nbuf into it -- no producer warp, no pair barrier, and
+    // nobody waits for DRAM unless DRAM is the bottleneck.
     {
-        const int lane = threadIdx.x & 31, pair = warp >> 1, cls = warp & 1, npairs = rp.nwarps >> 1;
-        // layout: weights[L] float4 | mbar[npairs] | per pair: raw words | staging of warp 2k, 2k+1
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pair = warp >> 1, cls = warp & 1, npairs = rp.nwarps >> 1;
+        const int nbuf = rp.nbuf;
+        // layout: weights[L] float4 | nbuf frame buffers | staging of every warp
         float4 *W = reinterpret_cast<float4 *>(smem);
-        uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)L * 16);
-        unsigned char *pair_base = reinterpret_cast<unsigned char *>(bars) + (((size_t)npairs * 8 + 127) & ~(size_t)127);
-        const size_t per_pair = (size_t)rp.raw_words * 4 + (APPLY ? 2 * SSTAGE_WORDS * 4 : 0);
-        unsigned char *raw = pair_base + (size_t)pair * per_pair;
-
+        const uint32_t bufs_off = (uint32_t)L * 16, buf_bytes = (uint32_t)rp.raw_words * 4;
         for (int e = threadIdx.x; e < L; e += blockDim.x) {     // fp64 weights of A:265 at fraction j/L + delta, narrowed
             const int j = (int)(((long long)e * M) % L);
             const double x = (double)j / (double)L + (double)rp.delta;
@@ -538,18 +548,25 @@ __global__ void __launch_bounds__(APPLY ? 576 : 704, 1) run_static_kernel(pipe_a
             W[e] = make_float4((float)(-0.5 * x3 + x2 - 0.5 * x), (float)(1.5 * x3 - 2.5 * x2 + 1.0),
                                (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x), (float)(0.5 * x3 - 0.5 * x2));
         }
-        // Tile walk of a pair: tiles first, first + pairs_total, ...  The byte offset of a tile inside its 16-byte
-        // aligned bulk copy (sh) is the same for all of them (the tile pitch is a multiple of 16 bytes).
-        const unsigned long long pairs_total = (unsigned long long)gridDim.x * npairs;
-        const unsigned long long first = rp.tile0 + (unsigned long long)blockIdx.x * npairs + pair, t_end = rp.tile0 + rp.ntiles;
-        const size_t boff = (size_t)((long long)(first * (unsigned long long)(SPERIODS * M)) - 1 - (long long)a.in_first) * 4;
-        const int sh = (int)((boff & 15) >> 2);
+        if (lane == 0) {
+            warp_state &w = wst[warp];
+            w.dst = 0ull; w.i = pair; w.cls = cls; w.slot = 0;
+            w.stage_off = bufs_off + (uint32_t)nbuf * buf_bytes + (uint32_t)warp * SSTAGE_WORDS * 4;
+        }
         if (threadIdx.x == 0) {
-            cst.src_step = pairs_total * (unsigned long long)(SPERIODS * M * 4);
-            cst.dst_step = pairs_total * (unsigned long long)(SPERIODS * L * 4);
-            cst.bytes = (uint32_t)(((size_t)(SPERIODS * M + 3 + sh) * 4 + 15) & ~(size_t)15);
-            cst.prefetch = rp.flags & 1;
-            cst.sh = sh;
+            // the byte offset of a tile inside its 16-byte aligned bulk copy (sh) is the same for every tile: the tile
+            // pitch is a multiple of 16 bytes
+            const unsigned long long first = rp.tile0 + blockIdx.x, t_end = rp.tile0 + rp.ntiles;
+            const size_t boff = (size_t)((long long)(first * (unsigned long long)(SPERIODS * M)) - 1 - (long long)a.in_first) * 4;
+            const int sh = (int)((boff & 15) >> 2);
+            const int n = first < t_end ? (int)((t_end - first + gridDim.x - 1) / gridDim.x) : 0;
+            const uint32_t bytes = (uint32_t)(((size_t)(SPERIODS * M + 3 + sh) * 4 + 15) & ~(size_t)15);
+            cst.src0 = (unsigned long long)(uintptr_t)(a.in + (boff & ~(size_t)15));
+            cst.src_step = (unsigned long long)gridDim.x * (SPERIODS * M * 4);
+            cst.dst0 = APPLY ? (unsigned long long)(uintptr_t)(a.out + (size_t)(first * (unsigned long long)(SPERIODS * L) - a.out_first)) : 0ull;
+            cst.dst_step = (unsigned long long)gridDim.x * (SPERIODS * L * 4);
+            cst.bytes = bytes; cst.sh = sh; cst.n = n; cst.nbuf = nbuf; cst.npairs = npairs;
+            cst.bufs_off = bufs_off; cst.buf_bytes = buf_bytes;
             float mult = 0.f, one_hi = 1.0f;
             if (APPLY) {                                        // same scale and silence rule as run_kernel
                 const float mx0 = a.d_max[0];
@@ -557,20 +574,18 @@ __global__ void __launch_bounds__(APPLY ? 576 : 704, 1) run_static_kernel(pipe_a
                 if (!(mx0 > 0.f)) one_hi = mult;
             }
             cst.mult = mult; cst.one_hi = one_hi;
+            for (int j = 0; j < nbuf; j++) {
+                mbar_init(reinterpret_cast<uint64_t *>(&sst[j].full), 1);
+                sst[j].done = 0;
+                sst[j].issued = j < n ? 1 : 0;
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int j = 0; j < nbuf && j < n; j++) {           // fill the ring
+                mbar_expect_tx(reinterpret_cast<uint64_t *>(&sst[j].full), bytes);
+                bulk_load(smem + bufs_off + (size_t)j * buf_bytes, reinterpret_cast<const void *>(cst.src0 + (unsigned long long)j * cst.src_step),
+                          bytes, reinterpret_cast<uint64_t *>(&sst[j].full));
+            }
         }
-        if (lane == 0) {
-            warp_state &w = wst[warp];
-            w.src = (unsigned long long)(uintptr_t)(a.in + (boff & ~(size_t)15));
-            w.dst = APPLY ? (unsigned long long)(uintptr_t)(a.out + (size_t)(first * (unsigned long long)(SPERIODS * L) - a.out_first)) : 0ull;
-            w.k = 0;
-            w.n = first < t_end ? (int)((t_end - first + pairs_total - 1) / pairs_total) : 0;
-            w.bar = smem_u32(&bars[pair]);
-            w.raw_off = (uint32_t)(raw - smem);
-            w.stage_off = (uint32_t)(raw - smem) + (uint32_t)rp.raw_words * 4 + (uint32_t)cls * SSTAGE_WORDS * 4;
-            w.cls = cls; w.pair = pair;
-            if (cls == 0) mbar_init(&bars[pair], 1);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncthreads();
     }
 
@@ -583,30 +598,24 @@ __global__ void __launch_bounds__(APPLY ? 576 : 704, 1) run_static_kernel(pipe_a
         return &wst[t >> 5];
     };
     half_ctx hc;
-    // The pair's next tile into shared memory; false when the pair has no tile left.  Everything the body needs is
-    // rebuilt here from the lane id and the shared state (a handful of integer instructions per 1300-instruction
-    // tile): values carried in registers across the body are the ones ptxas spills.
+    // Wait for the warp's next tile; false when it has none left.  Everything the body needs is rebuilt here from the
+    // lane id and the shared state (a handful of integer instructions per 1300-instruction tile): values carried in
+    // registers across the body are the ones ptxas spills.
     auto fetch = [&]() -> bool {
         volatile warp_state *ws = my_state();
-        const int k = ws->k;
-        if (k >= ws->n) return false;
+        const int i = ws->i;
+        if (i >= cs->n) return false;
         uint32_t lane;
         asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
-        const int cls = ws->cls;
-        pair_sync(1 + ws->pair);                      // both warps are done with the previous tile's frames
-        if (cls == 0 && lane == 0) {
-            const unsigned long long src = ws->src;
-            const uint32_t bytes = cs->bytes;
-            fence_async_smem();
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ws->bar), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(smem + ws->raw_off)), "l"(src), "r"(bytes), "r"(ws->bar) : "memory");
-            // the tile after it: DRAM -> L2 now, so that its bulk load finds it there one iteration later
-            if (cs->prefetch && k + 1 < ws->n) bulk_prefetch_l2(reinterpret_cast<const void *>(src + cs->src_step), (uint32_t)(SPERIODS * M * 4 + 32));
-            ws->src = src + cs->src_step;
+        const int cls = ws->cls, nbuf = cs->nbuf;
+        const int slot = i % nbuf, use = i / nbuf;
+        volatile slot_state *ss = &sst[slot];
+        if (lane == 0) {
+            ws->slot = slot;
+            if (APPLY) ws->dst = cs->dst0 + (unsigned long long)i * cs->dst_step;
         }
-        const uint32_t stage_off = ws->stage_off;
-        hc.row = reinterpret_cast<const uint32_t *>(smem + ws->raw_off) + cs->sh + lane * M + (cls ? half_geom<L, M, 1>::FBASE : 0);
+        const uint32_t raw_off = cs->bufs_off + (uint32_t)slot * cs->buf_bytes, stage_off = ws->stage_off;
+        hc.row = reinterpret_cast<const uint32_t *>(smem + raw_off) + cs->sh + lane * M + (cls ? half_geom<L, M, 1>::FBASE : 0);
         hc.Wc = reinterpret_cast<const float4 *>(smem) + cls * (L / 2);
         hc.mult = cs->mult;
         hc.one_hi = cs->one_hi;
@@ -615,16 +624,34 @@ __global__ void __launch_bounds__(APPLY ? 576 : 704, 1) run_static_kernel(pipe_a
         hc.fsrc = reinterpret_cast<const float *>(smem + stage_off) + (lane >> 2) * 16 + 4 * ((lane & 3) ^ ((lane >> 3) & 3));
         hc.loff = (lane >> 2) * L + cls * (L / 2) + 4 * (lane & 3);
         hc.ws = ws;
-        mbar_wait32(ws->bar, (uint32_t)k & 1u);
+        // a parity wait cannot tell phase u from phase u - 2: make sure the copy of THIS use has been issued first
+        // (only a warp more than a whole ring ahead of the slowest one ever spins here)
+        while (ss->issued <= use) __nanosleep(64);
+        mbar_wait32(smem_u32(const_cast<unsigned long long *>(&ss->full)), (uint32_t)use & 1u);
+        __syncwarp();                                 // lane 0's ws->dst / ws->slot visible to the warp
         return true;
     };
-    // after a tile: lane 0 advances the warp's state
-    auto advance = [&]() {
+    // After a tile: hand the buffer back.  The second of its two warps to get here requests tile i + nbuf into it.
+    auto release = [&]() {
         volatile warp_state *ws = my_state();
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) {
-            ws->k = ws->k + 1;
-            if (APPLY) ws->dst = ws->dst + cs->dst_step;
+        __syncwarp();                                 // every lane has read its frames
+        uint32_t lane;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+        if (lane == 0) {
+            const int i = ws->i, slot = ws->slot, nbuf = cs->nbuf;
+            ws->i = i + cs->npairs;
+            __threadfence_block();
+            const int before = atomicAdd(const_cast<int *>(&sst[slot].done), 1);
+            if ((before & 1) && i + nbuf < cs->n) {
+                __threadfence_block();
+                fence_async_smem();                   // both warps' generic reads of the buffer vs the async write
+                const uint32_t bar = smem_u32(const_cast<unsigned long long *>(&sst[slot].full)), bytes = cs->bytes;
+                sst[slot].issued = (i + nbuf) / nbuf + 1;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(smem + cs->bufs_off + (uint32_t)slot * cs->buf_bytes)),
+                               "l"(cs->src0 + (unsigned long long)(i + nbuf) * cs->src_step), "r"(bytes), "r"(bar) : "memory");
+            }
         }
         __syncwarp();
     };
@@ -636,19 +663,19 @@ __global__ void __launch_bounds__(APPLY ? 576 : 704, 1) run_static_kernel(pipe_a
         const float mt = hc.ws->cls ? shalf<APPLY, false, CLAMP1, CVTA, L, M, 1>(hc, chk) : shalf<APPLY, false, CLAMP1, CVTA, L, M, 0>(hc, chk);
         if (__any_sync(0xffffffffu, chk > 32768.0f)) { bad = true; break; }
         mx = fmaxf(mx, mt);
-        advance();
+        release();
     }
-    // ... phase 2: that tile again (its frames are still in shared memory) and every later one with the clamping twin.
+    // ... phase 2: that tile again (its frames are still in the buffer) and every later one with the clamping twin.
     // Two loops rather than a call inside one: nothing is live across a call.
     if (bad) {
         do {
             float chk = 0.f;
             const float mt = hc.ws->cls ? shalf<APPLY, true, CLAMP1, CVTA, L, M, 1>(hc, chk) : shalf<APPLY, true, CLAMP1, CVTA, L, M, 0>(hc, chk);
             mx = fmaxf(mx, mt);
-            advance();
+            release();
         } while (fetch());
     }
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (!APPLY) {
         __shared__ float wm[32];
         mx = warp_max(mx) * (1.0f / 65536.0f);         // back from the scaled domain: 2^-15, and /2 for the mono mean
@@ -664,24 +691,27 @@ __global__ void __launch_bounds__(APPLY ? 576 : 704, 1) run_static_kernel(pipe_a
 
 template <bool APPLY, int L, int M>
 int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
-    rp.raw_words = ((SPERIODS * M + 3 + 3) + 31) / 32 * 32;       // tile + halo + alignment shift
-    const size_t fixed = (size_t)L * 16;
-    const size_t per_pair = (size_t)rp.raw_words * 4 + (APPLY ? 2 * SSTAGE_WORDS * 4 : 0);
-    const size_t budget = 224 * 1024;
-    int np = (int)((budget - fixed - 256 - 256) / per_pair);
-    if (np > (APPLY ? 9 : 11)) np = APPLY ? 9 : 11;                // launch bounds; named barriers 1..11
+    rp.raw_words = ((SPERIODS * M + 3 + 3) + 31) / 32 * 32;       // tile + halo + alignment shift; 128-byte pitch
+    const size_t fixed = (size_t)L * 16 + 128;
+    const size_t buf = (size_t)rp.raw_words * 4, stage = APPLY ? 2 * SSTAGE_WORDS * 4 : 0;   // per buffer; per pair
+    const size_t budget = 227 * 1024 - 2048;                       // opt-in maximum minus this kernel's static shared memory
+    int spare = 2;                                                 // buffers beyond one per pair (tiles in flight while all pairs compute)
+    if (const char *e = getenv("AUKIT_RUN_SPARE")) { const int m = atoi(e); if (m >= 0 && m <= 6) spare = m; }
+    int np = (int)((budget - fixed - (size_t)spare * buf) / (buf + stage));
+    if (np > (APPLY ? 8 : 9)) np = APPLY ? 8 : 9;                  // launch bounds
     if (const char *e = getenv("AUKIT_RUN_MAXWARPS")) { const int m = atoi(e) / 2; if (m >= 1 && m < np) np = m; }   // occupancy experiments
     if (np < 1) return 0;
+    int nbuf = (int)((budget - fixed - (size_t)np * stage) / buf);
+    if (nbuf > np + spare) nbuf = np + spare;
+    if (nbuf > SMAX_BUFS) nbuf = SMAX_BUFS;
+    if (nbuf < np) return 0;
     rp.nwarps = 2 * np;
-    const size_t smem = fixed + (((size_t)np * 8 + 127) & ~(size_t)127) + (size_t)np * per_pair + 128;
+    rp.nbuf = nbuf;
+    const size_t smem = fixed + (size_t)nbuf * buf + (size_t)np * stage;
     // the final clamp to +-1 can only act when peakAmplitude is (about) 1 or more
     const bool clamp1 = APPLY && !(a.peak < 1.0 - 9.5367431640625e-07);
     // max(u, 0) of the sample conversion on the ALU pipe (default: the FMA pipe is the busier one here); =0 for A/B runs
     static const bool cvt_alu = !(getenv("AUKIT_RUN_CVT_ALU") && getenv("AUKIT_RUN_CVT_ALU")[0] == '0');
-    // L2 prefetch of the pair's next tile: measured a loss on the apply pass (0.249 -> 0.295 ms; the write stream evicts
-    // the prefetched lines before they are used) and no gain on the peak pass, so it is off unless asked for
-    static const bool prefetch = getenv("AUKIT_RUN_PREFETCH") && getenv("AUKIT_RUN_PREFETCH")[0] == '1';
-    rp.flags = prefetch ? 1 : 0;
     auto kern = clamp1 ? run_static_kernel<APPLY, APPLY, false, L, M> : run_static_kernel<APPLY, false, false, L, M>;
     if (cvt_alu) kern = clamp1 ? run_static_kernel<APPLY, APPLY, true, L, M> : run_static_kernel<APPLY, false, true, L, M>;
     if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;

@@ -332,7 +332,7 @@ def run_b200(args):
                 "parallelism": "time-shard x%d" % world, "output_peak_check": checksum,
             },
             "roofline": {
-                "bound": "hbm", "kernel": "fused apply pass: run_kernel<APPLY=true> (interior) + poly_kernel edges", "achieved": achieved, "peak": peak_gbs,
+                "bound": "hbm", "kernel": "fused apply pass: run_static_kernel<APPLY=true> (interior) + poly_kernel edges", "achieved": achieved, "peak": peak_gbs,
                 "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                 "traffic_source": "profiles/r1_apply_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)" if traffic else None,
                 "peak_source": peak_src,
