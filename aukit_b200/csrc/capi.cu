@@ -61,6 +61,9 @@ extern "C" int aukit_cuda_init(int device, aukit_ctx **out) {
     ctx->num_sms = prop.multiProcessorCount;
     AUKIT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    AUKIT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    AUKIT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    AUKIT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     AUKIT_CUDA_TRY(cudaMalloc(&ctx->d_status, sizeof(int)));
     AUKIT_CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(int)));
     AUKIT_CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(int)));
@@ -83,6 +86,10 @@ extern "C" void aukit_cuda_shutdown(aukit_ctx *ctx) {
     cudaFree(ctx->d_status);
     cudaFree(ctx->d_scratch);
     cudaFreeHost(ctx->h_status);
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->side_stream);
     cudaStreamDestroy(ctx->own_stream);
     free(ctx);
 }

@@ -26,6 +26,9 @@ struct aukit_ctx {
     size_t h_stage_bytes;
     float *d_scratch;         // small device scratch (normalize maxima)
     int num_sms;
+    // fork/join pair for work that may overlap the main kernel of a pass (the fused pipeline's edge kernels)
+    cudaStream_t side_stream;
+    cudaEvent_t ev_fork, ev_join;
 };
 
 struct aukit_audio {

@@ -489,23 +489,40 @@ static int poly_range(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_d
         // headline shape: the run-per-lane kernel takes the interior, the kernels below the edges
         const double eps = fma(-(double)M, a.ratio, (double)L) / ((double)M * a.ratio);
         unsigned long long df = 0, dc = 0;
+        // The head and tail kernels are a few thousand outputs each but ~9 us of launch + table set-up apiece: 4 of them
+        // were 9 % of the step behind the interior kernel (profiles/r1_static_launches.txt).  They go to a side stream
+        // forked here and joined below, so they fill SMs as the interior kernel's CTAs drain.  The peak pass's
+        // atomicMax commutes and the apply pass's output ranges are disjoint, so nothing else orders them.
+        static const bool no_side = getenv("AUKIT_EDGE_SIDE_STREAM") && getenv("AUKIT_EDGE_SIDE_STREAM")[0] == '0';
+        cudaStream_t main_stream = ctx->stream;
+        if (!no_side && aukit_cuda_check(cudaEventRecord(ctx->ev_fork, main_stream), "fork event")) return -1;
         const int r = aukit_pipeline_run_try(ctx, a, p, apply, L, M, eps, pow2_ratio, &df, &dc);
         if (r < 0) return -1;
         if (r == 1) {
+            int rc = 1;
+            if (!no_side) {
+                if (aukit_cuda_check(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0), "fork wait")) return -1;
+                ctx->stream = ctx->side_stream;
+            }
             if (df > a.out_first) {
                 pipe_args h = a;
                 h.n_out = (size_t)(df - a.out_first);
-                if (poly_range(ctx, h, p, apply, false) != 1) return -1;
+                if (poly_range(ctx, h, p, apply, false) != 1) rc = -1;
             }
             const unsigned long long end = a.out_first + a.n_out;
-            if (df + dc < end) {
+            if (rc == 1 && df + dc < end) {
                 pipe_args t = a;
                 t.out_first = df + dc;
                 t.n_out = (size_t)(end - (df + dc));
                 if (apply) t.out = a.out + (size_t)(df + dc - a.out_first);
-                if (poly_range(ctx, t, p, apply, false) != 1) return -1;
+                if (poly_range(ctx, t, p, apply, false) != 1) rc = -1;
             }
-            return 1;
+            if (!no_side) {
+                ctx->stream = main_stream;
+                if (aukit_cuda_check(cudaEventRecord(ctx->ev_join, ctx->side_stream), "join event")) return -1;
+                if (aukit_cuda_check(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0), "join wait")) return -1;
+            }
+            return rc;
         }
     }
     const int kind = p->dataType == AUKIT_FLOAT ? K_FLOAT : (p->dataType == AUKIT_UNSIGNED ? K_UNSIGNED : K_SIGNED);

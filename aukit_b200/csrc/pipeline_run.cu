@@ -39,6 +39,7 @@ struct run_plan {
     unsigned long long tile0;     // first warp tile (32*L outputs each) of this launch
     unsigned long long ntiles;
     int nbuf;                     // static kernel: frame buffers in the CTA's ring
+    int dbg_oneclass;             // timing experiment only (wrong results): every warp runs the class-0 code
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -439,17 +440,25 @@ struct half_ctx {
     volatile warp_state *ws;
 };
 
-// 16 staged columns of all 32 rows -> global: 4 lanes write 64 contiguous bytes of one period's half
+// 16 staged columns of all 32 rows -> global: 4 lanes write 64 contiguous bytes of one period's half.
+// Staging traffic (STS.128 in semit, the warp barriers, LDS.128 and the global stores here) is written as volatile asm
+// WITHOUT a memory clobber: those statements keep their order among themselves, but the compiler may move the
+// weight / frame loads of the following outputs across them (with clobbers every group of four outputs began by
+// waiting for its own LDS: short-scoreboard was 23 % of the apply pass's stall samples).
 template <int L>
 __device__ __forceinline__ void sflush(const half_ctx &hc, int col0) {
-    __syncwarp();
+    asm volatile("bar.warp.sync 0xffffffff;");
     float *fdst = reinterpret_cast<float *>(hc.ws->dst) + hc.loff;
+    const uint32_t fs = smem_u32(hc.fsrc);
+    float4 v[4];
 #pragma unroll
-    for (int it = 0; it < 4; it++) {
-        const float4 v = *reinterpret_cast<const float4 *>(hc.fsrc + it * 8 * 16);
-        stg_stream(reinterpret_cast<float4 *>(fdst + (size_t)it * 8 * L + col0), v);
-    }
-    __syncwarp();
+    for (int it = 0; it < 4; it++)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[it].x), "=f"(v[it].y), "=f"(v[it].z), "=f"(v[it].w) : "r"(fs + it * 8 * 64));
+    asm volatile("bar.warp.sync 0xffffffff;");
+#pragma unroll
+    for (int it = 0; it < 4; it++)
+        asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                     :: "l"(fdst + (size_t)it * 8 * L + col0), "f"(v[it].x), "f"(v[it].y), "f"(v[it].z), "f"(v[it].w));
 }
 
 template <bool APPLY, bool CLAMPCH, bool CLAMP1, int L, int E>
@@ -473,7 +482,7 @@ __device__ __forceinline__ void semit(const half_ctx &hc, f32x2 p0, f32x2 p1, f3
         o[E & 3] = CLAMP1 ? fminf(fmaxf(v, hc.one_lo), hc.one_hi) : v;   // A:3455
         if ((E & 3) == 3)   // column quad (E >> 2) & 3 of this lane's row, quad index XORed with (lane >> 1) & 3
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hc.stage_x ^ (uint32_t)(((E >> 2) & 3) << 4)), "f"(o[0]), "f"(o[1]),
-                         "f"(o[2]), "f"(o[3]) : "memory");
+                         "f"(o[2]), "f"(o[3]));
         if ((E & 15) == 15) sflush<L>(hc, E - 15);
     } else {
         mx = fmaxf(mx, fabsf(sum));
@@ -550,7 +559,7 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
         }
         if (lane == 0) {
             warp_state &w = wst[warp];
-            w.dst = 0ull; w.i = pair; w.cls = cls; w.slot = 0;
+            w.dst = 0ull; w.i = pair; w.cls = rp.dbg_oneclass ? 0 : cls; w.slot = 0;
             w.stage_off = bufs_off + (uint32_t)nbuf * buf_bytes + (uint32_t)warp * SSTAGE_WORDS * 4;
         }
         if (threadIdx.x == 0) {
@@ -695,7 +704,9 @@ int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     const size_t fixed = (size_t)L * 16 + 128;
     const size_t buf = (size_t)rp.raw_words * 4, stage = APPLY ? 2 * SSTAGE_WORDS * 4 : 0;   // per buffer; per pair
     const size_t budget = 227 * 1024 - 2048;                       // opt-in maximum minus this kernel's static shared memory
-    int spare = 2;                                                 // buffers beyond one per pair (tiles in flight while all pairs compute)
+    // buffers beyond one per pair = tiles in flight while every pair computes.  Measured: the peak pass (no staging, no
+    // output stream) gains 9 % from 8 pairs + 4 over 9 + 2 (0.152 -> 0.139 ms); the apply pass is flat from 8 + 2 to 6 + 4
+    int spare = APPLY ? 2 : 4;
     if (const char *e = getenv("AUKIT_RUN_SPARE")) { const int m = atoi(e); if (m >= 0 && m <= 6) spare = m; }
     int np = (int)((budget - fixed - (size_t)spare * buf) / (buf + stage));
     if (np > (APPLY ? 8 : 9)) np = APPLY ? 8 : 9;                  // launch bounds
@@ -707,6 +718,7 @@ int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     if (nbuf < np) return 0;
     rp.nwarps = 2 * np;
     rp.nbuf = nbuf;
+    rp.dbg_oneclass = getenv("AUKIT_DEBUG_ONECLASS") ? 1 : 0;
     const size_t smem = fixed + (size_t)nbuf * buf + (size_t)np * stage;
     // the final clamp to +-1 can only act when peakAmplitude is (about) 1 or more
     const bool clamp1 = APPLY && !(a.peak < 1.0 - 9.5367431640625e-07);
