@@ -491,8 +491,10 @@ static int poly_range(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_d
         unsigned long long df = 0, dc = 0;
         // The head and tail kernels are a few thousand outputs each but ~9 us of launch + table set-up apiece: 4 of them
         // were 9 % of the step behind the interior kernel (profiles/r1_static_launches.txt).  They go to a side stream
-        // forked here and joined below, so they fill SMs as the interior kernel's CTAs drain.  The peak pass's
-        // atomicMax commutes and the apply pass's output ranges are disjoint, so nothing else orders them.
+        // forked here and joined below, and the interior kernel leaves two SMs free for them (launch_run_static), so
+        // they run beside it from the start.  The peak pass's atomicMax commutes and the apply pass's output ranges
+        // are disjoint, so nothing else orders them.  (Measured on one box: same stream 0.384 ms / step, side stream
+        // 0.370, + two reserved SMs 0.351; head and tail on two side streams was no better, 0.357.)
         static const bool no_side = getenv("AUKIT_EDGE_SIDE_STREAM") && getenv("AUKIT_EDGE_SIDE_STREAM")[0] == '0';
         cudaStream_t main_stream = ctx->stream;
         if (!no_side && aukit_cuda_check(cudaEventRecord(ctx->ev_fork, main_stream), "fork event")) return -1;

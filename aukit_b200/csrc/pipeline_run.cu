@@ -727,8 +727,12 @@ int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     auto kern = clamp1 ? run_static_kernel<APPLY, APPLY, false, L, M> : run_static_kernel<APPLY, false, false, L, M>;
     if (cvt_alu) kern = clamp1 ? run_static_kernel<APPLY, APPLY, true, L, M> : run_static_kernel<APPLY, false, true, L, M>;
     if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
+    // Two SMs stay free for the polyphase edge kernels running beside this one on the side stream (pipeline_poly.cu):
+    // this kernel's CTAs take a whole SM's shared memory, so otherwise the edges could only start as it drains.
+    int reserve = 2;
+    if (const char *e = getenv("AUKIT_RUN_RESERVE_SMS")) { const int m = atoi(e); if (m >= 0 && m < ctx->num_sms / 2) reserve = m; }
     unsigned long long g = (rp.ntiles + np - 1) / np;
-    if (g > (unsigned long long)ctx->num_sms) g = ctx->num_sms;
+    if (g > (unsigned long long)(ctx->num_sms - reserve)) g = ctx->num_sms - reserve;
     kern<<<(unsigned)g, rp.nwarps * 32, smem, ctx->stream>>>(a, rp);
     ctx->launches++;
     return aukit_cuda_check(cudaGetLastError(), "run_static_kernel launch") ? -1 : 1;
