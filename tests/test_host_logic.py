@@ -138,3 +138,28 @@ def test_numpy_window_reference(O):
             assert np.max(np.abs(got - ref)) <= 1e-15       # pow(fx, 3) vs fx**3: last-ulp differences only
             if interp == "none":
                 assert np.array_equal(got, ref)
+
+
+def test_static_run_kernel_half_period_script():
+    """The straight-line K10 kernel (csrc/pipeline_run.cu, half_geom) bakes, per half period, how many outputs every
+    input-frame step produces.  Restate its constexpr arithmetic and check it against the reference's own positions
+    (A:666: x = (i-1)/ratio + 1, floor taken per output): every output of a period is produced exactly once, by the
+    step whose frame is its floor position, at most CMIN + 1 per step, and the taps a half touches stay inside the
+    32-period tile plus its -1/+2 halo."""
+    for L, M in ((160, 147), (320, 147), (640, 147)):
+        LH = L // 2
+        produced = []
+        for cls in (0, 1):
+            eb = cls * LH
+            fbase = eb * M // L
+            nsteps = (eb + LH - 1) * M // L - fbase + 1
+            for s in range(nsteps):
+                f = fbase + s
+                lo, hi = max(-(-f * L // M), eb), min(-(-(f + 1) * L // M), eb + LH)
+                cnt = max(hi - lo, 0)
+                assert cnt <= L // M + 1
+                produced += [(e, f) for e in range(lo, lo + cnt)]
+            # rows read: floor position - 1 .. + 2 relative to the period start -> within [-1, M + 1]
+            assert fbase - 1 >= -1 and fbase + nsteps - 1 + 2 <= M + 1
+        assert [e for e, _ in produced] == list(range(L))
+        assert all(f == e * M // L for e, f in produced)
