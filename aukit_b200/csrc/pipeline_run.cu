@@ -1,27 +1,33 @@
-// pipeline_run.cu -- "run per lane" variant of the fused pipeline (K10) for the headline case:
+// pipeline_run.cu -- "run per lane" kernels of the fused pipeline (K10) for the headline case:
 // 16-bit little-endian STEREO input, cubic interpolation, mono mixdown, integer rates with
 // L = new/gcd a multiple of 32 and M = old/gcd odd (44.1 / 22.05 / 11.025 kHz -> 48 kHz).
 //
-// Why another kernel: pipeline_poly.cu maps lanes to consecutive outputs, so every output re-reads
+// Two kernels live here:
+//   run_static_kernel  (second half of the file)  44.1 -> 48 kHz: L = 160, M = 147 as template parameters, one class
+//                      of half periods per warp, the whole half period a straight line of code, a CTA-wide ring of
+//                      TMA-filled frame buffers.  This is the kernel bench.py measures.
+//   run_kernel         (first half)  the scripted predecessor, kept for 22.05 / 11.025 -> 48 kHz and for A/B runs
+//                      (AUKIT_RUN_STATIC=0): both classes of half periods in one warp, a byte script per frame.
+//
+// Why "run per lane" at all: pipeline_poly.cu maps lanes to consecutive outputs, so every output re-reads
 // its 4 taps from shared memory (32 B of the 128 B/clk/SM) -- measured 65 % shared-memory pipe,
-// 60 % issue, 42 instructions per output.  Here lane l of a warp owns one whole PERIOD of the
-// rational resampling pattern: outputs [l*L, (l+1)*L) of the warp's tile, i.e. input frames
-// [l*M - 1, (l+1)*M + 2).  All 32 lanes are therefore at the SAME phase at the same step:
-//   * the 4 Catmull-Rom weights of a step are warp-uniform: one broadcast LDS.128 from a table
+// 60 % issue, 42 instructions per output.  Here a lane owns a RUN of consecutive outputs of one PERIOD of the
+// rational resampling pattern (period p of a tile = outputs [p*L, (p+1)*L), input frames [p*M - 1, (p+1)*M + 2)).
+// All lanes of a class are therefore at the SAME phase at the same step:
+//   * the 4 Catmull-Rom weights of a step are uniform: one broadcast LDS.128 from a table
 //     built once per CTA (in fp64, narrowed), not per-lane registers or per-lane reads;
 //   * the taps slide in registers: each input frame is loaded from shared memory and converted
 //     ONCE per lane (0.92 loads per output instead of 4), with row stride M words (odd => the 32
 //     lanes hit 32 different banks);
-//   * whether a new input frame yields 1 or 2 outputs is warp-uniform too (a byte script per
-//     frame, no divergence); the loop is unrolled over the 4 register slots so no moves are needed.
-// The warp's input tile (32*M + 3 contiguous frames) is staged by ONE bulk async copy (TMA,
-// cp.async.bulk + mbarrier).  Outputs are transposed through a small shared staging buffer and
-// written with one 128-byte bulk async store per lane (cp.async.bulk.global.shared::cta), so
-// stores stay coalesced although a lane's outputs are L samples apart from its neighbour's.
-// Warps are independent (own buffers, own mbarrier, own tile loop): no __syncthreads after setup.
+//   * whether a new input frame yields 1 or 2 outputs is uniform too (a byte script per frame in run_kernel,
+//     compile-time constants in run_static_kernel); the register slots are addressed statically, so no moves.
+// Input tiles (contiguous frames) are staged by ONE bulk async copy each (TMA, cp.async.bulk + mbarrier).
+// Outputs are transposed through a small XOR-swizzled shared staging tile and written as full 64-byte row
+// segments (st.global.L1::no_allocate.v4), so stores stay coalesced although a lane's outputs are L samples
+// apart from its neighbour's.
 //
 // Positions: rational (n*M/L) plus a constant drift term per launch (delta = x*eps_r, see
-// pipeline_poly.cu / DESIGN.md 3.2); the host splits launches so delta stays within 3 % of its
+// pipeline_poly.cu / DESIGN.md 3.2); the host splits launches so delta stays within 11 % of its
 // true value.  Tiles that touch the ends of the signal or of the shard, other formats / modes and
 // exactness-sensitive cases stay on pipeline_poly.cu's kernels.
 #include "common.cuh"
