@@ -45,7 +45,6 @@ struct run_plan {
     unsigned long long tile0;     // first warp tile (32*L outputs each) of this launch
     unsigned long long ntiles;
     int nbuf;                     // static kernel: frame buffers in the CTA's ring
-    int dbg_oneclass;             // timing experiment only (wrong results): every warp runs the class-0 code
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -553,7 +552,7 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
         }
         if (lane == 0) {
             warp_state &w = wst[warp];
-            w.dst = 0ull; w.i = pair; w.cls = rp.dbg_oneclass ? 0 : cls; w.slot = 0;
+            w.dst = 0ull; w.i = pair; w.cls = cls; w.slot = 0;
             w.stage_off = bufs_off + (uint32_t)nbuf * buf_bytes + (uint32_t)warp * SSTAGE_WORDS * 4;
         }
         if (threadIdx.x == 0) {
@@ -712,7 +711,6 @@ int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     if (nbuf < np) return 0;
     rp.nwarps = 2 * np;
     rp.nbuf = nbuf;
-    rp.dbg_oneclass = getenv("AUKIT_DEBUG_ONECLASS") ? 1 : 0;
     const size_t smem = fixed + (size_t)nbuf * buf + (size_t)np * stage;
     // the final clamp to +-1 can only act when peakAmplitude is (about) 1 or more
     const bool clamp1 = APPLY && !(a.peak < 1.0 - 9.5367431640625e-07);
