@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
     __shared__ cta_state cst;
     // The CTA walks tiles  tile0 + blockIdx.x + i * gridDim.x,  i = 0 .. n-1.  Tile i lives in frame buffer i % nbuf and
     // is consumed by warp pair i % npairs (warp 2p: first halves of its 32 periods, warp 2p+1: second halves).  With
-    // nbuf = npairs + 2 or 3 a pair's next tile was requested a whole tile time earlier: whichever of a buffer's two
+    // nbuf = npairs + 2 (apply) or + 4 (peak) a pair's next tile was requested most of a tile time earlier: whichever of a buffer's two
     // warps finishes LAST issues the bulk copy of tile i + nbuf into it -- no producer warp, no pair barrier, and
     // nobody waits for DRAM unless DRAM is the bottleneck.
     {
