@@ -63,6 +63,8 @@ SIGNATURES = {
     "aukit_cuda_audio_stride": (_SZ, [_P]),
     "aukit_cuda_audio_sample_rate": (_D, [_P]),
     "aukit_cuda_audio_data": (_P, [_P]),
+    "aukit_cuda_audio_set_sample_rate": (_I, [_P, _D]),
+    "aukit_cuda_audio_stream_chunk": (_I, [_P, _P, _I, _I, _SZ, _SZ, _P, C.POINTER(_SZ)]),
     "aukit_cuda_audio_channel_frames": (_SZ, [_P, _I]),
     "aukit_cuda_audio_download": (_I, [_P, _P, _I, _SZ, _SZ, _P]),
     "aukit_cuda_audio_upload": (_I, [_P, _P, _I, _SZ, _SZ, _P]),

@@ -184,6 +184,11 @@ class Audio:
         r = self._ctx.lib.aukit_cuda_audio_sample_rate(self._h)
         return int(r) if r == int(r) else r
 
+    @sampleRate.setter
+    def sampleRate(self, rate):
+        # a plain writable field in the reference (effects.speed assigns it, A:3383): later device calls see it
+        _lib.check(self._ctx.lib.aukit_cuda_audio_set_sample_rate(self._h, float(rate)))
+
     @property
     def data(self):
         return _ChannelData(self)
@@ -198,9 +203,6 @@ class Audio:
         _expect(1, sampleRate, float)
         interpolation = _expect(2, interpolation, str, type(None)) or defaultInterpolation
         if interpolation not in _INTERPS:
-            # "sinc" is accepted by the reference (A:656) but is not part of the accelerated path
-            if interpolation == "sinc":
-                raise AukitError("aukit_b200: sinc interpolation is not implemented on the device")
             raise AukitError("bad argument #2 (invalid interpolation type)")
         out = C.c_void_p()
         _lib.check(self._ctx.lib.aukit_cuda_resample(self._ctx.handle, self._h, float(sampleRate),
@@ -262,6 +264,36 @@ class Audio:
         _lib.check(self._ctx.lib.aukit_cuda_audio_pcm(self._ctx.handle, self._h, int(bitDepth), _DATATYPES[dataType],
                                                       int(interleaved), C.c_void_p(out.ctypes.data)))
         return out
+
+    def stream(self, chunkSize=None, bitDepth=None, dataType=None):        # A:921-937
+        """Audio:stream: (iterator, total length in seconds).  Each step of the iterator returns
+        (chunks, position): one float64 array of un-rounded PCM values per channel (encodePCM, A:868-894)
+        and the position of the chunk in seconds -- (1-based pos) / sampleRate, as the reference computes it."""
+        chunkSize = _expect(1, chunkSize, float, type(None)) or 131072
+        bitDepth = _expect(2, bitDepth, float, type(None)) or 8
+        dataType = _expect(3, dataType, str, type(None)) or "signed"
+        if bitDepth not in (8, 16, 24, 32):
+            raise AukitError("bad argument #2 (invalid bit depth)")
+        if dataType not in _DATATYPES:
+            raise AukitError("bad argument #3 (invalid data type)")
+        if dataType == "float" and bitDepth != 32:
+            raise AukitError("bad argument #2 (float audio must have 32-bit depth)")
+        chunk, bits, dt = int(chunkSize), int(bitDepth), _DATATYPES[dataType]
+        rate = self._ctx.lib.aukit_cuda_audio_sample_rate(self._h)
+        nch = self.channels()
+
+        def it():
+            pos = 1                                                       # the reference's 1-based frame index
+            while True:
+                buf = np.empty((nch, chunk), dtype=np.float64)
+                got = C.c_size_t(0)
+                _lib.check(self._ctx.lib.aukit_cuda_audio_stream_chunk(self._ctx.handle, self._h, bits, dt, pos - 1, chunk,
+                                                                       C.c_void_p(buf.ctypes.data), C.byref(got)))
+                if got.value == 0:
+                    return
+                yield [buf[c, : got.value].copy() for c in range(nch)], pos / rate
+                pos += chunk
+        return it(), self.frames / rate
 
     def pcm_bytes(self, bitDepth=16, dataType="signed", interleaved=True, rounding="truncate") -> bytes:
         """The packed little-endian samples Audio:wav writes (A:981-985); `rounding` is the host

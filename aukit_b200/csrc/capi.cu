@@ -136,11 +136,11 @@ int aukit_upload_bytes(aukit_ctx *ctx, const void *h, size_t nbytes, void **d_ou
         const bool pinned = cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost;
         cudaGetLastError();
         if (pinned || nbytes <= 4096) {
-            if (aukit_cuda_check(cudaMemcpyAsync(d, h, nbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D")) return -1;
+            if (aukit_cuda_check(cudaMemcpyAsync(d, h, nbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D")) { aukit_dev_free(ctx, d); return -1; }
             if (!pinned) cudaStreamSynchronize(ctx->stream);   // small pageable copies are staged by the driver
         } else {
             if (!ctx->h_stage) {
-                if (aukit_cuda_check(cudaMallocHost(&ctx->h_stage, 2 * slice), "cudaMallocHost")) return -1;
+                if (aukit_cuda_check(cudaMallocHost(&ctx->h_stage, 2 * slice), "cudaMallocHost")) { aukit_dev_free(ctx, d); return -1; }
                 ctx->h_stage_bytes = 2 * slice;
             }
             cudaEvent_t ev[2];
@@ -159,7 +159,7 @@ int aukit_upload_bytes(aukit_ctx *ctx, const void *h, size_t nbytes, void **d_ou
             cudaEventSynchronize(ev[1]);
             cudaEventDestroy(ev[0]);
             cudaEventDestroy(ev[1]);
-            if (aukit_cuda_check(cudaGetLastError(), "staged H2D")) return -1;
+            if (aukit_cuda_check(cudaGetLastError(), "staged H2D")) { aukit_dev_free(ctx, d); return -1; }
         }
     }
     *d_out = d;
@@ -215,6 +215,11 @@ extern "C" size_t aukit_cuda_audio_frames(const aukit_audio *a) { return a ? a->
 extern "C" size_t aukit_cuda_audio_stride(const aukit_audio *a) { return a ? a->stride : 0; }
 extern "C" double aukit_cuda_audio_sample_rate(const aukit_audio *a) { return a ? a->sampleRate : 0; }
 extern "C" float *aukit_cuda_audio_data(const aukit_audio *a) { return a ? a->data : nullptr; }
+extern "C" int aukit_cuda_audio_set_sample_rate(aukit_audio *a, double sampleRate) {
+    if (!a) return aukit_fail("aukit_cuda: null argument");
+    a->sampleRate = sampleRate;      // a plain field in the reference (effects.speed assigns it, A:3383)
+    return 0;
+}
 extern "C" size_t aukit_cuda_audio_channel_frames(const aukit_audio *a, int channel) {
     if (!a || channel < 0 || channel >= a->channels) return 0;
     return a->ch_frames ? a->ch_frames[channel] : a->frames;
@@ -304,11 +309,12 @@ extern "C" int aukit_cuda_adpcm(aukit_ctx *ctx, const void *h_data, size_t nbyte
     }
     const size_t len = nbytes * 2 / (size_t)channels;                   // A:1231
     void *d_in = nullptr, *d_p = nullptr, *d_i = nullptr;
-    if (aukit_upload_bytes(ctx, h_data, nbytes, &d_in)) return -1;
-    if (predictor && aukit_upload_bytes(ctx, predictor, sizeof(int) * (size_t)channels, &d_p)) return -1;
-    if (step_index && aukit_upload_bytes(ctx, step_index, sizeof(int) * (size_t)channels, &d_i)) return -1;
+    auto drop = [&]() { aukit_dev_free(ctx, d_in); aukit_dev_free(ctx, d_p); aukit_dev_free(ctx, d_i); return -1; };
+    if (aukit_upload_bytes(ctx, h_data, nbytes, &d_in)) return drop();
+    if (predictor && aukit_upload_bytes(ctx, predictor, sizeof(int) * (size_t)channels, &d_p)) return drop();
+    if (step_index && aukit_upload_bytes(ctx, step_index, sizeof(int) * (size_t)channels, &d_i)) return drop();
     aukit_audio *a = nullptr;
-    if (aukit_audio_alloc(ctx, channels, len, sampleRate, &a)) return -1;
+    if (aukit_audio_alloc(ctx, channels, len, sampleRate, &a)) return drop();
     int rc = len ? aukit_launch_adpcm_stream(ctx, static_cast<const uint8_t *>(d_in), len, channels, topFirst, interleaved,
                                              static_cast<const int *>(d_p), static_cast<const int *>(d_i), a->data, a->stride)
                  : 0;
@@ -371,6 +377,15 @@ extern "C" int aukit_cuda_wav_parse(const void *h_data, size_t nbytes, aukit_wav
     const uint8_t *data = static_cast<const uint8_t *>(h_data);
     memset(info, 0, sizeof *info);
     info->format = AUKIT_WAV_NONE;
+    // The reference decodes every data chunk where it meets it, with the fmt state seen SO FAR (A:1505-1555); the
+    // last data chunk's Audio is returned.  The fmt fields are therefore parsed into `cur` and snapshotted into
+    // *info at each data chunk: a fmt chunk that follows the last data chunk changes nothing (it is still
+    // validated, as the reference would raise on an unsupported one).
+    struct fmt_state { int format, channels, sampleRate, blockAlign, bitDepth, have_fmt, ncoef; int coef1[256], coef2[256]; };
+    static thread_local fmt_state cur_s;
+    fmt_state *cur = &cur_s;
+    memset(cur, 0, sizeof *cur);
+    cur->format = AUKIT_WAV_NONE;
     static const uint8_t ksTail[12] = {0x00, 0x00, 0x10, 0x00, 0x80, 0x00, 0x00, 0xaa, 0x00, 0x38, 0x9b, 0x71};
     static const uint8_t dfpwm[16] = {0x3a, 0xc1, 0xfa, 0x38, 0x81, 0x1d, 0x43, 0x61,
                                       0xa4, 0x0d, 0xce, 0x53, 0xca, 0x60, 0x7c, 0xd1};
@@ -392,45 +407,45 @@ extern "C" int aukit_cuda_wav_parse(const void *h_data, size_t nbytes, aukit_wav
             pos += size;
             if (clen < 16) return aukit_fail("data string too short");
             const uint32_t format = rd_u16(ch);
-            info->channels = (int)rd_u16(ch + 2);
-            info->sampleRate = (int)rd_u32(ch + 4);
-            info->blockAlign = (int)rd_u16(ch + 12);
-            info->bitDepth = (int)rd_u16(ch + 14);
-            info->have_fmt = 1;
+            cur->channels = (int)rd_u16(ch + 2);
+            cur->sampleRate = (int)rd_u32(ch + 4);
+            cur->blockAlign = (int)rd_u16(ch + 12);
+            cur->bitDepth = (int)rd_u16(ch + 14);
+            cur->have_fmt = 1;
             switch (format) {
-            case 1: info->format = info->bitDepth == 8 ? AUKIT_WAV_PCM_UNSIGNED : AUKIT_WAV_PCM_SIGNED; break;
+            case 1: cur->format = cur->bitDepth == 8 ? AUKIT_WAV_PCM_UNSIGNED : AUKIT_WAV_PCM_SIGNED; break;
             case 2: {
-                info->format = AUKIT_WAV_MSADPCM;
+                cur->format = AUKIT_WAV_MSADPCM;
                 if (clen < 22) return aukit_fail("data string too short");
                 const int numcoeff = (int)rd_u16(ch + 20);
                 if (numcoeff > 256) return aukit_fail("aukit_cuda: more than 256 coefficient pairs");
                 for (int i = 0; i < numcoeff; i++) {
                     const size_t o = 22 + 4 * (size_t)i;
                     if (o + 4 > clen) return aukit_fail("data string too short");
-                    info->coef1[i] = rd_i16(ch + o);
-                    info->coef2[i] = rd_i16(ch + o + 2);
+                    cur->coef1[i] = rd_i16(ch + o);
+                    cur->coef2[i] = rd_i16(ch + o + 2);
                 }
-                if (numcoeff > 0) info->ncoef = numcoeff;
+                if (numcoeff > 0) cur->ncoef = numcoeff;
                 break;
             }
-            case 3: info->format = AUKIT_WAV_FLOAT; break;
-            case 6: info->format = AUKIT_WAV_ALAW; break;
-            case 7: info->format = AUKIT_WAV_ULAW; break;
-            case 0x11: info->format = AUKIT_WAV_ADPCM; break;
+            case 3: cur->format = AUKIT_WAV_FLOAT; break;
+            case 6: cur->format = AUKIT_WAV_ALAW; break;
+            case 7: cur->format = AUKIT_WAV_ULAW; break;
+            case 0x11: cur->format = AUKIT_WAV_ADPCM; break;
             case 0xFFFE: {
                 if (clen < 20) return aukit_fail("data string too short");
-                info->bitDepth = (int)rd_u16(ch + 18);
+                cur->bitDepth = (int)rd_u16(ch + 18);
                 if (clen < 40) return aukit_fail("unsupported WAV file");
                 const uint8_t *u = ch + 24;
-                if (!memcmp(u, dfpwm, 16)) { info->format = AUKIT_WAV_DFPWM; break; }
+                if (!memcmp(u, dfpwm, 16)) { cur->format = AUKIT_WAV_DFPWM; break; }
                 if (memcmp(u + 4, ksTail, 12) || u[1] || u[2] || u[3]) return aukit_fail("unsupported WAV file");
                 switch (u[0]) {
-                case 0x01: info->format = info->bitDepth == 8 ? AUKIT_WAV_PCM_UNSIGNED : AUKIT_WAV_PCM_SIGNED; break;
-                case 0x02: info->format = AUKIT_WAV_MSADPCM; break;
-                case 0x03: info->format = AUKIT_WAV_FLOAT; break;
-                case 0x06: info->format = AUKIT_WAV_ALAW; break;
-                case 0x07: info->format = AUKIT_WAV_ULAW; break;
-                case 0x11: info->format = AUKIT_WAV_ADPCM; break;
+                case 0x01: cur->format = cur->bitDepth == 8 ? AUKIT_WAV_PCM_UNSIGNED : AUKIT_WAV_PCM_SIGNED; break;
+                case 0x02: cur->format = AUKIT_WAV_MSADPCM; break;
+                case 0x03: cur->format = AUKIT_WAV_FLOAT; break;
+                case 0x06: cur->format = AUKIT_WAV_ALAW; break;
+                case 0x07: cur->format = AUKIT_WAV_ULAW; break;
+                case 0x11: cur->format = AUKIT_WAV_ADPCM; break;
                 default: return aukit_fail("unsupported WAV file");
                 }
                 break;
@@ -441,6 +456,11 @@ extern "C" int aukit_cuda_wav_parse(const void *h_data, size_t nbytes, aukit_wav
             if (size > nbytes - pos) return aukit_fail("invalid WAV file");
             info->data_off = pos;
             info->data_size = size;
+            info->format = cur->format; info->channels = cur->channels; info->sampleRate = cur->sampleRate;
+            info->blockAlign = cur->blockAlign; info->bitDepth = cur->bitDepth; info->have_fmt = cur->have_fmt;
+            info->ncoef = cur->ncoef;
+            memcpy(info->coef1, cur->coef1, sizeof info->coef1);
+            memcpy(info->coef2, cur->coef2, sizeof info->coef2);
             have_data = true;
             pos += size;
         } else if (!memcmp(id, "LIST", 4)) {
@@ -752,17 +772,22 @@ extern "C" int aukit_cuda_preloader_begin(aukit_preloader *pl, const aukit_pipel
     if (s.busy) {                                   // begun but never finished
         return aukit_fail("aukit_cuda: preloader slot %d is still between begin and finish", k);
     }
+    s.desc = *p; s.stride = stride;
+    // a failure below leaves the slot free and the rotation where it was (the caller may retry)
+    auto enqueue = [&]() -> int {
+        // upload: the slot's input buffer is free once the apply pass that last read it is done
+        AUKIT_CUDA_TRY(cudaStreamWaitEvent(pl->s_in, s.in_free, 0));
+        if (need) AUKIT_CUDA_TRY(cudaMemcpyAsync(s.d_in, h_in, need, cudaMemcpyHostToDevice, pl->s_in));
+        AUKIT_CUDA_TRY(cudaEventRecord(s.in_done, pl->s_in));
+        // peak pass
+        AUKIT_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, s.in_done, 0));
+        AUKIT_CUDA_TRY(cudaMemsetAsync(s.d_peak, 0, sizeof(float), pl->s_run));
+        stream_swap sw(pl->ctx, pl->s_run);
+        return aukit_cuda_dev_pipeline_peak(pl->ctx, &s.desc, s.d_in, s.d_peak);
+    };
+    if (enqueue()) return -1;
+    s.busy = true;
     pl->next = (k + 1) % pl->slots;
-    s.desc = *p; s.stride = stride; s.busy = true;
-    // upload: the slot's input buffer is free once the apply pass that last read it is done
-    AUKIT_CUDA_TRY(cudaStreamWaitEvent(pl->s_in, s.in_free, 0));
-    if (need) AUKIT_CUDA_TRY(cudaMemcpyAsync(s.d_in, h_in, need, cudaMemcpyHostToDevice, pl->s_in));
-    AUKIT_CUDA_TRY(cudaEventRecord(s.in_done, pl->s_in));
-    // peak pass
-    AUKIT_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, s.in_done, 0));
-    AUKIT_CUDA_TRY(cudaMemsetAsync(s.d_peak, 0, sizeof(float), pl->s_run));
-    stream_swap sw(pl->ctx, pl->s_run);
-    if (aukit_cuda_dev_pipeline_peak(pl->ctx, &s.desc, s.d_in, s.d_peak)) return -1;
     *slot_out = k;
     return 0;
 }

@@ -262,3 +262,28 @@ extern "C" int aukit_cuda_audio_pcm_bytes(aukit_ctx *ctx, const aukit_audio *a, 
     if (!rc) rc = aukit_cuda_synchronize(ctx);
     return rc;
 }
+
+// Audio:stream (A:921-937): one chunk of the iterator -- encodePCM with `multiple` set (A:881-891): frames
+// [first, first + count) of every channel as un-rounded values, planar h_out[c * count + k].  `count` is clipped to
+// the end of the audio; *got receives the frames written (0 past the end: the iterator then returns nil, A:878).
+extern "C" int aukit_cuda_audio_stream_chunk(aukit_ctx *ctx, const aukit_audio *a, int bitDepth, int dataType, size_t first,
+                                             size_t count, double *h_out, size_t *got) {
+    if (!ctx || !a || !got) return aukit_fail("aukit_cuda: null argument");
+    double maxv, add;
+    if (encode_args(bitDepth, dataType, &maxv, &add)) return -1;
+    *got = 0;
+    if (first >= a->frames || count == 0) return 0;
+    const size_t n = a->frames - first < count ? a->frames - first : count;
+    if (!h_out) return aukit_fail("aukit_cuda: null argument");
+    const size_t total = n * (size_t)a->channels;
+    void *d_out = nullptr;
+    if (aukit_dev_alloc(ctx, total * sizeof(double) + 16, &d_out)) return -1;
+    int rc = aukit_cuda_dev_encode_pcm(ctx, a->data + first, a->stride, a->channels, n, bitDepth, dataType, 0, static_cast<double *>(d_out));
+    // rows of the chunk are n apart on the device; the caller's rows are `count` apart only when n == count
+    if (!rc) rc = aukit_cuda_check(cudaMemcpy2DAsync(h_out, count * sizeof(double), d_out, n * sizeof(double), n * sizeof(double),
+                                                     (size_t)a->channels, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+    aukit_dev_free(ctx, d_out);
+    if (!rc) rc = aukit_cuda_synchronize(ctx);
+    if (!rc) *got = n;
+    return rc;
+}

@@ -73,7 +73,8 @@ __device__ __forceinline__ void lp_fetch_tile(float *tile, const float *base, in
 template <bool HIGH>
 __global__ void __launch_bounds__(LP_THREADS, LP_CTAS_PER_SM)
 lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, double a, double b,
-               lp_slot *slots, unsigned long long *ticket, unsigned long long tiles_per_ch, const float *__restrict__ xb) {
+               lp_slot *slots, unsigned long long *ticket, unsigned long long tiles_per_ch, const float *__restrict__ xb,
+               unsigned long long *poison) {
     extern __shared__ __align__(16) float lp_dyn[];                     // two tile buffers (double buffered: see the loop)
     float *const tiles[2] = {lp_dyn, lp_dyn + LP_THREADS * LP_ROW};
     __shared__ double pt_pow[LP_THREADS];        // (ratio^LP_PER)^t
@@ -194,7 +195,11 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
                 carry = acc;
             }
             if (lane == 0) {
-                st_slot(&slots[id], fma(p_tile, carry, agg), 2);
+                const double incl = fma(p_tile, carry, agg);
+                st_slot(&slots[id], incl, 2);
+                // a non-finite state never leaves the reference's recurrence (A:3592-3595); the bounded look-back
+                // above can miss it, so the first such tile of a channel is recorded for lp_poison_fix
+                if (!isfinite(incl)) atomicMin(&poison[ch], tl);
                 s_carry = carry;
             }
         }
@@ -239,17 +244,40 @@ __global__ void lp_save_boundaries(const float *__restrict__ data, size_t stride
     xb[id] = tl ? data[(size_t)ch * stride + (size_t)tl * LP_TILE - 1] : 0.0f;
 }
 
+// Non-finite input (float PCM can carry NaN / Inf): once the reference's state is non-finite every later sample of the
+// channel is too -- NaN for the low-pass (Inf + a (x - Inf) = NaN one step later), NaN or the same Inf for the
+// high-pass (a ((Inf + x) - x') = Inf).  Tiles further than the look-back's 2^-80 horizon behind such a tile never
+// poll it, so after the scan every tile past the first poisoned one of its channel is overwritten.  No-op (one
+// 8-byte read per CTA) for finite audio.
+template <bool HIGH>
+__global__ void lp_poison_fix(float *__restrict__ data, size_t stride, int channels, size_t n, const lp_slot *slots,
+                              unsigned long long tiles_per_ch, const unsigned long long *poison) {
+    for (int ch = 0; ch < channels; ch++) {
+        const unsigned long long T = poison[ch];
+        if (T >= tiles_per_ch) continue;
+        const double st = slots[(unsigned long long)ch * tiles_per_ch + T].v;
+        const float fill = (HIGH && isinf(st)) ? (float)st : __int_as_float(0x7FC00000);
+        float *row = data + (size_t)ch * stride;
+        for (size_t i = (size_t)(T + 1) * LP_TILE + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+             i += (size_t)gridDim.x * blockDim.x)
+            row[i] = fill;
+    }
+}
+
 static int lp_run(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n, double a, double ratio, bool high) {
     const unsigned long long tiles = (n + LP_TILE - 1) / LP_TILE, total = tiles * (unsigned long long)channels;
     // scratch: one 16-byte slot per (channel, tile) + the ticket counter (+ the boundary samples for highpass)
     void *scratch = nullptr;
     const size_t slot_bytes = (size_t)total * sizeof(lp_slot);
     const size_t xb_bytes = high ? (((size_t)total * sizeof(float) + 15) & ~(size_t)15) : 0;
-    if (aukit_dev_alloc(ctx, slot_bytes + 16 + xb_bytes, &scratch)) return -1;
+    const size_t poison_bytes = (((size_t)channels * sizeof(unsigned long long)) + 15) & ~(size_t)15;
+    if (aukit_dev_alloc(ctx, slot_bytes + 16 + poison_bytes + xb_bytes, &scratch)) return -1;
     lp_slot *slots = static_cast<lp_slot *>(scratch);
     unsigned long long *ticket = reinterpret_cast<unsigned long long *>(static_cast<char *>(scratch) + slot_bytes);
-    float *xb = high ? reinterpret_cast<float *>(static_cast<char *>(scratch) + slot_bytes + 16) : nullptr;
+    unsigned long long *poison = ticket + 2;
+    float *xb = high ? reinterpret_cast<float *>(static_cast<char *>(scratch) + slot_bytes + 16 + poison_bytes) : nullptr;
     int rc = aukit_cuda_check(cudaMemsetAsync(scratch, 0, slot_bytes + 16, ctx->stream), "memset");
+    if (!rc) rc = aukit_cuda_check(cudaMemsetAsync(poison, 0xFF, poison_bytes, ctx->stream), "memset");
     if (!rc && high) {
         lp_save_boundaries<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d, stride, tiles, total, xb);
         ctx->launches++;
@@ -261,13 +289,15 @@ static int lp_run(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t 
         if (high) {
             cudaFuncSetAttribute(lowpass_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(lowpass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP_SMEM);
-            lowpass_kernel<true><<<(unsigned)g, LP_THREADS, LP_SMEM, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb);
+            lowpass_kernel<true><<<(unsigned)g, LP_THREADS, LP_SMEM, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb, poison);
+            lp_poison_fix<true><<<ctx->num_sms, 256, 0, ctx->stream>>>(d, stride, channels, n, slots, tiles, poison);
         } else {
             cudaFuncSetAttribute(lowpass_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(lowpass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP_SMEM);
-            lowpass_kernel<false><<<(unsigned)g, LP_THREADS, LP_SMEM, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb);
+            lowpass_kernel<false><<<(unsigned)g, LP_THREADS, LP_SMEM, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb, poison);
+            lp_poison_fix<false><<<ctx->num_sms, 256, 0, ctx->stream>>>(d, stride, channels, n, slots, tiles, poison);
         }
-        ctx->launches++;
+        ctx->launches += 2;
         rc = aukit_cuda_check(cudaGetLastError(), "lowpass_kernel launch");
     }
     aukit_dev_free(ctx, scratch);

@@ -300,6 +300,36 @@ static int l_normalize(lua_State *L) {
     return 0;
 }
 
+/* cu.set_sample_rate(audio, rate): audio.sampleRate is a plain writable field in the reference (A:3383) */
+static int l_set_sample_rate(lua_State *L) {
+    if (aukit_cuda_audio_set_sample_rate(check_audio(L, 1), luaL_checknumber(L, 2))) return fail(L);
+    return 0;
+}
+
+/* cu.stream_chunk(audio, bitDepth, dataType, pos (1-based), count) -> {{ch1 values}, {ch2 values}, ...} or nil past the
+ * end: one step of Audio:stream's iterator (A:921-937, encodePCM's `multiple` branch A:881-891) */
+static int l_stream_chunk(lua_State *L) {
+    aukit_audio *a = check_audio(L, 1);
+    const size_t first = (size_t)luaL_checknumber(L, 4) - 1, count = (size_t)luaL_checknumber(L, 5);
+    const int nch = aukit_cuda_audio_channels(a);
+    double *buf = (double *)malloc(sizeof(double) * (count ? count : 1) * (size_t)(nch > 0 ? nch : 1));
+    size_t got = 0;
+    if (!buf) return luaL_error(L, "out of memory");
+    if (aukit_cuda_audio_stream_chunk(ctx(L), a, (int)luaL_checkinteger(L, 2), (int)luaL_checkinteger(L, 3), first, count, buf, &got)) {
+        free(buf);
+        return fail(L);
+    }
+    if (got == 0) { free(buf); lua_pushnil(L); return 1; }
+    lua_createtable(L, nch, 0);
+    for (int c = 0; c < nch; c++) {
+        lua_createtable(L, (int)got, 0);
+        for (size_t i = 0; i < got; i++) { lua_pushnumber(L, buf[(size_t)c * count + i]); lua_rawseti(L, -2, (int)i + 1); }
+        lua_rawseti(L, -2, c + 1);
+    }
+    free(buf);
+    return 1;
+}
+
 static int l_channels(lua_State *L) { lua_pushinteger(L, aukit_cuda_audio_channels(check_audio(L, 1))); return 1; }
 static int l_sample_rate(lua_State *L) { lua_pushnumber(L, aukit_cuda_audio_sample_rate(check_audio(L, 1))); return 1; }
 
@@ -381,7 +411,8 @@ static const luaL_Reg funcs[] = {
     {"pcm", l_pcm}, {"g711", l_g711}, {"adpcm", l_adpcm}, {"ima_adpcm_wav", l_ima_wav}, {"msadpcm", l_msadpcm},
     {"wav", l_wav}, {"new", l_new}, {"resample", l_resample}, {"mono", l_mono}, {"concat", l_concat},
     {"au", l_au}, {"aiff", l_aiff}, {"amplify", l_amplify}, {"invert", l_invert}, {"fade", l_fade}, {"delay", l_delay}, {"center", l_center}, {"lowpass", l_lowpass}, {"highpass", l_highpass}, {"pcm_out", l_pcm_out}, {"pcm_bytes", l_pcm_bytes}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
-    {"frames", l_frames}, {"read", l_read}, {"write", l_write}, {NULL, NULL}};
+    {"frames", l_frames}, {"read", l_read}, {"write", l_write}, {"set_sample_rate", l_set_sample_rate},
+    {"stream_chunk", l_stream_chunk}, {NULL, NULL}};
 
 int luaopen_aukit_cuda(lua_State *L) {
     luaL_newmetatable(L, AUDIO_MT);

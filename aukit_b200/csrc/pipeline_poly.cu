@@ -509,7 +509,8 @@ static int poly_range(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_d
             if (df > a.out_first) {
                 pipe_args h = a;
                 h.n_out = (size_t)(df - a.out_first);
-                if (poly_range(ctx, h, p, apply, false) != 1) rc = -1;
+                const int e = poly_range(ctx, h, p, apply, false);
+                if (e != 1) { if (e == 0) aukit_fail("aukit_cuda: no polyphase kernel for the head of the range"); rc = -1; }
             }
             const unsigned long long end = a.out_first + a.n_out;
             if (rc == 1 && df + dc < end) {
@@ -517,7 +518,8 @@ static int poly_range(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_d
                 t.out_first = df + dc;
                 t.n_out = (size_t)(end - (df + dc));
                 if (apply) t.out = a.out + (size_t)(df + dc - a.out_first);
-                if (poly_range(ctx, t, p, apply, false) != 1) rc = -1;
+                const int e = poly_range(ctx, t, p, apply, false);
+                if (e != 1) { if (e == 0) aukit_fail("aukit_cuda: no polyphase kernel for the tail of the range"); rc = -1; }
             }
             if (!no_side) {
                 ctx->stream = main_stream;

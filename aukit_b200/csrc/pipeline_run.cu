@@ -103,6 +103,14 @@ __device__ __forceinline__ f32x2 cvt_frame(uint32_t w) {
     return fma2(pack2(ul + fabsf(ul), ur + fabsf(ur)), pack2(c, c), pack2(ul, ur));
 }
 
+// clamp(v, -32768, 32768) of A:668 in the scaled domain as ONE instruction: sign(v) * min(|v|, 32768)
+// (min.xorsign.abs: the result takes the XOR of the operands' signs, the bound is positive).  Inputs are finite here.
+__device__ __forceinline__ float clamp_scaled(float v) {
+    float r;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(32768.0f));
+    return r;
+}
+
 constexpr int STAGE_COLS = 16;        // outputs per lane per flush (64 bytes per lane-row)
 constexpr int STAGE_RING = 32;        // staged columns per lane (ring): the two classes drift by a few outputs
 constexpr int STAGE_STRIDE = 36;      // floats per staging row: 16-byte aligned rows
@@ -244,8 +252,8 @@ __global__ void __launch_bounds__(768, 1) run_kernel(pipe_args a, run_plan rp) {
             acc = fma2(p3, pack2(w.w, w.w), acc);
             float vl, vr;
             unpack2(acc, vl, vr);
-            vl = fminf(fmaxf(vl, -32768.0f), 32768.0f);   // A:668 in the scaled domain (inputs finite, |v| <= 1)
-            vr = fminf(fmaxf(vr, -32768.0f), 32768.0f);
+            vl = clamp_scaled(vl);                        // A:668 in the scaled domain (inputs finite, |v| <= 1)
+            vr = clamp_scaled(vr);
             const float sum = vl + vr;                    // (0 + L) + R, A:686; the /2 is in the final scale
             if (APPLY) {
                 const float o = sum * mult;
@@ -344,8 +352,8 @@ int launch_run(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     rp.nwarps = nw;
     const size_t smem = fixed + (((size_t)nw * 8 + 127) & ~(size_t)127) + (size_t)nw * per_warp + 128;
     const int cmin = L / M;
-    // the final clamp to +-1 can only act when peakAmplitude is (about) 1 or more
-    const bool clamp1 = APPLY && !(a.peak < 1.0 - 9.5367431640625e-07);
+    // the final clamp to +-1 can only act when |peakAmplitude| is (about) 1 or more (negative peaks included: normalize(a, -2))
+    const bool clamp1 = APPLY && !(fabs(a.peak) < 1.0 - 9.5367431640625e-07);
     auto kern = cmin == 1 ? run_kernel<APPLY, 1, false> : (cmin == 2 ? run_kernel<APPLY, 2, false> : run_kernel<APPLY, 4, false>);
     if (clamp1) kern = cmin == 1 ? run_kernel<APPLY, 1, true> : (cmin == 2 ? run_kernel<APPLY, 2, true> : run_kernel<APPLY, 4, true>);
     if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
@@ -465,8 +473,8 @@ __device__ __forceinline__ void semit(const half_ctx &hc, f32x2 p0, f32x2 p1, f3
     float vl, vr;
     unpack2(acc, vl, vr);
     if (CLAMPCH) {
-        vl = fminf(fmaxf(vl, -32768.0f), 32768.0f);       // A:668 in the scaled domain
-        vr = fminf(fmaxf(vr, -32768.0f), 32768.0f);
+        vl = clamp_scaled(vl);                            // A:668 in the scaled domain, one FMNMX per channel
+        vr = clamp_scaled(vr);
     } else {
         chk = fmaxf(chk, fmaxf(fabsf(vl), fabsf(vr)));    // one FMNMX3: did A:668 have anything to do?
     }
@@ -712,8 +720,8 @@ int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     rp.nwarps = 2 * np;
     rp.nbuf = nbuf;
     const size_t smem = fixed + (size_t)nbuf * buf + (size_t)np * stage;
-    // the final clamp to +-1 can only act when peakAmplitude is (about) 1 or more
-    const bool clamp1 = APPLY && !(a.peak < 1.0 - 9.5367431640625e-07);
+    // the final clamp to +-1 can only act when |peakAmplitude| is (about) 1 or more (negative peaks included: normalize(a, -2))
+    const bool clamp1 = APPLY && !(fabs(a.peak) < 1.0 - 9.5367431640625e-07);
     // max(u, 0) of the sample conversion on the ALU pipe (default: the FMA pipe is the busier one here); =0 for A/B runs
     static const bool cvt_alu = !(getenv("AUKIT_RUN_CVT_ALU") && getenv("AUKIT_RUN_CVT_ALU")[0] == '0');
     auto kern = clamp1 ? run_static_kernel<APPLY, APPLY, false, L, M> : run_static_kernel<APPLY, false, false, L, M>;

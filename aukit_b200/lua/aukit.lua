@@ -5,8 +5,9 @@
 -- the C module `aukit_cuda` (luaopen_aukit_cuda, csrc/lua_binding.c -> libaukit_cuda.so).
 -- auplay.lua's load -> :resample(48000) -> :mono() -> effects.normalize(mono, 0.8) runs unchanged.
 --
--- In scope (device-backed): aukit.pcm, aukit.g711, aukit.adpcm, aukit.msadpcm, aukit.wav, aukit.new,
---   Audio:len/channels/resample/mono/concat/pcm/wav, aukit.effects.amplify/normalize/lowpass, aukit.defaultInterpolation.
+-- In scope (device-backed): aukit.pcm, aukit.g711, aukit.adpcm, aukit.msadpcm, aukit.wav, aukit.au, aukit.aiff, aukit.new,
+--   Audio:len/channels/resample (none, linear, cubic, sinc)/mono/concat/pcm/stream/wav,
+--   aukit.effects.amplify/normalize/lowpass/highpass/invert/fade/delay/center, aukit.defaultInterpolation.
 -- Everything else of the reference (players, streams, FLAC/QOA/DFPWM, editing ops, writers) is out of
 -- scope of this accelerated path; load the reference module alongside for those.
 --
@@ -84,7 +85,14 @@ local function wrap(handle, metadata, info)
                          metadata = metadata or {}, info = info or {}}, Audio_mt)
 end
 
-local function handle(audio) return audio.data._h end
+-- `sampleRate` is a plain writable field, as in the reference (effects.speed assigns it, A:3383), and `data` may have
+-- been rebound to another Audio's: every device call goes through handle(), which first tells the C side the rate
+-- this Audio table currently carries.
+local function handle(audio)
+    local h = audio.data._h
+    if type(audio.sampleRate) == "number" then cu.set_sample_rate(h, audio.sampleRate) end
+    return h
+end
 local function invalidate(audio) end -- channel proxies are created per access; nothing cached on the Audio
 
 -- ---------------------------------------------------------------------------------------------
@@ -100,7 +108,6 @@ function Audio:channels() return #self.data end
 function Audio:resample(sampleRate, interpolation)
     expect(1, sampleRate, "number")
     interpolation = expect(2, interpolation, "string", "nil") or aukit.defaultInterpolation
-    if interpolation == "sinc" then error("sinc interpolation is not available on the accelerated path", 2) end
     if not INTERP[interpolation] then error("bad argument #2 (invalid interpolation type)", 2) end
     local out = wrap(cu.resample(handle(self), sampleRate, INTERP[interpolation]), copy(self.metadata), copy(self.info))
     out.sampleRate = sampleRate
@@ -124,6 +131,25 @@ function Audio:pcm(bitDepth, dataType, interleaved)
     if dataType ~= "signed" and dataType ~= "unsigned" and dataType ~= "float" then error("bad argument #3 (invalid data type)", 2) end
     if dataType == "float" and bitDepth ~= 32 then error("bad argument #2 (float audio must have 32-bit depth)", 2) end
     return cu.pcm_out(handle(self), bitDepth, DATATYPE[dataType], interleaved)
+end
+
+--- Returns a function that can be called to encode PCM samples in chunks, and the total length in seconds. (A:921)
+function Audio:stream(chunkSize, bitDepth, dataType)
+    chunkSize = expect(1, chunkSize, "number", "nil") or 131072
+    bitDepth = expect(2, bitDepth, "number", "nil") or 8
+    dataType = expect(3, dataType, "string", "nil") or "signed"
+    if bitDepth ~= 8 and bitDepth ~= 16 and bitDepth ~= 24 and bitDepth ~= 32 then error("bad argument #2 (invalid bit depth)", 2) end
+    if dataType ~= "signed" and dataType ~= "unsigned" and dataType ~= "float" then error("bad argument #3 (invalid data type)", 2) end
+    if dataType == "float" and bitDepth ~= 32 then error("bad argument #2 (float audio must have 32-bit depth)", 2) end
+    local pos, done = 1, false
+    return function()
+        if done then return nil end
+        local p = pos / self.sampleRate
+        local v = cu.stream_chunk(handle(self), bitDepth, DATATYPE[dataType], pos, chunkSize)   -- nil past the end (A:878)
+        if v == nil then done = true return nil end
+        pos = pos + chunkSize
+        return v, p
+    end, #self.data[1] / self.sampleRate
 end
 
 --- Converts the audio data to a WAV file (PCM depths; DFPWM is outside this module). (A:942)

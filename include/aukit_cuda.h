@@ -74,6 +74,9 @@ size_t aukit_cuda_audio_frames(const aukit_audio *a);                        /* 
 size_t aukit_cuda_audio_stride(const aukit_audio *a);
 double aukit_cuda_audio_sample_rate(const aukit_audio *a);
 float *aukit_cuda_audio_data(const aukit_audio *a);                          /* device pointer */
+/* audio.sampleRate = x: a plain writable field in the reference (effects.speed assigns it, A:3383); every later
+ * device call (resample, fade, delay, center, low/highpass, Audio:len) reads this value. */
+int aukit_cuda_audio_set_sample_rate(aukit_audio *a, double sampleRate);
 /* Per-channel length; differs from frames only for ragged G.711 input (A:1379). */
 size_t aukit_cuda_audio_channel_frames(const aukit_audio *a, int channel);
 /* Copy channel `channel` frames [first, first+count) to host floats (synchronises). */
@@ -186,6 +189,12 @@ int aukit_cuda_audio_pcm(aukit_ctx *ctx, const aukit_audio *a, int bitDepth, int
  * the reference leaves this to the host's string.pack.  Out-of-range values saturate. */
 int aukit_cuda_audio_pcm_bytes(aukit_ctx *ctx, const aukit_audio *a, int bitDepth, int dataType,
                                int interleaved, int rounding, void *h_out);
+
+/* Audio:stream(chunkSize, bitDepth, dataType) A:921-937: one step of the chunk iterator.  Frames [first, first+count)
+ * of every channel through encodePCM (A:868-894, `multiple` branch), un-rounded doubles, planar
+ * h_out[c * count + k]; *got = frames written (clipped at the end of the audio; 0 => the iterator is done, A:878). */
+int aukit_cuda_audio_stream_chunk(aukit_ctx *ctx, const aukit_audio *a, int bitDepth, int dataType,
+                                  size_t first, size_t count, double *h_out, size_t *got);
 
 /* ------------------------------------------------------------------ device-pointer level */
 /* Same kernels on caller-owned DEVICE buffers (inputs already resident in HBM; what

@@ -657,6 +657,11 @@ int auko_wav_parse(const uint8_t *data, size_t nbytes, auko_wav_info *info) {
     g_err[0] = 0;
     memset(info, 0, sizeof *info);
     info->format = AUKO_WAV_NONE;
+    /* every data chunk is decoded where it is met, with the fmt state seen so far (A:1505-1555); `coefficients`
+     * and `dataType` are locals of the whole walk (A:1458), so they survive a later fmt chunk that does not set them */
+    static __thread auko_wav_info cur;
+    memset(&cur, 0, sizeof cur);
+    cur.format = AUKO_WAV_NONE;
     if (nbytes < 4) return fail("data string too short");
     if (memcmp(data, "RIFF", 4)) return fail("bad argument #1 (not a WAV file)");   /* A:1460 */
     if (nbytes < 12) return fail("data string too short");
@@ -673,15 +678,14 @@ int auko_wav_parse(const uint8_t *data, size_t nbytes, auko_wav_info *info) {
             pos += size;
             if (clen < 16) return fail("data string too short");
             int format = rd_u16(ch);                                         /* A:1473 */
-            info->channels = rd_u16(ch + 2);
-            info->sampleRate = (int)rd_u32(ch + 4);
-            info->blockAlign = rd_u16(ch + 12);
-            info->bitDepth = rd_u16(ch + 14);
-            info->have_fmt = 1;
-            info->ncoef = 0;
-            if (format == 1) info->format = info->bitDepth == 8 ? AUKO_WAV_PCM_UNSIGNED : AUKO_WAV_PCM_SIGNED;
+            cur.channels = rd_u16(ch + 2);
+            cur.sampleRate = (int)rd_u32(ch + 4);
+            cur.blockAlign = rd_u16(ch + 12);
+            cur.bitDepth = rd_u16(ch + 14);
+            cur.have_fmt = 1;
+            if (format == 1) cur.format = cur.bitDepth == 8 ? AUKO_WAV_PCM_UNSIGNED : AUKO_WAV_PCM_SIGNED;
             else if (format == 2) {
-                info->format = AUKO_WAV_MSADPCM;
+                cur.format = AUKO_WAV_MSADPCM;
                 if (clen < 22) return fail("data string too short");
                 int numcoeff = rd_u16(ch + 20);                              /* A:1478 */
                 if (numcoeff > 0) {
@@ -689,30 +693,30 @@ int auko_wav_parse(const uint8_t *data, size_t nbytes, auko_wav_info *info) {
                     for (int i = 1; i <= numcoeff; i++) {                    /* A:1481-1483 */
                         size_t o = (size_t)i * 4 + 18;
                         if (o + 4 > clen) return fail("data string too short");
-                        info->coef1[i - 1] = rd_i16(ch + o);
-                        info->coef2[i - 1] = rd_i16(ch + o + 2);
+                        cur.coef1[i - 1] = rd_i16(ch + o);
+                        cur.coef2[i - 1] = rd_i16(ch + o + 2);
                     }
-                    info->ncoef = numcoeff;
+                    cur.ncoef = numcoeff;
                 }
-            } else if (format == 3) info->format = AUKO_WAV_FLOAT;
-            else if (format == 6) info->format = AUKO_WAV_ALAW;
-            else if (format == 7) info->format = AUKO_WAV_ULAW;
-            else if (format == 0x11) info->format = AUKO_WAV_ADPCM;
+            } else if (format == 3) cur.format = AUKO_WAV_FLOAT;
+            else if (format == 6) cur.format = AUKO_WAV_ALAW;
+            else if (format == 7) cur.format = AUKO_WAV_ULAW;
+            else if (format == 0x11) cur.format = AUKO_WAV_ADPCM;
             else if (format == 0xFFFE) {                                     /* A:1493-1503 */
                 if (clen < 20) return fail("data string too short");
-                info->bitDepth = rd_u16(ch + 18);
+                cur.bitDepth = rd_u16(ch + 18);
                 uint8_t uuid[16] = {0};
                 size_t have = clen > 24 ? (clen - 24 < 16 ? clen - 24 : 16) : 0;
                 memcpy(uuid, ch + 24, have);
-                if (have == 16 && !memcmp(uuid, guid_dfpwm, 16)) info->format = AUKO_WAV_DFPWM;
+                if (have == 16 && !memcmp(uuid, guid_dfpwm, 16)) cur.format = AUKO_WAV_DFPWM;
                 else if (have == 16 && !memcmp(uuid + 4, guid_tail, 12) && uuid[1] == 0 && uuid[2] == 0 && uuid[3] == 0) {
                     switch (uuid[0]) {
-                    case 0x01: info->format = info->bitDepth == 8 ? AUKO_WAV_PCM_UNSIGNED : AUKO_WAV_PCM_SIGNED; break;
-                    case 0x02: info->format = AUKO_WAV_MSADPCM; break;
-                    case 0x03: info->format = AUKO_WAV_FLOAT; break;
-                    case 0x06: info->format = AUKO_WAV_ALAW; break;
-                    case 0x07: info->format = AUKO_WAV_ULAW; break;
-                    case 0x11: info->format = AUKO_WAV_ADPCM; break;
+                    case 0x01: cur.format = cur.bitDepth == 8 ? AUKO_WAV_PCM_UNSIGNED : AUKO_WAV_PCM_SIGNED; break;
+                    case 0x02: cur.format = AUKO_WAV_MSADPCM; break;
+                    case 0x03: cur.format = AUKO_WAV_FLOAT; break;
+                    case 0x06: cur.format = AUKO_WAV_ALAW; break;
+                    case 0x07: cur.format = AUKO_WAV_ULAW; break;
+                    case 0x11: cur.format = AUKO_WAV_ADPCM; break;
                     default: return fail("unsupported WAV file");
                     }
                 } else return fail("unsupported WAV file");
@@ -722,6 +726,11 @@ int auko_wav_parse(const uint8_t *data, size_t nbytes, auko_wav_info *info) {
             info->data_off = pos;
             info->data_size = size;
             info->have_data = 1;
+            info->format = cur.format; info->channels = cur.channels; info->sampleRate = cur.sampleRate;
+            info->blockAlign = cur.blockAlign; info->bitDepth = cur.bitDepth; info->have_fmt = cur.have_fmt;
+            info->ncoef = cur.ncoef;
+            memcpy(info->coef1, cur.coef1, sizeof info->coef1);
+            memcpy(info->coef2, cur.coef2, sizeof info->coef2);
             pos += size;
         } else if (!memcmp(id, "LIST", 4)) {                                 /* A:1559-1568 */
             if (pos + 4 > nbytes) return fail("data string too short");

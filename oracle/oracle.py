@@ -247,6 +247,39 @@ def audio_pcm(x: np.ndarray, bitDepth=8, dataType="signed", interleaved=True) ->
     return out[: ch * n]
 
 
+def audio_stream(x: np.ndarray, sampleRate, chunkSize=None, bitDepth=None, dataType=None):
+    """Audio:stream (A:921-937): list of (per-channel value arrays, position in seconds) and the total length.
+    Each step is encodePCM with `multiple` set (A:881-891) over frames [pos, pos + chunkSize), pos 1-based."""
+    chunkSize = 131072 if chunkSize is None else int(chunkSize)
+    bitDepth = 8 if bitDepth is None else bitDepth
+    dataType = "signed" if dataType is None else dataType
+    if bitDepth not in (8, 16, 24, 32):
+        raise OracleError("bad argument #2 (invalid bit depth)")
+    if dataType not in DATATYPES:
+        raise OracleError("bad argument #3 (invalid data type)")
+    if dataType == "float" and bitDepth != 32:
+        raise OracleError("bad argument #2 (float audio must have 32-bit depth)")
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    n = x.shape[1]
+    vals = audio_pcm(x, bitDepth, dataType, False).reshape(x.shape[0], n)
+    steps, pos = [], 1
+    while pos <= n:                                     # A:878: pos > len ends the iteration
+        steps.append(([vals[c, pos - 1: pos - 1 + chunkSize].copy() for c in range(x.shape[0])], pos / sampleRate))
+        pos += chunkSize
+    return steps, n / sampleRate
+
+
+def stream_adpcm_48k(data, blockAlign, channels):
+    """aukit.stream.adpcm (A:2738-2834) at sampleRate = 48000, mono = false: the ratio is 1, every position is an
+    exact hit, so each output is clamp(floor(p / (p < 0 and 128 or 127)), -128, 127) of the decoded predictor p
+    (A:2810, A:2826).  The block layout is the N-channel one of A:2798-2815, i.e. this oracle's GENERAL dialect; the
+    reference stops 8 samples early in the LAST block (its bounds check `#data < n + i + channels*4`, A:2801)."""
+    v = wav_ima(data, blockAlign, channels, GENERAL)
+    p = np.where(v < 0, np.rint(v * 32768.0), np.rint(v * 32767.0))          # predictors back from p / 32768|32767
+    q = np.floor(np.where(p < 0, p / 128.0, p / 127.0))
+    return np.clip(q, -128, 127)[:, : v.shape[1] - 8]
+
+
 WAV_METADATA = {"IPRD": "album", "INAM": "title", "IART": "artist", "IWRI": "author", "IMUS": "composer", "IPRO": "producer",
                 "IPRT": "trackNumber", "ITRK": "trackNumber", "IFRM": "trackCount", "PRT1": "partNumber", "PRT2": "partCount",
                 "TLEN": "length", "IRTD": "rating", "ICRD": "date", "ITCH": "encodedBy", "ISFT": "encoder", "ISRF": "media",

@@ -94,6 +94,53 @@ def run_case(R, case, blobs):
         out = R.call("new", 0, 1, A["sampleRate"])[0]          # carrier: one "channel" holding the flat result
         out.get(b"data").arr[0].arr = list(t.arr)
         return out
+    elif op == "chain3":                      # BASELINE config 3 per clip: aukit.pcm -> Audio:resample -> effects.amplify
+        a = R.call("pcm", blobs["in"], A["bitDepth"], A["dataType"], A["channels"], A["sampleRate"], True, A["bigEndian"])[0]
+        a = R.method(a, "resample", A["targetRate"], A.get("interpolation"))[0]
+        r = R.call(("effects", "amplify"), a, A["multiplier"])[0]
+        assert r is a
+    elif op == "chain5":                      # BASELINE config 5: aukit.pcm (f32, 8 ch) -> Audio:resample -> effects.normalize
+        a = R.call("pcm", blobs["in"], 32, "float", A["channels"], A["sampleRate"], True, False)[0]
+        a = R.method(a, "resample", A["targetRate"], A.get("interpolation"))[0]
+        r = call(R.fn("effects", "normalize"), [a, to_lua(A.get("peak")), to_lua(A.get("independent"))])[0]
+        assert r is a
+    elif op == "stream_adpcm":                # aukit.stream.adpcm (A:2798-2815): the N-channel IMA block layout's authority
+        it = R.call(("stream", "adpcm"), blobs["in"], A["blockAlign"], A["channels"], A["sampleRate"], False)[0]
+        chans = None
+        while True:
+            r = call(it, [])
+            if not r or r[0] is None:
+                break
+            if chans is None:
+                chans = [[] for _ in r[0].arr]
+            for c, t in enumerate(r[0].arr):
+                chans[c].extend(t.arr)
+        out = R.call("new", 0, len(chans), 48000)[0]
+        for c, v in enumerate(chans):
+            out.get(b"data").arr[c].arr = [float(x) for x in v]
+        return out
+    elif op == "stream_out":                  # Audio:stream (A:921-937): chunks of encodePCM values + positions
+        a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
+        r = R.method(a, "stream", A.get("chunkSize"), A.get("bitDepth"), A.get("dataType"))
+        it, total = r[0], r[1]
+        chans, poss, sizes = None, [], []
+        while True:
+            r = call(it, [])
+            if not r or r[0] is None:
+                break
+            if chans is None:
+                chans = [[] for _ in r[0].arr]
+            for c, t in enumerate(r[0].arr):
+                chans[c].extend(t.arr)
+            poss.append(float(r[1]))
+            sizes.append(float(len(r[0].arr[0].arr)))
+        chans = chans or [[]]
+        out = R.call("new", 0, len(chans) + 2, A["sampleRate"])[0]      # carrier: channels, then positions, then [total, sizes...]
+        for c, v in enumerate(chans):
+            out.get(b"data").arr[c].arr = [float(x) for x in v]
+        out.get(b"data").arr[len(chans)].arr = poss
+        out.get(b"data").arr[len(chans) + 1].arr = [float(total)] + sizes
+        return out
     elif op in ("lowpass", "highpass"):
         a = audio_from_numpy(R, blobs["x"], A["sampleRate"])
         r = R.call(("effects", op), a, A["frequency"])[0]
@@ -356,6 +403,48 @@ def main():
     add("wavout_metadata", "wav_out", dict(sampleRate=44100, bitDepth=16, metadata={"title": "A song"}), x=wl)
     add("wavout_short_raises", "wav_out", dict(sampleRate=44100, bitDepth=16), x=w2)
     add("wavout_bad_depth", "wav_out", dict(sampleRate=44100, bitDepth=12), x=w2[:, :50])
+
+    # ==== round 2 (appended: earlier vectors keep their seeds) ====
+    rng3 = np.random.default_rng(20260103)
+    # aukit.wav decodes each data chunk with the fmt state seen so far (A:1505-1555)
+    d16 = rng3.integers(0, 256, 64, dtype=np.uint8).tobytes()
+    add("wav_fmt_after_data", "wav", {}, **{"in": riff([(b"fmt ", fmt_chunk(1, 2, 32000, 4, 16)), (b"data", d16), (b"fmt ", fmt_chunk(1, 1, 8000, 1, 8))])})
+    add("wav_data_before_fmt", "wav", {}, **{"in": riff([(b"data", d16), (b"fmt ", fmt_chunk(1, 2, 32000, 4, 16))])})
+    extra0 = struct.pack("<HHH", 4, 100, 0)
+    add("wav_msadpcm_coefs_persist", "wav", {}, **{"in": riff([(b"fmt ", fmt_chunk(2, 2, 11025, 64, 4, extra)), (b"fmt ", fmt_chunk(2, 2, 11025, 64, 4, extra0)),
+                                                                (b"data", blk.tobytes())])})
+    # effects.normalize with a negative / large peak (the final clamp acts; A:3455)
+    add("normalize_neg2", "normalize", dict(sampleRate=48000, peak=-2.0, independent=False), x=y * 0.5)
+    add("normalize_1p5", "normalize", dict(sampleRate=48000, peak=1.5, independent=False), x=y * 0.5)
+    # non-finite input through the one-pole filters: the state never recovers (A:3592-3595, A:3613-3615)
+    zl = rng3.uniform(-1, 1, (2, 30000))
+    zl[0, 12345] = np.nan
+    zl[1, 20000] = np.inf
+    add("lowpass_nonfinite", "lowpass", dict(sampleRate=48000, frequency=12000.0), x=zl)
+    add("highpass_nonfinite", "highpass", dict(sampleRate=48000, frequency=200.0), x=zl)
+    # BASELINE config 3 per clip: s24 big-endian stereo -> 48 kHz cubic -> amplify(0.5); full-scale noise, 0.05 s
+    for src in (22050, 44100, 96000):
+        n3 = src // 20
+        raw3 = rng3.integers(0, 256, n3 * 2 * 3, dtype=np.uint8)
+        add("chain3_s24be_%d" % src, "chain3", dict(bitDepth=24, dataType="signed", channels=2, sampleRate=src, bigEndian=True,
+                                                    targetRate=48000, interpolation="cubic", multiplier=0.5), **{"in": raw3.tobytes()})
+    add("chain3_s24be_44100_linear_boost", "chain3", dict(bitDepth=24, dataType="signed", channels=2, sampleRate=44100, bigEndian=True,
+                                                          targetRate=48000, interpolation="linear", multiplier=1.7), **{"in": raw3[: 2205 * 6].tobytes()})
+    # BASELINE config 5 / 5': f32 8-channel interleaved -> 48 kHz / 44.1 kHz cubic -> normalize
+    f5 = (rng3.standard_normal(1200 * 8) * 0.25).astype("<f4")
+    for dst in (48000, 44100):
+        add("chain5_f32x8_96000_%d" % dst, "chain5", dict(channels=8, sampleRate=96000, targetRate=dst, interpolation="cubic", peak=None, independent=None),
+            **{"in": f5.tobytes()})
+    # aukit.stream.adpcm at 48 kHz (ratio 1: every position is an exact hit): pins the N-channel IMA block layout and step
+    for ch, ba, nb in ((1, 36, 3), (2, 72, 3), (3, 108, 2), (8, 288, 2)):
+        add("stream_adpcm_c%d" % ch, "stream_adpcm", dict(blockAlign=ba, channels=ch, sampleRate=48000), **{"in": ima_blocks(nb, ba, ch, seed=40 + ch).tobytes()})
+    # Audio:stream (A:921-937)
+    xs = rng3.uniform(-1, 1, (2, 1000)).astype(np.float32).astype(np.float64)
+    add("audiostream_default_depth", "stream_out", dict(sampleRate=48000, chunkSize=300, bitDepth=None, dataType=None), x=xs)
+    add("audiostream_s16", "stream_out", dict(sampleRate=44100, chunkSize=256, bitDepth=16, dataType="signed"), x=xs)
+    add("audiostream_u8_exact_chunks", "stream_out", dict(sampleRate=8000, chunkSize=250, bitDepth=8, dataType="unsigned"), x=xs)
+    add("audiostream_default_chunk", "stream_out", dict(sampleRate=48000, chunkSize=None, bitDepth=None, dataType=None), x=xs[:1])
+    add("audiostream_bad_depth", "stream_out", dict(sampleRate=48000, chunkSize=100, bitDepth=12, dataType=None), x=xs[:1])
 
     # ---- run everything through the reference
     manifest = []

@@ -172,8 +172,29 @@ def make_module(ak):
             raise LuaError(lib.aukit_cuda_last_error())
         return [Handle(ak.Audio(ctx, out))]
 
+    def l_set_sample_rate(a):
+        if lib.aukit_cuda_audio_set_sample_rate(a[0].audio._h, float(a[1])) != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        return []
+
+    def l_stream_chunk(a):
+        au, bits, dt, first, count = a[0].audio, int(a[1]), int(a[2]), int(a[3]) - 1, int(a[4])
+        nch = au.channels()
+        out = np.empty((nch, max(count, 1)), dtype=np.float64)
+        got = C.c_size_t(0)
+        if lib.aukit_cuda_audio_stream_chunk(ctx.handle, au._h, bits, dt, first, count, C.c_void_p(out.ctypes.data), C.byref(got)) != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        if got.value == 0:
+            return [None]
+        t = LuaTable()
+        for c in range(nch):
+            e = LuaTable()
+            e.arr = [float(v) for v in out[c, : got.value]]
+            t.set(c + 1, e)
+        return [t]
+
     mod = LuaTable()
-    for name, f in {"pcm": l_pcm, "g711": l_g711, "wav": l_wav, "resample": l_resample, "mono": l_mono, "amplify": l_amplify,
+    for name, f in {"set_sample_rate": l_set_sample_rate, "stream_chunk": l_stream_chunk, "pcm": l_pcm, "g711": l_g711, "wav": l_wav, "resample": l_resample, "mono": l_mono, "amplify": l_amplify,
                     "lowpass": l_lowpass, "pcm_out": l_pcm_out, "pcm_bytes": l_pcm_bytes, "invert": simple(lib.aukit_cuda_invert, 0),
                     "fade": simple(lib.aukit_cuda_fade, 4), "delay": simple(lib.aukit_cuda_delay, 2, (None, 0.5)),
                     "center": simple(lib.aukit_cuda_center, 0), "highpass": simple(lib.aukit_cuda_highpass, 1), "au": l_au, "aiff": l_aiff, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,

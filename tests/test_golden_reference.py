@@ -90,7 +90,27 @@ def oracle_run(O, m, i):
         out, info = O.wav(raw)
         r = O.resample(out, info["sampleRate"], A["targetRate"], A["interpolation"])
         return list(O.normalize(O.mono(r), A["peak"], False))
+    if op == "chain3":
+        d = O.pcm(raw, A["bitDepth"], A["dataType"], A["channels"], True, A["bigEndian"])
+        return list(O.amplify(O.resample(d, A["sampleRate"], A["targetRate"], A["interpolation"]), A["multiplier"]))
+    if op == "chain5":
+        d = O.pcm(raw, 32, "float", A["channels"], True, False)
+        r = O.resample(d, A["sampleRate"], A["targetRate"], A["interpolation"])
+        return list(O.normalize(r, 1.0 if A["peak"] is None else A["peak"], bool(A["independent"])))
+    if op == "stream_adpcm":
+        return list(O.stream_adpcm_48k(raw, A["blockAlign"], A["channels"]))
+    if op == "stream_out":
+        steps, total = O.audio_stream(x, A["sampleRate"], A["chunkSize"], A["bitDepth"], A["dataType"])
+        return stream_carrier(steps, total, x.shape[0])
     raise AssertionError(op)
+
+
+def stream_carrier(steps, total, nch):
+    """The layout tests/golden/generate.py stores an Audio:stream run in: the channels' concatenated chunks, then the
+    chunk positions, then [total length, chunk sizes...]."""
+    chans = [np.concatenate([s[0][c] for s in steps]) if steps else np.zeros(0) for c in range(nch)]
+    return chans + [np.array([s[1] for s in steps], dtype=np.float64),
+                    np.array([total] + [float(len(s[0][0])) for s in steps], dtype=np.float64)]
 
 
 @pytest.mark.parametrize("i", range(len(MANIFEST)), ids=IDS)
@@ -151,6 +171,27 @@ def cuda_run(ak, m, i):
         return np.frombuffer(a.wav(A.get("bitDepth"), "floor", ak.DIALECT_LITERAL), dtype=np.uint8).astype(np.float64)
     if op == "pcm_out":
         return ak.Audio.from_numpy(x.astype(np.float32), A["sampleRate"]).pcm(A["bitDepth"], A["dataType"], A["interleaved"])
+    if op == "chain3":
+        a = ak.pcm(raw, A["bitDepth"], A["dataType"], A["channels"], A["sampleRate"], True, A["bigEndian"])
+        return ak.effects.amplify(a.resample(A["targetRate"], A["interpolation"]), A["multiplier"])
+    if op == "chain5":
+        a = ak.pcm(raw, 32, "float", A["channels"], A["sampleRate"], True, False).resample(A["targetRate"], A["interpolation"])
+        args = [] if A.get("peak") is None and A.get("independent") is None else [A.get("peak"), A.get("independent")]
+        return ak.effects.normalize(a, *args)
+    if op == "stream_adpcm":
+        import ctypes as C
+        ctx = ak.context()
+        buf = np.frombuffer(raw, dtype=np.uint8)
+        out = C.c_void_p()
+        ak._lib.check(ctx.lib.aukit_cuda_ima_adpcm_wav(ctx.handle, C.c_void_p(buf.ctypes.data), buf.size, A["blockAlign"], A["channels"],
+                                                       48000.0, ak.DIALECT_GENERAL, C.byref(out)))
+        v = ak.Audio(ctx, out).numpy().astype(np.float64)
+        p = np.where(v < 0, np.rint(v * 32768.0), np.rint(v * 32767.0))
+        return np.clip(np.floor(np.where(p < 0, p / 128.0, p / 127.0)), -128, 127)[:, : v.shape[1] - 8]
+    if op == "stream_out":
+        a = ak.Audio.from_numpy(x.astype(np.float32), A["sampleRate"])
+        it, total = a.stream(A["chunkSize"], A["bitDepth"], A["dataType"])
+        return stream_carrier(list(it), total, x.shape[0])
     a = ak.wav(raw) if op == "chain" else ak.Audio.from_numpy(x.astype(np.float32), A["sampleRate"])
     if op in ("resample", "chain"):
         a = a.resample(A["targetRate"], A.get("interpolation"))
@@ -196,6 +237,12 @@ def test_cuda_matches_reference(ak, i):
         # the inputs are f32-representable, so the fp64 products are the reference's own numbers
         assert a.dtype == np.float64 and same_f64(a, exp[0])
         return
+    if m["op"] in ("stream_adpcm", "stream_out"):
+        # integer predictors / fp64 products of f32-representable inputs: the reference's own numbers, bit for bit
+        assert len(a) == len(exp)
+        for g, e in zip(a, exp):
+            assert same_f64(g, e), m["name"]
+        return
     assert a.channels() == m["channels"]
     assert float(a.sampleRate) == float(m["sampleRate"])
     decode = m["op"] in ("pcm", "g711", "adpcm", "msadpcm", "wav", "au", "aiff")
@@ -206,12 +253,19 @@ def test_cuda_matches_reference(ak, i):
         if decode:
             assert f32_equal_bits(g, e.astype(np.float32)), "decode must be bit-exact"
         else:
-            # inputs were narrowed to f32 on upload: allow for that in the comparison of float stages
             assert np.array_equal(np.isnan(g), np.isnan(e))
-            fin = ~np.isnan(e)
+            fin = np.isfinite(e)
+            assert np.array_equal(g[~fin & ~np.isnan(e)], e[~fin & ~np.isnan(e)])          # infinities keep their sign
             scale = max(1.0, float(np.max(np.abs(e[fin])))) if fin.any() else 1.0
             err = float(np.max(np.abs(g[fin] - e[fin]))) if fin.any() else 0.0
-            assert err <= TOL * scale * (2 if m["op"] != "chain" else 1), (m["name"], float(err))
+            # north_star's bound for the float stages is 2^-20 absolute (per unit of signal scale where an effect
+            # leaves [-1, 1]).  Where the test hands float64 inputs to the device as float32, that narrowing alone
+            # moves the reference's own result by up to 2^-25 |x| gain (gain <= 2: Catmull-Rom weights sum to 1.25 in
+            # magnitude, normalize / fade / delay scale by <= 2 here); it is added explicitly instead of doubling TOL.
+            narrowed = x is not None and np.issubdtype(np.asarray(x).dtype, np.floating)
+            xs = float(np.max(np.abs(np.asarray(x)[np.isfinite(np.asarray(x))]))) if narrowed else 0.0
+            bound = TOL * scale + ((2.0 ** -24) * max(xs, scale) if narrowed else 0.0)
+            assert err <= bound, (m["name"], float(err), bound)
     if m["op"] in ("au", "aiff"):
         got_meta = {k: (v.decode("latin-1") if isinstance(v, bytes) else v) for k, v in a.metadata.items()}
         assert got_meta == m["metadata"] and a.info == m["info"]
