@@ -5,9 +5,9 @@ aukit_b200/lib/libaukit_cuda.so by `python -m aukit_b200.build`), plus this Pyth
 that mirrors the reference's Lua API names, argument order, defaults and error strings.
 There is no CPU fallback: without the built library and a B200 every call raises.
 """
-from ._lib import AukitError, ContainerInfo, PipelineDesc, WavInfo, SIGNATURES, LIB_PATH  # noqa: F401
+from ._lib import AukitError, Clip, ContainerInfo, PipelineDesc, WavInfo, SIGNATURES, LIB_PATH  # noqa: F401
 from .aukit import (  # noqa: F401
-    Audio, Context, context, effects, pcm, g711, adpcm, msadpcm, wav, wav_info, new, preload, Preloader, au, aiff,
+    Audio, Context, context, effects, pcm, g711, adpcm, msadpcm, wav, wav_info, new, preload, preload_clips, Preloader, au, aiff,
     DIALECT_LITERAL, DIALECT_GENERAL, _VERSION,
 )
 from . import aukit as _aukit

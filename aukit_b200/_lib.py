@@ -35,6 +35,12 @@ class ContainerInfo(C.Structure):
                 ("nmeta", C.c_int), ("meta", _ContainerMeta * 16)]
 
 
+class Clip(C.Structure):
+    """aukit_clip (include/aukit_cuda.h)."""
+    _fields_ = [("in_offset", C.c_uint64), ("frames", C.c_uint64), ("srcRate", C.c_double), ("out_offset", C.c_uint64),
+                ("out_stride", C.c_uint64), ("n_out", C.c_uint64)]
+
+
 class PipelineDesc(C.Structure):
     _fields_ = [("bitDepth", C.c_int), ("dataType", C.c_int), ("channels", C.c_int), ("bigEndian", C.c_int),
                 ("srcRate", C.c_double), ("dstRate", C.c_double), ("interpolation", C.c_int), ("mono", C.c_int),
@@ -113,6 +119,10 @@ SIGNATURES = {
     "aukit_cuda_dev_lowpass": (_I, [_P, _P, _SZ, _I, _SZ, _D, _D]),
     "aukit_cuda_dev_pipeline_peak": (_I, [_P, C.POINTER(PipelineDesc), _P, _P]),
     "aukit_cuda_dev_pipeline_apply": (_I, [_P, C.POINTER(PipelineDesc), _P, _D, _P, _P, _SZ]),
+    "aukit_batch_plan": (_U64, [C.POINTER(Clip), _SZ, _I, _D]),
+    "aukit_cuda_dev_batch_resample_amplify": (_I, [_P, C.POINTER(Clip), _SZ, _I, _I, _I, _I, _D, _I, _D, _P, _P]),
+    "aukit_cuda_batch_resample_amplify": (_I, [_P, C.POINTER(_P), C.POINTER(_SZ), C.POINTER(_D), _SZ, _I, _I, _I, _I, _D, _I, _D,
+                                               C.POINTER(_P)]),
     "aukit_cuda_pipeline_host": (_I, [_P, C.POINTER(PipelineDesc), _P, _SZ, _D, _P]),
     "aukit_cuda_preloader_create": (_I, [_P, _SZ, _SZ, _I, C.POINTER(_P)]),
     "aukit_cuda_preloader_destroy": (None, [_P]),

@@ -666,6 +666,32 @@ def preload(data, bitDepth=16, dataType="signed", channels=2, sampleRate=44100, 
     return out
 
 
+def preload_clips(clips: Sequence, sampleRates, bitDepth=16, dataType="signed", channels=2, targetRate=48000,
+                  interpolation=None, multiplier=1.0, bigEndian=False, ctx: Optional[Context] = None):
+    """A playlist of clips through aukit.pcm -> :resample(targetRate, interpolation) -> effects.amplify(multiplier)
+    (A:1049, A:653, A:3356) in one fused pass per rate class (BASELINE config 3).  `clips`: packed interleaved PCM
+    (bytes / uint8 arrays) sharing one sample format; `sampleRates`: one rate per clip (or a single number).
+    Returns one Audio per clip."""
+    interpolation = interpolation or defaultInterpolation
+    if interpolation not in _INTERPS:
+        raise AukitError("bad argument #2 (invalid interpolation type)")
+    if dataType not in _DATATYPES:
+        raise AukitError("bad argument #3 (invalid data type)")
+    ctx = ctx or context()
+    n = len(clips)
+    if isinstance(sampleRates, (int, float)):
+        sampleRates = [sampleRates] * n
+    bufs = [_buf(_as_bytes(c)) for c in clips]
+    ptrs = (C.c_void_p * max(n, 1))(*[b[0] for b in bufs])
+    sizes = (C.c_size_t * max(n, 1))(*[b[1] for b in bufs])
+    rates = (C.c_double * max(n, 1))(*[float(r) for r in sampleRates])
+    outs = (C.c_void_p * max(n, 1))()
+    _lib.check(ctx.lib.aukit_cuda_batch_resample_amplify(ctx.handle, ptrs, sizes, rates, n, int(bitDepth), _DATATYPES[dataType], int(channels),
+                                                         int(bool(bigEndian)), float(targetRate), _INTERPS[interpolation], float(multiplier),
+                                                         outs))
+    return [Audio(ctx, C.c_void_p(outs[k]), {}, {"bitDepth": bitDepth, "dataType": dataType}) for k in range(n)]
+
+
 class Preloader:
     """Pipelined preload() for a playlist of clips (aukit_cuda_preloader_*): clip i's download overlaps
     clip i+1's upload, `slots` device buffers in rotation.  submit() is asynchronous; results are valid

@@ -127,41 +127,44 @@ void aukit_dev_free(aukit_ctx *ctx, void *d) {
 
 // Lua strings / Python bytes are pageable: stage through a pinned buffer in slices so the
 // copy runs at PCIe rate and overlaps the next slice's memcpy.
+int aukit_upload_into(aukit_ctx *ctx, const void *h, size_t nbytes, void *d) {
+    const size_t slice = (size_t)16 << 20;
+    if (nbytes == 0) return 0;
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned || nbytes <= 4096) {
+        if (aukit_cuda_check(cudaMemcpyAsync(d, h, nbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D")) return -1;
+        if (!pinned) cudaStreamSynchronize(ctx->stream);   // small pageable copies are staged by the driver
+        return 0;
+    }
+    if (!ctx->h_stage) {
+        if (aukit_cuda_check(cudaMallocHost(&ctx->h_stage, 2 * slice), "cudaMallocHost")) return -1;
+        ctx->h_stage_bytes = 2 * slice;
+    }
+    cudaEvent_t ev[2];
+    cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+    int k = 0;
+    for (size_t off = 0; off < nbytes; off += slice, k ^= 1) {
+        const size_t n = nbytes - off < slice ? nbytes - off : slice;
+        char *st = static_cast<char *>(ctx->h_stage) + (size_t)k * slice;
+        if (off >= 2 * slice) cudaEventSynchronize(ev[k]);
+        memcpy(st, static_cast<const char *>(h) + off, n);
+        cudaMemcpyAsync(static_cast<char *>(d) + off, st, n, cudaMemcpyHostToDevice, ctx->stream);
+        cudaEventRecord(ev[k], ctx->stream);
+    }
+    cudaEventSynchronize(ev[0]);
+    cudaEventSynchronize(ev[1]);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    return aukit_cuda_check(cudaGetLastError(), "staged H2D") ? -1 : 0;
+}
+
 int aukit_upload_bytes(aukit_ctx *ctx, const void *h, size_t nbytes, void **d_out) {
     void *d = nullptr;
     if (aukit_dev_alloc(ctx, nbytes, &d)) return -1;
-    const size_t slice = (size_t)16 << 20;
-    if (nbytes > 0) {
-        cudaPointerAttributes at{};
-        const bool pinned = cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost;
-        cudaGetLastError();
-        if (pinned || nbytes <= 4096) {
-            if (aukit_cuda_check(cudaMemcpyAsync(d, h, nbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D")) { aukit_dev_free(ctx, d); return -1; }
-            if (!pinned) cudaStreamSynchronize(ctx->stream);   // small pageable copies are staged by the driver
-        } else {
-            if (!ctx->h_stage) {
-                if (aukit_cuda_check(cudaMallocHost(&ctx->h_stage, 2 * slice), "cudaMallocHost")) { aukit_dev_free(ctx, d); return -1; }
-                ctx->h_stage_bytes = 2 * slice;
-            }
-            cudaEvent_t ev[2];
-            cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
-            int k = 0;
-            for (size_t off = 0; off < nbytes; off += slice, k ^= 1) {
-                const size_t n = nbytes - off < slice ? nbytes - off : slice;
-                char *st = static_cast<char *>(ctx->h_stage) + (size_t)k * slice;
-                if (off >= 2 * slice) cudaEventSynchronize(ev[k]);
-                memcpy(st, static_cast<const char *>(h) + off, n);
-                cudaMemcpyAsync(static_cast<char *>(d) + off, st, n, cudaMemcpyHostToDevice, ctx->stream);
-                cudaEventRecord(ev[k], ctx->stream);
-            }
-            cudaEventSynchronize(ev[0]);
-            cudaEventSynchronize(ev[1]);
-            cudaEventDestroy(ev[0]);
-            cudaEventDestroy(ev[1]);
-            if (aukit_cuda_check(cudaGetLastError(), "staged H2D")) { aukit_dev_free(ctx, d); return -1; }
-        }
-    }
+    if (aukit_upload_into(ctx, h, nbytes, d)) { aukit_dev_free(ctx, d); return -1; }
     *d_out = d;
     return 0;
 }
@@ -205,7 +208,12 @@ extern "C" int aukit_cuda_audio_wrap(aukit_ctx *ctx, float *d_data, int channels
 
 extern "C" void aukit_cuda_audio_free(aukit_ctx *ctx, aukit_audio *a) {
     if (!a) return;
-    if (a->owned && ctx) aukit_dev_free(ctx, a->data);
+    if (a->block) {                                  // a slice of a shared allocation (batch calls): last one out frees it
+        if (--a->block->refs == 0) {
+            if (ctx) aukit_dev_free(ctx, a->block->d);
+            free(a->block);
+        }
+    } else if (a->owned && ctx) aukit_dev_free(ctx, a->data);
     free(a->ch_frames);
     free(a);
 }
@@ -645,6 +653,63 @@ extern "C" int aukit_cuda_pipeline_host(aukit_ctx *ctx, const aukit_pipeline_des
     aukit_dev_free(ctx, d_in);
     aukit_dev_free(ctx, d_out);
     if (!rc) rc = aukit_cuda_synchronize(ctx);
+    return rc;
+}
+
+// ------------------------------------------------------------------ clip batches (BASELINE config 3)
+extern "C" int aukit_cuda_batch_resample_amplify(aukit_ctx *ctx, const void *const *h_clips, const size_t *clip_bytes,
+                                                 const double *srcRates, size_t nclips, int bitDepth, int dataType, int channels,
+                                                 int bigEndian, double dstRate, int interpolation, double multiplier,
+                                                 aukit_audio **out) {
+    if (!ctx || !out || (nclips && (!h_clips || !clip_bytes || !srcRates))) return aukit_fail("aukit_cuda: null argument");
+    // argument validation in aukit.pcm's order (A:1058-1064), before any device work
+    if (bitDepth != 8 && bitDepth != 16 && bitDepth != 24 && bitDepth != 32) return aukit_fail("bad argument #2 (invalid bit depth)");
+    if (dataType != AUKIT_SIGNED && dataType != AUKIT_UNSIGNED && dataType != AUKIT_FLOAT) return aukit_fail("bad argument #3 (invalid data type)");
+    if (dataType == AUKIT_FLOAT && bitDepth != 32) return aukit_fail("bad argument #2 (float audio must have 32-bit depth)");
+    if (channels < 1) return aukit_fail("number outside of range (expected %d to be at least 1)", channels);
+    if (interpolation < 0 || interpolation > 2) return aukit_fail("bad argument #2 (invalid interpolation type)");
+    if (nclips == 0) return 0;
+    const size_t FB = (size_t)(bitDepth / 8) * (size_t)channels;
+    aukit_clip *clips = static_cast<aukit_clip *>(calloc(nclips, sizeof(aukit_clip)));
+    if (!clips) return aukit_fail("aukit_cuda: out of host memory");
+    size_t in_total = 0;
+    for (size_t k = 0; k < nclips; k++) {
+        if (clip_bytes[k] % FB) { free(clips); return aukit_fail("bad argument #1 (uneven amount of data per channel)"); }
+        if (srcRates[k] < 1) { free(clips); return aukit_fail("number outside of range (expected %g to be at least 1)", srcRates[k]); }
+        clips[k].in_offset = in_total;
+        clips[k].frames = clip_bytes[k] / FB;
+        clips[k].srcRate = srcRates[k];
+        in_total += (clip_bytes[k] + 15) & ~(size_t)15;               // 16-byte aligned clip starts
+    }
+    const uint64_t out_floats = aukit_batch_plan(clips, nclips, channels, dstRate);
+    void *d_in = nullptr, *d_out = nullptr;
+    aukit_block *blk = static_cast<aukit_block *>(calloc(1, sizeof(aukit_block)));
+    int rc = blk ? 0 : aukit_fail("aukit_cuda: out of host memory");
+    if (!rc) rc = aukit_dev_alloc(ctx, in_total + 16, &d_in);
+    if (!rc) rc = aukit_dev_alloc(ctx, (size_t)out_floats * sizeof(float) + 16, &d_out);
+    for (size_t k = 0; k < nclips && !rc; k++)
+        rc = aukit_upload_into(ctx, h_clips[k], clip_bytes[k], static_cast<char *>(d_in) + clips[k].in_offset);
+    if (!rc) rc = aukit_cuda_dev_batch_resample_amplify(ctx, clips, nclips, bitDepth, dataType, channels, bigEndian, dstRate, interpolation,
+                                                        multiplier, d_in, static_cast<float *>(d_out));
+    aukit_dev_free(ctx, d_in);
+    size_t made = 0;
+    for (; made < nclips && !rc; made++) {
+        aukit_audio *a = static_cast<aukit_audio *>(calloc(1, sizeof(aukit_audio)));
+        if (!a) { rc = aukit_fail("aukit_cuda: out of host memory"); break; }
+        a->data = static_cast<float *>(d_out) + clips[made].out_offset;
+        a->channels = channels; a->frames = (size_t)clips[made].n_out; a->stride = (size_t)clips[made].out_stride;
+        a->sampleRate = dstRate; a->owned = false; a->block = blk;
+        out[made] = a;
+    }
+    if (rc) {
+        for (size_t k = 0; k < made; k++) { free(out[k]); out[k] = nullptr; }
+        aukit_dev_free(ctx, d_out);
+        free(blk);
+    } else {
+        blk->d = d_out;
+        blk->refs = (long)nclips;
+    }
+    free(clips);
     return rc;
 }
 

@@ -31,6 +31,8 @@ struct aukit_ctx {
     cudaEvent_t ev_fork, ev_join;
 };
 
+struct aukit_block { void *d; long refs; };   // a device allocation shared by several Audio handles (batch results)
+
 struct aukit_audio {
     float *data;
     int channels;
@@ -39,6 +41,7 @@ struct aukit_audio {
     double sampleRate;
     bool owned;
     size_t *ch_frames;  // per-channel lengths when ragged (G.711), else nullptr
+    aukit_block *block; // non-null: `data` points into a shared allocation released with its last handle
 };
 
 int aukit_fail(const char *fmt, ...);
@@ -54,6 +57,8 @@ static inline size_t aukit_round_stride(size_t frames) { return (frames + 31) / 
 int aukit_audio_alloc(aukit_ctx *ctx, int channels, size_t frames, double rate, aukit_audio **out);
 // Uploads host bytes to a temporary device buffer on the ctx stream (freed with aukit_dev_free).
 int aukit_upload_bytes(aukit_ctx *ctx, const void *h, size_t nbytes, void **d_out);
+// The same copy into existing device memory (pageable sources are staged through the context's pinned slices).
+int aukit_upload_into(aukit_ctx *ctx, const void *h, size_t nbytes, void *d);
 int aukit_dev_alloc(aukit_ctx *ctx, size_t nbytes, void **d_out);
 void aukit_dev_free(aukit_ctx *ctx, void *d);
 

@@ -1,0 +1,543 @@
+// pipeline_tile.cu -- K14: fused decode -> resample -> amplify over a BATCH of clips (BASELINE config 3).
+//
+// Per clip the reference runs aukit.pcm (A:1049-1171) -> Audio:resample (A:653-673) -> effects.amplify
+// (A:3356-3369): three interpreted passes with two materialised intermediates.  Amplify has no barrier (unlike
+// normalize), so the whole chain is ONE pass here: algorithmic traffic B_in + B_out, nothing in between.
+//
+// One launch covers every clip of one rate class (same srcRate -> same L / M); a clip table on the device says
+// where each clip's packed frames and output rows live.  The work unit is a TILE: K iterations x Sp = L*m
+// consecutive outputs of one clip, which needs the K*Q + 3 input frames [T*K*Q - 1, (T+1)*K*Q + 2)  (Q = M*m).
+//
+//   * persistent CTAs (two per SM), tiles strided over the grid; a tile's packed bytes arrive by ONE bulk async
+//     copy (TMA, cp.async.bulk + mbarrier) into a 2-deep ring of raw buffers: the copy of tile i+2 is issued as soon
+//     as tile i has been converted, so ~2 x 32 KB per CTA is in flight while the math runs;
+//   * phase A converts the tile's frames once, shared -> shared, into float2 (stereo) / float (mono) samples with
+//     the exact scaling of aukit.pcm (see conv_* below);
+//   * phase B: thread t owns outputs base + k*Sp + t, so its phase j_t = (t*M) mod L and its four Catmull-Rom
+//     weights are loop invariants in registers, packed as f32x2 so one FFMA2 blends both channels; 4 x LDS.64 taps,
+//     clamp (A:668) as one FMNMX.XORSIGN per channel, amplify, two coalesced 128-byte-per-warp stores;
+//   * the first / last tiles of a clip (frame -1, frames past the end: the nil substitutions of A:259 / A:264 are a
+//     clamped index) and clips whose tail is too short for a bulk copy are staged by a generic clamped-index path.
+//
+// Positions are the rational n*M/L: this kernel is only used where that is indistinguishable from the reference's
+// fp64 x (PX_RATIONAL): bounded sample formats, cubic / linear, clip positions below 2^28 frames;
+// and for L == 1 with a power-of-two M (96 -> 48 kHz), where every position is an exact integer and the reference
+// copies the sample (A:667).  Everything else goes through the per-clip calls.
+#include "common.cuh"
+#include "sample_formats.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float x, float y) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &x, float &y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// clamp(v, -1, 1) of A:668 for finite v: sign(v) * min(|v|, 1), one FMNMX.XORSIGN
+__device__ __forceinline__ float clamp_unit(float v) {
+    float r;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(1.0f));
+    return r;
+}
+
+// ---- sample formats this kernel takes (bounded: the PX_RATIONAL argument needs |sample| <= 1)
+enum { TF_S16LE = 0, TF_S16BE = 1, TF_S24LE = 2, TF_S24BE = 3, TF_S8 = 4, TF_U8 = 5, TF_S32LE = 6, TF_S32BE = 7, TF_COUNT = 8 };
+
+template <int FMT> struct tfmt;
+template <> struct tfmt<TF_S16LE> { static constexpr int B = 2; };
+template <> struct tfmt<TF_S16BE> { static constexpr int B = 2; };
+template <> struct tfmt<TF_S24LE> { static constexpr int B = 3; };
+template <> struct tfmt<TF_S24BE> { static constexpr int B = 3; };
+template <> struct tfmt<TF_S8> { static constexpr int B = 1; };
+template <> struct tfmt<TF_U8> { static constexpr int B = 1; };
+template <> struct tfmt<TF_S32LE> { static constexpr int B = 4; };
+template <> struct tfmt<TF_S32BE> { static constexpr int B = 4; };
+
+// One sample from the 4 bytes `v` that start at the sample's first byte (little-endian register image of memory).
+// All forms reproduce (float)((double)s / (s < 0 ? 2^(b-1) : 2^(b-1) - 1)), A:1133:
+//   16 bit: common.cuh::s16_to_float;
+//   24 bit: with lo = s * 2^-23 (exact) the value is fma(max(lo, 0), RN(1 / (2^23 - 1)), lo) -- checked against the
+//           double division for all 2^23 non-negative s on the host (tests/test_host_logic.py) and on the device;
+//   8 bit: sample_formats.cuh::convert8;  32 bit: the fp64 division itself (float(s) is inexact there).
+template <int FMT>
+__device__ __forceinline__ float conv_sample(uint32_t v) {
+    if (FMT == TF_S16LE) return s16_to_float((int)(int16_t)(v & 0xFFFFu));
+    if (FMT == TF_S16BE) return s16_to_float((int)(int16_t)__byte_perm(v, 0, 0x4401));
+    if (FMT == TF_S24LE || FMT == TF_S24BE) {
+        // top-aligned: x = s * 256 as an int32, so (float)x is exact
+        const int x = (int)(FMT == TF_S24BE ? __byte_perm(v, 0, 0x0124) : __byte_perm(v, 0, 0x2104));
+        const float lo = __fmul_rn((float)x, 1.0f / 2147483648.0f);
+        return __fmaf_rn(__saturatef(lo), 1.0f / 8388607.0f, lo);
+    }
+    if (FMT == TF_S8) return aukit_fmt::convert8<aukit_fmt::K_SIGNED>(v & 0xFFu);
+    if (FMT == TF_U8) return aukit_fmt::convert8<aukit_fmt::K_UNSIGNED>(v & 0xFFu);
+    const int s = (int)(FMT == TF_S32BE ? __byte_perm(v, 0, 0x0123) : v);
+    const double d = (double)s;
+    return (float)(s < 0 ? d / 2147483648.0 : d / 2147483647.0);
+}
+
+// 4 bytes starting at byte offset `o` of a shared-memory buffer (any alignment): two aligned words + funnel shift
+__device__ __forceinline__ uint32_t lds_unaligned(const uint32_t *words, uint32_t o) {
+    const uint32_t w = o >> 2;
+    return __funnelshift_r(words[w], words[w + 1], (o & 3u) * 8u);
+}
+__device__ __forceinline__ uint32_t ldg_bytes(const uint8_t *p, int n) {
+    uint32_t v = 0;
+    for (int k = n - 1; k >= 0; k--) v = (v << 8) | p[k];
+    return v;
+}
+
+struct clip_rec {                 // one clip of the launch's rate class (device copy of aukit_clip + derived fields)
+    unsigned long long in_off;    // byte offset of frame 0 in d_in
+    unsigned long long frames;    // input frames
+    unsigned long long out_off;   // float offset of (channel 0, output 0) in d_out
+    unsigned long long out_stride;
+    unsigned long long n_out;
+};
+
+struct tile_args {
+    const uint8_t *in;
+    float *out;
+    const clip_rec *clips;
+    const unsigned int *tile_prefix;   // [nclips + 1]: tiles before clip k
+    int nclips;
+    unsigned int ntiles;
+    int L, M, m, Sp, Q, K;        // outputs / frames per period; periods per iteration; per iteration; iterations per tile
+    int nfr;                      // frames staged per tile = K*Q + 3
+    int raw_bytes;                // pitch of one raw buffer (multiple of 128)
+    float mult;                   // (float)multiplier
+    int mult_exact;               // the multiplier is a float: x * m in fp32 IS the reference's product rounded once
+    double mult_d;                // otherwise (float)((double)x * m), like effects.amplify's own kernel (K7)
+    int clamp_out;                // |multiplier| > 1: the clamp of A:3364 can act
+};
+
+struct tile_geom {                // everything a CTA needs about one tile; written by thread 0, read by all
+    unsigned long long src;       // 16-byte aligned global address of the bulk copy
+    unsigned long long clip_in;   // global address of the clip's frame 0
+    unsigned long long out0;      // global address of (channel 0, first output of the tile)
+    unsigned long long out_stride;
+    long long first_frame;        // F0 - 1: frame index (within the clip) of staged frame 0
+    long long frames;             // clip length
+    unsigned int bytes;           // bulk copy size (multiple of 16)
+    unsigned int sh;              // byte offset of staged frame 0 inside the copy
+    int n_valid;                  // outputs of this tile that exist (<= K*Sp)
+    int edge;                     // 1: staged by the clamped-index path (no bulk copy)
+    int exists;
+};
+
+// `hint`: the clip the CTA's previous tile belonged to (tiles are visited in increasing order, a grid apart: usually
+// the same clip or the next one, so the walk below is one or two L2 reads; the first call does a binary search)
+template <int FMT, int CT>
+__device__ __forceinline__ void tile_lookup(const tile_args &a, unsigned int tile, tile_geom *g, int &hint) {
+    constexpr int FB = tfmt<FMT>::B * CT;
+    if (tile >= a.ntiles) { g->exists = 0; return; }
+    int lo = hint;
+    if (lo < 0) {
+        lo = 0;
+        int hi = a.nclips;                                             // last k with tile_prefix[k] <= tile
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+        }
+    } else {
+        while (lo + 1 < a.nclips && a.tile_prefix[lo + 1] <= tile) lo++;
+    }
+    hint = lo;
+    const clip_rec c = a.clips[lo];
+    const unsigned long long T = tile - a.tile_prefix[lo];
+    const long long F0 = (long long)(T * (unsigned long long)a.K * (unsigned long long)a.Q);
+    const unsigned long long o0 = T * (unsigned long long)a.K * (unsigned long long)a.Sp;
+    g->exists = 1;
+    g->first_frame = F0 - 1;
+    g->frames = (long long)c.frames;
+    g->clip_in = (unsigned long long)(uintptr_t)(a.in + c.in_off);
+    g->out0 = (unsigned long long)(uintptr_t)(a.out + c.out_off + o0);
+    g->out_stride = c.out_stride;
+    const unsigned long long left = c.n_out - o0;
+    g->n_valid = left < (unsigned long long)(a.K * a.Sp) ? (int)left : a.K * a.Sp;
+    // bulk copy: every staged frame must exist (no clamping) and the 16-byte rounding must stay inside the clip's bytes
+    const unsigned long long b0 = c.in_off + (unsigned long long)(F0 - 1) * FB;
+    const unsigned long long a0 = b0 & ~15ull;
+    const unsigned int sh = (unsigned int)(b0 - a0);
+    const unsigned int bytes = (sh + (unsigned int)a.nfr * FB + 15u) & ~15u;
+    // (a0 may lie up to 15 bytes before the clip's first byte: still inside d_in, whose base is 16-byte aligned)
+    g->edge = (F0 - 1 < 0) || (a0 + bytes > c.in_off + c.frames * FB) || (F0 - 1 + a.nfr > (long long)c.frames) ||
+              (((uintptr_t)a.in & 15) != 0);
+    g->src = (unsigned long long)(uintptr_t)(a.in + a0);
+    g->sh = sh;
+    g->bytes = bytes;
+}
+
+template <int FMT, int CT, int MODE>
+__global__ void __launch_bounds__(512, 2) tile_kernel(tile_args a) {
+    constexpr int B = tfmt<FMT>::B, FB = B * CT;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ tile_geom geom[3];
+    // layout: float tile [nfr + 1] x CT floats | raw buffer 0 | raw buffer 1
+    float *ftile = reinterpret_cast<float *>(smem);
+    const uint32_t ft_bytes = ((uint32_t)(a.nfr + 1) * CT * 4u + 127u) & ~127u;
+    unsigned char *raw0 = smem + ft_bytes;
+    const int t = threadIdx.x;
+    const bool active = t < a.Sp;
+
+    // loop-invariant phase of this thread (outputs base + k*Sp + t): floor offset and weights at fraction j/L
+    const long long tm = (long long)t * a.M;
+    const int off_t = (int)(tm / a.L), j_t = (int)(tm % a.L);
+    f32x2 W0 = 0, W1 = 0, W2 = 0, W3 = 0;
+    float fx = 0.f;
+    {
+        const double x = (double)j_t / (double)a.L;
+        fx = (float)x;
+        if (MODE == AUKIT_INTERP_CUBIC) {                                // Catmull-Rom weights of A:265, fp64 then narrowed
+            const double x2 = x * x, x3 = x2 * x;
+            const float w0 = (float)(-0.5 * x3 + x2 - 0.5 * x), w1 = (float)(1.5 * x3 - 2.5 * x2 + 1.0);
+            const float w2 = (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x), w3 = (float)(0.5 * x3 - 0.5 * x2);
+            W0 = pack2(w0, w0); W1 = pack2(w1, w1); W2 = pack2(w2, w2); W3 = pack2(w3, w3);
+        }
+    }
+    const f32x2 FX = pack2(fx, fx);
+    const float mult = a.mult;
+
+    int hint = -1;                                                      // thread 0's clip cursor
+    if (t == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int j = 0; j < 2; j++) {
+            tile_lookup<FMT, CT>(a, blockIdx.x + (unsigned)j * gridDim.x, &geom[j], hint);
+            if (geom[j].exists && !geom[j].edge) {
+                mbar_expect_tx(&bars[j], geom[j].bytes);
+                bulk_load(raw0 + (size_t)j * a.raw_bytes, reinterpret_cast<const void *>(geom[j].src), geom[j].bytes, &bars[j]);
+            }
+        }
+    }
+    __syncthreads();
+
+    uint32_t phase0 = 0, phase1 = 0;
+    for (unsigned int i = 0;; i++) {
+        const tile_geom *g = &geom[i % 3];
+        if (!g->exists) break;
+        const int slot = (int)(i & 1u);
+        const bool edge = g->edge != 0;
+        const long long first_frame = g->first_frame, nframes = g->frames;
+        // ---------------- phase A: packed frames -> float samples (each frame converted once)
+        if (!edge) {
+            mbar_wait(&bars[slot], slot ? phase1 : phase0);
+            if (slot) phase1 ^= 1u; else phase0 ^= 1u;
+            const uint32_t *words = reinterpret_cast<const uint32_t *>(raw0 + (size_t)slot * a.raw_bytes);
+            const uint32_t sh = g->sh;
+            for (int f = t; f < a.nfr; f += blockDim.x) {
+                const uint32_t o = sh + (uint32_t)f * FB;
+                if (CT == 2) {
+                    const float l = conv_sample<FMT>(lds_unaligned(words, o));
+                    const float r = conv_sample<FMT>(lds_unaligned(words, o + B));
+                    reinterpret_cast<float2 *>(ftile)[f] = make_float2(l, r);
+                } else {
+                    ftile[f] = conv_sample<FMT>(lds_unaligned(words, o));
+                }
+            }
+        } else {
+            // clamped index = the reference's nil substitutions (A:259, A:264); plain byte loads
+            const uint8_t *cin = reinterpret_cast<const uint8_t *>(g->clip_in);
+            for (int f = t; f < a.nfr; f += blockDim.x) {
+                long long gi = first_frame + f;
+                gi = gi < 0 ? 0 : (gi >= nframes ? nframes - 1 : gi);
+                const uint8_t *p = cin + (size_t)gi * FB;
+                if (CT == 2) {
+                    reinterpret_cast<float2 *>(ftile)[f] = make_float2(conv_sample<FMT>(ldg_bytes(p, B)), conv_sample<FMT>(ldg_bytes(p + B, B)));
+                } else {
+                    ftile[f] = conv_sample<FMT>(ldg_bytes(p, B));
+                }
+            }
+        }
+        __syncthreads();                                               // float tile complete; raw[slot] and geom[(i+2)%3] are free
+        if (t == 0) {
+            tile_geom *gn = &geom[(i + 2) % 3];
+            tile_lookup<FMT, CT>(a, blockIdx.x + (i + 2) * gridDim.x, gn, hint);
+            if (gn->exists && !gn->edge) {
+                fence_async_smem();                                    // generic reads of raw[slot] before the async write
+                mbar_expect_tx(&bars[slot], gn->bytes);
+                bulk_load(raw0 + (size_t)slot * a.raw_bytes, reinterpret_cast<const void *>(gn->src), gn->bytes, &bars[slot]);
+            }
+        }
+        // ---------------- phase B: taps -> blend -> clamp (A:668) -> amplify (A:3364) -> store
+        if (active) {
+            const int n_valid = g->n_valid;
+            int k1 = n_valid > t ? (n_valid - t + a.Sp - 1) / a.Sp : 0;
+            if (k1 > a.K) k1 = a.K;
+            float *o0 = reinterpret_cast<float *>(g->out0) + t;
+            const size_t ostride = (size_t)g->out_stride;
+            int s = off_t;
+#pragma unroll 4
+            for (int k = 0; k < k1; k++, s += a.Q, o0 += a.Sp) {
+                float vl, vr = 0.f;
+                if (CT == 2) {
+                    const f32x2 *f = reinterpret_cast<const f32x2 *>(ftile) + s;
+                    f32x2 acc;
+                    if (MODE == AUKIT_INTERP_CUBIC) {
+                        acc = mul2(f[0], W0);
+                        acc = fma2(f[1], W1, acc);
+                        acc = fma2(f[2], W2, acc);
+                        acc = fma2(f[3], W3, acc);
+                    } else if (MODE == AUKIT_INTERP_LINEAR) {
+                        float p1l, p1r, p2l, p2r;
+                        unpack2(f[1], p1l, p1r);
+                        unpack2(f[2], p2l, p2r);
+                        acc = fma2(pack2(p2l - p1l, p2r - p1r), FX, f[1]);
+                    } else {
+                        acc = f[1];
+                    }
+                    unpack2(acc, vl, vr);
+                } else {
+                    const float *f = ftile + s;
+                    if (MODE == AUKIT_INTERP_CUBIC) {
+                        float w0, w1, w2, w3, d;
+                        unpack2(W0, w0, d); unpack2(W1, w1, d); unpack2(W2, w2, d); unpack2(W3, w3, d);
+                        vl = __fmaf_rn(w3, f[3], __fmaf_rn(w2, f[2], __fmaf_rn(w1, f[1], w0 * f[0])));
+                    } else if (MODE == AUKIT_INTERP_LINEAR) {
+                        vl = __fmaf_rn(f[2] - f[1], fx, f[1]);
+                    } else {
+                        vl = f[1];
+                    }
+                }
+                if (MODE != AUKIT_INTERP_NONE) {                       // exact hits (NONE here) are copied unclamped, A:667
+                    vl = clamp_unit(vl);
+                    if (CT == 2) vr = clamp_unit(vr);
+                }
+                // x * multiplier rounded once (A:3364 computes it in double)
+                float ol, orr;
+                if (a.mult_exact) { ol = vl * mult; orr = vr * mult; }
+                else { ol = (float)((double)vl * a.mult_d); orr = (float)((double)vr * a.mult_d); }
+                if (a.clamp_out) { ol = clamp_unit(ol); orr = clamp_unit(orr); }
+                asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(o0), "f"(ol) : "memory");
+                if (CT == 2) asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(o0 + ostride), "f"(orr) : "memory");
+            }
+        }
+        __syncthreads();                                               // float tile consumed
+    }
+}
+
+long long gcd_ll(long long x, long long y) { while (y) { long long r = x % y; x = y; y = r; } return x; }
+
+int tile_format(int bitDepth, int dataType, int bigEndian) {
+    if (dataType == AUKIT_SIGNED) {
+        switch (bitDepth) {
+        case 8: return TF_S8;
+        case 16: return bigEndian ? TF_S16BE : TF_S16LE;
+        case 24: return bigEndian ? TF_S24BE : TF_S24LE;
+        case 32: return bigEndian ? TF_S32BE : TF_S32LE;
+        }
+    }
+    if (dataType == AUKIT_UNSIGNED && bitDepth == 8) return TF_U8;
+    return -1;                                                          // float / unsigned > 8 bit: not bounded by 1
+}
+
+template <int FMT, int CT>
+int launch_mode(aukit_ctx *ctx, const tile_args &a, int mode, int threads, size_t smem) {
+    auto go = [&](auto kern) -> int {
+        if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
+        unsigned g = (unsigned)ctx->num_sms * 2u;
+        if (g > a.ntiles) g = a.ntiles;
+        kern<<<g, threads, smem, ctx->stream>>>(a);
+        ctx->launches++;
+        return aukit_cuda_check(cudaGetLastError(), "tile_kernel launch");
+    };
+    if (mode == AUKIT_INTERP_CUBIC) return go(tile_kernel<FMT, CT, AUKIT_INTERP_CUBIC>);
+    if (mode == AUKIT_INTERP_LINEAR) return go(tile_kernel<FMT, CT, AUKIT_INTERP_LINEAR>);
+    return go(tile_kernel<FMT, CT, AUKIT_INTERP_NONE>);
+}
+
+template <int FMT>
+int launch_ch(aukit_ctx *ctx, const tile_args &a, int channels, int mode, int threads, size_t smem) {
+    return channels == 2 ? launch_mode<FMT, 2>(ctx, a, mode, threads, smem) : launch_mode<FMT, 1>(ctx, a, mode, threads, smem);
+}
+
+}  // namespace
+
+// floor(frames * (dstRate / srcRate)) in double: the loop bound of A:658-664
+extern "C" uint64_t aukit_resample_out_len(uint64_t n_in, double srcRate, double dstRate);
+
+extern "C" uint64_t aukit_batch_plan(aukit_clip *clips, size_t nclips, int out_channels, double dstRate) {
+    uint64_t pos = 0;
+    if (!clips || out_channels < 1) return 0;
+    for (size_t k = 0; k < nclips; k++) {
+        clips[k].n_out = aukit_resample_out_len(clips[k].frames, clips[k].srcRate, dstRate);
+        if (clips[k].out_stride == 0) {
+            clips[k].out_stride = (clips[k].n_out + 31) / 32 * 32;
+            if (clips[k].out_stride == 0) clips[k].out_stride = 32;
+            clips[k].out_offset = pos;
+        }
+        const uint64_t end = clips[k].out_offset + clips[k].out_stride * (uint64_t)out_channels;
+        if (end > pos) pos = end;
+    }
+    return pos;
+}
+
+// Returns 1 when the tile kernel can take clips of this description, 0 when the caller must use the per-clip calls.
+static int tile_shape(const aukit_clip &c, int fmt, int channels, double dstRate, int interpolation, long long *Lo, long long *Mo) {
+    if (fmt < 0 || (channels != 1 && channels != 2)) return 0;
+    const double sr = c.srcRate, dr = dstRate;
+    if (!(sr >= 1 && dr >= 1 && sr < 2147483648.0 && dr < 2147483648.0) || sr != floor(sr) || dr != floor(dr)) return 0;
+    const long long g = gcd_ll((long long)sr, (long long)dr);
+    const long long L = (long long)dr / g, M = (long long)sr / g;
+    if (L > 512 || M > 4096) return 0;
+    if (L == 1) {
+        if (M & (M - 1)) return 0;                                      // only exact (power-of-two) integer ratios: always a hit
+    } else {
+        if (interpolation != AUKIT_INTERP_CUBIC && interpolation != AUKIT_INTERP_LINEAR) return 0;
+        if ((double)c.frames >= 268435456.0) return 0;                  // 2^28: beyond the rational-position regime
+    }
+    *Lo = L; *Mo = M;
+    return 1;
+}
+
+extern "C" int aukit_cuda_dev_batch_resample_amplify(aukit_ctx *ctx, const aukit_clip *clips, size_t nclips, int bitDepth, int dataType,
+                                                     int channels, int bigEndian, double dstRate, int interpolation, double multiplier,
+                                                     const void *d_in, float *d_out) {
+    if (!ctx || (!clips && nclips) || !d_out) return aukit_fail("aukit_cuda: null argument");
+    if (bitDepth != 8 && bitDepth != 16 && bitDepth != 24 && bitDepth != 32) return aukit_fail("bad argument #2 (invalid bit depth)");
+    if (dataType != AUKIT_SIGNED && dataType != AUKIT_UNSIGNED && dataType != AUKIT_FLOAT) return aukit_fail("bad argument #3 (invalid data type)");
+    if (dataType == AUKIT_FLOAT && bitDepth != 32) return aukit_fail("bad argument #2 (float audio must have 32-bit depth)");
+    if (channels < 1) return aukit_fail("number outside of range (expected %d to be at least 1)", channels);
+    if (interpolation < 0 || interpolation > 2) return aukit_fail("bad argument #2 (invalid interpolation type)");
+    if (nclips == 0) return 0;
+    const int B = bitDepth / 8, FB = B * channels;
+    const int fmt = (B == 1 || !bigEndian) ? tile_format(bitDepth, dataType, 0) : tile_format(bitDepth, dataType, 1);
+    // group the clips by rate class; classes the tile kernel cannot take run clip by clip through the general kernels
+    struct cls { long long L, M; double srcRate; size_t first; };
+    size_t *order = static_cast<size_t *>(malloc(sizeof(size_t) * nclips));
+    unsigned char *done = static_cast<unsigned char *>(calloc(nclips, 1));
+    clip_rec *h_rec = static_cast<clip_rec *>(malloc(sizeof(clip_rec) * nclips));
+    unsigned int *h_pre = static_cast<unsigned int *>(malloc(sizeof(unsigned int) * (nclips + 1)));
+    if (!order || !done || !h_rec || !h_pre) { free(order); free(done); free(h_rec); free(h_pre); return aukit_fail("aukit_cuda: out of host memory"); }
+    int rc = 0;
+    const float mh = (float)multiplier;
+    for (size_t k0 = 0; k0 < nclips && !rc; k0++) {
+        if (done[k0]) continue;
+        long long L = 0, M = 0;
+        const bool can_tile = tile_shape(clips[k0], fmt, channels, dstRate, interpolation, &L, &M) != 0;
+        if (!can_tile) {
+            // general path, one clip: K1 -> K5 -> K7 semantics through the fused pipeline kernels is not available without a
+            // normalize; decode + resample + amplify as three launches on scratch memory
+            done[k0] = 1;
+            const aukit_clip &c = clips[k0];
+            const uint64_t n_out = aukit_resample_out_len(c.frames, c.srcRate, dstRate);
+            if (c.frames == 0 || n_out == 0) continue;
+            void *tmp = nullptr;
+            const size_t st = aukit_round_stride(c.frames);
+            if (aukit_dev_alloc(ctx, st * (size_t)channels * sizeof(float), &tmp)) { rc = -1; break; }
+            rc = aukit_cuda_dev_pcm(ctx, static_cast<const uint8_t *>(d_in) + c.in_offset, c.frames * (size_t)FB, bitDepth, dataType, channels, 1,
+                                    bigEndian, static_cast<float *>(tmp), st);
+            if (!rc) rc = aukit_cuda_dev_resample(ctx, static_cast<const float *>(tmp), st, channels, c.frames, 0, c.frames, c.srcRate, dstRate,
+                                                  interpolation, 0, n_out, d_out + c.out_offset, c.out_stride);
+            if (!rc && multiplier != 1.0) rc = aukit_cuda_dev_amplify(ctx, d_out + c.out_offset, c.out_stride, channels, n_out, multiplier);
+            aukit_dev_free(ctx, tmp);
+            continue;
+        }
+        // ---- tile plan for this class
+        tile_args a{};
+        a.L = (int)L; a.M = (int)M;
+        a.m = (int)(L >= 512 ? 1 : 512 / L);
+        if ((long long)a.m * M > 2048) a.m = (int)(2048 / M) > 0 ? (int)(2048 / M) : 1;
+        a.Sp = a.L * a.m;
+        a.Q = a.M * a.m;
+        const int threads = (a.Sp + 31) / 32 * 32;
+        // shared memory per CTA (two per SM): float tile + two raw buffers, 20 bytes per staged stereo s24 frame
+        const size_t budget = 110 * 1024;
+        const size_t per_frame = (size_t)channels * 4 + 2 * (size_t)FB;
+        long long K = ((long long)((budget - 1024) / per_frame) - 24) / a.Q;
+        if (K < 1) K = 1;
+        if (K > 64) K = 64;
+        a.K = (int)K;
+        a.nfr = a.K * a.Q + 3;
+        a.raw_bytes = (int)(((size_t)a.nfr * FB + 16 + 16 + 127) & ~(size_t)127);
+        const size_t ft_bytes = (((size_t)(a.nfr + 1) * channels * 4) + 127) & ~(size_t)127;
+        const size_t smem = ft_bytes + 2 * (size_t)a.raw_bytes;
+        if (smem > 113 * 1024) { free(order); free(done); free(h_rec); free(h_pre); return aukit_fail("aukit_cuda: tile does not fit in shared memory"); }
+        const unsigned long long tile_out = (unsigned long long)a.K * a.Sp;
+        size_t n = 0;
+        unsigned long long tiles = 0;
+        for (size_t k = k0; k < nclips; k++) {
+            if (done[k] || clips[k].srcRate != clips[k0].srcRate) continue;
+            long long L2, M2;
+            if (!tile_shape(clips[k], fmt, channels, dstRate, interpolation, &L2, &M2)) continue;   // e.g. a >= 2^28-frame clip of the same rate
+            done[k] = 1;
+            const uint64_t n_out = aukit_resample_out_len(clips[k].frames, clips[k].srcRate, dstRate);
+            if (n_out == 0) continue;
+            if (channels > 1 && clips[k].out_stride < n_out) { rc = aukit_fail("aukit_cuda: clip %zu: out_stride < n_out", k); break; }
+            h_rec[n].in_off = clips[k].in_offset; h_rec[n].frames = clips[k].frames;
+            h_rec[n].out_off = clips[k].out_offset; h_rec[n].out_stride = clips[k].out_stride; h_rec[n].n_out = n_out;
+            h_pre[n] = (unsigned int)tiles;
+            tiles += (n_out + tile_out - 1) / tile_out;
+            n++;
+            if (tiles >= 0xFFFFFFF0ull) { rc = aukit_fail("aukit_cuda: more than 2^32 tiles in one rate class"); break; }
+        }
+        if (rc || n == 0) continue;
+        h_pre[n] = (unsigned int)tiles;
+        void *d_rec = nullptr, *d_pre = nullptr;
+        if (aukit_upload_bytes(ctx, h_rec, sizeof(clip_rec) * n, &d_rec)) { rc = -1; break; }
+        if (aukit_upload_bytes(ctx, h_pre, sizeof(unsigned int) * (n + 1), &d_pre)) { aukit_dev_free(ctx, d_rec); rc = -1; break; }
+        // pageable staging memory is reused by the next class: the uploads above must have left it
+        if (aukit_cuda_check(cudaStreamSynchronize(ctx->stream), "sync")) { aukit_dev_free(ctx, d_rec); aukit_dev_free(ctx, d_pre); rc = -1; break; }
+        a.in = static_cast<const uint8_t *>(d_in);
+        a.out = d_out;
+        a.clips = static_cast<const clip_rec *>(d_rec);
+        a.tile_prefix = static_cast<const unsigned int *>(d_pre);
+        a.nclips = (int)n;
+        a.ntiles = (unsigned int)tiles;
+        a.mult = mh; a.mult_exact = ((double)mh == multiplier) ? 1 : 0; a.mult_d = multiplier;
+        a.clamp_out = fabs(multiplier) > 1.0 ? 1 : 0;
+        const int mode = a.L == 1 ? AUKIT_INTERP_NONE : interpolation;   // integer positions: the sample itself (A:667)
+        switch (fmt) {
+        case TF_S16LE: rc = launch_ch<TF_S16LE>(ctx, a, channels, mode, threads, smem); break;
+        case TF_S16BE: rc = launch_ch<TF_S16BE>(ctx, a, channels, mode, threads, smem); break;
+        case TF_S24LE: rc = launch_ch<TF_S24LE>(ctx, a, channels, mode, threads, smem); break;
+        case TF_S24BE: rc = launch_ch<TF_S24BE>(ctx, a, channels, mode, threads, smem); break;
+        case TF_S8: rc = launch_ch<TF_S8>(ctx, a, channels, mode, threads, smem); break;
+        case TF_U8: rc = launch_ch<TF_U8>(ctx, a, channels, mode, threads, smem); break;
+        case TF_S32LE: rc = launch_ch<TF_S32LE>(ctx, a, channels, mode, threads, smem); break;
+        default: rc = launch_ch<TF_S32BE>(ctx, a, channels, mode, threads, smem); break;
+        }
+        aukit_dev_free(ctx, d_rec);
+        aukit_dev_free(ctx, d_pre);
+    }
+    free(order); free(done); free(h_rec); free(h_pre);
+    return rc;
+}

@@ -265,6 +265,34 @@ int aukit_cuda_dev_pipeline_peak(aukit_ctx *ctx, const aukit_pipeline_desc *p, c
 int aukit_cuda_dev_pipeline_apply(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *d_in,
                                   double peakAmplitude, const float *d_max, float *d_out,
                                   size_t out_stride);
+/* A batch of clips through aukit.pcm (A:1049) -> Audio:resample(dstRate, interpolation) (A:653) -> effects.amplify(multiplier)
+ * (A:3356) in ONE pass per rate class (BASELINE config 3; replaces a loop of those three calls over a playlist).
+ * All clips share the sample format; every clip has its own length and rate.  d_in holds the packed interleaved
+ * frames of all clips (16-byte aligned base; clip k starts at byte in_offset), d_out receives planar float32 rows:
+ * sample (c, i) of clip k = d_out[out_offset + c * out_stride + i].  aukit_batch_plan fills n_out
+ * (= floor(frames * dstRate / srcRate), A:658-664) and, for clips whose out_stride is 0, lays the outputs out back to back
+ * (rows padded to 32 floats); it returns the number of floats d_out must hold. */
+typedef struct {
+    uint64_t in_offset;     /* bytes */
+    uint64_t frames;        /* input frames */
+    double srcRate;
+    uint64_t out_offset;    /* floats */
+    uint64_t out_stride;    /* floats between channel rows; 0 => let aukit_batch_plan choose */
+    uint64_t n_out;         /* output frames (written by aukit_batch_plan) */
+} aukit_clip;
+uint64_t aukit_batch_plan(aukit_clip *clips, size_t nclips, int out_channels, double dstRate);
+int aukit_cuda_dev_batch_resample_amplify(aukit_ctx *ctx, const aukit_clip *clips, size_t nclips, int bitDepth,
+                                          int dataType, int channels, int bigEndian, double dstRate,
+                                          int interpolation, double multiplier, const void *d_in, float *d_out);
+
+/* The same from HOST clips (one pointer / byte count / rate per clip, e.g. a table of Lua strings): uploads them into one
+ * device buffer, runs the batch, returns one Audio per clip in out[0..nclips).  The Audios share one device allocation
+ * that is released with the last of them. */
+int aukit_cuda_batch_resample_amplify(aukit_ctx *ctx, const void *const *h_clips, const size_t *clip_bytes,
+                                      const double *srcRates, size_t nclips, int bitDepth, int dataType,
+                                      int channels, int bigEndian, double dstRate, int interpolation,
+                                      double multiplier, aukit_audio **out);
+
 /* Host-buffer convenience = the end-to-end call (H2D + peak + apply + D2H), single device. */
 int aukit_cuda_pipeline_host(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *h_in,
                              size_t nbytes, double peakAmplitude, float *h_out);

@@ -898,3 +898,21 @@ int auko_aiff_parse(const uint8_t *data, size_t nbytes, auko_container_info *inf
     }
     return fail("invalid AIFF file");                                        /* A:1632 */
 }
+
+/* ---------------------------------------------------------------- host check of a device formula (test helper)
+ * The CUDA kernels convert a non-negative 24-bit sample as fmaf(lo, RN(1 / (2^23 - 1)), lo) with lo = s * 2^-23 (and an
+ * 8-bit one alike with 127 / 128).  Returns how many s in [0, 2^(bits-1)) give a float that differs from
+ * (float)((double)s / (2^(bits-1) - 1)), the reference's value (A:1133) narrowed: must be 0. */
+long auko_selftest_fma_scale(int bits) {
+    const long n = 1L << (bits - 1);
+    const float inv = 1.0f / (float)n;
+    const float c = (float)(1.0 / (double)(n - 1));
+    long bad = 0;
+    for (long s = 0; s < n; s++) {
+        const float ref = (float)((double)s / (double)(n - 1));
+        const float lo = (float)s * inv;
+        const float r = fmaf(lo, c, lo);
+        if (memcmp(&r, &ref, sizeof r)) bad++;
+    }
+    return bad;
+}

@@ -144,6 +144,8 @@ int auko_aiff_parse(const uint8_t *data, size_t nbytes, auko_container_info *inf
 double *auko_chain_s16(const uint8_t *data, size_t nbytes, int channels, double srcRate,
                        double dstRate, int interp, double peak, size_t *n_out);
 void auko_free(void *p);
+/* test helper: mismatches of the kernels' FMA sample scaling against the double division, over every non-negative sample */
+long auko_selftest_fma_scale(int bits);
 
 #ifdef __cplusplus
 }

@@ -163,3 +163,12 @@ def test_static_run_kernel_half_period_script():
             assert fbase - 1 >= -1 and fbase + nsteps - 1 + 2 <= M + 1
         assert [e for e, _ in produced] == list(range(L))
         assert all(f == e * M // L for e, f in produced)
+
+
+def test_fma_sample_scaling_equals_the_double_division(O):
+    """csrc/pipeline_tile.cu::conv_sample converts s >= 0 as fma(lo, RN(1/(2^(b-1) - 1)), lo), lo = s * 2^-(b-1); that must
+    be the reference's s / (2^(b-1) - 1) (A:1133) narrowed to float, for every 24-bit (and 16-bit) sample."""
+    import ctypes as C
+    f = O.lib().auko_selftest_fma_scale
+    f.restype, f.argtypes = C.c_long, [C.c_int]
+    assert f(24) == 0 and f(16) == 0
