@@ -137,6 +137,7 @@ SIGNATURES = {
     "aukit_resample_out_len": (_U64, [_U64, _D, _D]),
     "aukit_resample_position": (_D, [_U64, _D, _D]),
     "aukit_resample_window": (_I, [_U64, _D, _D, _I, _U64, _U64, C.POINTER(_U64), C.POINTER(_U64)]),
+    "aukit_block_shard": (_I, [_U64, _I, _I, C.POINTER(_U64), C.POINTER(_U64)]),
     "aukit_ima_adpcm_wav_frames": (_SZ, [_SZ, _I, _I, _I]),
     "aukit_msadpcm_frames": (_SZ, [_SZ, _I, _I]),
 }

@@ -656,6 +656,18 @@ extern "C" int aukit_cuda_pipeline_host(aukit_ctx *ctx, const aukit_pipeline_des
     return rc;
 }
 
+// ------------------------------------------------------------------ ADPCM block-range shards
+extern "C" int aukit_block_shard(uint64_t nblocks, int world, int rank, uint64_t *first, uint64_t *count) {
+    if (!first || !count) return aukit_fail("aukit_cuda: null argument");
+    if (world < 1 || rank < 0 || rank >= world) return aukit_fail("aukit_cuda: rank %d outside world %d", rank, world);
+    // near-equal contiguous ranges; the __int128 product keeps nblocks * rank exact
+    const uint64_t b0 = (uint64_t)((unsigned __int128)nblocks * (unsigned)rank / (unsigned)world);
+    const uint64_t b1 = (uint64_t)((unsigned __int128)nblocks * (unsigned)(rank + 1) / (unsigned)world);
+    *first = b0;
+    *count = b1 - b0;
+    return 0;
+}
+
 // ------------------------------------------------------------------ clip batches (BASELINE config 3)
 extern "C" int aukit_cuda_batch_resample_amplify(aukit_ctx *ctx, const void *const *h_clips, const size_t *clip_bytes,
                                                  const double *srcRates, size_t nclips, int bitDepth, int dataType, int channels,

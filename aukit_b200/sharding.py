@@ -47,6 +47,19 @@ def plan_time_shards(n_in_total: int, srcRate: float, dstRate: float, interpolat
     return shards
 
 
+def plan_block_shards(n_blocks: int, world: int):
+    """ADPCM files shard by contiguous BLOCK range: every block header carries the full decoder state (A:1310,
+    A:1513), so ranges are independent -- no halo, no collective.  Returns [(first_block, count)] per rank
+    (aukit_block_shard in the C ABI)."""
+    lib = _lib.load()
+    out = []
+    for r in range(world):
+        f, c = C.c_uint64(0), C.c_uint64(0)
+        _lib.check(lib.aukit_block_shard(n_blocks, world, r, C.byref(f), C.byref(c)))
+        out.append((int(f.value), int(c.value)))
+    return out
+
+
 def shard_clips(n_clips: int, world: int, rank: int, sizes: Optional[List[int]] = None) -> List[int]:
     """Clip indices owned by `rank`: round-robin, or greedy size-balanced when sizes are given."""
     if sizes is None:

@@ -315,7 +315,94 @@ def run_b200(args):
     e2e_value = n_out_total / (ms_e2e * 1e-3) / 1e6
     checksum = float(h_out.abs().max())
     same = bool(torch.equal(h_out, h_out2))
+
+    # ---- raw PCIe ceiling of the same byte counts: concurrent pinned H2D + D2H on two streams, no kernels
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    d_tmp_in = torch.empty(in_bytes, dtype=torch.uint8, device="cuda")
+
+    def copies(steps):
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        s_up.wait_event(ev)
+        s_dn.wait_event(ev)
+        for i in range(steps):
+            with torch.cuda.stream(s_up):
+                d_tmp_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                outs[i & 1].copy_(sp.d_out[:, : shard.n_out], non_blocking=True)
+        stream.wait_stream(s_up)
+        stream.wait_stream(s_dn)
+
+    copies(2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    copies(e2e_steps)
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_ceiling = float(t.item())
+    del d_tmp_in
+    # ---- what a Lua string really costs: the same clip from PAGEABLE host memory through aukit_cuda_pipeline_host
+    # (staged through the context's pinned slices), results to pageable memory; host-synchronous call, wall clock
+    ms_pageable = None
+    if world == 1 and not args.emulate_shard:
+        import numpy as np
+        pg_in = np.empty(in_bytes, dtype=np.uint8)
+        pg_in[:] = h_in.numpy()
+        pg_out = np.empty((1, shard.n_out), dtype=np.float32)
+        ctx.set_stream(None)
+        for it in range(3):
+            if it == 1:
+                t0 = time.perf_counter()
+            ak._lib.check(lib.aukit_cuda_pipeline_host(ctx.handle, C.byref(sp.desc), C.c_void_p(pg_in.ctypes.data), in_bytes, PEAK,
+                                                       C.c_void_p(pg_out.ctypes.data)))
+        ms_pageable = (time.perf_counter() - t0) / 2 * 1e3
+        ctx.use_torch_stream()
+        del pg_in, pg_out
+
+    # ---- sustained figure: the same step back to back for >= 2 s (clocks settle; MEASURED_PEAKS saw 1245 MHz under load)
+    sustained = None
+    if args.sustained_steps > 0:
+        barrier()
+        with ClockSampler(local) as clk2:
+            ms_sus, _ = timed(lambda: sp.run_device(d_in), args.sustained_steps, 3)
+        sustained = {"steps": args.sustained_steps, "ms_per_step": ms_sus, "seconds": ms_sus * args.sustained_steps * 1e-3,
+                     "value": n_out_total / (ms_sus * 1e-3) / 1e6, "clocks": clk2.summary(),
+                     "whole_step_frac": (2 * in_bytes + out_bytes) / (ms_sus * 1e-3) / 1e9 / peak_gbs}
+
+    # ---- K10 worst case + the other BASELINE configs + per-kernel table (bench_configs.py)
+    import bench_configs as BC
+    env = BC.Env(torch, dist, ak, ctx, rank, world, local, peak_gbs, ClockSampler)
+    noise = None
+    if not args.no_configs:
+        noise = BC.bench_c2_noise(env, lambda: (sp, shard), n_in_total, args.steps, args.warmup)
+        noise["value"] = n_out_total / (noise["ms_per_step"] * 1e-3) / 1e6
     sp.close()
+    del sp, d_in, h_in, h_out, h_out2, outs
+    torch.cuda.empty_cache()
+    configs, kernels = None, None
+    if not args.no_configs:
+        configs = {}
+        want = [c.strip() for c in args.configs.split(",") if c.strip()]
+        if "c3" in want:
+            configs["c3"] = BC.bench_c3(env)
+        if "c4" in want:
+            configs["c4_ima"] = BC.bench_c4(env, "ima")
+            configs["c4_ms"] = BC.bench_c4(env, "ms")
+            wild = BC.bench_c4(env, "ms", wild=True)
+            configs["c4_ms"]["worst_case_random_nibbles"] = {k: wild[k] for k in ("ms", "GB/s", "frac", "value", "parity_ok", "clocks", "data")}
+        if "c5" in want:
+            cache = {}
+            configs["c5"] = BC.bench_c5(env, 48000, cache=cache)
+            configs["c5p"] = BC.bench_c5(env, 44100, cache=cache)
+            cache.clear()
+            torch.cuda.empty_cache()
+        if world == 1 and not args.no_kernels:
+            import bench_kernels
+            kernels = bench_kernels.table(ClockSampler, local, scale=args.kernel_scale)
 
     line = None
     if rank == 0:
@@ -348,10 +435,24 @@ def run_b200(args):
                     "ms_per_step": ms_e2e, "steps": e2e_steps,
                     "mode": "pipelined preloader (C-ABI aukit_cuda_preloader_*): clip i's D2H overlaps clip i+1's H2D, 2 device slots",
                     "single_clip_ms": ms_single, "single_clip_value": n_out_total / (ms_single * 1e-3) / 1e6,
-                    "outputs_identical_across_slots": same},
+                    "outputs_identical_across_slots": same,
+                    "pcie_ceiling": {"ms_per_step": ms_ceiling, "value": n_out_total / (ms_ceiling * 1e-3) / 1e6,
+                                     "frac_of_ceiling": ms_ceiling / ms_e2e,
+                                     "how": "the same pinned H2D + D2H byte counts per clip on two streams, no kernels, max over ranks"},
+                    "pageable_single_clip_ms": ms_pageable,
+                    "pageable_note": "aukit_cuda_pipeline_host from pageable memory (what a Lua string is): staged through pinned slices"},
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if noise is not None:
+            line["value_noise"] = noise["value"]
+            line["noise"] = noise
+        if sustained is not None:
+            line["sustained"] = sustained
+        if configs is not None:
+            line["configs"] = configs
+        if kernels is not None:
+            line["kernels"] = kernels
         if world == 1 and not args.no_cpu:
             val, ms, _ = cpu_port_rate(args.cpu_seconds, 1)
             line["cpu_baseline"] = {"value": val, "unit": "Msamples/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
@@ -373,6 +474,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=1200.0, help="audio seconds of the 1-core cpu_baseline sample")
     ap.add_argument("--cpu-clip-seconds", type=float, default=30.0, help="--impl reference: audio seconds per thread per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline only (skip c3/c4/c5/c5p, the noise signal and the kernel table)")
+    ap.add_argument("--configs", default="c3,c4,c5", help="which BASELINE configs to run beside the headline")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel table (N = 1 only)")
+    ap.add_argument("--kernel-scale", type=float, default=0.5, help="size of the per-kernel table's buffers relative to config 2")
+    ap.add_argument("--sustained-steps", type=int, default=6000, help="extra back-to-back steps for the sustained figure (0 = skip)")
     ap.add_argument("--emulate-shard", default="", help="diagnostics: 'r/w' = run shard r of a w-GPU time-sharded buffer on one GPU")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -25,6 +25,21 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warm", type=int, default=3, help="untimed launches before timing (0 for ncu captures)")
     args = ap.parse_args()
+    from bench import ClockSampler
+    t = table(ClockSampler, 0, args.scale, args.iters, args.warm)
+    for rec in t["rows"]:
+        print(json.dumps(rec), flush=True)
+    print(json.dumps({"clocks": t["clocks"]}), flush=True)
+
+
+def table(sampler_cls, gpu_index=0, scale=1.0, iters=10, warm=3):
+    """Times K1..K13 one by one; returns one record per kernel, each with the clocks sampled over the whole table's run
+    attached once under the last record's sibling key (see bench.py: line["kernels"])."""
+    class A:
+        pass
+    args = A()
+    args.scale, args.iters, args.warm = scale, iters, warm
+    records = []
     import numpy as np
     import torch
     import aukit_b200 as ak
@@ -52,9 +67,12 @@ def main():
 
     def report(name, ms, bytes_, units, unit_name, note=""):
         gbs = bytes_ / (ms * 1e-3) / 1e9
-        print(json.dumps({"kernel": name, "ms": round(ms, 4), "algorithmic_bytes": int(bytes_), "GB/s": round(gbs, 1),
-                          "frac_of_measured_peak": round(gbs / peak, 3), "peak_GB/s": peak, unit_name + "/s": units / (ms * 1e-3),
-                          "note": note}), flush=True)
+        records.append({"kernel": name, "ms": round(ms, 4), "algorithmic_bytes": int(bytes_), "GB/s": round(gbs, 1),
+                        "frac_of_measured_peak": round(gbs / peak, 3), "peak_GB/s": peak, unit_name + "/s": units / (ms * 1e-3),
+                        "note": note})
+
+    sampler = sampler_cls(gpu_index)
+    sampler.__enter__()
 
     frames = int(158_760_000 * args.scale) // 64 * 64            # config 2: 1 h at 44.1 kHz
 
@@ -145,6 +163,8 @@ def main():
         report("K11 lowpass 2ch f=%g Hz" % f, ms, n * 2 * 8, n * 2, "samples", "chained-tile scan, fp64 state")
     ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_highpass(ctx.handle, x.data_ptr(), n, 2, n, 200.0, 48000.0)))
     report("K11 highpass 2ch f=200 Hz", ms, n * 2 * 8, n * 2, "samples", "same scan, ratio a, saved tile-boundary inputs")
+    sampler.__exit__(None, None, None)
+    return {"clocks": sampler.summary(), "scale": scale, "iters": iters, "rows": records}
 
 
 if __name__ == "__main__":

@@ -334,6 +334,9 @@ double aukit_resample_position(uint64_t i, double srcRate, double dstRate);
 int aukit_resample_window(uint64_t n_in_total, double srcRate, double dstRate, int interpolation,
                           uint64_t out_first, uint64_t n_out, uint64_t *in_first,
                           uint64_t *in_count);
+/* ADPCM data shards by contiguous block range (every block header is the full decoder state, A:1310 / A:1513): rank's
+ * blocks are [*first, *first + *count); decode them with the dev_* ADPCM calls on that byte range -- no halo, no collective. */
+int aukit_block_shard(uint64_t nblocks, int world, int rank, uint64_t *first, uint64_t *count);
 size_t aukit_ima_adpcm_wav_frames(size_t nbytes, int blockAlign, int channels, int dialect);
 size_t aukit_msadpcm_frames(size_t nbytes, int blockAlign, int channels);
 
