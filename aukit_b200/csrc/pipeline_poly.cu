@@ -485,6 +485,11 @@ static int poly_range(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_d
     if (big && last_pos >= 1099511627776.0) return 0;                   // 2^40: beyond the proved range
     const int B = p->bitDepth / 8;
     if ((B == 2 || B == 4) && ((uintptr_t)a.in % B)) return 0;
+    if (L == 1 && pow2_ratio) {
+        // ratio 2^-k: every position is an exact integer, every output a copied sample (A:667): strided gather (K15)
+        const int r = aukit_pipeline_decim_try(ctx, a, p, apply, M);
+        if (r != 0) return r;
+    }
     if (allow_run) {
         // headline shape: the run-per-lane kernel takes the interior, the kernels below the edges
         const double eps = fma(-(double)M, a.ratio, (double)L) / ((double)M * a.ratio);
