@@ -16,6 +16,7 @@
 #include "pipeline.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 using namespace aukit_fmt;
 
@@ -85,6 +86,112 @@ __global__ void __launch_bounds__(256) pipeline_kernel(pipe_args a) {
             if (threadIdx.x == 0) atomic_max_nonneg(a.d_max, m);
         }
     }
+}
+
+// K16 -- wide float frames: 32-bit float little-endian input with 4 or 8 interleaved channels (BASELINE config 5':
+// 96 -> 44.1 kHz, 8 channels).  A frame is 16 / 32 bytes, so the four taps of an output frame are 64 / 128 CONTIGUOUS,
+// 16-byte aligned bytes: one thread per output frame fetches them with 128-bit loads straight from global memory
+// (neighbouring outputs overlap by one or two frames: L1 serves that), evaluates the reference's fp64 position once
+// for all channels (exact at ANY position -- no polyphase position modes, no shared memory, no barriers), blends,
+// and writes one coalesced 128-byte line per warp and channel.
+template <int C, int MODE, bool MONO, bool APPLY>
+__global__ void __launch_bounds__(256) wide_f32_kernel(pipe_args a) {
+    constexpr int V = C / 4;
+    __shared__ float wm[8];
+    float mult = 0.f;
+    if (APPLY) mult = (float)(a.peak / (double)a.d_max[0]);            // A:3444
+    float m = 0.f;
+    const uint4 *in = reinterpret_cast<const uint4 *>(a.in);
+    const long long n = (long long)a.n_total, first = (long long)a.in_first;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < a.n_out; o += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long i0 = a.out_first + o;
+        const double x = __dadd_rn(__ddiv_rn((double)i0, a.ratio), 1.0);   // A:666
+        const double fl = floor(x);
+        const bool hit = (x == fl);
+        const long long f = (long long)fl;                             // 1-based index of p1
+        const double t = x - fl;
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+        const float fx = (float)t;
+        if (MODE == AUKIT_INTERP_CUBIC) {
+            const double t2 = t * t, t3 = t2 * t;
+            w0 = (float)(-0.5 * t3 + t2 - 0.5 * t);
+            w1 = (float)(1.5 * t3 - 2.5 * t2 + 1.0);
+            w2 = (float)(-1.5 * t3 + 2.0 * t2 + 0.5 * t);
+            w3 = (float)(0.5 * t3 - 0.5 * t2);
+        }
+        // nil neighbours == clamped index (A:259, A:264)
+        const long long g1 = f - 1 - first;
+        const long long g0 = (f - 1 >= 1 ? f - 2 : f - 1) - first;
+        const long long g2 = (f + 1 <= n ? f : f - 1) - first;
+        const long long g3 = (f + 2 <= n ? f + 1 : (f + 1 <= n ? f : f - 1)) - first;
+        uint4 q1[V], q0[V], q2[V], q3[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) {
+            q1[k] = __ldg(in + (size_t)g1 * V + k);
+            if (MODE == AUKIT_INTERP_CUBIC) { q0[k] = __ldg(in + (size_t)g0 * V + k); q3[k] = __ldg(in + (size_t)g3 * V + k); }
+            if (MODE != AUKIT_INTERP_NONE) q2[k] = __ldg(in + (size_t)g2 * V + k);
+        }
+        const float *p1 = reinterpret_cast<const float *>(q1), *p0 = reinterpret_cast<const float *>(q0);
+        const float *p2 = reinterpret_cast<const float *>(q2), *p3 = reinterpret_cast<const float *>(q3);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            float v;
+            if (hit) v = p1[c];                                        // copied unclamped, A:667
+            else if (MODE == AUKIT_INTERP_NONE) v = clamp_ref(p1[c]);
+            else if (MODE == AUKIT_INTERP_LINEAR) v = clamp_ref(__fmaf_rn(p2[c] - p1[c], fx, p1[c]));
+            else v = clamp_ref(__fmaf_rn(w3, p3[c], __fmaf_rn(w2, p2[c], __fmaf_rn(w1, p1[c], w0 * p0[c]))));
+            if (MONO) s += v;                                          // A:686
+            else if (APPLY) a.out[(size_t)c * a.out_stride + o] = clamp_ref(v * mult);
+            else m = fmaxf(m, fabsf(v));
+        }
+        if (MONO) {
+            const float mv = s * a.inv_cn;                             // C is a power of two: s / cn exactly (A:687)
+            if (APPLY) a.out[o] = clamp_ref(mv * mult);
+            else m = fmaxf(m, fabsf(mv));
+        }
+    }
+    if (!APPLY) {
+        m = warp_max(m);
+        if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            m = threadIdx.x < (blockDim.x >> 5) ? wm[threadIdx.x] : 0.0f;
+            m = warp_max(m);
+            if (threadIdx.x == 0) atomic_max_nonneg(a.d_max, m);
+        }
+    }
+}
+
+template <int C, bool APPLY>
+int launch_wide_c(aukit_ctx *ctx, const pipe_args &a, int interp) {
+    const unsigned grid = aukit_grid(a.n_out, 256, (size_t)ctx->num_sms * 8 * 4);
+#define AUKIT_WIDE(MODE)                                                                      \
+    if (a.mono) wide_f32_kernel<C, MODE, true, APPLY><<<grid, 256, 0, ctx->stream>>>(a);      \
+    else wide_f32_kernel<C, MODE, false, APPLY><<<grid, 256, 0, ctx->stream>>>(a)
+    switch (interp) {
+    case AUKIT_INTERP_NONE: AUKIT_WIDE(AUKIT_INTERP_NONE); break;
+    case AUKIT_INTERP_LINEAR: AUKIT_WIDE(AUKIT_INTERP_LINEAR); break;
+    default: AUKIT_WIDE(AUKIT_INTERP_CUBIC); break;
+    }
+#undef AUKIT_WIDE
+    ctx->launches++;
+    return aukit_cuda_check(cudaGetLastError(), "wide_f32_kernel launch");
+}
+
+// 1: handled, 0: not this shape, -1: error.  The choice depends on the format only (never on the position), so every
+// time shard of a buffer takes the same kernel and shards stay bit-identical to a single pass.
+template <bool APPLY>
+int wide_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p) {
+    static const bool disabled = getenv("AUKIT_DISABLE_WIDE") && getenv("AUKIT_DISABLE_WIDE")[0] == '1';
+    if (disabled) return 0;
+    if (p->dataType != AUKIT_FLOAT || p->bitDepth != 32 || p->bigEndian) return 0;
+    if (p->channels != 4 && p->channels != 8) return 0;
+    if (((uintptr_t)a.in & 15) != 0) return 0;
+    int e2 = 0;
+    if (frexp(a.ratio, &e2) == 0.5 && a.ratio <= 1.0) return 0;        // 1 / 2^k: the strided gather (K15) is the better kernel
+    const int rc = p->channels == 8 ? launch_wide_c<8, APPLY>(ctx, a, p->interpolation) : launch_wide_c<4, APPLY>(ctx, a, p->interpolation);
+    return rc ? -1 : 1;
 }
 
 template <int B, int KIND, bool BE, bool APPLY>
@@ -162,6 +269,8 @@ extern "C" int aukit_cuda_dev_pipeline_peak(aukit_ctx *ctx, const aukit_pipeline
     if (validate(ctx, p, d_in, &a)) return -1;
     if (a.n_out == 0) return 0;
     a.d_max = d_max;
+    const int w = wide_try<false>(ctx, a, p);
+    if (w != 0) return w < 0 ? -1 : 0;
     const int r = aukit_pipeline_poly_try(ctx, a, p, false);
     if (r != 0) return r < 0 ? -1 : 0;
     return launch_fmt<false>(ctx, a, p);
@@ -178,6 +287,8 @@ extern "C" int aukit_cuda_dev_pipeline_apply(aukit_ctx *ctx, const aukit_pipelin
     a.peak = peakAmplitude;
     a.out = d_out;
     a.out_stride = out_stride;
+    const int w = wide_try<true>(ctx, a, p);
+    if (w != 0) return w < 0 ? -1 : 0;
     const int r = aukit_pipeline_poly_try(ctx, a, p, true);
     if (r != 0) return r < 0 ? -1 : 0;
     return launch_fmt<true>(ctx, a, p);

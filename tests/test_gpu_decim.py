@@ -86,3 +86,62 @@ def test_config5_time_shards_equal_the_single_pass(ak):
     finally:
         ctx.set_stream(None)
     assert f32_equal_bits(got, whole)
+
+
+# ------------------------------------------------------------------ K16: wide float frames (config 5': 96 -> 44.1 kHz, 8 channels)
+@pytest.mark.parametrize("ch", [8, 4])
+@pytest.mark.parametrize("src,dst", [(96000, 44100), (44100, 48000), (48000, 8000), (44056.5, 48000)])
+@pytest.mark.parametrize("interp", ["none", "linear", "cubic"])
+def test_wide_float_frames_against_oracle(ak, O, ch, src, dst, interp):
+    rng = np.random.default_rng(ch + int(src))
+    n = 40009
+    x = (rng.standard_normal((n, ch)) * 0.6).astype("<f4")          # exceeds [-1, 1]: hit (unclamped) vs near hit (clamped) is visible
+    for mono in (False, True):
+        got = ak.preload(x.tobytes(), 32, "float", ch, src, dst, interp, mono, 0.9)
+        r = O.resample(O.pcm(x, 32, "float", ch), src, dst, interp)
+        ref = O.normalize(O.mono(r) if mono else r, 0.9)
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= (2.0 ** -22 if interp == "none" else TOL * 4)   # |values| reach ~4 before normalize
+
+
+@pytest.mark.parametrize("interp", ["none", "linear", "cubic"])
+def test_wide_float_frames_at_huge_positions_and_shard_equality(ak, interp):
+    """Shards of a 24 h 96 kHz buffer (positions up to 2^33): the kernel evaluates the reference's fp64 position itself,
+    so it must follow the numpy restatement of A:653-673 anywhere, and two abutting shards must equal one shard."""
+    import torch
+    from util import ref_resample_window
+    lib, ctx = ak._lib.load(), ak.context()
+    n_total, src, dst, CH = 8_294_400_000, 96000, 44100, 8
+    mode = {"none": 0, "linear": 1, "cubic": 2}[interp]
+    total_out = int(lib.aukit_resample_out_len(n_total, float(src), float(dst)))
+    rng = np.random.default_rng(mode)
+    ctx.use_torch_stream()
+    try:
+        for o0 in (total_out - 60_000, int(total_out * 0.613), int(2 ** 30.5 * dst / src) - 30_000, 0):
+            cnt = 60_000
+            f, c = C.c_uint64(), C.c_uint64()
+            assert lib.aukit_resample_window(n_total, float(src), float(dst), mode, o0, cnt, C.byref(f), C.byref(c)) == 0
+            x = (rng.standard_normal((int(c.value), CH)) * 0.3).astype(np.float32)
+            ref = ref_resample_window(x.T.astype(np.float64), int(f.value), n_total, src, dst, o0, cnt, interp)
+            want = np.clip(ref * (1.0 / np.max(np.abs(ref))), -1, 1)
+            t = torch.from_numpy(x).cuda()
+            dmax = torch.zeros(1, device="cuda")
+            out = torch.empty((CH, cnt), device="cuda")
+            d = ak.PipelineDesc(32, 2, CH, 0, float(src), float(dst), mode, 0, n_total, f.value, c.value, o0, cnt)
+            ak._lib.check(lib.aukit_cuda_dev_pipeline_peak(ctx.handle, C.byref(d), t.data_ptr(), dmax.data_ptr()))
+            ak._lib.check(lib.aukit_cuda_dev_pipeline_apply(ctx.handle, C.byref(d), t.data_ptr(), 1.0, dmax.data_ptr(), out.data_ptr(), cnt))
+            got = out.cpu().numpy()
+            assert np.max(np.abs(got - want)) <= TOL, (o0, float(np.max(np.abs(got - want))))
+            # the same range as two shards (each with its own window) == one shard, bit for bit
+            parts = []
+            for a0, a1 in ((o0, o0 + 25_001), (o0 + 25_001, o0 + cnt)):
+                f2, c2 = C.c_uint64(), C.c_uint64()
+                lib.aukit_resample_window(n_total, float(src), float(dst), mode, a0, a1 - a0, C.byref(f2), C.byref(c2))
+                t2 = torch.from_numpy(x[f2.value - f.value: f2.value - f.value + c2.value].copy()).cuda()
+                o2 = torch.empty((CH, a1 - a0), device="cuda")
+                d2 = ak.PipelineDesc(32, 2, CH, 0, float(src), float(dst), mode, 0, n_total, f2.value, c2.value, a0, a1 - a0)
+                ak._lib.check(lib.aukit_cuda_dev_pipeline_apply(ctx.handle, C.byref(d2), t2.data_ptr(), 1.0, dmax.data_ptr(), o2.data_ptr(), a1 - a0))
+                parts.append(o2.cpu().numpy())
+            assert f32_equal_bits(np.concatenate(parts, axis=1), got)
+    finally:
+        ctx.set_stream(None)
