@@ -29,6 +29,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -123,6 +125,42 @@ __device__ __forceinline__ uint32_t ldg_bytes(const uint8_t *p, int n) {
     return v;
 }
 
+// ---- vectorised phase A: a lane converts the G frames that make up ONE 16-byte chunk of the float tile (G = 2 stereo
+// frames or 4 mono frames) from G*FB/4 whole words of the raw buffer; every byte position is a compile-time constant,
+// so a sample costs one PRMT (bytes -> sign-extended integer), one I2F and the scaling FMAs.
+template <int FMT, int K>
+__device__ __forceinline__ float group_sample(const uint32_t *w) {
+    constexpr int B = tfmt<FMT>::B, off = K * B, wi = off >> 2, bo = off & 3;
+    if (B == 3) {
+        // bytes (bo, bo+1, bo+2) of the pair (w[wi], w[wi+1]) -> sign-extended 24-bit integer: selector nibble n picks
+        // byte n of the pair, n | 8 replicates that byte's sign bit (the top byte of the result)
+        constexpr bool BE = (FMT == TF_S24BE);
+        constexpr uint32_t msb = BE ? bo : bo + 2, mid = bo + 1, lsb = BE ? bo + 2 : bo;
+        constexpr uint32_t sel = ((msb | 8u) << 12) | (msb << 8) | (mid << 4) | lsb;
+        const uint32_t hi = (bo + 2 > 3) ? w[wi + 1] : 0u;
+        int sgn;                                                         // prmt.b32: selector bit 3 = replicate the byte's sign bit
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sgn) : "r"(w[wi]), "r"(hi), "r"(sel));
+        const float lo = __fmul_rn((float)sgn, 1.0f / 8388608.0f);
+        return __fmaf_rn(__saturatef(lo), 1.0f / 8388607.0f, lo);
+    }
+    if (B == 2) {
+        const uint32_t v = (bo == 0) ? w[wi] : (w[wi] >> 16);
+        return conv_sample<FMT>(v);
+    }
+    if (B == 1) return conv_sample<FMT>(w[wi] >> (8 * bo));
+    return conv_sample<FMT>(w[wi]);
+}
+
+template <int FMT, int CT>
+__device__ __forceinline__ float4 group_convert(const uint32_t *src) {
+    constexpr int NW = tfmt<FMT>::B;                                     // 4 samples of B bytes = B words
+    uint32_t w[NW + 1];
+#pragma unroll
+    for (int k = 0; k < NW; k++) w[k] = src[k];
+    w[NW] = 0;
+    return make_float4(group_sample<FMT, 0>(w), group_sample<FMT, 1>(w), group_sample<FMT, 2>(w), group_sample<FMT, 3>(w));
+}
+
 struct clip_rec {                 // one clip of the launch's rate class (device copy of aukit_clip + derived fields)
     unsigned long long in_off;    // byte offset of frame 0 in d_in
     unsigned long long frames;    // input frames
@@ -156,6 +194,7 @@ struct tile_geom {                // everything a CTA needs about one tile; writ
     long long frames;             // clip length
     unsigned int bytes;           // bulk copy size (multiple of 16)
     unsigned int sh;              // byte offset of staged frame 0 inside the copy
+    int fshift;                   // extra frames staged in front so that the copy starts on a word boundary (0..3)
     int n_valid;                  // outputs of this tile that exist (<= K*Sp)
     int edge;                     // 1: staged by the clamped-index path (no bulk copy)
     int exists;
@@ -184,7 +223,13 @@ __device__ __forceinline__ void tile_lookup(const tile_args &a, unsigned int til
     const long long F0 = (long long)(T * (unsigned long long)a.K * (unsigned long long)a.Q);
     const unsigned long long o0 = T * (unsigned long long)a.K * (unsigned long long)a.Sp;
     g->exists = 1;
-    g->first_frame = F0 - 1;
+    // stage up to 3 extra frames in front when that puts the first staged byte on a 4-byte boundary: the vectorised
+    // conversion (group_convert) reads whole words
+    int e = 0;
+    while (e < 4 && (F0 - 1 - e < 0 || ((c.in_off + (unsigned long long)(F0 - 1 - e) * FB) & 3ull) != 0)) e++;
+    if (e == 4) e = 0;
+    g->fshift = e;
+    g->first_frame = F0 - 1 - e;
     g->frames = (long long)c.frames;
     g->clip_in = (unsigned long long)(uintptr_t)(a.in + c.in_off);
     g->out0 = (unsigned long long)(uintptr_t)(a.out + c.out_off + o0);
@@ -192,12 +237,12 @@ __device__ __forceinline__ void tile_lookup(const tile_args &a, unsigned int til
     const unsigned long long left = c.n_out - o0;
     g->n_valid = left < (unsigned long long)(a.K * a.Sp) ? (int)left : a.K * a.Sp;
     // bulk copy: every staged frame must exist (no clamping) and the 16-byte rounding must stay inside the clip's bytes
-    const unsigned long long b0 = c.in_off + (unsigned long long)(F0 - 1) * FB;
+    const unsigned long long b0 = c.in_off + (unsigned long long)(F0 - 1 - e) * FB;
     const unsigned long long a0 = b0 & ~15ull;
     const unsigned int sh = (unsigned int)(b0 - a0);
-    const unsigned int bytes = (sh + (unsigned int)a.nfr * FB + 15u) & ~15u;
+    const unsigned int bytes = (sh + (unsigned int)(a.nfr + e) * FB + 15u) & ~15u;
     // (a0 may lie up to 15 bytes before the clip's first byte: still inside d_in, whose base is 16-byte aligned)
-    g->edge = (F0 - 1 < 0) || (a0 + bytes > c.in_off + c.frames * FB) || (F0 - 1 + a.nfr > (long long)c.frames) ||
+    g->edge = (F0 - 1 - e < 0) || (a0 + bytes > c.in_off + c.frames * FB) || (F0 - 1 + a.nfr > (long long)c.frames) ||
               (((uintptr_t)a.in & 15) != 0);
     g->src = (unsigned long long)(uintptr_t)(a.in + a0);
     g->sh = sh;
@@ -212,7 +257,7 @@ __global__ void __launch_bounds__(512, 2) tile_kernel(tile_args a) {
     __shared__ tile_geom geom[3];
     // layout: float tile [nfr + 1] x CT floats | raw buffer 0 | raw buffer 1
     float *ftile = reinterpret_cast<float *>(smem);
-    const uint32_t ft_bytes = ((uint32_t)(a.nfr + 1) * CT * 4u + 127u) & ~127u;
+    const uint32_t ft_bytes = ((uint32_t)(a.nfr + 8) * CT * 4u + 127u) & ~127u;
     unsigned char *raw0 = smem + ft_bytes;
     const int t = threadIdx.x;
     const bool active = t < a.Sp;
@@ -258,25 +303,39 @@ __global__ void __launch_bounds__(512, 2) tile_kernel(tile_args a) {
         const bool edge = g->edge != 0;
         const long long first_frame = g->first_frame, nframes = g->frames;
         // ---------------- phase A: packed frames -> float samples (each frame converted once)
+        // integer ratios (MODE NONE here means L == 1): phase B reads the ONE frame an output needs straight from the
+        // raw buffer, nothing is converted twice and nothing unused is converted at all
+        const bool direct = (MODE == AUKIT_INTERP_NONE) && !edge;
+        const int nstage = a.nfr + g->fshift;
         if (!edge) {
             mbar_wait(&bars[slot], slot ? phase1 : phase0);
             if (slot) phase1 ^= 1u; else phase0 ^= 1u;
+        }
+        if (!edge && !direct) {
             const uint32_t *words = reinterpret_cast<const uint32_t *>(raw0 + (size_t)slot * a.raw_bytes);
             const uint32_t sh = g->sh;
-            for (int f = t; f < a.nfr; f += blockDim.x) {
-                const uint32_t o = sh + (uint32_t)f * FB;
-                if (CT == 2) {
-                    const float l = conv_sample<FMT>(lds_unaligned(words, o));
-                    const float r = conv_sample<FMT>(lds_unaligned(words, o + B));
-                    reinterpret_cast<float2 *>(ftile)[f] = make_float2(l, r);
-                } else {
-                    ftile[f] = conv_sample<FMT>(lds_unaligned(words, o));
+            if ((sh & 3u) == 0) {
+                constexpr int G = 4 / CT, NW = B;                      // frames / raw words per 16-byte float chunk
+                const uint32_t *w0 = words + (sh >> 2);
+                const int ngroups = (nstage + G - 1) / G;
+                for (int gi = t; gi < ngroups; gi += blockDim.x)
+                    reinterpret_cast<float4 *>(ftile)[gi] = group_convert<FMT, CT>(w0 + gi * NW);
+            } else {
+                for (int f = t; f < nstage; f += blockDim.x) {
+                    const uint32_t o = sh + (uint32_t)f * FB;
+                    if (CT == 2) {
+                        const float l = conv_sample<FMT>(lds_unaligned(words, o));
+                        const float r = conv_sample<FMT>(lds_unaligned(words, o + B));
+                        reinterpret_cast<float2 *>(ftile)[f] = make_float2(l, r);
+                    } else {
+                        ftile[f] = conv_sample<FMT>(lds_unaligned(words, o));
+                    }
                 }
             }
-        } else {
+        } else if (edge) {
             // clamped index = the reference's nil substitutions (A:259, A:264); plain byte loads
             const uint8_t *cin = reinterpret_cast<const uint8_t *>(g->clip_in);
-            for (int f = t; f < a.nfr; f += blockDim.x) {
+            for (int f = t; f < nstage; f += blockDim.x) {
                 long long gi = first_frame + f;
                 gi = gi < 0 ? 0 : (gi >= nframes ? nframes - 1 : gi);
                 const uint8_t *p = cin + (size_t)gi * FB;
@@ -287,8 +346,8 @@ __global__ void __launch_bounds__(512, 2) tile_kernel(tile_args a) {
                 }
             }
         }
-        __syncthreads();                                               // float tile complete; raw[slot] and geom[(i+2)%3] are free
-        if (t == 0) {
+        __syncthreads();                                               // float tile complete; geom[(i+2)%3] is free
+        auto issue_next = [&]() {                                      // thread 0: look up tile i+2 and start its copy into raw[slot]
             tile_geom *gn = &geom[(i + 2) % 3];
             tile_lookup<FMT, CT>(a, blockIdx.x + (i + 2) * gridDim.x, gn, hint);
             if (gn->exists && !gn->edge) {
@@ -296,7 +355,8 @@ __global__ void __launch_bounds__(512, 2) tile_kernel(tile_args a) {
                 mbar_expect_tx(&bars[slot], gn->bytes);
                 bulk_load(raw0 + (size_t)slot * a.raw_bytes, reinterpret_cast<const void *>(gn->src), gn->bytes, &bars[slot]);
             }
-        }
+        };
+        if (t == 0 && !direct) issue_next();                           // raw[slot] was consumed by phase A
         // ---------------- phase B: taps -> blend -> clamp (A:668) -> amplify (A:3364) -> store
         if (active) {
             const int n_valid = g->n_valid;
@@ -304,53 +364,71 @@ __global__ void __launch_bounds__(512, 2) tile_kernel(tile_args a) {
             if (k1 > a.K) k1 = a.K;
             float *o0 = reinterpret_cast<float *>(g->out0) + t;
             const size_t ostride = (size_t)g->out_stride;
-            int s = off_t;
+            const uint32_t *rwords = reinterpret_cast<const uint32_t *>(raw0 + (size_t)slot * a.raw_bytes);
+            const uint32_t rsh = g->sh;
+            const int Q = a.Q, Sp = a.Sp;
+            // EXACT: the multiplier is a float, so x * m in fp32 is the reference's double product rounded once; otherwise
+            // the product is formed in fp64 like effects.amplify's own kernel (K7).  Two copies of the loop, chosen per tile.
+            auto run = [&](auto exact_tag) {
+                constexpr bool EXACT = decltype(exact_tag)::value;
+                int s = off_t + g->fshift;
 #pragma unroll 4
-            for (int k = 0; k < k1; k++, s += a.Q, o0 += a.Sp) {
-                float vl, vr = 0.f;
-                if (CT == 2) {
-                    const f32x2 *f = reinterpret_cast<const f32x2 *>(ftile) + s;
-                    f32x2 acc;
-                    if (MODE == AUKIT_INTERP_CUBIC) {
-                        acc = mul2(f[0], W0);
-                        acc = fma2(f[1], W1, acc);
-                        acc = fma2(f[2], W2, acc);
-                        acc = fma2(f[3], W3, acc);
-                    } else if (MODE == AUKIT_INTERP_LINEAR) {
-                        float p1l, p1r, p2l, p2r;
-                        unpack2(f[1], p1l, p1r);
-                        unpack2(f[2], p2l, p2r);
-                        acc = fma2(pack2(p2l - p1l, p2r - p1r), FX, f[1]);
+                for (int k = 0; k < k1; k++, s += Q, o0 += Sp) {
+                    float vl, vr = 0.f;
+                    if (CT == 2) {
+                        const f32x2 *f = reinterpret_cast<const f32x2 *>(ftile) + s;
+                        f32x2 acc;
+                        if (MODE == AUKIT_INTERP_CUBIC) {
+                            acc = mul2(f[0], W0);
+                            acc = fma2(f[1], W1, acc);
+                            acc = fma2(f[2], W2, acc);
+                            acc = fma2(f[3], W3, acc);
+                        } else if (MODE == AUKIT_INTERP_LINEAR) {
+                            float p1l, p1r, p2l, p2r;
+                            unpack2(f[1], p1l, p1r);
+                            unpack2(f[2], p2l, p2r);
+                            acc = fma2(pack2(p2l - p1l, p2r - p1r), FX, f[1]);
+                        } else if (direct) {
+                            const uint32_t o = rsh + (uint32_t)(s + 1) * FB;
+                            acc = pack2(conv_sample<FMT>(lds_unaligned(rwords, o)), conv_sample<FMT>(lds_unaligned(rwords, o + B)));
+                        } else {
+                            acc = f[1];
+                        }
+                        unpack2(acc, vl, vr);
                     } else {
-                        acc = f[1];
+                        const float *f = ftile + s;
+                        if (MODE == AUKIT_INTERP_CUBIC) {
+                            float w0, w1, w2, w3, d;
+                            unpack2(W0, w0, d); unpack2(W1, w1, d); unpack2(W2, w2, d); unpack2(W3, w3, d);
+                            vl = __fmaf_rn(w3, f[3], __fmaf_rn(w2, f[2], __fmaf_rn(w1, f[1], w0 * f[0])));
+                        } else if (MODE == AUKIT_INTERP_LINEAR) {
+                            vl = __fmaf_rn(f[2] - f[1], fx, f[1]);
+                        } else if (direct) {
+                            vl = conv_sample<FMT>(lds_unaligned(rwords, rsh + (uint32_t)(s + 1) * FB));
+                        } else {
+                            vl = f[1];
+                        }
                     }
-                    unpack2(acc, vl, vr);
-                } else {
-                    const float *f = ftile + s;
-                    if (MODE == AUKIT_INTERP_CUBIC) {
-                        float w0, w1, w2, w3, d;
-                        unpack2(W0, w0, d); unpack2(W1, w1, d); unpack2(W2, w2, d); unpack2(W3, w3, d);
-                        vl = __fmaf_rn(w3, f[3], __fmaf_rn(w2, f[2], __fmaf_rn(w1, f[1], w0 * f[0])));
-                    } else if (MODE == AUKIT_INTERP_LINEAR) {
-                        vl = __fmaf_rn(f[2] - f[1], fx, f[1]);
-                    } else {
-                        vl = f[1];
+                    if (MODE != AUKIT_INTERP_NONE) {                   // exact hits (NONE here) are copied unclamped, A:667
+                        vl = clamp_unit(vl);
+                        if (CT == 2) vr = clamp_unit(vr);
+                    }
+                    float ol, orr;
+                    if (EXACT) { ol = vl * mult; orr = vr * mult; }
+                    else { ol = (float)((double)vl * a.mult_d); orr = (float)((double)vr * a.mult_d); }
+                    // A:3364's clamp: a no-op whenever |multiplier| <= 1 (|v| <= 1 here), so it is simply always applied
+                    ol = clamp_unit(ol);
+                    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(o0), "f"(ol) : "memory");
+                    if (CT == 2) {
+                        orr = clamp_unit(orr);
+                        asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(o0 + ostride), "f"(orr) : "memory");
                     }
                 }
-                if (MODE != AUKIT_INTERP_NONE) {                       // exact hits (NONE here) are copied unclamped, A:667
-                    vl = clamp_unit(vl);
-                    if (CT == 2) vr = clamp_unit(vr);
-                }
-                // x * multiplier rounded once (A:3364 computes it in double)
-                float ol, orr;
-                if (a.mult_exact) { ol = vl * mult; orr = vr * mult; }
-                else { ol = (float)((double)vl * a.mult_d); orr = (float)((double)vr * a.mult_d); }
-                if (a.clamp_out) { ol = clamp_unit(ol); orr = clamp_unit(orr); }
-                asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(o0), "f"(ol) : "memory");
-                if (CT == 2) asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(o0 + ostride), "f"(orr) : "memory");
-            }
+            };
+            if (a.mult_exact) run(std::true_type{}); else run(std::false_type{});
         }
-        __syncthreads();                                               // float tile consumed
+        __syncthreads();                                               // float tile (or, direct, raw[slot]) consumed
+        if (t == 0 && direct) issue_next();
     }
 }
 
@@ -373,7 +451,7 @@ template <int FMT, int CT>
 int launch_mode(aukit_ctx *ctx, const tile_args &a, int mode, int threads, size_t smem) {
     auto go = [&](auto kern) -> int {
         if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
-        unsigned g = (unsigned)ctx->num_sms * 2u;
+        unsigned g = (unsigned)ctx->num_sms * (smem <= 74 * 1024 ? 3u : 2u);
         if (g > a.ntiles) g = a.ntiles;
         kern<<<g, threads, smem, ctx->stream>>>(a);
         ctx->launches++;
@@ -479,16 +557,18 @@ extern "C" int aukit_cuda_dev_batch_resample_amplify(aukit_ctx *ctx, const aukit
         a.Sp = a.L * a.m;
         a.Q = a.M * a.m;
         const int threads = (a.Sp + 31) / 32 * 32;
-        // shared memory per CTA (two per SM): float tile + two raw buffers, 20 bytes per staged stereo s24 frame
-        const size_t budget = 110 * 1024;
+        // shared memory per CTA: float tile + two raw buffers, 20 bytes per staged stereo s24 frame.  Two CTAs per SM, three
+        // when a CTA is at most 11 warps (L = 320: 22.05 -> 48 kHz), so that enough warps are resident to hide the barriers
+        const int ctas = threads <= 352 ? 3 : 2;
+        const size_t budget = (ctas == 3 ? 73 : 110) * 1024;
         const size_t per_frame = (size_t)channels * 4 + 2 * (size_t)FB;
         long long K = ((long long)((budget - 1024) / per_frame) - 24) / a.Q;
         if (K < 1) K = 1;
         if (K > 64) K = 64;
         a.K = (int)K;
         a.nfr = a.K * a.Q + 3;
-        a.raw_bytes = (int)(((size_t)a.nfr * FB + 16 + 16 + 127) & ~(size_t)127);
-        const size_t ft_bytes = (((size_t)(a.nfr + 1) * channels * 4) + 127) & ~(size_t)127;
+        a.raw_bytes = (int)(((size_t)(a.nfr + 3) * FB + 16 + 16 + 127) & ~(size_t)127);
+        const size_t ft_bytes = (((size_t)(a.nfr + 8) * channels * 4) + 127) & ~(size_t)127;
         const size_t smem = ft_bytes + 2 * (size_t)a.raw_bytes;
         if (smem > 113 * 1024) { free(order); free(done); free(h_rec); free(h_pre); return aukit_fail("aukit_cuda: tile does not fit in shared memory"); }
         const unsigned long long tile_out = (unsigned long long)a.K * a.Sp;

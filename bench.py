@@ -388,7 +388,7 @@ def run_b200(args):
         configs = {}
         want = [c.strip() for c in args.configs.split(",") if c.strip()]
         if "c3" in want:
-            configs["c3"] = BC.bench_c3(env)
+            configs["c3"] = BC.bench_c3(env, nclips=args.c3_clips)
         if "c4" in want:
             configs["c4_ima"] = BC.bench_c4(env, "ima")
             configs["c4_ms"] = BC.bench_c4(env, "ms")
@@ -476,6 +476,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="headline only (skip c3/c4/c5/c5p, the noise signal and the kernel table)")
     ap.add_argument("--configs", default="c3,c4,c5", help="which BASELINE configs to run beside the headline")
+    ap.add_argument("--c3-clips", type=int, default=1024, help="clips in config 3 (1024 = BASELINE; fewer for profiler captures)")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel table (N = 1 only)")
     ap.add_argument("--kernel-scale", type=float, default=0.5, help="size of the per-kernel table's buffers relative to config 2")
     ap.add_argument("--sustained-steps", type=int, default=6000, help="extra back-to-back steps for the sustained figure (0 = skip)")
