@@ -68,6 +68,8 @@ extern "C" int aukit_cuda_init(int device, aukit_ctx **out) {
     AUKIT_CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(int)));
     AUKIT_CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(int)));
     AUKIT_CUDA_TRY(cudaMalloc(&ctx->d_scratch, 1024 * sizeof(float)));
+    AUKIT_CUDA_TRY(cudaMalloc(&ctx->d_hint, sizeof(int)));
+    AUKIT_CUDA_TRY(cudaMemset(ctx->d_hint, 0, sizeof(int)));
     // keep freed blocks in the pool: the end-to-end calls allocate per call
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -85,6 +87,7 @@ extern "C" void aukit_cuda_shutdown(aukit_ctx *ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaFree(ctx->d_status);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_hint);
     cudaFreeHost(ctx->h_status);
     cudaStreamSynchronize(ctx->side_stream);
     cudaEventDestroy(ctx->ev_fork);

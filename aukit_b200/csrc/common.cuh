@@ -29,6 +29,8 @@ struct aukit_ctx {
     // fork/join pair for work that may overlap the main kernel of a pass (the fused pipeline's edge kernels)
     cudaStream_t side_stream;
     cudaEvent_t ev_fork, ev_join;
+    int *d_hint;              // device word: epoch of the last fused peak pass that saw the channel clamp act
+    int epoch;                // incremented by every aukit_cuda_dev_pipeline_peak call
 };
 
 struct aukit_block { void *d; long refs; };   // a device allocation shared by several Audio handles (batch results)

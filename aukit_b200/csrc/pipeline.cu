@@ -260,12 +260,15 @@ static int validate(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *d_
     a->mono = p->mono != 0;
     a->inv_cn = 1.0f / (float)p->channels;
     a->cn_pow2 = (p->channels & (p->channels - 1)) == 0;
+    a->hint = ctx->d_hint;
+    a->epoch = ctx->epoch;
     return 0;
 }
 
 extern "C" int aukit_cuda_dev_pipeline_peak(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *d_in,
                                             float *d_max) {
     pipe_args a{};
+    if (ctx) ctx->epoch = ctx->epoch >= 0x7FFFFFF0 ? 1 : ctx->epoch + 1;   // a new call: hints of earlier calls no longer apply
     if (validate(ctx, p, d_in, &a)) return -1;
     if (a.n_out == 0) return 0;
     a.d_max = d_max;

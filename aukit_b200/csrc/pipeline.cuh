@@ -21,6 +21,10 @@ struct pipe_args {
     int planar_f32;               // `in` holds float rows, in_stride floats apart (instead of packed interleaved bytes)
     size_t in_stride;
     int raw_out;                  // store the resampled value itself (no normalize scale / clamp)
+    // Performance hint only (results do not depend on it): *hint == epoch means an earlier launch of the same call found
+    // that the per-channel clamp of A:668 acts on this signal, so run_static_kernel starts on its clamping twin.
+    int *hint;
+    int epoch;
 };
 
 // implemented in pipeline_poly.cu; returns 1 when it handled the launch, 0 when the generic

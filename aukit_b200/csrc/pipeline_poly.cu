@@ -500,7 +500,7 @@ static int poly_range(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_d
         // they run beside it from the start.  The peak pass's atomicMax commutes and the apply pass's output ranges
         // are disjoint, so nothing else orders them.  (Measured on one box: same stream 0.384 ms / step, side stream
         // 0.370, + two reserved SMs 0.351; head and tail on two side streams was no better, 0.357.)
-        static const bool no_side = getenv("AUKIT_EDGE_SIDE_STREAM") && getenv("AUKIT_EDGE_SIDE_STREAM")[0] == '0';
+        constexpr bool no_side = false;
         cudaStream_t main_stream = ctx->stream;
         if (!no_side && aukit_cuda_check(cudaEventRecord(ctx->ev_fork, main_stream), "fork event")) return -1;
         const int r = aukit_pipeline_run_try(ctx, a, p, apply, L, M, eps, pow2_ratio, &df, &dc);

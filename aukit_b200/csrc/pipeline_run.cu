@@ -347,7 +347,6 @@ int launch_run(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     const size_t budget = 224 * 1024;
     int nw = (int)((budget - fixed - 256 - 256) / per_warp);
     if (nw > 24) nw = 24;
-    if (const char *e = getenv("AUKIT_RUN_MAXWARPS")) { const int m = atoi(e); if (m >= 2 && m < nw) nw = m; }   // occupancy experiments
     if (nw < 2) return 0;                                         // not worth it: let the caller fall back
     rp.nwarps = nw;
     const size_t smem = fixed + (((size_t)nw * 8 + 127) & ~(size_t)127) + (size_t)nw * per_warp + 128;
@@ -430,6 +429,7 @@ struct __align__(16) cta_state {
     int n, nbuf, npairs;                 // tiles of this CTA; frame buffers; warp pairs
     uint32_t bufs_off, buf_bytes;        // ring: offset from the dynamic shared memory base, pitch
     float mult, one_hi;
+    int start_twin;                      // the call already knows that the channel clamp acts: skip the checking code
 };
 
 struct half_ctx {
@@ -491,8 +491,11 @@ __device__ __forceinline__ void semit(const half_ctx &hc, f32x2 p0, f32x2 p1, f3
     }
 }
 
+// Returns true when the CHECKING variant gave up early: right after output 15 of the half (the first flush point) the
+// warp votes on chk; with a near-full-scale signal the clamp of A:668 acts within the first few outputs of some lane,
+// so the tile is handed to the clamping twin after a fifth of its work instead of after all of it.
 template <bool APPLY, bool CLAMPCH, bool CLAMP1, bool CVTA, int L, int M, int CLS, int S>
-__device__ __forceinline__ void ssteps(const half_ctx &hc, f32x2 (&c)[8], float (&o)[4], float &mx, float &chk) {
+__device__ __forceinline__ bool ssteps(const half_ctx &hc, f32x2 (&c)[8], float (&o)[4], float &mx, float &chk) {
     using G = half_geom<L, M, CLS>;
     if constexpr (S < G::NSTEPS) {
         if constexpr (S + 6 <= G::NSTEPS + 2) c[(S + 6) & 7] = cvt_frame<CVTA>(hc.row[S + 6]);
@@ -503,13 +506,17 @@ __device__ __forceinline__ void ssteps(const half_ctx &hc, f32x2 (&c)[8], float 
         if constexpr (N > 2) semit<APPLY, CLAMPCH, CLAMP1, L, E0 + 2>(hc, c[S & 7], c[(S + 1) & 7], c[(S + 2) & 7], c[(S + 3) & 7], o, mx, chk);
         if constexpr (N > 3) semit<APPLY, CLAMPCH, CLAMP1, L, E0 + 3>(hc, c[S & 7], c[(S + 1) & 7], c[(S + 2) & 7], c[(S + 3) & 7], o, mx, chk);
         if constexpr (N > 4) semit<APPLY, CLAMPCH, CLAMP1, L, E0 + 4>(hc, c[S & 7], c[(S + 1) & 7], c[(S + 2) & 7], c[(S + 3) & 7], o, mx, chk);
-        ssteps<APPLY, CLAMPCH, CLAMP1, CVTA, L, M, CLS, S + 1>(hc, c, o, mx, chk);
+        if constexpr (!CLAMPCH && E0 <= 15 && 15 < E0 + N) {
+            if (__any_sync(0xffffffffu, chk > 32768.0f)) return true;
+        }
+        return ssteps<APPLY, CLAMPCH, CLAMP1, CVTA, L, M, CLS, S + 1>(hc, c, o, mx, chk);
     }
+    return false;
 }
 
 // one half period of one lane, start to end; returns max |l + r| of its outputs, chk = max |channel value|
 template <bool APPLY, bool CLAMPCH, bool CLAMP1, bool CVTA, int L, int M, int CLS>
-__device__ __forceinline__ float shalf(const half_ctx &hc, float &chk) {
+__device__ __forceinline__ float shalf(const half_ctx &hc, float &chk, bool &gave_up) {
     using G = half_geom<L, M, CLS>;
     static_assert(G::before(G::NSTEPS) == L / 2, "every output of the half is produced");
     static_assert((L / 2) % 16 == 0, "whole flush groups");
@@ -519,7 +526,7 @@ __device__ __forceinline__ float shalf(const half_ctx &hc, float &chk) {
     c[6] = c[7] = 0;
     float o[4] = {0.f, 0.f, 0.f, 0.f};
     float mx = 0.f;
-    ssteps<APPLY, CLAMPCH, CLAMP1, CVTA, L, M, CLS, 0>(hc, c, o, mx, chk);
+    gave_up = ssteps<APPLY, CLAMPCH, CLAMP1, CVTA, L, M, CLS, 0>(hc, c, o, mx, chk);
     return mx;
 }
 
@@ -584,6 +591,7 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
                 if (!(mx0 > 0.f)) one_hi = mult;
             }
             cst.mult = mult; cst.one_hi = one_hi;
+            cst.start_twin = (a.hint && *reinterpret_cast<volatile int *>(a.hint) == a.epoch) ? 1 : 0;
             for (int j = 0; j < nbuf; j++) {
                 mbar_init(reinterpret_cast<uint64_t *>(&sst[j].full), 1);
                 sst[j].done = 0;
@@ -666,21 +674,33 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
         __syncwarp();
     };
     // Phase 1: the checking code.  It ends at the first tile in which the clamp of A:668 acted somewhere ...
+    // (not entered at all when an earlier launch of the same call -- the peak pass before this apply pass, or an
+    // earlier split of the same pass -- already found that the signal needs the clamp: a.hint / a.epoch)
     float mx = 0.f;
-    bool bad = false;
-    while (fetch()) {
-        float chk = 0.f;
-        const float mt = hc.ws->cls ? shalf<APPLY, false, CLAMP1, CVTA, L, M, 1>(hc, chk) : shalf<APPLY, false, CLAMP1, CVTA, L, M, 0>(hc, chk);
-        if (__any_sync(0xffffffffu, chk > 32768.0f)) { bad = true; break; }
-        mx = fmaxf(mx, mt);
-        release();
+    bool bad = false;                              // true: a fetched tile is waiting for the clamping twin
+    if (!cs->start_twin) {
+        while (fetch()) {
+            float chk = 0.f;
+            bool gave_up = false;
+            const float mt = hc.ws->cls ? shalf<APPLY, false, CLAMP1, CVTA, L, M, 1>(hc, chk, gave_up) : shalf<APPLY, false, CLAMP1, CVTA, L, M, 0>(hc, chk, gave_up);
+            if (gave_up || __any_sync(0xffffffffu, chk > 32768.0f)) {
+                bad = true;
+                if (a.hint && (threadIdx.x & 31) == 0) atomicMax(a.hint, a.epoch);
+                break;
+            }
+            mx = fmaxf(mx, mt);
+            release();
+        }
+    } else {
+        bad = fetch();
     }
     // ... phase 2: that tile again (its frames are still in the buffer) and every later one with the clamping twin.
     // Two loops rather than a call inside one: nothing is live across a call.
     if (bad) {
         do {
             float chk = 0.f;
-            const float mt = hc.ws->cls ? shalf<APPLY, true, CLAMP1, CVTA, L, M, 1>(hc, chk) : shalf<APPLY, true, CLAMP1, CVTA, L, M, 0>(hc, chk);
+            bool gave_up = false;
+            const float mt = hc.ws->cls ? shalf<APPLY, true, CLAMP1, CVTA, L, M, 1>(hc, chk, gave_up) : shalf<APPLY, true, CLAMP1, CVTA, L, M, 0>(hc, chk, gave_up);
             mx = fmaxf(mx, mt);
             release();
         } while (fetch());
@@ -707,11 +727,9 @@ int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     const size_t budget = 227 * 1024 - 2048;                       // opt-in maximum minus this kernel's static shared memory
     // buffers beyond one per pair = tiles in flight while every pair computes.  Measured: the peak pass (no staging, no
     // output stream) gains 9 % from 8 pairs + 4 over 9 + 2 (0.152 -> 0.139 ms); the apply pass is flat from 8 + 2 to 6 + 4
-    int spare = APPLY ? 2 : 4;
-    if (const char *e = getenv("AUKIT_RUN_SPARE")) { const int m = atoi(e); if (m >= 0 && m <= 6) spare = m; }
+    const int spare = APPLY ? 2 : 4;
     int np = (int)((budget - fixed - (size_t)spare * buf) / (buf + stage));
     if (np > (APPLY ? 8 : 9)) np = APPLY ? 8 : 9;                  // launch bounds
-    if (const char *e = getenv("AUKIT_RUN_MAXWARPS")) { const int m = atoi(e) / 2; if (m >= 1 && m < np) np = m; }   // occupancy experiments
     if (np < 1) return 0;
     int nbuf = (int)((budget - fixed - (size_t)np * stage) / buf);
     if (nbuf > np + spare) nbuf = np + spare;
@@ -722,15 +740,13 @@ int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     const size_t smem = fixed + (size_t)nbuf * buf + (size_t)np * stage;
     // the final clamp to +-1 can only act when |peakAmplitude| is (about) 1 or more (negative peaks included: normalize(a, -2))
     const bool clamp1 = APPLY && !(fabs(a.peak) < 1.0 - 9.5367431640625e-07);
-    // max(u, 0) of the sample conversion on the ALU pipe (default: the FMA pipe is the busier one here); =0 for A/B runs
-    static const bool cvt_alu = !(getenv("AUKIT_RUN_CVT_ALU") && getenv("AUKIT_RUN_CVT_ALU")[0] == '0');
-    auto kern = clamp1 ? run_static_kernel<APPLY, APPLY, false, L, M> : run_static_kernel<APPLY, false, false, L, M>;
-    if (cvt_alu) kern = clamp1 ? run_static_kernel<APPLY, APPLY, true, L, M> : run_static_kernel<APPLY, false, true, L, M>;
+    // max(u, 0) of the sample conversion rides on the ALU pipe (CVTA): the FMA pipe is the busier one here
+    // (measured 0.352 vs 0.371 ms / step, profiles/r2_noise_cvt{1,0}.json)
+    auto kern = clamp1 ? run_static_kernel<APPLY, APPLY, true, L, M> : run_static_kernel<APPLY, false, true, L, M>;
     if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
     // Two SMs stay free for the polyphase edge kernels running beside this one on the side stream (pipeline_poly.cu):
     // this kernel's CTAs take a whole SM's shared memory, so otherwise the edges could only start as it drains.
-    int reserve = 2;
-    if (const char *e = getenv("AUKIT_RUN_RESERVE_SMS")) { const int m = atoi(e); if (m >= 0 && m < ctx->num_sms / 2) reserve = m; }
+    const int reserve = 2;
     unsigned long long g = (rp.ntiles + np - 1) / np;
     if (g > (unsigned long long)(ctx->num_sms - reserve)) g = ctx->num_sms - reserve;
     kern<<<(unsigned)g, rp.nwarps * 32, smem, ctx->stream>>>(a, rp);

@@ -329,6 +329,11 @@ def bench_c2_noise(env, sp_factory, n_in, steps, warmup):
     d_in = torch.randint(-32768, 32768, (shard.in_count, 2), dtype=torch.int16, device="cuda", generator=g).view(torch.uint8).reshape(-1)
     ms, launches, clocks = env.timed(lambda: sp.run_device(d_in), steps, warmup)
     mx = float(sp.d_max.item())
+    ak, lib, ctx = env.ak, env.lib, env.ctx
+    ms_peak, _, _ = env.timed(lambda: ak._lib.check(lib.aukit_cuda_dev_pipeline_peak(ctx.handle, C.byref(sp.desc), d_in.data_ptr(), sp.d_max.data_ptr())),
+                              steps, 2)
+    ms_apply, _, _ = env.timed(lambda: ak._lib.check(lib.aukit_cuda_dev_pipeline_apply(ctx.handle, C.byref(sp.desc), d_in.data_ptr(), sp.peak,
+                                                                                       sp.d_max.data_ptr(), sp.d_out.data_ptr(), sp.stride)), steps, 2)
     worst = 0.0
     for o_rel in (0, shard.n_out // 2 // 4 * 4, shard.n_out - 4096):
         cnt = 4096
@@ -344,7 +349,7 @@ def bench_c2_noise(env, sp_factory, n_in, steps, warmup):
     ok = env.all_ok(worst <= TOL)
     in_bytes, out_bytes = d_in.numel(), shard.n_out * 4
     del d_in
-    return {"ms_per_step": ms, "value": None, "achieved_GB/s_per_gpu": (2 * in_bytes + out_bytes) / (ms * 1e-3) / 1e9,
+    return {"ms_per_step": ms, "ms_peak_pass": ms_peak, "ms_apply_pass": ms_apply, "value": None, "achieved_GB/s_per_gpu": (2 * in_bytes + out_bytes) / (ms * 1e-3) / 1e9,
             "frac": (2 * in_bytes + out_bytes) / (ms * 1e-3) / 1e9 / env.peak, "gpu_launches_per_step": launches, "clocks": clocks,
             "signal": "torch CUDA generator seed 2, integers in [-32768, 32768): full-scale white noise, the channel clamp of A:668 acts in every tile",
             "parity_ok": ok, "parity": {"ok": ok, "max_abs_err": worst, "tolerance": TOL,
