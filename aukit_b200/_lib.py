@@ -137,6 +137,16 @@ SIGNATURES = {
     "aukit_resample_out_len": (_U64, [_U64, _D, _D]),
     "aukit_resample_position": (_D, [_U64, _D, _D]),
     "aukit_resample_window": (_I, [_U64, _D, _D, _I, _U64, _U64, C.POINTER(_U64), C.POINTER(_U64)]),
+    "aukit_cuda_comm_create": (_I, [_P, _I, _I, C.POINTER(_P)]),
+    "aukit_cuda_comm_handle_bytes": (_SZ, []),
+    "aukit_cuda_comm_handle": (_I, [_P, _P]),
+    "aukit_cuda_comm_connect": (_I, [_P, _P]),
+    "aukit_cuda_comm_connect_local": (_I, [C.POINTER(_P), _I]),
+    "aukit_cuda_comm_destroy": (None, [_P]),
+    "aukit_cuda_comm_allreduce_max": (_I, [_P, _P, _I]),
+    "aukit_cuda_comm_values": (_P, [_P]),
+    "aukit_cuda_comm_normalize": (_I, [_P, _P, _D, _I]),
+    "aukit_cuda_comm_pipeline": (_I, [_P, C.POINTER(PipelineDesc), _P, _D, _P, _SZ]),
     "aukit_block_shard": (_I, [_U64, _I, _I, C.POINTER(_U64), C.POINTER(_U64)]),
     "aukit_ima_adpcm_wav_frames": (_SZ, [_SZ, _I, _I, _I]),
     "aukit_msadpcm_frames": (_SZ, [_SZ, _I, _I]),

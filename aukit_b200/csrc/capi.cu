@@ -113,6 +113,8 @@ extern "C" int aukit_cuda_synchronize(aukit_ctx *ctx) {
     const int st = *ctx->h_status;
     if (st) {
         cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream);
+        if (st & AUKIT_DEVERR_COMM_TIMEOUT)
+            return aukit_fail("aukit_cuda: a rank never arrived at the normalize MAX exchange (10 s timeout); the output of this call is invalid");
         if (st & AUKIT_DEVERR_IMA_INDEX)
             return aukit_fail("number outside of range (expected step index to be within 0 and 88)");   // A:1213
         return aukit_fail("attempt to perform arithmetic on a nil value (MS-ADPCM predictor index has no coefficients)");

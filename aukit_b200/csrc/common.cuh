@@ -12,7 +12,8 @@
 // Deferred device-side decode errors (checked at aukit_cuda_synchronize / download).
 enum : int {
     AUKIT_DEVERR_IMA_INDEX = 1,   // step index > 88 in a block header (A:1213 expect.range)
-    AUKIT_DEVERR_MS_PREDICTOR = 2 // predictor index >= #coefficients (A:1311 nil arithmetic)
+    AUKIT_DEVERR_MS_PREDICTOR = 2,// predictor index >= #coefficients (A:1311 nil arithmetic)
+    AUKIT_DEVERR_COMM_TIMEOUT = 4 // a rank never arrived at the normalize exchange (comm.cu)
 };
 
 struct aukit_ctx {

@@ -31,19 +31,44 @@ class TimeShard:
     in_count: int
 
 
-def plan_time_shards(n_in_total: int, srcRate: float, dstRate: float, interpolation: str, world: int) -> List[TimeShard]:
-    """Contiguous, near-equal output ranges; input windows overlap by the halo only."""
+def shard_alignment(srcRate: float, dstRate: float) -> int:
+    """Output frames per warp tile of the fused kernels for this ratio: 32 periods of L = dstRate / gcd outputs
+    (5120 for 44.1 -> 48 kHz).  A shard that starts on a multiple of it has no partial head tile, so every rank runs
+    the same interior kernel from its first output; 4 (a 16-byte store) when the ratio has no such tile."""
+    import math
+    if srcRate != int(srcRate) or dstRate != int(dstRate):
+        return 4
+    g = math.gcd(int(srcRate), int(dstRate))
+    L = int(dstRate) // g
+    return 32 * L if 1 < L <= 512 and (32 * L) % 4 == 0 else 4
+
+
+def plan_time_shards(n_in_total: int, srcRate: float, dstRate: float, interpolation: str, world: int,
+                     align: Optional[int] = None, pad: int = 8) -> List[TimeShard]:
+    """Contiguous, near-equal output ranges; input windows overlap by the halo only.
+
+    Interior boundaries fall on multiples of `align` outputs (default: shard_alignment) and every window is widened by
+    up to `pad` frames on each side where the signal has them: the bulk copies of the run-per-lane kernels round their
+    start down to 16 bytes and read a few frames past the last tap, and with that slack present a shard's first and
+    last full tiles stay on the fast kernel instead of the edge kernels."""
     lib = _lib.load()
     n_out = int(lib.aukit_resample_out_len(n_in_total, float(srcRate), float(dstRate)))
+    if align is None:
+        align = shard_alignment(srcRate, dstRate)
+    if n_out // max(world, 1) < 4 * align:
+        align = 4
     shards = []
     for r in range(world):
-        # interior boundaries on multiples of 4 outputs keep every shard's stores 16-byte aligned
-        o0 = n_out * r // world // 4 * 4
-        o1 = n_out if r == world - 1 else n_out * (r + 1) // world // 4 * 4
+        o0 = n_out * r // world // align * align
+        o1 = n_out if r == world - 1 else n_out * (r + 1) // world // align * align
         f, c = C.c_uint64(0), C.c_uint64(0)
         _lib.check(lib.aukit_resample_window(n_in_total, float(srcRate), float(dstRate), _INTERPS[interpolation], o0, o1 - o0,
                                              C.byref(f), C.byref(c)))
-        shards.append(TimeShard(r, o0, o1 - o0, int(f.value), int(c.value)))
+        first, end = int(f.value), int(f.value) + int(c.value)
+        if pad and c.value:
+            first = max(0, first - pad) // 4 * 4 if first >= pad else first
+            end = min(n_in_total, end + pad)
+        shards.append(TimeShard(r, o0, o1 - o0, first, end - first))
     return shards
 
 
@@ -82,16 +107,56 @@ def allreduce_max_(t, group=None):
     return t
 
 
+class PeerExchange:
+    """aukit_comm of this rank (include/aukit_cuda.h): the library's own MAX exchange over peer-mapped device memory.
+    The 64-byte IPC handles are swapped once, at construction, through torch.distributed (any backend)."""
+
+    def __init__(self, ctx, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.lib = ctx, ctx.lib
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        h = C.c_void_p()
+        _lib.check(self.lib.aukit_cuda_comm_create(ctx.handle, self.world, self.rank, C.byref(h)))
+        self.handle = h
+        nb = int(self.lib.aukit_cuda_comm_handle_bytes())
+        mine = (C.c_ubyte * nb)()
+        _lib.check(self.lib.aukit_cuda_comm_handle(h, mine))
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        allh = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(allh, t, group=group)
+        blob = b"".join(bytes(x.cpu().tolist()) for x in allh)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _lib.check(self.lib.aukit_cuda_comm_connect(h, buf))
+        dist.barrier(group)                                  # every rank has mapped every block before the first exchange
+
+    def allreduce_max_(self, t):
+        _lib.check(self.lib.aukit_cuda_comm_allreduce_max(self.handle, t.data_ptr(), t.numel()))
+        return t
+
+    def close(self):
+        if self.handle:
+            self.lib.aukit_cuda_comm_destroy(self.handle)
+            self.handle = None
+
+
 class ShardedPreload:
     """auplay's chain (unpack -> resample -> mono -> normalize) on ONE rank's time shard.
 
-    peak pass -> all-reduce MAX over ranks -> apply pass.  All launches go to torch's current
-    stream so the collective is ordered with the kernels without host synchronisation."""
+    peak pass -> MAX over ranks -> apply pass.  All launches go to torch's current stream, nothing synchronises the
+    host.  On GPUs the exchange is the library's own peer-memory kernel (PeerExchange / aukit_comm, one tiny launch
+    between the passes); `exchange="torch"` keeps it on torch.distributed (NCCL, or gloo for the CPU-side tests)."""
 
     def __init__(self, ctx, shard: TimeShard, n_in_total: int, bitDepth=16, dataType="signed", channels=2,
-                 srcRate=44100.0, dstRate=48000.0, interpolation="cubic", mono=True, peak=0.8, bigEndian=False):
+                 srcRate=44100.0, dstRate=48000.0, interpolation="cubic", mono=True, peak=0.8, bigEndian=False,
+                 exchange="peer"):
         import torch
+        import torch.distributed as dist
         self.torch = torch
+        self.comm = None
+        if exchange == "peer" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.comm = PeerExchange(ctx)
         self.ctx = ctx
         self.lib = ctx.lib
         self.shard = shard
@@ -114,7 +179,10 @@ class ShardedPreload:
         """d_in: uint8 CUDA tensor holding this shard's packed frames (halo included)."""
         self.d_max.zero_()
         _lib.check(self.lib.aukit_cuda_dev_pipeline_peak(self.ctx.handle, C.byref(self.desc), d_in.data_ptr(), self.d_max.data_ptr()))
-        allreduce_max_(self.d_max)
+        if self.comm is not None:
+            self.comm.allreduce_max_(self.d_max)
+        else:
+            allreduce_max_(self.d_max)
         _lib.check(self.lib.aukit_cuda_dev_pipeline_apply(self.ctx.handle, C.byref(self.desc), d_in.data_ptr(), self.peak,
                                                           self.d_max.data_ptr(), self.d_out.data_ptr(), self.stride))
         return self.d_out
@@ -155,8 +223,17 @@ class ShardedPreload:
         _lib.check(self.lib.aukit_cuda_preloader_begin(pl, C.byref(self.desc), h_in.data_ptr(), h_in.numel(), C.byref(k)))
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            with self.torch.cuda.stream(self._pl_stream):
-                allreduce_max_(self._peak_tensor(k.value))
+            if self.comm is not None:
+                # the exchange kernel goes where the slot's passes go: the preloader's run stream
+                old = int(self.lib.aukit_cuda_get_stream(self.ctx.handle) or 0)
+                self.ctx.set_stream(int(self.lib.aukit_cuda_preloader_stream(pl)))
+                try:
+                    _lib.check(self.lib.aukit_cuda_comm_allreduce_max(self.comm.handle, self.lib.aukit_cuda_preloader_peak_ptr(pl, k.value), 1))
+                finally:
+                    self.ctx.set_stream(old)
+            else:
+                with self.torch.cuda.stream(self._pl_stream):
+                    allreduce_max_(self._peak_tensor(k.value))
         _lib.check(self.lib.aukit_cuda_preloader_finish(pl, k.value, self.peak, h_out.data_ptr()))
 
     def drain(self):
@@ -167,3 +244,6 @@ class ShardedPreload:
         if getattr(self, "_pl", None) is not None:
             self.lib.aukit_cuda_preloader_destroy(self._pl)
             self._pl = None
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None

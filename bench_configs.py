@@ -244,7 +244,7 @@ def bench_c5(env, dst_rate, steps=3, warmup=3, hours=24.0, shards=8, cache=None)
     import numpy as np
     from util import ref_resample_window
     from aukit_b200._lib import PipelineDesc
-    from aukit_b200.sharding import plan_time_shards, allreduce_max_
+    from aukit_b200.sharding import PeerExchange, plan_time_shards
     torch, ak, lib, ctx = env.torch, env.ak, env.lib, env.ctx
     CH, SRC = 8, 96000
     n_in_total = int(hours * 3600 * SRC)
@@ -269,13 +269,18 @@ def bench_c5(env, dst_rate, steps=3, warmup=3, hours=24.0, shards=8, cache=None)
     d_out = torch.empty((CH, stride), dtype=torch.float32, device="cuda")
     d_max = torch.zeros(1, dtype=torch.float32, device="cuda")
     PEAK = 1.0
+    comm = PeerExchange(ctx) if env.world > 1 else None        # the library's own MAX exchange (csrc/comm.cu)
 
     def step():
         d_max.zero_()
         ak._lib.check(lib.aukit_cuda_dev_pipeline_peak(ctx.handle, C.byref(desc), d_in.data_ptr(), d_max.data_ptr()))
-        allreduce_max_(d_max)
+        if comm is not None:
+            comm.allreduce_max_(d_max)
         ak._lib.check(lib.aukit_cuda_dev_pipeline_apply(ctx.handle, C.byref(desc), d_in.data_ptr(), PEAK, d_max.data_ptr(), d_out.data_ptr(), stride))
     ms, launches, clocks = env.timed(step, steps, warmup)
+    if comm is not None:
+        torch.cuda.synchronize()
+        comm.close()
     # parity: middle and last slices against the numpy restatement of A:653-673 (global fp64 positions) + A:3444-3455
     mx = float(d_max.item())
     worst, checked = 0.0, 0

@@ -323,6 +323,31 @@ int aukit_cuda_preloader_drain(aukit_preloader *pl);
 int aukit_cuda_host_alloc(size_t nbytes, void **out);
 void aukit_cuda_host_free(void *p);
 
+/* ------------------------------------------------------------------ multi-GPU: the one collective
+ * effects.normalize (A:3431-3459) on a buffer that is time-sharded over several GPUs needs the GLOBAL max of A:3438-3443:
+ * a MAX of one float per rank (one per channel when `independent`).  aukit_comm does that exchange inside the library,
+ * over peer-mapped device memory (NVLink / NVSwitch): one tiny kernel per rank between the two passes, no NCCL launch, no
+ * host round trip.  Results are bit-identical to a single GPU (MAX is exact and order-free).
+ *   one process per GPU (torchrun / MPI): comm_create on every rank, exchange the comm_handle blobs (comm_handle_bytes
+ *     each) by any host means (torch.distributed all_gather, MPI, a file), comm_connect with all of them in rank order;
+ *   one process driving all GPUs (the Lua module, a single host thread): comm_create per device, comm_connect_local.
+ * Every rank must make the same sequence of exchange calls. */
+typedef struct aukit_comm aukit_comm;
+int aukit_cuda_comm_create(aukit_ctx *ctx, int world, int rank, aukit_comm **out);
+size_t aukit_cuda_comm_handle_bytes(void);
+int aukit_cuda_comm_handle(aukit_comm *c, void *handle_out);
+int aukit_cuda_comm_connect(aukit_comm *c, const void *handles_in_rank_order);
+int aukit_cuda_comm_connect_local(aukit_comm *const *comms, int world);
+void aukit_cuda_comm_destroy(aukit_comm *c);
+/* MAX-combine nvals (<= 16) non-negative device floats over the ranks, in place, in stream order. */
+int aukit_cuda_comm_allreduce_max(aukit_comm *c, float *d_vals, int nvals);
+float *aukit_cuda_comm_values(aukit_comm *c);      /* the communicator's own 16-float device scratch */
+/* effects.normalize(audio, peakAmplitude, independent) where `a` is THIS rank's time shard of the Audio. */
+int aukit_cuda_comm_normalize(aukit_comm *c, aukit_audio *a, double peakAmplitude, int independent);
+/* The fused chain (aukit_cuda_dev_pipeline_peak -> exchange -> aukit_cuda_dev_pipeline_apply) on this rank's shard. */
+int aukit_cuda_comm_pipeline(aukit_comm *c, const aukit_pipeline_desc *p, const void *d_in,
+                             double peakAmplitude, float *d_out, size_t out_stride);
+
 /* ------------------------------------------------------------------ pure host helpers */
 /* floor(n_in * (dstRate/srcRate)) in double, the reference's loop bound (A:658-664). */
 uint64_t aukit_resample_out_len(uint64_t n_in, double srcRate, double dstRate);

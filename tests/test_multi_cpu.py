@@ -74,3 +74,32 @@ def test_time_sharded_normalize_over_gloo(O, src, dst, interp):
     assert sorted(results[0][5] + results[1][5]) == list(range(6))
     loads = [sum([9, 1, 1, 1, 4, 4][i] for i in r[5]) for r in results]
     assert max(loads) - min(loads) <= 2
+
+
+def test_shard_planners_are_aligned_and_complete(O):
+    """plan_time_shards: interior boundaries on the fused kernels' warp tile (5120 outputs at 44.1 -> 48 kHz), windows
+    padded but always covering the needed halo; plan_block_shards / aukit_block_shard: contiguous, complete, near-equal."""
+    import ctypes as C
+    from aukit_b200 import _lib
+    from aukit_b200.sharding import plan_block_shards, plan_time_shards, shard_alignment
+    lib = _lib.load()
+    assert shard_alignment(44100, 48000) == 5120 and shard_alignment(22050, 48000) == 32 * 320
+    assert shard_alignment(96000, 48000) == 4 and shard_alignment(44056.5, 48000) == 4
+    n_in = 8 * 3600 * 44100
+    for world in (1, 2, 4, 8):
+        sh = plan_time_shards(n_in, 44100, 48000, "cubic", world)
+        n_out = int(lib.aukit_resample_out_len(n_in, 44100.0, 48000.0))
+        assert sh[0].out_first == 0 and sh[-1].out_first + sh[-1].n_out == n_out
+        for a, b in zip(sh, sh[1:]):
+            assert a.out_first + a.n_out == b.out_first and b.out_first % 5120 == 0
+        for s in sh:
+            f, c = C.c_uint64(0), C.c_uint64(0)
+            assert lib.aukit_resample_window(n_in, 44100.0, 48000.0, 2, s.out_first, s.n_out, C.byref(f), C.byref(c)) == 0
+            assert s.in_first <= f.value and s.in_first + s.in_count >= f.value + c.value      # halo covered
+            assert s.in_first + s.in_count <= n_in and (s.in_first % 4 == 0 or s.in_first == f.value)
+            assert f.value - s.in_first <= 12 and s.in_first + s.in_count - (f.value + c.value) <= 8
+    for nb, world in ((778_236, 8), (779_765, 3), (5, 8), (0, 2)):
+        parts = plan_block_shards(nb, world)
+        assert parts[0][0] == 0 and sum(c for _, c in parts) == nb
+        assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
