@@ -45,7 +45,14 @@ struct run_plan {
     unsigned long long tile0;     // first warp tile (32*L outputs each) of this launch
     unsigned long long ntiles;
     int nbuf;                     // static kernel: frame buffers in the CTA's ring
+    // static kernel: the launch's tile range as up to RUN_MAXSEG segments of constant drift (the weight table of a
+    // segment is rebuilt in place by the first warp that reaches it -- one launch per pass instead of one per segment,
+    // which cost a drain + refill of the persistent kernel each, ~8 us)
+    int nseg;
+    unsigned long long seg_end[8];   // first tile (global index) past segment k
+    float seg_delta[8];
 };
+constexpr int RUN_MAXSEG = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -415,6 +422,7 @@ struct __align__(16) warp_state {
     int i;                     // the warp's current tile of the CTA's sequence (pair, pair + npairs, ...)
     uint32_t stage_off;        // byte offset of this warp's staging tile from the dynamic shared memory base
     int cls, slot;             // half-period class; frame buffer holding tile i
+    int seg;                   // drift segment of the warp's current tile
 };
 struct __align__(16) slot_state {       // one frame buffer of the CTA's ring
     unsigned long long full;   // mbarrier: the bulk copy of the buffer's current tile has landed
@@ -430,6 +438,9 @@ struct __align__(16) cta_state {
     uint32_t bufs_off, buf_bytes;        // ring: offset from the dynamic shared memory base, pitch
     float mult, one_hi;
     int start_twin;                      // the call already knows that the channel clamp acts: skip the checking code
+    unsigned long long tile_first, tile_step;   // global index of the CTA's tile 0; tiles between consecutive ones
+    int wclaim[2], wtag[2];              // weight-table ring: segment being built into / available in slot (seg & 1)
+    int nseg;
 };
 
 struct half_ctx {
@@ -555,19 +566,22 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pair = warp >> 1, cls = warp & 1, npairs = rp.nwarps >> 1;
         const int nbuf = rp.nbuf;
-        // layout: weights[L] float4 | nbuf frame buffers | staging of every warp
+        // layout: weights[nW][L] float4 (nW = 2 when the launch spans several drift segments) | nbuf frame buffers | staging
         float4 *W = reinterpret_cast<float4 *>(smem);
-        const uint32_t bufs_off = (uint32_t)L * 16, buf_bytes = (uint32_t)rp.raw_words * 4;
+        const int nW = rp.nseg > 1 ? 2 : 1;
+        const uint32_t bufs_off = (uint32_t)(nW * L) * 16, buf_bytes = (uint32_t)rp.raw_words * 4;
+        int seg0 = 0;
+        while (seg0 + 1 < rp.nseg && rp.tile0 + blockIdx.x >= rp.seg_end[seg0]) seg0++;
         for (int e = threadIdx.x; e < L; e += blockDim.x) {     // fp64 weights of A:265 at fraction j/L + delta, narrowed
             const int j = (int)(((long long)e * M) % L);
-            const double x = (double)j / (double)L + (double)rp.delta;
+            const double x = (double)j / (double)L + (double)rp.seg_delta[seg0];
             const double x2 = x * x, x3 = x2 * x;
-            W[e] = make_float4((float)(-0.5 * x3 + x2 - 0.5 * x), (float)(1.5 * x3 - 2.5 * x2 + 1.0),
-                               (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x), (float)(0.5 * x3 - 0.5 * x2));
+            W[(seg0 & (nW - 1)) * L + e] = make_float4((float)(-0.5 * x3 + x2 - 0.5 * x), (float)(1.5 * x3 - 2.5 * x2 + 1.0),
+                                                       (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x), (float)(0.5 * x3 - 0.5 * x2));
         }
         if (lane == 0) {
             warp_state &w = wst[warp];
-            w.dst = 0ull; w.i = pair; w.cls = cls; w.slot = 0;
+            w.dst = 0ull; w.i = pair; w.cls = cls; w.slot = 0; w.seg = seg0;
             w.stage_off = bufs_off + (uint32_t)nbuf * buf_bytes + (uint32_t)warp * SSTAGE_WORDS * 4;
         }
         if (threadIdx.x == 0) {
@@ -584,6 +598,10 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
             cst.dst_step = (unsigned long long)gridDim.x * (SPERIODS * L * 4);
             cst.bytes = bytes; cst.sh = sh; cst.n = n; cst.nbuf = nbuf; cst.npairs = npairs;
             cst.bufs_off = bufs_off; cst.buf_bytes = buf_bytes;
+            cst.tile_first = first; cst.tile_step = gridDim.x;
+            cst.nseg = rp.nseg;
+            cst.wclaim[0] = cst.wclaim[1] = cst.wtag[0] = cst.wtag[1] = -1;
+            cst.wclaim[seg0 & 1] = cst.wtag[seg0 & 1] = seg0;
             float mult = 0.f, one_hi = 1.0f;
             if (APPLY) {                                        // same scale and silence rule as run_kernel
                 const float mx0 = a.d_max[0];
@@ -634,7 +652,41 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
         }
         const uint32_t raw_off = cs->bufs_off + (uint32_t)slot * cs->buf_bytes, stage_off = ws->stage_off;
         hc.row = reinterpret_cast<const uint32_t *>(smem + raw_off) + cs->sh + lane * M + (cls ? half_geom<L, M, 1>::FBASE : 0);
-        hc.Wc = reinterpret_cast<const float4 *>(smem) + cls * (L / 2);
+        // drift segment of this tile; the first warp to reach a new segment rebuilds the table in slot (seg & 1) -- the
+        // other slot still serves warps on the previous segment (a warp is never a whole segment behind: segments are
+        // thousands of tiles long, the ring a dozen)
+        int wslot = 0;
+        if (cs->nseg > 1) {
+            const unsigned long long tile = cs->tile_first + (unsigned long long)i * cs->tile_step;
+            int seg = ws->seg;
+            while (seg + 1 < cs->nseg && tile >= rp.seg_end[seg]) seg++;
+            wslot = seg & 1;
+            if (seg != ws->seg) {
+                int owner = 0;
+                if (lane == 0) {
+                    ws->seg = seg;
+                    owner = atomicMax(const_cast<int *>(&cs->wclaim[wslot]), seg) < seg;
+                }
+                owner = __shfl_sync(0xffffffffu, owner, 0);
+                if (owner) {
+                    float4 *Wn = reinterpret_cast<float4 *>(smem) + wslot * L;
+                    for (int e = (int)lane; e < L; e += 32) {
+                        const int j = (int)(((long long)e * M) % L);
+                        const double x = (double)j / (double)L + (double)rp.seg_delta[seg];
+                        const double x2 = x * x, x3 = x2 * x;
+                        Wn[e] = make_float4((float)(-0.5 * x3 + x2 - 0.5 * x), (float)(1.5 * x3 - 2.5 * x2 + 1.0),
+                                            (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x), (float)(0.5 * x3 - 0.5 * x2));
+                    }
+                    __syncwarp();
+                    __threadfence_block();
+                    if (lane == 0) cs->wtag[wslot] = seg;
+                } else {
+                    while (cs->wtag[wslot] < seg) __nanosleep(64);
+                    __threadfence_block();
+                }
+            }
+        }
+        hc.Wc = reinterpret_cast<const float4 *>(smem) + wslot * L + cls * (L / 2);
         hc.mult = cs->mult;
         hc.one_hi = cs->one_hi;
         hc.one_lo = -hc.one_hi;
@@ -722,14 +774,20 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
 template <bool APPLY, int L, int M>
 int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     rp.raw_words = ((SPERIODS * M + 3 + 3) + 31) / 32 * 32;       // tile + halo + alignment shift; 128-byte pitch
-    const size_t fixed = (size_t)L * 16 + 128;
+    const size_t fixed = (size_t)(rp.nseg > 1 ? 2 : 1) * L * 16 + 128;
     const size_t buf = (size_t)rp.raw_words * 4, stage = APPLY ? 2 * SSTAGE_WORDS * 4 : 0;   // per buffer; per pair
     const size_t budget = 227 * 1024 - 2048;                       // opt-in maximum minus this kernel's static shared memory
     // buffers beyond one per pair = tiles in flight while every pair computes.  Measured: the peak pass (no staging, no
     // output stream) gains 9 % from 8 pairs + 4 over 9 + 2 (0.152 -> 0.139 ms); the apply pass is flat from 8 + 2 to 6 + 4
-    const int spare = APPLY ? 2 : 4;
-    int np = (int)((budget - fixed - (size_t)spare * buf) / (buf + stage));
-    if (np > (APPLY ? 8 : 9)) np = APPLY ? 8 : 9;                  // launch bounds
+    // Warp pairs first (they are what issues instructions), spare buffers with what is left: 8 pairs + 2 (apply) or
+    // + 4 (peak; + 3 when a second weight table is resident).
+    const int want_spare = APPLY ? 2 : 4, cap = APPLY ? 8 : 9;     // cap = launch bounds
+    int np = 0, spare = want_spare;
+    for (; spare >= 0; spare--) {
+        np = (int)((budget - fixed - (size_t)spare * buf) / (buf + stage));
+        if (np > cap) np = cap;
+        if (np >= 8 || spare == 0) break;
+    }
     if (np < 1) return 0;
     int nbuf = (int)((budget - fixed - (size_t)np * stage) / buf);
     if (nbuf > np + spare) nbuf = np + spare;
@@ -793,13 +851,15 @@ int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipel
     // value (an error below 2^-25.5 in the position, i.e. < 6e-8 in the output)
     unsigned long long t = t_lo;
     int rc = 1;
+    rp.nseg = 0;
+    unsigned long long batch_first = t_lo;
     while (t < t_hi && rc == 1) {
         unsigned long long t_end = t_hi;
         const double x0 = (double)(t * tile_in);
         float delta = 0.f;
         if (!pow2_ratio && (double)(t_hi * tile_in) >= 268435456.0) {
             if (x0 < 268435456.0 / 1.25) {
-                // below 2^28 the drift is under 2^-25 and ignored; stop this launch where it starts to matter
+                // below 2^28 the drift is under 2^-25 and ignored; stop this segment where it starts to matter
                 const unsigned long long lim = (unsigned long long)(268435456.0 / 1.25 / (double)tile_in);
                 if (lim > t && lim < t_hi) t_end = lim;
             } else {
@@ -808,11 +868,26 @@ int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipel
                 delta = (float)(0.5 * (x0 + (double)(t_end * tile_in)) * eps_r);
             }
         }
-        rp.tile0 = t;
-        rp.ntiles = t_end - t;
-        rp.delta = delta;
-        if (use_static) rc = apply ? launch_run_static<true, 160, 147>(ctx, a, rp) : launch_run_static<false, 160, 147>(ctx, a, rp);
-        else rc = apply ? launch_run<true>(ctx, a, rp) : launch_run<false>(ctx, a, rp);
+        if (use_static) {
+            // the straight-line kernel takes the whole range in ONE launch: segments of constant drift, tables rebuilt in place
+            rp.seg_end[rp.nseg] = t_end;
+            rp.seg_delta[rp.nseg] = delta;
+            rp.nseg++;
+            if (rp.nseg == RUN_MAXSEG || t_end == t_hi) {
+                rp.tile0 = batch_first;
+                rp.ntiles = t_end - batch_first;
+                rp.delta = rp.seg_delta[0];
+                rc = apply ? launch_run_static<true, 160, 147>(ctx, a, rp) : launch_run_static<false, 160, 147>(ctx, a, rp);
+                rp.nseg = 0;
+                batch_first = t_end;
+            }
+        } else {
+            rp.tile0 = t;
+            rp.ntiles = t_end - t;
+            rp.delta = delta;
+            rp.nseg = 0;
+            rc = apply ? launch_run<true>(ctx, a, rp) : launch_run<false>(ctx, a, rp);
+        }
         t = t_end;
     }
     if (rc != 1) return rc;

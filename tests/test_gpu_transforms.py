@@ -271,7 +271,7 @@ def test_huge_global_positions(ak, src, dst, interp, n_total):
     total_out = int(lib.aukit_resample_out_len(n_total, float(src), float(dst)))
     rng = np.random.default_rng(src + mode)
     starts = [total_out - 150_000, int(total_out * 0.37)]
-    for pos in (2 ** 28, 2 ** 29, 2 ** 30, 2 ** 30.5):                      # shards straddling every mode boundary
+    for pos in (2 ** 28 / 1.25, 2 ** 28, 2 ** 29, 2 ** 30, 2 ** 30.5):          # shards straddling every mode / drift-segment boundary
         o = int(pos * dst / src) - 70_000
         if 0 < o < total_out - 150_000:
             starts.append(o)
