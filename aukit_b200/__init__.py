@@ -7,7 +7,7 @@ There is no CPU fallback: without the built library and a B200 every call raises
 """
 from ._lib import AukitError, Clip, ContainerInfo, PipelineDesc, WavInfo, SIGNATURES, LIB_PATH  # noqa: F401
 from .aukit import (  # noqa: F401
-    Audio, Context, context, effects, pcm, g711, adpcm, msadpcm, wav, wav_info, new, preload, preload_clips, Preloader, au, aiff,
+    Audio, Context, context, effects, pcm, g711, adpcm, msadpcm, wav, wav_info, new, preload, preload_clips, Preloader, Group, au, aiff,
     DIALECT_LITERAL, DIALECT_GENERAL, _VERSION,
 )
 from . import aukit as _aukit

@@ -59,6 +59,7 @@ SIGNATURES = {
     "aukit_cuda_shutdown": (None, [_P]),
     "aukit_cuda_set_stream": (_I, [_P, _P]),
     "aukit_cuda_get_stream": (_P, [_P]),
+    "aukit_cuda_make_current": (_I, [_P]),
     "aukit_cuda_synchronize": (_I, [_P]),
     "aukit_cuda_launch_count": (_U64, [_P]),
     "aukit_cuda_audio_new": (_I, [_P, _I, _SZ, _D, _PP]),
@@ -147,6 +148,13 @@ SIGNATURES = {
     "aukit_cuda_comm_values": (_P, [_P]),
     "aukit_cuda_comm_normalize": (_I, [_P, _P, _D, _I]),
     "aukit_cuda_comm_pipeline": (_I, [_P, C.POINTER(PipelineDesc), _P, _D, _P, _SZ]),
+    "aukit_cuda_group_create": (_I, [C.POINTER(_I), _I, C.POINTER(_P)]),
+    "aukit_cuda_group_destroy": (None, [_P]),
+    "aukit_cuda_group_size": (_I, [_P]),
+    "aukit_cuda_group_ctx": (_P, [_P, _I]),
+    "aukit_cuda_group_comm": (_P, [_P, _I]),
+    "aukit_cuda_group_normalize": (_I, [_P, C.POINTER(_P), _D, _I]),
+    "aukit_cuda_group_preload": (_I, [_P, C.POINTER(PipelineDesc), _P, _SZ, _D, _P]),
     "aukit_block_shard": (_I, [_U64, _I, _I, C.POINTER(_U64), C.POINTER(_U64)]),
     "aukit_ima_adpcm_wav_frames": (_SZ, [_SZ, _I, _I, _I]),
     "aukit_msadpcm_frames": (_SZ, [_SZ, _I, _I]),

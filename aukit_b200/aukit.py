@@ -54,11 +54,19 @@ _WAV_METADATA = {
 class Context:
     """One aukit_ctx (device + stream).  Kernels are enqueued on its stream."""
 
-    def __init__(self, device: int = -1):
+    def __init__(self, device: int = -1, _borrowed=None):
         self.lib = _lib.load()
+        self._owned = _borrowed is None
+        if _borrowed is not None:                     # a context that belongs to a Group
+            self.handle = C.c_void_p(_borrowed)
+            return
         h = C.c_void_p()
         _lib.check(self.lib.aukit_cuda_init(device, C.byref(h)))
         self.handle = h
+
+    def make_current(self):
+        """cudaSetDevice to this context's device (needed only when one process holds contexts on several devices)."""
+        _lib.check(self.lib.aukit_cuda_make_current(self.handle))
 
     def set_stream(self, cuda_stream: Optional[int]):
         """None -> the context's own stream.  A raw cudaStream_t handle otherwise; torch reports the
@@ -83,7 +91,8 @@ class Context:
 
     def close(self):
         if self.handle:
-            self.lib.aukit_cuda_shutdown(self.handle)
+            if self._owned:
+                self.lib.aukit_cuda_shutdown(self.handle)
             self.handle = None
 
 
@@ -690,6 +699,67 @@ def preload_clips(clips: Sequence, sampleRates, bitDepth=16, dataType="signed", 
                                                          int(bool(bigEndian)), float(targetRate), _INTERPS[interpolation], float(multiplier),
                                                          outs))
     return [Audio(ctx, C.c_void_p(outs[k]), {}, {"bitDepth": bitDepth, "dataType": dataType}) for k in range(n)]
+
+
+class Group:
+    """One host thread driving several GPUs (aukit_cuda_group_*): what the Lua module uses when more than one B200 is
+    visible.  `devices`: list of device ordinals (None = all visible); the same ordinal may appear more than once."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        if devices is None:
+            _lib.check(self.lib.aukit_cuda_group_create(None, 0, C.byref(h)))
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _lib.check(self.lib.aukit_cuda_group_create(arr, len(devices), C.byref(h)))
+        self.handle = h
+        self.size = int(self.lib.aukit_cuda_group_size(h))
+        self.contexts = [Context(_borrowed=self.lib.aukit_cuda_group_ctx(h, i)) for i in range(self.size)]
+
+    def preload(self, data, bitDepth=16, dataType="signed", channels=2, sampleRate=44100, targetRate=48000,
+                interpolation=None, mono=True, peakAmplitude=0.8, bigEndian=False) -> np.ndarray:
+        """preload() time-sharded over the group's GPUs: same arguments, same bits as on one GPU."""
+        interpolation = interpolation or defaultInterpolation
+        if interpolation not in _INTERPS:
+            raise AukitError("bad argument #2 (invalid interpolation type)")
+        if dataType not in _DATATYPES:
+            raise AukitError("bad argument #3 (invalid data type)")
+        if bitDepth not in (8, 16, 24, 32):
+            raise AukitError("bad argument #2 (invalid bit depth)")
+        p, n, keep = _buf(_as_bytes(data))
+        B = bitDepth // 8
+        if n % (B * channels):
+            raise AukitError("bad argument #1 (uneven amount of data per channel)")
+        frames = n // (B * channels)
+        n_out = int(self.lib.aukit_resample_out_len(frames, float(sampleRate), float(targetRate)))
+        d = PipelineDesc(bitDepth, _DATATYPES[dataType], channels, int(bool(bigEndian)), float(sampleRate), float(targetRate),
+                         _INTERPS[interpolation], int(bool(mono)), frames, 0, frames, 0, n_out)
+        out = np.empty((1 if mono else channels, n_out), dtype=np.float32)
+        _lib.check(self.lib.aukit_cuda_group_preload(self.handle, C.byref(d), p, n, float(peakAmplitude), C.c_void_p(out.ctypes.data)))
+        return out
+
+    def normalize(self, shards: Sequence["Audio"], peakAmplitude=None, independent=None):
+        """effects.normalize on an Audio held as one time shard per member (shards[i] created on self.contexts[i])."""
+        if len(shards) != self.size:
+            raise AukitError("aukit_b200: one shard per group member")
+        arr = (C.c_void_p * self.size)(*[s._h for s in shards])
+        _lib.check(self.lib.aukit_cuda_group_normalize(self.handle, arr, 1.0 if peakAmplitude is None else float(peakAmplitude),
+                                                       int(bool(independent))))
+        return shards
+
+    def close(self):
+        if self.handle:
+            for c in self.contexts:
+                c.handle = None
+            self.lib.aukit_cuda_group_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Preloader:

@@ -103,6 +103,11 @@ extern "C" int aukit_cuda_set_stream(aukit_ctx *ctx, void *cuda_stream) {
     return 0;
 }
 
+extern "C" int aukit_cuda_make_current(aukit_ctx *ctx) {
+    if (!ctx) return aukit_fail("aukit_cuda: null context");
+    return aukit_cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice");
+}
+
 extern "C" void *aukit_cuda_get_stream(aukit_ctx *ctx) { return ctx ? ctx->stream : nullptr; }
 extern "C" uint64_t aukit_cuda_launch_count(aukit_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

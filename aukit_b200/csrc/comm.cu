@@ -5,35 +5,35 @@
 // tree protocol (measured 18-30 us between the two passes of the fused chain).  Here every rank owns an exchange block
 // in ITS device memory, peer-mapped by all other ranks (CUDA IPC between processes, cudaDeviceEnablePeerAccess inside
 // one process), and ONE tiny kernel per rank does the whole exchange over NVLink / NVSwitch:
-//     thread r < world : atomicMax of my local maxima into rank r's block (remote atomics), __threadfence_system,
-//                        then +1 on rank r's arrival counter
-//     thread 0         : spins on MY arrival counter until all `world` ranks have arrived, then copies the combined
-//                        maxima to where the apply pass reads them.
-// No host round trip, no NCCL launch; the kernel sits in stream order between the peak pass and the apply pass.
-// Float MAX over non-negative values is exact and order-free, so N-GPU results stay bit-identical to one GPU.
-// Blocks are rings of EPOCHS slots (a slot is reused every EPOCHS exchanges and cleared half a ring ahead), so no
-// reset can race with a slow peer.  A peer that never arrives trips a 10 s timeout that raises an error instead of
-// hanging the GPU.
+//     thread r < world : ONE 8-byte store {epoch tag, my local max} into slot [my rank] of rank r's block (a posted
+//                        write over NVLink; value and validity tag cannot tear), then polls slot [r] of MY block until
+//                        rank r's tag for this epoch shows up;
+//     after a barrier  : the `world` values are max-combined locally and written where the apply pass reads them.
+// No remote atomics, no fences, no host round trip, no NCCL launch; the kernel sits in stream order between the peak
+// pass and the apply pass.  Float MAX over non-negative values is exact and order-free, so N-GPU results stay
+// bit-identical to one GPU.  Slots form a ring of 4 epochs (a rank can be at most one exchange ahead of the slowest
+// one, and the tag is the full epoch number), so nothing is ever cleared.  A peer that never arrives trips a 10 s
+// timeout that raises an error instead of hanging the GPU.
 #include "common.cuh"
 
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 namespace {
 
-constexpr int COMM_EPOCHS = 64;
+constexpr int COMM_RING = 4;              // exchanges in flight at most: a rank is never more than one ahead of the slowest
 constexpr int COMM_MAXVALS = 16;          // floats per exchange (global normalize: 1; independent: channels <= 16)
 constexpr int COMM_MAXWORLD = 64;
 
+// word[src][k] = (epoch + 1) << 32 | float bits: value and its validity tag travel in ONE 8-byte store, so a rank's
+// contribution is a single posted write per peer -- no remote atomics, no fences, nothing to clear.
 struct comm_slot {
-    unsigned int max_bits[COMM_MAXVALS];  // non-negative floats order like their bit patterns
-    unsigned int arrived;
-    unsigned int pad[15];
+    unsigned long long word[COMM_MAXWORLD][COMM_MAXVALS];
 };
 struct comm_block {
-    comm_slot slot[COMM_EPOCHS];
-    unsigned int error;                   // set by the timeout
+    comm_slot slot[COMM_RING];
 };
 
 struct exchange_args {
@@ -51,36 +51,39 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 __global__ void __launch_bounds__(64) exchange_max_kernel(exchange_args a) {
+    __shared__ float part[COMM_MAXWORLD][COMM_MAXVALS];
+    __shared__ int failed;
     const int r = threadIdx.x;
-    const unsigned int e = a.epoch % COMM_EPOCHS;
+    const unsigned int e = a.epoch % COMM_RING;
+    const unsigned long long tag = (unsigned long long)(a.epoch + 1u) << 32;
+    if (r == 0) failed = 0;
+    __syncthreads();
     if (r < a.world) {
-        comm_slot *s = &a.peer[r]->slot[e];
-        for (int k = 0; k < a.nvals; k++) atomicMax(&s->max_bits[k], __float_as_uint(a.vals[k]));   // NaN never reaches here (fmaxf)
-        __threadfence_system();
-        atomicAdd(&s->arrived, 1u);
+        // push: my maxima into slot [e][my rank] of rank r's block (NVLink posted writes; r == rank is a local store)
+        unsigned long long *dst = a.peer[r]->slot[e].word[a.rank];
+        for (int k = 0; k < a.nvals; k++)
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + k), "l"(tag | (unsigned long long)__float_as_uint(a.vals[k])) : "memory");
+        // pull: rank r's maxima out of MY block, as soon as its tag says this epoch
+        const unsigned long long *src = a.peer[a.rank]->slot[e].word[r];
+        const unsigned long long t0 = globaltimer_ns();
+        for (int k = 0; k < a.nvals; k++) {
+            unsigned long long w;
+            for (;;) {
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src + k) : "memory");
+                if ((w >> 32) == (tag >> 32)) break;
+                if (globaltimer_ns() - t0 > 10000000000ull) { failed = 1; w = 0; break; }
+                __nanosleep(100);
+            }
+            part[r][k] = __uint_as_float((unsigned int)w);
+        }
     }
     __syncthreads();
-    if (r == 0) {
-        comm_block *me = a.peer[a.rank];
-        volatile unsigned int *arrived = &me->slot[e].arrived;
-        const unsigned long long t0 = globaltimer_ns();
-        bool ok = true;
-        while (*arrived < (unsigned)a.world) {
-            if (globaltimer_ns() - t0 > 10000000000ull) { ok = false; break; }
-            __nanosleep(200);
-        }
-        __threadfence_system();
-        if (ok) {
-            for (int k = 0; k < a.nvals; k++) a.vals[k] = __uint_as_float(*(volatile unsigned int *)&me->slot[e].max_bits[k]);
-        } else {
-            me->error = 1u;
-            atomicOr(a.d_status, AUKIT_DEVERR_COMM_TIMEOUT);
-        }
-        // clear the slot half a ring ahead: every rank passed it at least EPOCHS / 2 exchanges ago
-        comm_slot *z = &me->slot[(e + COMM_EPOCHS / 2) % COMM_EPOCHS];
-        for (int k = 0; k < COMM_MAXVALS; k++) z->max_bits[k] = 0u;
-        z->arrived = 0u;
+    if (r < a.nvals) {
+        float m = 0.f;
+        for (int q = 0; q < a.world; q++) m = fmaxf(m, part[q][r]);     // non-negative, NaN-free (fmaxf upstream): exact, order-free
+        a.vals[r] = m;
     }
+    if (r == 0 && failed) atomicOr(a.d_status, AUKIT_DEVERR_COMM_TIMEOUT);
 }
 
 }  // namespace
@@ -218,4 +221,163 @@ extern "C" int aukit_cuda_comm_pipeline(aukit_comm *c, const aukit_pipeline_desc
     if (aukit_cuda_dev_pipeline_peak(ctx, p, d_in, c->d_vals)) return -1;
     if (aukit_cuda_comm_allreduce_max(c, c->d_vals, 1)) return -1;
     return aukit_cuda_dev_pipeline_apply(ctx, p, d_in, peakAmplitude, c->d_vals, d_out, out_stride);
+}
+
+// ------------------------------------------------------------------ one host thread, all GPUs
+// The reference is a single Lua coroutine, so the Lua module drives every GPU of the box from one thread: a group is
+// one context + one communicator per device, connected through plain peer pointers.
+// the group calls hop between devices; the caller's current device is restored when they return
+struct device_guard {
+    int prev = -1;
+    device_guard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~device_guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct aukit_group {
+    int n;
+    aukit_ctx *ctx[COMM_MAXWORLD];
+    aukit_comm *comm[COMM_MAXWORLD];
+};
+
+extern "C" void aukit_cuda_group_destroy(aukit_group *g) {
+    if (!g) return;
+    device_guard guard;
+    for (int i = 0; i < g->n; i++) {
+        if (g->comm[i]) aukit_cuda_comm_destroy(g->comm[i]);
+        if (g->ctx[i]) aukit_cuda_shutdown(g->ctx[i]);
+    }
+    free(g);
+}
+
+// devices == NULL: devices 0 .. ndev-1 (ndev <= 0: every visible device).  The same device may be listed more than once
+// (each entry gets its own context and stream): that is how the exchange is exercised on a one-GPU box.
+extern "C" int aukit_cuda_group_create(const int *devices, int ndev, aukit_group **out) {
+    if (!out) return aukit_fail("aukit_cuda: null argument");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return aukit_fail("aukit_cuda: no CUDA device available; there is no CPU fallback");
+    if (ndev <= 0) { ndev = count; devices = nullptr; }
+    if (ndev > COMM_MAXWORLD) return aukit_fail("aukit_cuda: at most %d shards per group", COMM_MAXWORLD);
+    device_guard guard;
+    aukit_group *g = static_cast<aukit_group *>(calloc(1, sizeof(aukit_group)));
+    if (!g) return aukit_fail("aukit_cuda: out of host memory");
+    g->n = ndev;
+    for (int i = 0; i < ndev; i++) {
+        const int dev = devices ? devices[i] : i;
+        if (aukit_cuda_init(dev, &g->ctx[i]) || aukit_cuda_comm_create(g->ctx[i], ndev, i, &g->comm[i])) { aukit_cuda_group_destroy(g); return -1; }
+    }
+    if (aukit_cuda_comm_connect_local(g->comm, ndev)) { aukit_cuda_group_destroy(g); return -1; }
+    *out = g;
+    return 0;
+}
+
+extern "C" int aukit_cuda_group_size(const aukit_group *g) { return g ? g->n : 0; }
+extern "C" aukit_ctx *aukit_cuda_group_ctx(aukit_group *g, int i) { return (g && i >= 0 && i < g->n) ? g->ctx[i] : nullptr; }
+extern "C" aukit_comm *aukit_cuda_group_comm(aukit_group *g, int i) { return (g && i >= 0 && i < g->n) ? g->comm[i] : nullptr; }
+
+// effects.normalize (A:3431) on an Audio whose time shards live one per group member: shards[i] belongs to context i.
+extern "C" int aukit_cuda_group_normalize(aukit_group *g, aukit_audio *const *shards, double peakAmplitude, int independent) {
+    if (!g || !shards) return aukit_fail("aukit_cuda: null argument");
+    device_guard guard;
+    // Three sweeps -- every abs-max, every exchange, every scale -- NOT member by member: between the first and the
+    // last exchange launch nothing else may be launched for the first time.  (CUDA loads a kernel's code lazily at its
+    // first launch and may wait for the device to drain to do so; an exchange kernel that is already spinning for a
+    // peer whose own exchange is still behind that load would wait for its full timeout.)
+    int nmax = 1;
+    for (int i = 0; i < g->n; i++) {
+        if (!shards[i]) return aukit_fail("aukit_cuda: null shard");
+        nmax = independent ? shards[i]->channels : 1;
+        if (nmax > COMM_MAXVALS) return aukit_fail("aukit_cuda: independent normalize over more than %d channels", COMM_MAXVALS);
+        aukit_ctx *ctx = g->ctx[i];
+        if (aukit_cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
+        AUKIT_CUDA_TRY(cudaMemsetAsync(g->comm[i]->d_vals, 0, sizeof(float) * (size_t)nmax, ctx->stream));
+        if (aukit_cuda_absmax(ctx, shards[i], independent, g->comm[i]->d_vals)) return -1;
+    }
+    for (int i = 0; i < g->n; i++) {
+        if (aukit_cuda_check(cudaSetDevice(g->ctx[i]->device), "cudaSetDevice")) return -1;
+        if (aukit_cuda_comm_allreduce_max(g->comm[i], g->comm[i]->d_vals, nmax)) return -1;
+    }
+    for (int i = 0; i < g->n; i++) {
+        if (aukit_cuda_check(cudaSetDevice(g->ctx[i]->device), "cudaSetDevice")) return -1;
+        if (aukit_cuda_scale_clamp(g->ctx[i], shards[i], peakAmplitude, independent, g->comm[i]->d_vals)) return -1;
+    }
+    return 0;
+}
+
+// auplay's chain (aukit.pcm -> Audio:resample -> [Audio:mono] -> effects.normalize; A:1049, A:653, A:677, A:3431) on ONE
+// host buffer, time-sharded over the group: contiguous output ranges on whole warp tiles, each shard's input window with
+// its interpolation halo, local peak passes, the MAX exchange, local apply passes, results gathered into
+// h_out[c * n_out + i].  `whole` describes the unsharded call (in_first = 0, in_avail = n_in_total, out_first = 0,
+// n_out = floor(n_in_total * ratio)).  Bit-identical to the same call on one GPU.
+extern "C" int aukit_cuda_group_preload(aukit_group *g, const aukit_pipeline_desc *whole, const void *h_in, size_t nbytes,
+                                        double peakAmplitude, float *h_out) {
+    if (!g || !whole || !h_out) return aukit_fail("aukit_cuda: null argument");
+    device_guard guard;
+    const size_t FB = (size_t)whole->channels * (size_t)(whole->bitDepth / 8);
+    if (FB == 0 || nbytes < whole->n_in_total * FB) return aukit_fail("aukit_cuda: host buffer smaller than n_in_total frames");
+    const uint64_t n_out = aukit_resample_out_len(whole->n_in_total, whole->srcRate, whole->dstRate);
+    const int out_ch = whole->mono ? 1 : whole->channels;
+    const int W = g->n;
+    // warp-tile aligned shard boundaries (see aukit_b200/sharding.py: shard_alignment)
+    uint64_t align = 4;
+    if (whole->srcRate == floor(whole->srcRate) && whole->dstRate == floor(whole->dstRate) && whole->srcRate >= 1 && whole->dstRate >= 1) {
+        long long x = (long long)whole->srcRate, y = (long long)whole->dstRate;
+        while (y) { const long long r = x % y; x = y; y = r; }
+        const long long L = (long long)whole->dstRate / x;
+        if (L > 1 && L <= 512) align = 32ull * (uint64_t)L;
+    }
+    if (n_out / (uint64_t)W < 4 * align) align = 4;
+    struct part { aukit_pipeline_desc d; void *d_in; float *d_out; size_t stride; };
+    part parts[COMM_MAXWORLD];
+    memset(parts, 0, sizeof parts);
+    int rc = 0;
+    // 1. upload every window and enqueue every peak pass (pageable sources are staged synchronously: do it before any
+    //    exchange kernel starts to wait)
+    for (int i = 0; i < W && !rc; i++) {
+        aukit_ctx *ctx = g->ctx[i];
+        part &p = parts[i];
+        const uint64_t o0 = n_out * (uint64_t)i / (uint64_t)W / align * align;
+        const uint64_t o1 = i == W - 1 ? n_out : n_out * (uint64_t)(i + 1) / (uint64_t)W / align * align;
+        p.d = *whole;
+        p.d.out_first = o0; p.d.n_out = (size_t)(o1 - o0);
+        uint64_t f = 0, c = 0;
+        if (o1 > o0 && aukit_resample_window(whole->n_in_total, whole->srcRate, whole->dstRate, whole->interpolation, o0, o1 - o0, &f, &c)) { rc = -1; break; }
+        uint64_t first = f, end = f + c;
+        if (c) {                                                       // the slack the bulk copies of the run kernels want
+            if (first >= 8) first = (first - 8) / 4 * 4;
+            end = end + 8 < whole->n_in_total ? end + 8 : whole->n_in_total;
+        }
+        p.d.in_first = first; p.d.in_avail = (size_t)(end - first);
+        p.stride = aukit_round_stride(p.d.n_out ? p.d.n_out : 1);
+        if ((rc = aukit_cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice"))) break;
+        if ((rc = aukit_upload_bytes(ctx, static_cast<const char *>(h_in) + first * FB, p.d.in_avail * FB, &p.d_in))) break;
+        void *o = nullptr;
+        if ((rc = aukit_dev_alloc(ctx, p.stride * (size_t)out_ch * sizeof(float), &o))) break;
+        p.d_out = static_cast<float *>(o);
+        float *mx = aukit_cuda_comm_values(g->comm[i]);
+        if ((rc = aukit_cuda_check(cudaMemsetAsync(mx, 0, sizeof(float), ctx->stream), "memset"))) break;
+        rc = aukit_cuda_dev_pipeline_peak(ctx, &p.d, p.d_in, mx);
+    }
+    // 2. the exchange, 3. apply passes and downloads
+    for (int i = 0; i < W && !rc; i++) {
+        if ((rc = aukit_cuda_check(cudaSetDevice(g->ctx[i]->device), "cudaSetDevice"))) break;
+        rc = aukit_cuda_comm_allreduce_max(g->comm[i], aukit_cuda_comm_values(g->comm[i]), 1);
+    }
+    for (int i = 0; i < W && !rc; i++) {
+        aukit_ctx *ctx = g->ctx[i];
+        part &p = parts[i];
+        if ((rc = aukit_cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice"))) break;
+        if ((rc = aukit_cuda_dev_pipeline_apply(ctx, &p.d, p.d_in, peakAmplitude, aukit_cuda_comm_values(g->comm[i]), p.d_out, p.stride))) break;
+        if (p.d.n_out)
+            rc = aukit_cuda_check(cudaMemcpy2DAsync(h_out + p.d.out_first, (size_t)n_out * sizeof(float), p.d_out, p.stride * sizeof(float),
+                                                    p.d.n_out * sizeof(float), (size_t)out_ch, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+    }
+    for (int i = 0; i < W; i++) {
+        cudaSetDevice(g->ctx[i]->device);
+        aukit_dev_free(g->ctx[i], parts[i].d_in);
+        aukit_dev_free(g->ctx[i], parts[i].d_out);
+        const int s = aukit_cuda_synchronize(g->ctx[i]);
+        if (!rc && s) rc = s;
+    }
+    return rc;
 }

@@ -26,8 +26,8 @@
 // segments (st.global.L1::no_allocate.v4), so stores stay coalesced although a lane's outputs are L samples
 // apart from its neighbour's.
 //
-// Positions: rational (n*M/L) plus a constant drift term per launch (delta = x*eps_r, see
-// pipeline_poly.cu / DESIGN.md 3.2); the host splits launches so delta stays within 11 % of its
+// Positions: rational (n*M/L) plus a drift term that is constant over a segment of a fixed global grid (delta = x*eps_r, see
+// pipeline_poly.cu / DESIGN.md 3.2); the grid keeps delta within 11 % of its
 // true value.  Tiles that touch the ends of the signal or of the shard, other formats / modes and
 // exactness-sensitive cases stay on pipeline_poly.cu's kernels.
 #include "common.cuh"
@@ -847,27 +847,21 @@ int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipel
     if (!pow2_ratio && (double)(t_hi * tile_in) >= 1518500249.0) return 0;              // beyond 2^30.5: exact-position kernels
     run_plan rp{};
     rp.L = (int)L; rp.M = (int)M;
-    // the drift x*eps_r (<= 2^-22.5) is baked into the weight table: split the range so it stays within ~11 % of its
-    // value (an error below 2^-25.5 in the position, i.e. < 6e-8 in the output)
+    // The drift x*eps_r (<= 2^-22.5 frames) is baked into the weight table, constant over a SEGMENT of tiles.  The
+    // segments form a fixed GLOBAL grid -- [0, b0) with no drift (below 2^28 / 1.25 frames it is under 2^-25), then
+    // [b_k, b_k+1) with b_k+1 = 1.25 b_k and the drift of the segment's middle (within 11 % of the true value: an error
+    // below 2^-25.5 in the position, < 6e-8 in the output) -- so what an output frame gets does not depend on how the
+    // buffer was sharded: any two shardings give the same bits.
+    const unsigned long long b0 = (unsigned long long)(268435456.0 / 1.25 / (double)tile_in);
     unsigned long long t = t_lo;
     int rc = 1;
     rp.nseg = 0;
     unsigned long long batch_first = t_lo;
+    unsigned long long seg_lo = 0, seg_hi = pow2_ratio ? ~0ull : b0;     // grid cell containing t
+    while (t >= seg_hi) { seg_lo = seg_hi; seg_hi = seg_hi + seg_hi / 4 + 1; }
     while (t < t_hi && rc == 1) {
-        unsigned long long t_end = t_hi;
-        const double x0 = (double)(t * tile_in);
-        float delta = 0.f;
-        if (!pow2_ratio && (double)(t_hi * tile_in) >= 268435456.0) {
-            if (x0 < 268435456.0 / 1.25) {
-                // below 2^28 the drift is under 2^-25 and ignored; stop this segment where it starts to matter
-                const unsigned long long lim = (unsigned long long)(268435456.0 / 1.25 / (double)tile_in);
-                if (lim > t && lim < t_hi) t_end = lim;
-            } else {
-                const unsigned long long lim = (unsigned long long)(x0 * 1.25 / (double)tile_in) + 1;
-                if (lim < t_hi) t_end = lim;
-                delta = (float)(0.5 * (x0 + (double)(t_end * tile_in)) * eps_r);
-            }
-        }
+        const unsigned long long t_end = seg_hi < t_hi ? seg_hi : t_hi;
+        const float delta = (pow2_ratio || seg_lo == 0) ? 0.f : (float)(0.5 * ((double)(seg_lo * tile_in) + (double)(seg_hi * tile_in)) * eps_r);
         if (use_static) {
             // the straight-line kernel takes the whole range in ONE launch: segments of constant drift, tables rebuilt in place
             rp.seg_end[rp.nseg] = t_end;
@@ -889,6 +883,7 @@ int aukit_pipeline_run_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipel
             rc = apply ? launch_run<true>(ctx, a, rp) : launch_run<false>(ctx, a, rp);
         }
         t = t_end;
+        if (t >= seg_hi) { seg_lo = seg_hi; seg_hi = seg_hi + seg_hi / 4 + 1; }
     }
     if (rc != 1) return rc;
     *done_first = t_lo * tile_out;

@@ -61,14 +61,8 @@ def plan_time_shards(n_in_total: int, srcRate: float, dstRate: float, interpolat
     for r in range(world):
         o0 = n_out * r // world // align * align
         o1 = n_out if r == world - 1 else n_out * (r + 1) // world // align * align
-        f, c = C.c_uint64(0), C.c_uint64(0)
-        _lib.check(lib.aukit_resample_window(n_in_total, float(srcRate), float(dstRate), _INTERPS[interpolation], o0, o1 - o0,
-                                             C.byref(f), C.byref(c)))
-        first, end = int(f.value), int(f.value) + int(c.value)
-        if pad and c.value:
-            first = max(0, first - pad) // 4 * 4 if first >= pad else first
-            end = min(n_in_total, end + pad)
-        shards.append(TimeShard(r, o0, o1 - o0, first, end - first))
+        first, count = padded_window(n_in_total, srcRate, dstRate, interpolation, o0, o1 - o0, pad)
+        shards.append(TimeShard(r, o0, o1 - o0, first, count))
     return shards
 
 
@@ -83,6 +77,20 @@ def plan_block_shards(n_blocks: int, world: int):
         _lib.check(lib.aukit_block_shard(n_blocks, world, r, C.byref(f), C.byref(c)))
         out.append((int(f.value), int(c.value)))
     return out
+
+
+def padded_window(n_in_total: int, srcRate: float, dstRate: float, interpolation: str, out_first: int, n_out: int, pad: int = 8):
+    """(in_first, in_count) for global output frames [out_first, out_first + n_out): the halo of
+    aukit_resample_window plus the slack plan_time_shards adds (see there)."""
+    lib = _lib.load()
+    f, c = C.c_uint64(0), C.c_uint64(0)
+    _lib.check(lib.aukit_resample_window(n_in_total, float(srcRate), float(dstRate), _INTERPS[interpolation], out_first, n_out,
+                                         C.byref(f), C.byref(c)))
+    first, end = int(f.value), int(f.value) + int(c.value)
+    if pad and c.value:
+        first = max(0, first - pad) // 4 * 4 if first >= pad else first
+        end = min(n_in_total, end + pad)
+    return first, end - first
 
 
 def shard_clips(n_clips: int, world: int, rank: int, sizes: Optional[List[int]] = None) -> List[int]:

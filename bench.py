@@ -263,7 +263,8 @@ def run_b200(args):
     multi = None
     if world > 1 and not args.emulate_shard:
         from aukit_b200._lib import PipelineDesc
-        CHK = min(1 << 20, shard.n_out)
+        from aukit_b200.sharding import padded_window, shard_alignment
+        CHK = min(200 * shard_alignment(SRC_RATE, DST_RATE), shard.n_out)       # whole warp tiles, like the shards themselves
         mine = sp.d_out[0, :CHK].clone()
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
@@ -271,11 +272,9 @@ def run_b200(args):
         if rank == 0:
             shards_all = plan_time_shards(n_in_total, SRC_RATE, DST_RATE, INTERP, world)
             for r in range(1, world):
-                f, c = C.c_uint64(0), C.c_uint64(0)
-                ak._lib.check(lib.aukit_resample_window(n_in_total, float(SRC_RATE), float(DST_RATE), 2, shards_all[r].out_first, CHK,
-                                                        C.byref(f), C.byref(c)))
-                din_r = synth_frames_cuda(int(f.value), int(c.value), torch).view(torch.uint8).reshape(-1)
-                desc_r = PipelineDesc(BITS, 0, CHANNELS, 0, float(SRC_RATE), float(DST_RATE), 2, 1, n_in_total, int(f.value), int(c.value),
+                wf, wc = padded_window(n_in_total, SRC_RATE, DST_RATE, INTERP, shards_all[r].out_first, CHK)
+                din_r = synth_frames_cuda(wf, wc, torch).view(torch.uint8).reshape(-1)
+                desc_r = PipelineDesc(BITS, 0, CHANNELS, 0, float(SRC_RATE), float(DST_RATE), 2, 1, n_in_total, wf, wc,
                                       shards_all[r].out_first, CHK)
                 out_r = torch.empty(CHK, dtype=torch.float32, device="cuda")
                 ak._lib.check(lib.aukit_cuda_dev_pipeline_apply(ctx.handle, C.byref(desc_r), din_r.data_ptr(), PEAK, sp.d_max.data_ptr(),

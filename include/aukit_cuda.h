@@ -55,6 +55,9 @@ void aukit_cuda_shutdown(aukit_ctx *ctx);
  * default stream is cudaStreamLegacy ((void *)1), not NULL. */
 int aukit_cuda_set_stream(aukit_ctx *ctx, void *cuda_stream);
 void *aukit_cuda_get_stream(aukit_ctx *ctx);
+/* A process that holds contexts on SEVERAL devices makes one current (cudaSetDevice) before issuing calls on it; the
+ * aukit_cuda_group_* calls do this themselves. */
+int aukit_cuda_make_current(aukit_ctx *ctx);
 /* Waits for the stream and reports deferred device-side decode errors (bad IMA step index,
  * A:1213; bad MS-ADPCM predictor index, A:1311). */
 int aukit_cuda_synchronize(aukit_ctx *ctx);
@@ -347,6 +350,23 @@ int aukit_cuda_comm_normalize(aukit_comm *c, aukit_audio *a, double peakAmplitud
 /* The fused chain (aukit_cuda_dev_pipeline_peak -> exchange -> aukit_cuda_dev_pipeline_apply) on this rank's shard. */
 int aukit_cuda_comm_pipeline(aukit_comm *c, const aukit_pipeline_desc *p, const void *d_in,
                              double peakAmplitude, float *d_out, size_t out_stride);
+
+/* One host thread driving several GPUs (what the Lua module does: the reference is a single coroutine): a
+ * group = one context + one communicator per listed device, connected by plain peer pointers.  devices == NULL: devices
+ * 0..ndev-1; ndev <= 0: every visible device.  A device may be listed twice (two contexts / streams on it). */
+typedef struct aukit_group aukit_group;
+int aukit_cuda_group_create(const int *devices, int ndev, aukit_group **out);
+void aukit_cuda_group_destroy(aukit_group *g);
+int aukit_cuda_group_size(const aukit_group *g);
+aukit_ctx *aukit_cuda_group_ctx(aukit_group *g, int i);
+aukit_comm *aukit_cuda_group_comm(aukit_group *g, int i);
+/* effects.normalize (A:3431) on an Audio held as one time shard per group member (shards[i] lives on context i). */
+int aukit_cuda_group_normalize(aukit_group *g, aukit_audio *const *shards, double peakAmplitude, int independent);
+/* auplay's chain on ONE host buffer, time-sharded over the group (tile-aligned output ranges, halo windows, local peak
+ * passes, the MAX exchange, local apply passes); h_out[c * n_out + i], n_out = floor(n_in_total * dstRate / srcRate).
+ * `whole` describes the unsharded call (in_first = 0, in_avail = n_in_total, out_first = 0).  Same bits as one GPU. */
+int aukit_cuda_group_preload(aukit_group *g, const aukit_pipeline_desc *whole, const void *h_in, size_t nbytes,
+                             double peakAmplitude, float *h_out);
 
 /* ------------------------------------------------------------------ pure host helpers */
 /* floor(n_in * (dstRate/srcRate)) in double, the reference's loop bound (A:658-664). */

@@ -545,3 +545,37 @@ np.save(%r, ak.preload(pcm.tobytes(), 16, "signed", 2, 44100, 48000, "cubic", Tr
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **extra), timeout=600)
         assert r.returncode == 0, (extra, r.stdout + r.stderr)
         assert f32_equal_bits(np.load(outp), got), extra
+
+
+def test_far_shards_do_not_depend_on_the_sharding(ak):
+    """Positions of several 10^8 frames (hours 3-8 of a time-sharded buffer): the drift baked into the run-per-lane
+    kernel's weight table comes from a fixed GLOBAL grid of segments, so a range computed as one shard, as two shards,
+    or as part of a longer shard that starts elsewhere gives the same bits."""
+    import torch
+    from aukit_b200.sharding import padded_window
+    lib, ctx = ak._lib.load(), ak.context()
+    n_total, src, dst, TILE = 8 * 3600 * 44100, 44100, 48000, 5120
+    rng = np.random.default_rng(11)
+    ctx.use_torch_stream()
+    try:
+        for pos in (3.3e8, 2 ** 28 / 1.25 * 1.25 ** 3, 9.1e8):          # inside a segment, across a segment boundary, far out
+            o_mid = int(pos * dst / src) // TILE * TILE
+            o0, o1 = o_mid - 40 * TILE, o_mid + 40 * TILE
+            f_all, c_all = padded_window(n_total, src, dst, "cubic", o0 - 30 * TILE, (o1 - o0) + 30 * TILE)
+            pcm = rng.integers(-32768, 32768, (c_all, 2)).astype(np.int16)
+            dmax = torch.full((1,), 0.9, device="cuda")
+
+            def run(a0, a1):
+                f, c = padded_window(n_total, src, dst, "cubic", a0, a1 - a0)
+                t = torch.from_numpy(pcm[f - f_all: f - f_all + c].copy()).cuda()
+                out = torch.empty(a1 - a0, device="cuda")
+                d = ak.PipelineDesc(16, 0, 2, 0, float(src), float(dst), 2, 1, n_total, f, c, a0, a1 - a0)
+                ak._lib.check(lib.aukit_cuda_dev_pipeline_apply(ctx.handle, C.byref(d), t.data_ptr(), 0.8, dmax.data_ptr(), out.data_ptr(), a1 - a0))
+                torch.cuda.synchronize()
+                return out.cpu().numpy()
+            whole = run(o0, o1)
+            two = np.concatenate([run(o0, o_mid + 7 * TILE), run(o_mid + 7 * TILE, o1)])
+            longer = run(o0 - 30 * TILE, o1)[30 * TILE:]
+            assert f32_equal_bits(two, whole) and f32_equal_bits(longer, whole), pos
+    finally:
+        ctx.set_stream(None)
