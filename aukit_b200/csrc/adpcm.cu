@@ -320,72 +320,94 @@ __device__ __forceinline__ void ima_word(const char *tab, uint32_t w, float &u, 
     b.w = ima_tab_step(tab, (w >> 26) & 0x3C, u, e);
 }
 
-// general / literal-stereo block layout, 4-byte aligned input, 16-byte aligned output rows
-template <int NQ, int MINB>
-__global__ void __launch_bounds__(128, MINB)
-ima_wav_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, size_t nblocks, size_t spb,
-                     int groups, float *__restrict__ out, size_t stride, int *status) {
-    constexpr int GP = NQ / 2;                                          // 8-sample groups per flush
+// ---- IMA, general / literal-stereo block layout, output segments aligned in absolute address.  A row (one block of one channel, spb = 8 * groups floats)
+// starts on a 32-byte boundary but rarely on a 256-byte one (config 4: 8160-byte rows), so 256-byte flushes that
+// start at the row start straddle 128-byte lines: measured 0.73 of the copy rate, against 0.82 for the same kernel on
+// rows that are a multiple of 256 bytes.  Here a lane's iteration i decodes the words of ITS row that fall into the
+// row's i-th 256-byte ALIGNED segment: words 8 i - G0 + s, s = 0..7, with G0 = (row address % 256) / 32 -- the lanes of
+// a warp run up to 7 words apart through their blocks, and every interior flush writes whole aligned segments.
+// Iteration 0 (short by G0 words) and the last one or two (partial) take a per-word loop.
+// Requires 4-byte aligned input, 32-byte aligned rows (out % 32 == 0, stride % 8 == 0).
+__global__ void __launch_bounds__(128, 5)
+ima_wav_aligned_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, size_t nblocks, size_t spb,
+                       int groups, float *__restrict__ out, size_t stride, int *status) {
+    constexpr int NQ = 16, GP = 8;
     __shared__ __align__(16) uint32_t tab[IMA_TAB];
     __shared__ float4 stage_all[4][32 * NQ];
-    __shared__ size_t rowb_all[4][32];
+    __shared__ uintptr_t rowp_all[4][32];
     ima_build_tab(tab);
     __syncthreads();
     const char *tb = reinterpret_cast<const char *>(tab);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *st = stage_all[warp];
-    size_t *rowb = rowb_all[warp];
+    uintptr_t *rowp = rowp_all[warp];
     const size_t nchains = nblocks * (size_t)C;
     const size_t ntiles = (nchains + 31) / 32;
     const size_t hdr = 4 * (size_t)C;
+    const int M = groups / GP;                                           // iterations 1 .. M - 1 are full for every lane
+    const int niter = (groups + 7 + GP - 1) / GP;                        // segments a row can touch (G0 <= 7)
+    const int q = lane & 15;
     for (size_t tile = (size_t)blockIdx.x * 4 + warp; tile < ntiles; tile += (size_t)gridDim.x * 4) {
         const size_t id = min(tile * 32 + lane, nchains - 1);            // surplus lanes shadow the last chain
         const size_t b = id / (size_t)C;
         const int c = (int)(id % (size_t)C);
-        rowb[lane] = tile * 32 + lane < nchains ? (size_t)c * stride + b * spb : ROW_NONE;
+        const uintptr_t orow = (uintptr_t)(out + (size_t)c * stride + b * spb);
+        const int G0 = (int)((orow & 255) >> 5);
+        rowp[lane] = tile * 32 + lane < nchains ? orow : 0;
         const uint8_t *gp = data + b * (size_t)blockAlign + 4 * (size_t)c;
         const uint32_t hw = *reinterpret_cast<const uint32_t *>(gp);
         float pred = (float)((int)(int16_t)(hw & 0xFFFF) + 32768) * (1.0f / 65536.0f);      // u, see above
         int idx = (hw >> 16) & 0xFF;
         if (idx > 88) { atomicOr(status, AUKIT_DEVERR_IMA_INDEX); idx = 88; }
         uint32_t row = (uint32_t)idx;                                    // "previous entry": only its index bits matter
-        const int nper = groups / GP;
+        gp += hdr;                                                       // word 0 of this chain
         uint32_t w[GP];
-        gp += hdr;                                                       // first group word of this chain
-        if (nper > 0) {
+        // words of iteration 1 (if it is a full one): 8 - G0 + s
+        if (M > 1) {
 #pragma unroll
-            for (int g = 0; g < GP; g++) w[g] = *reinterpret_cast<const uint32_t *>(gp + (size_t)g * hdr);
+            for (int g = 0; g < GP; g++) w[g] = *reinterpret_cast<const uint32_t *>(gp + (size_t)(GP - G0 + g) * hdr);
         }
-        size_t col = 0;
-        for (int per = 0; per < nper; per++, col += 4 * NQ) {
-            gp += GP * hdr;
-            uint32_t n[GP];
+        for (int i = 0; i < niter; i++) {
+            const int w0 = GP * i - G0;                                  // word in slot 0
+            if (i >= 1 && i < M) {
+                uint32_t n[GP];
 #pragma unroll
-            for (int g = 0; g < GP; g++)                                 // prefetch: the chain itself is serial
-                n[g] = (per + 1 < nper) ? *reinterpret_cast<const uint32_t *>(gp + (size_t)g * hdr) : 0u;
+                for (int g = 0; g < GP; g++)                             // prefetch: the chain itself is serial
+                    n[g] = (i + 1 < M) ? *reinterpret_cast<const uint32_t *>(gp + (size_t)(w0 + GP + g) * hdr) : 0u;
 #pragma unroll
-            for (int g = 0; g < GP; g++) {
-                float4 a, bq;
-                ima_word(tb, w[g], pred, row, a, bq);
-                stage_put<NQ>(st, lane, 2 * g, a);
-                stage_put<NQ>(st, lane, 2 * g + 1, bq);
+                for (int g = 0; g < GP; g++) {
+                    float4 a, bq;
+                    ima_word(tb, w[g], pred, row, a, bq);
+                    stage_put<NQ>(st, lane, 2 * g, a);
+                    stage_put<NQ>(st, lane, 2 * g + 1, bq);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < NQ; k++) {                           // rows 2k / 2k + 1: whole aligned 256-byte segments
+                    const int r = 2 * k + (lane >> 4);
+                    const float4 v = st[r * NQ + (q ^ stage_swz<NQ>(r))];
+                    const uintptr_t p = rowp[r];
+                    if (p) stg_stream(reinterpret_cast<float4 *>((p & ~(uintptr_t)255) + (size_t)i * (16 * NQ)) + q, v);
+                }
+#pragma unroll
+                for (int g = 0; g < GP; g++) w[g] = n[g];
+            } else {
+                const int sa = max(0, -w0), sb = min(GP, groups - w0);
+                for (int sl = sa; sl < sb; sl++) {
+                    float4 a, bq;
+                    ima_word(tb, *reinterpret_cast<const uint32_t *>(gp + (size_t)(w0 + sl) * hdr), pred, row, a, bq);
+                    stage_put<NQ>(st, lane, 2 * sl, a);
+                    stage_put<NQ>(st, lane, 2 * sl + 1, bq);
+                }
+                __syncwarp();
+                for (int k = 0; k < NQ; k++) {
+                    const int r = 2 * k + (lane >> 4);
+                    const float4 v = st[r * NQ + (q ^ stage_swz<NQ>(r))];
+                    const uintptr_t p = rowp[r];
+                    const int j = 2 * (GP * i - (int)((p & 255) >> 5)) + q;      // row r's quad in slot q
+                    if (p && j >= 0 && j < 2 * groups) stg_stream(reinterpret_cast<float4 *>(p) + j, v);
+                }
             }
-            __syncwarp();
-            stage_flush<NQ>(st, out, rowb, col, lane, NQ);
-            __syncwarp();
-#pragma unroll
-            for (int g = 0; g < GP; g++) w[g] = n[g];
-        }
-        const int rem = groups - nper * GP;
-        if (rem) {
-            for (int g = 0; g < rem; g++) {
-                float4 a, bq;
-                ima_word(tb, *reinterpret_cast<const uint32_t *>(gp + (size_t)g * hdr), pred, row, a, bq);
-                stage_put<NQ>(st, lane, 2 * g, a);
-                stage_put<NQ>(st, lane, 2 * g + 1, bq);
-            }
-            __syncwarp();
-            stage_flush<NQ>(st, out, rowb, col, lane, 2 * rem);
             __syncwarp();
         }
     }
@@ -588,6 +610,212 @@ ms_adpcm_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, i
     }
 }
 
+
+// ---- MS-ADPCM, 8 channels (config 4): staged input, straight-line periods, bulk-copy output.
+// ncu on the kernel above (profiles/r2_ms_adpcm_ncu.txt): a warp issued in 12 % of its cycles.  The chains waited on
+// their record loads although these were issued four quads ahead, every quad was its own basic block (the
+// `quick` test branches to the out-of-line general step), so no load could move across a quad, and the flush's
+// LDS.128 -> STG.128 pairs stalled on each other's registers; the ALU pipe -- half rate on sm_100
+// (profiles/r2_microbench_int.txt) -- carried 11 of the 25.6 instructions per sample.  Here
+//   * a warp's records travel global -> shared with cp.async one period (1 KB per warp) ahead of their use; the
+//     chain reads its record with one LDS.128 (the 8 lanes of a block share it: a broadcast);
+//   * a period (16 quads = 64 samples) is SPECULATED in the 32-bit fast arithmetic as one straight-line block:
+//     the `delta < 2^14` test of each quad only ORs into a flag, and a lane whose flag is set at the end restores
+//     the state it had at the start of the period and redoes it through the checked / general code (never for
+//     encoder-made data; wrapping int arithmetic cannot trap);
+//   * the predictor pair is carried offset-binary, u = s + 32768 in [0, 65535]: the offset's contribution to
+//     s1*c1 + s2*c2 is a per-chain constant folded into the first IMAD, both clamps of A:1322 are ONE
+//     VIMNMX.RELU (min(x, 65535) then max(., 0)), and u + 0x4B000000 is already the float 2^23 + u, from which
+//     the output p / (p < 0 and 32768 or 32767) follows with three FFMAs and no int->float convert; the nibble
+//     is isolated with a multiply (FMA pipe) + one arithmetic shift;
+//   * output segments are aligned in absolute address (below) and leave through the transposed, XOR-swizzled staging
+//     tile of the kernels above (a per-lane cp.async.bulk shared -> global was tried: UBLKCP takes uniform operands,
+//     so ptxas serialises the 32 lanes in a loop and the wait for its reads cost 27 % of the samples).
+// Same integers as the kernels above at every step (tests: staged == tiled == chain == oracle).
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+constexpr int MS8_NQ = 16;                        // quads per iteration = float4 slots of a staging row = one 256-byte output segment
+constexpr int MS8_RING = 4 * 16 * MS8_NQ;         // record ring of one block: 4 stages of 16 records ...
+constexpr int MS8_BLK_PITCH = MS8_RING + 16 * MS8_NQ + 16;   // ... + a mirror of stage slot 0 (a lane's 16 records never wrap) + bank skew
+
+// requires C == 8, spb % 4 == 0, 16-byte aligned input / output rows, blockAlign % 16 == 0.
+//
+// Output segments are aligned in ABSOLUTE address: a row (one block of one channel, spb floats) starts wherever
+// c * stride + b * spb puts it -- 16 bytes past a 32-byte sector for every other block of config 4 -- and 256-byte
+// flushes that start there straddle sectors and 128-byte lines (measured: 0.52 of the copy rate against 0.75 for the
+// same kernel when spb * 4 is a multiple of 256).  So a lane's iteration i produces the quads of ITS row that fall
+// into the i-th 256-byte aligned segment: local quads j = 16 i - Q0 + q, q = 0..15, with Q0 = (row address % 256) / 16.
+// The lanes of a warp are therefore up to 15 quads apart in their blocks; they read their records out of a 4-stage
+// ring per block (stage s = records 16 s .. 16 s + 15, filled by cp.async one iteration ahead).  Iteration 0 (short by
+// Q0 quads, holds the header samples) and the last one or two (partial) run a plain per-quad loop.
+__global__ void __launch_bounds__(128, 4)
+ms_adpcm_staged8_kernel(const uint8_t *__restrict__ data, int blockAlign, size_t nblocks, size_t spb,
+                        const __grid_constant__ ms_coefs coefs, float *__restrict__ out, size_t stride, int *status) {
+    constexpr int NQ = MS8_NQ, C = 8;
+    extern __shared__ __align__(16) uint8_t ms8_smem[];
+    float4 *stage_all = reinterpret_cast<float4 *>(ms8_smem);            // [4 warps][32 rows][NQ], XOR-swizzled (stage_put)
+    uint8_t *rec_all = ms8_smem + 4 * 32 * NQ * 16;                      // [4 warps][4 blocks][MS8_BLK_PITCH]
+    uintptr_t *rowp_all = reinterpret_cast<uintptr_t *>(rec_all + 4 * 4 * MS8_BLK_PITCH);   // [4 warps][32]: row address, 0 = no chain
+    int *adapt_s = reinterpret_cast<int *>(rowp_all + 4 * 32);           // [48]
+    if (threadIdx.x < 16) adapt_s[threadIdx.x * 3] = c_ms_adapt[(threadIdx.x - 8) & 15];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *st = stage_all + warp * 32 * NQ;
+    uintptr_t *rowp = rowp_all + warp * 32;
+    uint8_t *rec_w = rec_all + warp * 4 * MS8_BLK_PITCH;
+    const size_t ntiles = (nblocks + 3) / 4;
+    const int ncoef = coefs.n;
+    const int nquads = (int)(spb / 4);
+    const int nstage = (nquads + NQ - 1) / NQ;                           // record stages of a block
+    const int M = nquads / NQ;                                           // iterations 1 .. M - 1 are full for every lane
+    // shared-window address of adapt[0], opaque so that it is held in a register instead of being rebuilt per quad
+    uint32_t adapt_mid = (uint32_t)__cvta_generic_to_shared(adapt_s + 24);
+    asm volatile("mov.u32 %0, %0;" : "+r"(adapt_mid));
+    const int c = lane & 7, bl = lane >> 3;                              // channel, block within the tile
+    const int cs = 8 * (c >> 1) + ((c & 1) ? 0 : 4);                     // bit offset of the chain's nibble in a frame word
+    uint32_t mul = 1u << (28 - cs);
+    asm volatile("mov.u32 %0, %0;" : "+r"(mul));                         // opaque: keeps w * mul an IMAD, not a shift on the ALU pipe
+    const uint8_t *rb = rec_w + bl * MS8_BLK_PITCH;                      // my block's record ring
+    for (size_t tile = (size_t)blockIdx.x * 4 + warp; tile < ntiles; tile += (size_t)gridDim.x * 4) {
+        const bool live = tile * 4 + (size_t)bl < nblocks;               // surplus lanes shadow the last block, write nothing
+        const size_t b = min(tile * 4 + (size_t)bl, nblocks - 1);
+        float *orow = out + (size_t)c * stride + b * spb;
+        const int Q0 = (int)(((uintptr_t)orow & 255) >> 4);
+        rowp[lane] = live ? (uintptr_t)orow : 0;
+        const uint8_t *blk = data + b * (size_t)blockAlign;
+        // staging: chunk k = lane + 32 h covers record k % 16 of a stage of block k / 16 of the tile
+        const uint8_t *src[2];
+        uint8_t *dst[2];
+        int rec_of[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int k = lane + 32 * h;
+            const size_t kb = min(tile * 4 + (size_t)(k >> 4), nblocks - 1);
+            rec_of[h] = k & 15;
+            src[h] = data + kb * (size_t)blockAlign + 16 * (3 + rec_of[h]);
+            dst[h] = rec_w + (k >> 4) * MS8_BLK_PITCH + 16 * rec_of[h];
+        }
+        auto issue = [&](int s) {
+            if (s < nstage) {
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    if (NQ * s + rec_of[h] < nquads) {
+                        cp_async16(dst[h] + (s & 3) * (16 * NQ), src[h] + (size_t)s * (16 * NQ));
+                        if ((s & 3) == 0) cp_async16(dst[h] + MS8_RING, src[h] + (size_t)s * (16 * NQ));   // the mirror
+                    }
+            }
+            cp_async_commit();
+        };
+        issue(0);
+        int pi = blk[c];
+        if (pi >= ncoef) { atomicOr(status, AUKIT_DEVERR_MS_PREDICTOR); pi = 0; }
+        const int c1 = coefs.c1[pi], c2 = coefs.c2[pi];
+        auto rd16 = [&](size_t off) { return (int)(int16_t)((uint32_t)blk[off] | ((uint32_t)blk[off + 1] << 8)); };
+        int delta = rd16((size_t)C + 2 * (size_t)c);
+        int u1 = rd16(3 * (size_t)C + 2 * (size_t)c) + 32768;
+        int u2 = rd16(5 * (size_t)C + 2 * (size_t)c) + 32768;
+        const bool narrow = (abs(c1) + abs(c2)) <= 16384;                // |u1 c1 + u2 c2 + kc| < 2^31
+        const int kc = (int)((1u << 23) - 32768u * (unsigned)(c1 + c2)); // (s1 c1 + s2 c2) + 2^23 = u1 c1 + u2 c2 + kc
+        ms_state gs;
+        gs.big = 0;
+        auto fast = [&](int nib) -> float {
+            const int t = u1 * c1 + (u2 * c2 + kc);
+            const int u = __vimin_s32_relu((t >> 8) + nib * delta, 65535);      // A:1321-1322, both clamps
+            u2 = u1; u1 = u;
+            int ad;
+            asm("ld.shared.s32 %0, [%1];" : "=r"(ad) : "r"(adapt_mid + (uint32_t)(nib * 12)));
+            delta = max((ad * delta) >> 8, 16);                                 // A:1324
+            const float x = __int_as_float(u + 0x4B000000);                     // 2^23 + u
+            const float lo = __fmaf_rn(x, 1.0f / 32768.0f, -257.0f);            // (u - 32768) / 32768, exact
+            return __fmaf_rn(__saturatef(lo), (1.0f / (32767.0f * 32768.0f)) * 32768.0f, lo);   // s16_to_float's FMA
+        };
+        auto general = [&](int nib) -> float {
+            gs.s1 = u1 - 32768; gs.s2 = u2 - 32768; gs.delta = delta;
+            const float v = ms_general_step(&gs, nib, c1, c2);
+            u1 = gs.s1 + 32768; u2 = gs.s2 + 32768; delta = gs.delta;
+            return v;
+        };
+        auto nibs = [&](const uint8_t *rp, int (&n)[4]) {
+            const uint4 r = *reinterpret_cast<const uint4 *>(rp);
+            n[0] = (int)(r.x * mul) >> 28; n[1] = (int)(r.y * mul) >> 28;
+            n[2] = (int)(r.z * mul) >> 28; n[3] = (int)(r.w * mul) >> 28;
+        };
+        // the fast arithmetic is exact for a quad that starts with -65535 < delta < 2^14 (delta <= 3^4 * 2^14 inside it)
+        auto quick = [&]() { return (unsigned)(delta + 65535) < (unsigned)(16384 + 65535); };
+        // local quads [j0 + qa, j0 + qb) into slots [qa, qb), each with its own validity test
+        auto checked = [&](int j0, int qa, int qb) {
+            for (int q = qa; q < qb; q++) {
+                const int j = j0 + q;
+                int n[4];
+                nibs(rb + ((16 * j) & (MS8_RING - 1)), n);
+                const bool qk = narrow && quick();
+                float4 v;
+                if (j == 0) { v.x = s16_to_float(u2 - 32768); v.y = s16_to_float(u1 - 32768); }   // the header samples lead (A:1312-1315)
+                else if (qk) { v.x = fast(n[0]); v.y = fast(n[1]); }
+                else { v.x = general(n[0]); v.y = general(n[1]); }
+                if (qk) { v.z = fast(n[2]); v.w = fast(n[3]); }
+                else { v.z = general(n[2]); v.w = general(n[3]); }
+                stage_put<NQ>(st, lane, q, v);
+            }
+        };
+        const int niter = (nquads + 15 + NQ - 1) / NQ;                   // segments a row can touch (Q0 <= 15)
+        for (int i = 0; i < niter; i++) {
+            issue(i + 1);
+            cp_async_wait<1>();
+            __syncwarp();                                                // every lane's chunks of stages <= i have landed
+            const int j0 = NQ * i - Q0;                                  // local quad of slot 0
+            if (i >= 1 && i < M && narrow) {
+                // straight line: 16 quads, no branch; `bad` collects the per-quad validity tests
+                const int su1 = u1, su2 = u2, sdelta = delta;
+                const uint8_t *rp = rb + ((16 * j0) & (MS8_RING - 1));   // 16 records from here never wrap (mirror)
+                bool bad = false;
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    int n[4];
+                    nibs(rp + 16 * q, n);
+                    bad |= (unsigned)delta >= 16384u;                    // delta >= 16 after the first step of a block
+                    float4 v;
+                    v.x = fast(n[0]); v.y = fast(n[1]); v.z = fast(n[2]); v.w = fast(n[3]);
+                    stage_put<NQ>(st, lane, q, v);
+                }
+                if (bad) {
+                    u1 = su1; u2 = su2; delta = sdelta;
+                    checked(j0, 0, NQ);
+                }
+                __syncwarp();
+                // transposed flush: lanes 0..15 / 16..31 write the 16 pieces of rows 2k / 2k + 1 -- whole aligned 256-byte segments
+                const int q = lane & 15;
+#pragma unroll
+                for (int k = 0; k < NQ; k++) {
+                    const int r = 2 * k + (lane >> 4);
+                    const float4 v = st[r * NQ + (q ^ stage_swz<NQ>(r))];
+                    const uintptr_t p = rowp[r];
+                    if (p) stg_stream(reinterpret_cast<float4 *>((p & ~(uintptr_t)255) + (size_t)i * (16 * NQ)) + q, v);
+                }
+            } else {
+                const int qa = max(0, -j0), qb = min(NQ, nquads - j0);
+                if (qb > qa) checked(j0, qa, qb);
+                __syncwarp();
+                const int q = lane & 15;
+                for (int k = 0; k < NQ; k++) {
+                    const int r = 2 * k + (lane >> 4);
+                    const float4 v = st[r * NQ + (q ^ stage_swz<NQ>(r))];
+                    const uintptr_t p = rowp[r];
+                    const int j = NQ * i - (int)((p & 255) >> 4) + q;    // row r's local quad in slot q
+                    if (p && j >= 0 && j < nquads) stg_stream(reinterpret_cast<float4 *>(p) + j, v);
+                }
+            }
+            __syncwarp();                                                // staging tile and this iteration's records are free again
+        }
+        cp_async_wait<0>();
+    }
+}
+
+constexpr size_t MS8_SMEM = 4 * 32 * MS8_NQ * 16 + 4 * 4 * MS8_BLK_PITCH + 4 * 32 * sizeof(uintptr_t) + 48 * sizeof(int);
+
 }  // namespace
 
 extern "C" size_t aukit_ima_adpcm_wav_frames(size_t nbytes, int blockAlign, int channels, int dialect) {
@@ -649,21 +877,16 @@ extern "C" int aukit_cuda_dev_ima_adpcm_wav(aukit_ctx *ctx, const void *d_in, si
     if (channels > 1 && out_stride < frames) return aukit_fail("aukit_cuda: out_stride < frames");
     const int word_aligned = ((uintptr_t)d_in % 4 == 0) && (blockAlign % 4 == 0);
     const int threads = 128;
-    unsigned grid = aukit_grid(nblocks * (size_t)channels, threads, (size_t)ctx->num_sms * 64);
-    if (const char *g = getenv("AUKIT_ADPCM_CTAS_PER_SM")) grid = aukit_grid(nblocks * (size_t)channels, threads, (size_t)ctx->num_sms * atoi(g));
+    const unsigned grid = aukit_grid(nblocks * (size_t)channels, threads, (size_t)ctx->num_sms * 64);
     const int out_aligned = ((uintptr_t)d_out % 16 == 0) && (out_stride % 4 == 0);
-    if (mode != IMA_LITERAL_MONO && word_aligned && out_aligned && groups > 0 && !getenv("AUKIT_DISABLE_TILED_ADPCM")) {
-        const char *e = getenv("AUKIT_ADPCM_NQ");
-        const int nq = e ? atoi(e) : 16;
-#define AUKIT_IMA_TILED(NQ, MB)                                                                                              \
-    ima_wav_tiled_kernel<NQ, MB><<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels, \
-                                                                    nblocks, spb, groups, d_out, out_stride, ctx->d_status)
-        if (nq >= 16) AUKIT_IMA_TILED(16, 4);
-        else if (nq >= 8) AUKIT_IMA_TILED(8, 8);
-        else AUKIT_IMA_TILED(4, 9);
-#undef AUKIT_IMA_TILED
+    // AUKIT_DISABLE_TILED_ADPCM=1 (diagnostic, tests): the chain-per-lane kernel for everything
+    if (mode != IMA_LITERAL_MONO && word_aligned && groups > 0 && (uintptr_t)d_out % 32 == 0 && out_stride % 8 == 0 &&
+        !getenv("AUKIT_DISABLE_TILED_ADPCM")) {
+        const unsigned g5 = aukit_grid(nblocks * (size_t)channels, threads, (size_t)ctx->num_sms * 5);
+        ima_wav_aligned_kernel<<<g5, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels, nblocks, spb,
+                                                              groups, d_out, out_stride, ctx->d_status);
         ctx->launches++;
-        return aukit_cuda_check(cudaGetLastError(), "ima_wav_tiled_kernel launch");
+        return aukit_cuda_check(cudaGetLastError(), "ima_wav_aligned_kernel launch");
     }
     ima_wav_kernel<<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), nbytes, blockAlign, channels,
                                                       mode, nblocks, spb, groups, d_out, out_stride, ctx->d_status,
@@ -699,20 +922,27 @@ extern "C" int aukit_cuda_dev_msadpcm(aukit_ctx *ctx, const void *d_in, size_t n
     const size_t spb = 2 + (bA - 7 * C) * 2 / C;
     if (channels > 1 && out_stride < nblocks * spb) return aukit_fail("aukit_cuda: out_stride < frames");
     const int threads = 128;
-    unsigned grid = aukit_grid(nblocks * C, threads, (size_t)ctx->num_sms * 64);
-    if (const char *g = getenv("AUKIT_ADPCM_CTAS_PER_SM")) grid = aukit_grid(nblocks * C, threads, (size_t)ctx->num_sms * atoi(g));
+    const unsigned grid = aukit_grid(nblocks * C, threads, (size_t)ctx->num_sms * 64);
     const int vec_ok = ((uintptr_t)d_out % 16 == 0) && (out_stride % 4 == 0);
+    // diagnostic switches (tests hold the three implementations to the same bits): AUKIT_DISABLE_TILED_ADPCM=1 -> the
+    // chain-per-lane kernel for everything, AUKIT_DISABLE_STAGED_ADPCM=1 -> the register-staged tiled kernel for 8 channels too
     if (vec_ok && spb % 4 == 0 && !getenv("AUKIT_DISABLE_TILED_ADPCM")) {
         const bool rec_aligned = ((uintptr_t)d_in % 16 == 0) && (bA % (2 * C) == 0);
         const int tc = (rec_aligned && (channels == 1 || channels == 2 || channels == 4 || channels == 8)) ? channels : 0;
-        const char *e = getenv("AUKIT_ADPCM_NQ");
-        const int nq = e ? atoi(e) : 16;
-#define AUKIT_MS_LAUNCH(TC, NQ)                                                                                          \
-    ms_adpcm_tiled_kernel<TC, NQ><<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels, \
+        if (tc == 8 && bA % 16 == 0 && dialect != AUKIT_DIALECT_LITERAL && !getenv("AUKIT_DISABLE_STAGED_ADPCM")) {
+            // per device, and a process may hold contexts on several: set on every launch (microseconds against a multi-ms kernel)
+            if (aukit_cuda_check(cudaFuncSetAttribute(ms_adpcm_staged8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MS8_SMEM),
+                                 "cudaFuncSetAttribute")) return -1;
+            const unsigned g4 = aukit_grid(nblocks * C, threads, (size_t)ctx->num_sms * 4);
+            ms_adpcm_staged8_kernel<<<g4, threads, MS8_SMEM, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, nblocks, spb, h,
+                                                                          d_out, out_stride, ctx->d_status);
+            ctx->launches++;
+            return aukit_cuda_check(cudaGetLastError(), "ms_adpcm_staged8_kernel launch");
+        }
+#define AUKIT_MS_TILED(TC)                                                                                               \
+    ms_adpcm_tiled_kernel<TC, 16><<<grid, threads, 0, ctx->stream>>>(static_cast<const uint8_t *>(d_in), blockAlign, channels, \
                                                                  dialect == AUKIT_DIALECT_LITERAL && channels == 1, nblocks, \
                                                                  spb, h, d_out, out_stride, ctx->d_status)
-#define AUKIT_MS_TILED(TC)                                                                                               \
-    if (nq >= 16) AUKIT_MS_LAUNCH(TC, 16); else if (nq >= 8) AUKIT_MS_LAUNCH(TC, 8); else AUKIT_MS_LAUNCH(TC, 4)
         switch (tc) {
             case 8: AUKIT_MS_TILED(8); break;
             case 4: AUKIT_MS_TILED(4); break;
@@ -720,7 +950,6 @@ extern "C" int aukit_cuda_dev_msadpcm(aukit_ctx *ctx, const void *d_in, size_t n
             case 1: AUKIT_MS_TILED(1); break;
             default: AUKIT_MS_TILED(0); break;
         }
-#undef AUKIT_MS_LAUNCH
 #undef AUKIT_MS_TILED
         ctx->launches++;
         return aukit_cuda_check(cudaGetLastError(), "ms_adpcm_tiled_kernel launch");

@@ -135,11 +135,14 @@ def test_msadpcm(ak, O, channels, block_align, dialect, tame):
 
 @pytest.mark.parametrize("channels,block_align,nblocks,tame", [
     (1, 256, 37, True), (1, 258, 5, False), (2, 256, 33, True), (2, 1028, 7, False), (4, 512, 9, True), (4, 520, 3, False),
-    (8, 2048, 5, True), (8, 2064, 4, False), (3, 300, 11, True), (5, 1000, 3, False), (6, 516, 7, True), (2, 254, 9, True)])
+    (8, 2048, 5, True), (8, 2064, 4, False), (3, 300, 11, True), (5, 1000, 3, False), (6, 516, 7, True), (2, 254, 9, True),
+    (8, 8192, 9, True), (8, 8192, 6, False), (8, 112, 21, True), (8, 80, 3, True), (8, 1040, 14, False), (8, 8240, 5, True)])
 def test_msadpcm_tiled_and_chain_kernels_agree(ak, O, monkeypatch, channels, block_align, nblocks, tame):
-    """The warp-tiled kernel (aligned record loads for 1/2/4/8 channels, byte reads otherwise), the
+    """The staged 8-channel kernel (records through shared memory, speculated straight-line periods, output segments
+    aligned in absolute address: rows that start at every 16-byte phase of a 256-byte segment, blocks shorter than one
+    segment), the warp-tiled kernel (aligned record loads for 1/2/4/8 channels, byte reads otherwise), the
     chain-per-lane kernel and the oracle agree bit for bit; chains not a multiple of 32, partial last
-    flush, deltas that leave the 32-bit fast path mid-block."""
+    flush, deltas that leave the 32-bit fast path mid-block (the speculated period is redone)."""
     raw = ms_blocks(nblocks, block_align, channels, seed=7 * block_align + channels, tame=tame)
     blocks = raw.reshape(nblocks, block_align)
     blocks[::3, channels:3 * channels] = np.array([0xFF, 0x7F] * channels, dtype=np.uint8)      # delta 32767 in the header
@@ -147,12 +150,15 @@ def test_msadpcm_tiled_and_chain_kernels_agree(ak, O, monkeypatch, channels, blo
     ref = O.msadpcm(raw, block_align, channels, None, 1)
     got = ak.msadpcm(raw, block_align, channels, 44100, None, 1).numpy()
     _check(got, ref)
+    monkeypatch.setenv("AUKIT_DISABLE_STAGED_ADPCM", "1")
+    _check(ak.msadpcm(raw, block_align, channels, 44100, None, 1).numpy(), ref)
     monkeypatch.setenv("AUKIT_DISABLE_TILED_ADPCM", "1")
     _check(ak.msadpcm(raw, block_align, channels, 44100, None, 1).numpy(), ref)
 
 
 @pytest.mark.parametrize("channels,block_align,nblocks", [(1, 256, 37), (1, 36, 70), (2, 264, 33), (2, 1024, 3), (3, 600, 9),
-                                                          (8, 2048, 5), (8, 96, 13), (5, 40, 7)])
+                                                          (8, 2048, 5), (8, 96, 13), (5, 40, 7), (8, 8192, 7), (8, 8224, 5), (8, 64, 40),
+                                                          (6, 1560, 9)])
 def test_ima_tiled_and_chain_kernels_agree(ak, O, monkeypatch, channels, block_align, nblocks):
     """Transition-table + transposed-store kernel vs the chain-per-lane kernel vs the oracle: odd and
     even group counts, a single group, chains not a multiple of 32, every step index reached."""
