@@ -155,6 +155,8 @@ SIGNATURES = {
     "aukit_cuda_group_comm": (_P, [_P, _I]),
     "aukit_cuda_group_normalize": (_I, [_P, C.POINTER(_P), _D, _I]),
     "aukit_cuda_group_preload": (_I, [_P, C.POINTER(PipelineDesc), _P, _SZ, _D, _P]),
+    "aukit_cuda_group_preload_audio": (_I, [_P, _P, C.POINTER(PipelineDesc), _P, _SZ, _D, _PP]),
+    "aukit_cuda_preload_audio": (_I, [_P, C.POINTER(PipelineDesc), _P, _SZ, _D, _PP]),
     "aukit_block_shard": (_I, [_U64, _I, _I, C.POINTER(_U64), C.POINTER(_U64)]),
     "aukit_ima_adpcm_wav_frames": (_SZ, [_SZ, _I, _I, _I]),
     "aukit_msadpcm_frames": (_SZ, [_SZ, _I, _I]),

@@ -718,8 +718,9 @@ class Group:
         self.contexts = [Context(_borrowed=self.lib.aukit_cuda_group_ctx(h, i)) for i in range(self.size)]
 
     def preload(self, data, bitDepth=16, dataType="signed", channels=2, sampleRate=44100, targetRate=48000,
-                interpolation=None, mono=True, peakAmplitude=0.8, bigEndian=False) -> np.ndarray:
-        """preload() time-sharded over the group's GPUs: same arguments, same bits as on one GPU."""
+                interpolation=None, mono=True, peakAmplitude=0.8, bigEndian=False, owner: Optional[Context] = None):
+        """preload() time-sharded over the group's GPUs: same arguments, same bits as on one GPU.  Returns a host array,
+        or -- with `owner` (a Context) -- one device-resident Audio on that context (what the Lua module's cu.preload does)."""
         interpolation = interpolation or defaultInterpolation
         if interpolation not in _INTERPS:
             raise AukitError("bad argument #2 (invalid interpolation type)")
@@ -735,6 +736,10 @@ class Group:
         n_out = int(self.lib.aukit_resample_out_len(frames, float(sampleRate), float(targetRate)))
         d = PipelineDesc(bitDepth, _DATATYPES[dataType], channels, int(bool(bigEndian)), float(sampleRate), float(targetRate),
                          _INTERPS[interpolation], int(bool(mono)), frames, 0, frames, 0, n_out)
+        if owner is not None:                             # gathered device-to-device into one Audio on `owner`'s device
+            h = C.c_void_p()
+            _lib.check(self.lib.aukit_cuda_group_preload_audio(self.handle, owner.handle, C.byref(d), p, n, float(peakAmplitude), C.byref(h)))
+            return Audio(owner, h, {}, {"bitDepth": bitDepth, "dataType": dataType})
         out = np.empty((1 if mono else channels, n_out), dtype=np.float32)
         _lib.check(self.lib.aukit_cuda_group_preload(self.handle, C.byref(d), p, n, float(peakAmplitude), C.c_void_p(out.ctypes.data)))
         return out

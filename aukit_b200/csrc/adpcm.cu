@@ -631,7 +631,7 @@ ms_adpcm_tiled_kernel(const uint8_t *__restrict__ data, int blockAlign, int C, i
 //   * output segments are aligned in absolute address (below) and leave through the transposed, XOR-swizzled staging
 //     tile of the kernels above (a per-lane cp.async.bulk shared -> global was tried: UBLKCP takes uniform operands,
 //     so ptxas serialises the 32 lanes in a loop and the wait for its reads cost 27 % of the samples).
-// Same integers as the kernels above at every step (tests: staged == tiled == chain == oracle).
+// Same integers as the kernels above at every step (tests hold the staged, tiled and chain-per-lane kernels to the same bits).
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }

@@ -666,6 +666,27 @@ extern "C" int aukit_cuda_pipeline_host(aukit_ctx *ctx, const aukit_pipeline_des
     return rc;
 }
 
+// auplay's chain (A:1049 -> A:653 -> A:677 -> A:3431) from a host string to a device-resident Audio: what the Lua module's
+// cu.preload returns on a one-GPU box (aukit_cuda_group_preload_audio is the several-GPU twin).
+extern "C" int aukit_cuda_preload_audio(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *h_in, size_t nbytes,
+                                        double peakAmplitude, aukit_audio **out) {
+    if (!ctx || !p || !out) return aukit_fail("aukit_cuda: null argument");
+    const size_t need = p->in_avail * (size_t)p->channels * (size_t)(p->bitDepth / 8);
+    if (nbytes < need) return aukit_fail("aukit_cuda: host buffer smaller than in_avail frames");
+    void *d_in = nullptr;
+    if (aukit_upload_bytes(ctx, h_in, need, &d_in)) return -1;
+    aukit_audio *a = nullptr;
+    if (aukit_audio_alloc(ctx, p->mono ? 1 : p->channels, p->n_out, p->dstRate, &a)) { aukit_dev_free(ctx, d_in); return -1; }
+    int rc = aukit_cuda_check(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(float), ctx->stream), "memset");
+    if (!rc) rc = aukit_cuda_dev_pipeline_peak(ctx, p, d_in, ctx->d_scratch);
+    if (!rc) rc = aukit_cuda_dev_pipeline_apply(ctx, p, d_in, peakAmplitude, ctx->d_scratch, a->data, a->stride);
+    aukit_dev_free(ctx, d_in);
+    if (!rc) rc = aukit_cuda_synchronize(ctx);
+    if (rc) { aukit_cuda_audio_free(ctx, a); return rc; }
+    *out = a;
+    return 0;
+}
+
 // ------------------------------------------------------------------ ADPCM block-range shards
 extern "C" int aukit_block_shard(uint64_t nblocks, int world, int rank, uint64_t *first, uint64_t *count) {
     if (!first || !count) return aukit_fail("aukit_cuda: null argument");

@@ -309,9 +309,10 @@ extern "C" int aukit_cuda_group_normalize(aukit_group *g, aukit_audio *const *sh
 // its interpolation halo, local peak passes, the MAX exchange, local apply passes, results gathered into
 // h_out[c * n_out + i].  `whole` describes the unsharded call (in_first = 0, in_avail = n_in_total, out_first = 0,
 // n_out = floor(n_in_total * ratio)).  Bit-identical to the same call on one GPU.
-extern "C" int aukit_cuda_group_preload(aukit_group *g, const aukit_pipeline_desc *whole, const void *h_in, size_t nbytes,
-                                        double peakAmplitude, float *h_out) {
-    if (!g || !whole || !h_out) return aukit_fail("aukit_cuda: null argument");
+// dst[c * dst_pitch + i]: host memory (kind = DeviceToHost) or device memory of any device (kind = Default: peer copies)
+static int group_preload_into(aukit_group *g, const aukit_pipeline_desc *whole, const void *h_in, size_t nbytes,
+                              double peakAmplitude, float *dst, size_t dst_pitch, cudaMemcpyKind kind) {
+    if (!g || !whole || !dst) return aukit_fail("aukit_cuda: null argument");
     device_guard guard;
     const size_t FB = (size_t)whole->channels * (size_t)(whole->bitDepth / 8);
     if (FB == 0 || nbytes < whole->n_in_total * FB) return aukit_fail("aukit_cuda: host buffer smaller than n_in_total frames");
@@ -369,8 +370,8 @@ extern "C" int aukit_cuda_group_preload(aukit_group *g, const aukit_pipeline_des
         if ((rc = aukit_cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice"))) break;
         if ((rc = aukit_cuda_dev_pipeline_apply(ctx, &p.d, p.d_in, peakAmplitude, aukit_cuda_comm_values(g->comm[i]), p.d_out, p.stride))) break;
         if (p.d.n_out)
-            rc = aukit_cuda_check(cudaMemcpy2DAsync(h_out + p.d.out_first, (size_t)n_out * sizeof(float), p.d_out, p.stride * sizeof(float),
-                                                    p.d.n_out * sizeof(float), (size_t)out_ch, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+            rc = aukit_cuda_check(cudaMemcpy2DAsync(dst + p.d.out_first, dst_pitch * sizeof(float), p.d_out, p.stride * sizeof(float),
+                                                    p.d.n_out * sizeof(float), (size_t)out_ch, kind, ctx->stream), "gather");
     }
     for (int i = 0; i < W; i++) {
         cudaSetDevice(g->ctx[i]->device);
@@ -380,4 +381,30 @@ extern "C" int aukit_cuda_group_preload(aukit_group *g, const aukit_pipeline_des
         if (!rc && s) rc = s;
     }
     return rc;
+}
+
+extern "C" int aukit_cuda_group_preload(aukit_group *g, const aukit_pipeline_desc *whole, const void *h_in, size_t nbytes,
+                                        double peakAmplitude, float *h_out) {
+    if (!whole) return aukit_fail("aukit_cuda: null argument");
+    return group_preload_into(g, whole, h_in, nbytes, peakAmplitude, h_out,
+                              (size_t)aukit_resample_out_len(whole->n_in_total, whole->srcRate, whole->dstRate), cudaMemcpyDeviceToHost);
+}
+
+// The same, gathered into ONE device-resident Audio that belongs to `owner` (any context, normally the caller's own on
+// device 0): the shards travel device to device.  This is what the Lua module's cu.preload returns on a box with several GPUs.
+extern "C" int aukit_cuda_group_preload_audio(aukit_group *g, aukit_ctx *owner, const aukit_pipeline_desc *whole, const void *h_in,
+                                              size_t nbytes, double peakAmplitude, aukit_audio **out) {
+    if (!g || !owner || !whole || !out) return aukit_fail("aukit_cuda: null argument");
+    const uint64_t n_out = aukit_resample_out_len(whole->n_in_total, whole->srcRate, whole->dstRate);
+    aukit_audio *a = nullptr;
+    {
+        device_guard guard;
+        if (aukit_cuda_check(cudaSetDevice(owner->device), "cudaSetDevice")) return -1;
+        if (aukit_audio_alloc(owner, whole->mono ? 1 : whole->channels, (size_t)n_out, whole->dstRate, &a)) return -1;
+        if (aukit_cuda_synchronize(owner)) { aukit_cuda_audio_free(owner, a); return -1; }   // the allocation is stream-ordered on owner's stream
+    }
+    const int rc = group_preload_into(g, whole, h_in, nbytes, peakAmplitude, a->data, a->stride, cudaMemcpyDefault);
+    if (rc) { device_guard guard; cudaSetDevice(owner->device); aukit_cuda_audio_free(owner, a); return rc; }
+    *out = a;
+    return 0;
 }

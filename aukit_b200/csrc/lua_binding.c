@@ -401,6 +401,59 @@ static int l_write(lua_State *L) {
     return 0;
 }
 
+/* cu.device_count() -> number of GPUs cu.preload spreads a buffer over */
+static aukit_group *g_group; /* created by the first cu.preload on a box with more than one GPU */
+static int g_ndev = -1;
+
+static int device_count(lua_State *L) {
+    if (g_ndev < 0) {
+        ctx(L);
+        g_ndev = 1;
+        aukit_group *g = NULL;
+        if (aukit_cuda_group_create(NULL, 0, &g) == 0) {
+            g_ndev = aukit_cuda_group_size(g);
+            if (g_ndev > 1) g_group = g; else aukit_cuda_group_destroy(g);
+        }
+    }
+    return g_ndev;
+}
+
+static int l_device_count(lua_State *L) { lua_pushinteger(L, device_count(L)); return 1; }
+
+/* cu.preload(data, bitDepth, dataType, channels, sampleRate, targetRate, interpolation, mono, peakAmplitude, bigEndian)
+ * -> audio: auplay.lua:12-27 (aukit.pcm -> :resample -> :mono -> effects.normalize) as the two fused passes on the host
+ * string; time-sharded over every visible GPU when there are several (same bits as one GPU). */
+static int l_preload(lua_State *L) {
+    size_t n;
+    const char *d = luaL_checklstring(L, 1, &n);
+    aukit_pipeline_desc p;
+    memset(&p, 0, sizeof p);
+    p.bitDepth = (int)luaL_optinteger(L, 2, 16);
+    p.dataType = (int)luaL_optinteger(L, 3, 0);
+    p.channels = (int)luaL_optinteger(L, 4, 2);
+    p.srcRate = luaL_optnumber(L, 5, 44100);
+    p.dstRate = luaL_optnumber(L, 6, 48000);
+    p.interpolation = (int)luaL_optinteger(L, 7, 1);
+    p.mono = optbool(L, 8, 1);
+    const double peak = luaL_optnumber(L, 9, 1.0);
+    p.bigEndian = optbool(L, 10, 0);
+    if (p.bitDepth != 8 && p.bitDepth != 16 && p.bitDepth != 24 && p.bitDepth != 32) return luaL_error(L, "bad argument #2 (invalid bit depth)");
+    if (p.dataType < 0 || p.dataType > 2) return luaL_error(L, "bad argument #3 (invalid data type)");
+    if (p.dataType == 2 && p.bitDepth != 32) return luaL_error(L, "bad argument #2 (float audio must have 32-bit depth)");
+    if (p.channels < 1) return luaL_error(L, "number outside of range (expected %d to be at least 1)", p.channels);
+    const size_t fb = (size_t)p.channels * (size_t)(p.bitDepth / 8);
+    if (n % fb) return luaL_error(L, "bad argument #1 (uneven amount of data per channel)");
+    p.n_in_total = n / fb;
+    p.in_first = 0; p.in_avail = (size_t)p.n_in_total;
+    p.out_first = 0; p.n_out = (size_t)aukit_resample_out_len(p.n_in_total, p.srcRate, p.dstRate);
+    aukit_audio *a = NULL;
+    aukit_ctx *c = ctx(L);
+    const int rc = device_count(L) > 1 ? aukit_cuda_group_preload_audio(g_group, c, &p, d, n, peak, &a)
+                                       : aukit_cuda_preload_audio(c, &p, d, n, peak, &a);
+    if (rc) return fail(L);
+    return push_audio(L, a);
+}
+
 static int l_gc(lua_State *L) {
     audio_ud *u = (audio_ud *)luaL_checkudata(L, 1, AUDIO_MT);
     if (u->a) { aukit_cuda_audio_free(g_ctx, u->a); u->a = NULL; }
@@ -412,7 +465,7 @@ static const luaL_Reg funcs[] = {
     {"wav", l_wav}, {"new", l_new}, {"resample", l_resample}, {"mono", l_mono}, {"concat", l_concat},
     {"au", l_au}, {"aiff", l_aiff}, {"amplify", l_amplify}, {"invert", l_invert}, {"fade", l_fade}, {"delay", l_delay}, {"center", l_center}, {"lowpass", l_lowpass}, {"highpass", l_highpass}, {"pcm_out", l_pcm_out}, {"pcm_bytes", l_pcm_bytes}, {"normalize", l_normalize}, {"channels", l_channels}, {"sample_rate", l_sample_rate},
     {"frames", l_frames}, {"read", l_read}, {"write", l_write}, {"set_sample_rate", l_set_sample_rate},
-    {"stream_chunk", l_stream_chunk}, {NULL, NULL}};
+    {"stream_chunk", l_stream_chunk}, {"preload", l_preload}, {"device_count", l_device_count}, {NULL, NULL}};
 
 int luaopen_aukit_cuda(lua_State *L) {
     luaL_newmetatable(L, AUDIO_MT);

@@ -5,7 +5,7 @@
 -- the C module `aukit_cuda` (luaopen_aukit_cuda, csrc/lua_binding.c -> libaukit_cuda.so).
 -- auplay.lua's load -> :resample(48000) -> :mono() -> effects.normalize(mono, 0.8) runs unchanged.
 --
--- In scope (device-backed): aukit.pcm, aukit.g711, aukit.adpcm, aukit.msadpcm, aukit.wav, aukit.au, aukit.aiff, aukit.new,
+-- In scope (device-backed): aukit.preload (the fused auplay chain, all GPUs of the box), aukit.pcm, aukit.g711, aukit.adpcm, aukit.msadpcm, aukit.wav, aukit.au, aukit.aiff, aukit.new,
 --   Audio:len/channels/resample (none, linear, cubic, sinc)/mono/concat/pcm/stream/wav,
 --   aukit.effects.amplify/normalize/lowpass/highpass/invert/fade/delay/center, aukit.defaultInterpolation.
 -- Everything else of the reference (players, streams, FLAC/QOA/DFPWM, editing ops, writers) is out of
@@ -76,7 +76,9 @@ local data_mt = {
     __len = function(self) return cu.channels(self._h) end,
     __index = function(self, c)
         if type(c) ~= "number" or c < 1 or c > cu.channels(self._h) then return nil end
-        return setmetatable({_h = self._h, _c = c}, channel_mt)
+        local ch = setmetatable({_h = self._h, _c = c}, channel_mt)
+        rawset(self, c, ch)                      -- kept: a loop over audio.data[c][i] then reads one 4096-sample block per 4096 samples
+        return ch
     end
 }
 
@@ -93,7 +95,14 @@ local function handle(audio)
     if type(audio.sampleRate) == "number" then cu.set_sample_rate(h, audio.sampleRate) end
     return h
 end
-local function invalidate(audio) end -- channel proxies are created per access; nothing cached on the Audio
+-- after an in-place device operation: the cached host blocks of every channel proxy are stale
+local function invalidate(audio)
+    local d = audio.data
+    for c = 1, cu.channels(d._h) do
+        local ch = rawget(d, c)
+        if ch then rawset(ch, "_cache", nil) end
+    end
+end
 
 -- ---------------------------------------------------------------------------------------------
 -- Audio methods
@@ -254,6 +263,39 @@ function aukit.adpcm(data, channels, sampleRate, topFirst, interleaved, predicto
     out.sampleRate = sampleRate
     return out
 end
+
+--- NOT in the reference: auplay.lua:12-27 -- aukit.pcm(data, ...) -> :resample(targetRate, interpolation) -> :mono()
+--- -> effects.normalize(peakAmplitude) -- as ONE call on the packed bytes (two fused GPU passes, no intermediate Audio;
+--- on a box with several GPUs the buffer is time-sharded over all of them).  Same result, within fp32 rounding, as the
+--- four reference calls; arguments and defaults are theirs (mono = true and peakAmplitude = 0.8 as auplay uses them).
+function aukit.preload(data, bitDepth, dataType, channels, sampleRate, targetRate, interpolation, mono, peakAmplitude, bigEndian)
+    expect(1, data, "string")
+    bitDepth = expect(2, bitDepth, "number", "nil") or 8
+    dataType = expect(3, dataType, "string", "nil") or "signed"
+    channels = expect(4, channels, "number", "nil") or 1
+    sampleRate = expect(5, sampleRate, "number", "nil") or 48000
+    targetRate = expect(6, targetRate, "number", "nil") or 48000
+    interpolation = expect(7, interpolation, "string", "nil") or aukit.defaultInterpolation
+    expect(8, mono, "boolean", "nil")
+    if mono == nil then mono = true end
+    peakAmplitude = expect(9, peakAmplitude, "number", "nil") or 0.8
+    expect(10, bigEndian, "boolean", "nil")
+    if bitDepth ~= 8 and bitDepth ~= 16 and bitDepth ~= 24 and bitDepth ~= 32 then error("bad argument #2 (invalid bit depth)", 2) end
+    if not DATATYPE[dataType] then error("bad argument #3 (invalid data type)", 2) end
+    if dataType == "float" and bitDepth ~= 32 then error("bad argument #2 (float audio must have 32-bit depth)", 2) end
+    if not INTERP[interpolation] then error("bad argument #7 (invalid interpolation type)", 2) end
+    expect.range(channels, 1)
+    expect.range(sampleRate, 1)
+    expect.range(targetRate, 1)
+    if #data % (channels * bitDepth / 8) ~= 0 then error("bad argument #1 (uneven amount of data per channel)", 2) end
+    local out = wrap(cu.preload(data, bitDepth, DATATYPE[dataType], channels, sampleRate, targetRate, INTERP[interpolation], mono,
+                                peakAmplitude, bigEndian or false), {}, {bitDepth = bitDepth, dataType = dataType})
+    out.sampleRate = targetRate
+    return out
+end
+
+--- Number of GPUs aukit.preload spreads a buffer over.
+function aukit.deviceCount() return cu.device_count() end
 
 --- Creates a new audio object from Microsoft ADPCM data. (A:1283)
 function aukit.msadpcm(data, blockAlign, channels, sampleRate, coefficients)

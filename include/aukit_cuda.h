@@ -296,6 +296,11 @@ int aukit_cuda_batch_resample_amplify(aukit_ctx *ctx, const void *const *h_clips
                                       int channels, int bigEndian, double dstRate, int interpolation,
                                       double multiplier, aukit_audio **out);
 
+/* Host string in, device-resident Audio out: aukit.pcm -> Audio:resample -> [Audio:mono] -> effects.normalize
+ * (A:1049, A:653, A:677, A:3431; auplay.lua:12-27) in the two fused passes.  p describes the whole call (in_first = 0,
+ * in_avail = n_in_total, out_first = 0, n_out = aukit_resample_out_len(...)). */
+int aukit_cuda_preload_audio(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *h_in, size_t nbytes,
+                             double peakAmplitude, aukit_audio **out);
 /* Host-buffer convenience = the end-to-end call (H2D + peak + apply + D2H), single device. */
 int aukit_cuda_pipeline_host(aukit_ctx *ctx, const aukit_pipeline_desc *p, const void *h_in,
                              size_t nbytes, double peakAmplitude, float *h_out);
@@ -367,6 +372,9 @@ int aukit_cuda_group_normalize(aukit_group *g, aukit_audio *const *shards, doubl
  * `whole` describes the unsharded call (in_first = 0, in_avail = n_in_total, out_first = 0).  Same bits as one GPU. */
 int aukit_cuda_group_preload(aukit_group *g, const aukit_pipeline_desc *whole, const void *h_in, size_t nbytes,
                              double peakAmplitude, float *h_out);
+/* The same, gathered device-to-device into ONE Audio owned by `owner` (any context; the Lua module passes its own). */
+int aukit_cuda_group_preload_audio(aukit_group *g, aukit_ctx *owner, const aukit_pipeline_desc *whole, const void *h_in,
+                                   size_t nbytes, double peakAmplitude, aukit_audio **out);
 
 /* ------------------------------------------------------------------ pure host helpers */
 /* floor(n_in * (dstRate/srcRate)) in double, the reference's loop bound (A:658-664). */

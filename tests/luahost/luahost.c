@@ -524,6 +524,36 @@ const char *lh_field(lua_State *L, int idx, int i) {
     return f->key;
 }
 
+/* bulk transfers for the driver: the array part of the table at idx as doubles (-1 if an element is not a number) ... */
+long lh_array_numbers(lua_State *L, int idx, double *out, long cap) {
+    value *v = slot(L, idx);
+    if (!v || v->t != LUA_TTABLE) return -1;
+    const obj *t = v->u.o;
+    if ((long)t->narr > cap) return -1;
+    for (size_t i = 0; i < t->narr; i++) {
+        if (t->arr[i].t != LUA_TNUMBER) return -1;
+        out[i] = t->arr[i].u.n;
+    }
+    return (long)t->narr;
+}
+
+/* ... and a new table {v[0], v[1], ...} pushed on the stack */
+int lh_push_number_array(lua_State *L, const double *v, long n) {
+    if (L->top >= STACK_MAX) return -1;
+    obj *o = (obj *)calloc(1, sizeof(obj));
+    if (!o) return -1;
+    o->t = LUA_TTABLE; o->refs = 1;
+    if (n > 0) {
+        o->arr = (value *)malloc(sizeof(value) * (size_t)n);
+        if (!o->arr) { free(o); return -1; }
+        o->cap = o->narr = (size_t)n;
+        for (long i = 0; i < n; i++) { o->arr[i].t = LUA_TNUMBER; o->arr[i].u.n = v[i]; }
+    }
+    value tv; tv.t = LUA_TTABLE; tv.u.o = o;
+    L->stack[L->top++] = tv;
+    return 0;
+}
+
 /* keeps the value at idx alive outside the stack (what a Lua variable holding it would do) */
 int lh_ref(lua_State *L, int idx) {
     value *v = slot(L, idx);

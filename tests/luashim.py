@@ -193,8 +193,22 @@ def make_module(ak):
             t.set(c + 1, e)
         return [t]
 
+    def l_preload(a):
+        a = list(a) + [None] * (10 - len(a))
+        data = a[0]
+        p, n = buf(data)
+        bits, ch = int(num(a[1], 16)), int(num(a[3], 2))
+        frames = n // (ch * bits // 8)
+        src, dst = float(num(a[4], 44100)), float(num(a[5], 48000))
+        d = ak.PipelineDesc(bits, int(num(a[2], 0)), ch, int(bool(num(a[9], False))), src, dst, int(num(a[6], 1)), int(bool(num(a[7], True))),
+                            frames, 0, frames, 0, int(lib.aukit_resample_out_len(frames, src, dst)))
+        out = C.c_void_p()
+        if lib.aukit_cuda_preload_audio(ctx.handle, C.byref(d), p, n, float(num(a[8], 1.0)), C.byref(out)) != 0:
+            raise LuaError(lib.aukit_cuda_last_error())
+        return [Handle(ak.Audio(ctx, out))]
+
     mod = LuaTable()
-    for name, f in {"set_sample_rate": l_set_sample_rate, "stream_chunk": l_stream_chunk, "pcm": l_pcm, "g711": l_g711, "wav": l_wav, "resample": l_resample, "mono": l_mono, "amplify": l_amplify,
+    for name, f in {"preload": l_preload, "device_count": lambda a: [1.0], "set_sample_rate": l_set_sample_rate, "stream_chunk": l_stream_chunk, "pcm": l_pcm, "g711": l_g711, "wav": l_wav, "resample": l_resample, "mono": l_mono, "amplify": l_amplify,
                     "lowpass": l_lowpass, "pcm_out": l_pcm_out, "pcm_bytes": l_pcm_bytes, "invert": simple(lib.aukit_cuda_invert, 0),
                     "fade": simple(lib.aukit_cuda_fade, 4), "delay": simple(lib.aukit_cuda_delay, 2, (None, 0.5)),
                     "center": simple(lib.aukit_cuda_center, 0), "highpass": simple(lib.aukit_cuda_highpass, 1), "au": l_au, "aiff": l_aiff, "normalize": l_normalize, "frames": l_frames, "read": l_read, "new": l_new,

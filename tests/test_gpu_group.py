@@ -34,6 +34,9 @@ def test_group_preload_equals_single_gpu(ak, O, kind):
             for _ in range(3):                                   # several exchanges: the epoch ring wraps
                 got = g.preload(pcm.tobytes(), 16, "signed", 2, 44100, 48000, "cubic", True, 0.8)
                 assert f32_equal_bits(got, whole), devs
+            a = g.preload(pcm.tobytes(), 16, "signed", 2, 44100, 48000, "cubic", True, 0.8, owner=ak.context())
+            assert a.sampleRate == 48000 and f32_equal_bits(a.numpy(), whole), devs     # gathered device to device
+            del a
         finally:
             g.close()
 

@@ -1,7 +1,9 @@
 """The Lua facade (aukit_b200/lua/aukit.lua) executed by oracle/luavm against the real CUDA library: the
 auplay.lua call chain (auplay.lua:12-27) written in Lua, unchanged from how a ComputerCraft script would
-write it, must reproduce the reference's own golden output.  The C binding (csrc/lua_binding.c) is
-replaced by tests/luashim.py because no Lua interpreter that could dlopen() it exists in the image."""
+write it, must reproduce the reference's own golden output.  Every test runs twice: with `require "aukit_cuda"`
+served by the REAL C binding (csrc/lua_binding.c -> lib/aukit_cuda.so, executed inside tests/luahost/luahost.c, a toy
+host for the Lua 5.2 C API -- no Lua interpreter that could dlopen() it exists in the image), and by tests/luashim.py,
+a Python stand-in with the same function table that reaches the library through ctypes."""
 import json
 import os
 
@@ -27,14 +29,19 @@ return out, #mono.data, mono:len(), mono.sampleRate, audio.info.dataType, audio.
 '''
 
 
-@pytest.fixture(scope="module")
-def lua(ak):
+@pytest.fixture(scope="module", params=["cbinding", "shim"])
+def lua(ak, request):
     from oracle.luavm.aukit_ref import EXPECT_LUA
     from oracle.luavm.lua import Interpreter
-    import luashim
     I = Interpreter()
     I.preload[b"cc.expect"] = lambda: I.run(EXPECT_LUA, "cc.expect")[0]
-    I.preload[b"aukit_cuda"] = lambda: luashim.make_module(ak)
+    if request.param == "cbinding":
+        import luahost
+        host = luahost.LuaHost()
+        I.preload[b"aukit_cuda"] = host.module
+    else:
+        import luashim
+        I.preload[b"aukit_cuda"] = lambda: luashim.make_module(ak)
     src = open(os.path.join(ROOT, "aukit_b200", "lua", "aukit.lua"), "rb").read()
     I.preload[b"aukit"] = lambda: I.run(src, "aukit.lua(facade)")[0]
     return I
@@ -114,3 +121,27 @@ def test_facade_audio_wav_writer(lua, ak):
     back = ak.wav(r[0])
     assert back.channels() == 2 and back.frames == 3000 and back.metadata == {"title": b"T"} or back.metadata == {"title": "T"}
     assert np.max(np.abs(back.numpy() - a.numpy())) <= 1.0 / 32767
+
+
+def test_facade_preload_is_the_four_reference_calls(lua, O):
+    """aukit.preload (the fused chain; through the C binding it also takes the all-GPUs path when the box has several)
+    against the same chain written with the reference's four calls, and against the oracle."""
+    pcm = tone_s16(5 * 44100 + 321, 2, 44100, seed=21)
+    lua.G.set(b"PCM_BYTES", pcm.tobytes())
+    r = lua.run('''
+        local aukit = require "aukit"
+        local fused = aukit.preload(PCM_BYTES, 16, "signed", 2, 44100, 48000, "cubic", true, 0.8)
+        local four = aukit.pcm(PCM_BYTES, 16, "signed", 2, 44100):resample(48000, "cubic"):mono()
+        aukit.effects.normalize(four, 0.8)
+        local n, worst = #fused.data[1], 0
+        for i = 1, n do worst = math.max(worst, math.abs(fused.data[1][i] - four.data[1][i])) end
+        local out = {}
+        for i = 1, n do out[i] = fused.data[1][i] end
+        return n, #four.data[1], worst, fused.sampleRate, fused:channels(), aukit.deviceCount(), out
+    ''')
+    ref = O.chain_s16(pcm.tobytes(), 2, 44100, 48000, "cubic", 0.8)
+    assert r[0] == r[1] == float(len(ref)) and r[2] <= 2 * TOL and r[3] == 48000.0 and r[4] == 1.0 and r[5] >= 1.0
+    assert np.max(np.abs(np.array(r[6].arr) - ref)) <= TOL
+    from oracle.luavm.lua import LuaError
+    with pytest.raises(LuaError, match=r"uneven amount of data per channel"):
+        lua.run('local aukit = require "aukit" return aukit.preload("\\0\\0\\0", 16, "signed", 2)')
