@@ -412,6 +412,21 @@ def test_audio_pcm_values_bit_exact_and_bytes(ak, O, bits, dtype, ch, interleave
         assert np.array_equal(raw, want), mode
 
 
+@pytest.mark.parametrize("n", [16, 4096, 100_000, 100_003, 7])
+@pytest.mark.parametrize("bits,dtype", [(8, "signed"), (8, "unsigned"), (16, "signed"), (16, "unsigned")])
+def test_audio_pcm_bytes_wide_kernel_shapes(ak, O, bits, dtype, n):
+    """The 16-bytes-per-thread requantisation kernel (mono, planar rows, interleaved stereo) at lengths that are and are
+    not multiples of its group size: same bytes as the sample-by-sample definition."""
+    rng = np.random.default_rng(n + bits)
+    for ch, interleaved in ((1, True), (2, True), (2, False), (4, False)):
+        x = rng.uniform(-1.2, 1.2, (ch, n)).astype(np.float32)
+        ref = O.audio_pcm(x.astype(np.float64), bits, dtype, interleaved)
+        lo, hi = (0, 2 ** bits - 1) if dtype == "unsigned" else (-2 ** (bits - 1), 2 ** (bits - 1) - 1)
+        q = np.clip(np.floor(ref).astype(np.int64), lo, hi)
+        want = q.astype("<u%d" % (bits // 8) if dtype == "unsigned" else "<i%d" % (bits // 8)).tobytes()
+        assert ak.Audio.from_numpy(x, 48000).pcm_bytes(bits, dtype, interleaved, "floor") == want, (ch, interleaved)
+
+
 def test_audio_pcm_requantisation_within_one_lsb_of_reference_chain(ak, O):
     """north_star's statement for the whole path: after requantisation to 8-bit signed (what speaker.playAudio
     takes, auplay.lua:34) the CUDA chain is within 1 LSB of the reference chain."""
