@@ -247,6 +247,9 @@ extern "C" int aukit_cuda_dev_resample(aukit_ctx *ctx, const float *d_in, size_t
     // integer rates with a short period: the polyphase kernels (pipeline_poly.cu) do the same arithmetic with
     // shared-memory tap reuse and loop-invariant weights; everything else takes the per-frame fp64 kernel below
     if (interpolation != AUKIT_INTERP_SINC) {
+        const int rp = aukit_planar_resample_try(ctx, d_in, in_stride, channels, n_in_total, in_first, in_avail, srcRate, dstRate,
+                                                 interpolation, out_first, n_out, d_out, out_stride);
+        if (rp != 0) return rp < 0 ? -1 : 0;
         const int r = aukit_poly_resample_try(ctx, d_in, in_stride, channels, n_in_total, in_first, in_avail, srcRate, dstRate,
                                               interpolation, out_first, n_out, d_out, out_stride);
         if (r != 0) return r < 0 ? -1 : 0;

@@ -1,0 +1,280 @@
+// resample_planar.cu -- K5 interior: Audio:resample (A:653-673) on planar float32 with TMA-staged, double-buffered tiles.
+//
+// The polyphase kernel of pipeline_poly.cu stages a tile, barriers, blends, barriers: ncu (profiles/r2_k5_ncu.txt)
+// showed its warps waiting at the barrier and on the staging loads (5.8 + 5.4 stalled warps per issue), 0.62 - 0.69 of
+// the copy rate.  Here the same tile geometry is kept (thread t owns outputs base + k*Sp + t, so its phase
+// j_t = (t*M) mod L and its weights are loop invariants; tile = K iterations, K*Q + 3 input frames), but
+//   * a tile's rows arrive by bulk async copies (TMA: cp.async.bulk + mbarrier), one per channel, into a 2-deep ring:
+//     the copy of tile i+1 is issued right after the barrier that ends tile i-1 and lands while tile i is blended;
+//   * there is ONE __syncthreads per tile (the j == 0 decision table of the next tile is written before it);
+//   * CTAs are small (one period group, <= 256 threads) so that many are resident and their phases interleave.
+// Arithmetic, weights, the exact-hit / near-hit decisions (A:666-667) and the NaN-transparent clamp (A:228, A:668) are
+// those of poly_kernel's PX_TABLE mode, bit for bit: only tiles that lie inside the output range, inside the signal
+// and inside the window held in memory take this path; the first and last tiles of a call, positions >= 2^28 frames
+// and non-integer rates stay with pipeline_poly.cu / resample.cu (tests: interior == edges == one-thread-per-frame kernel).
+#include "common.cuh"
+#include "pipeline.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+enum { HIT = 0, NEAR_BELOW = 1, NEAR_ABOVE = 2 };
+
+struct prs_args {
+    const float *in;              // frames [in_first, ...) of each channel row
+    size_t in_stride;
+    unsigned long long in_first;
+    int channels;
+    double ratio;
+    float *out;                   // output frame out_first of each channel row
+    size_t out_stride;
+    unsigned long long out_first;
+    int L, M, m, Sp, Q, K, nfr;
+    int pitch;                    // floats between the channel rows of a staged tile (multiple of 4)
+    unsigned long long tile0, ntiles;
+};
+
+// clamp of A:228-232 in two instructions: min.NaN / max.NaN return NaN when an operand is NaN, so NaN passes through
+// exactly as the reference's two failed comparisons let it; +-Inf -> +-1, -0 stays -0
+__device__ __forceinline__ float clamp_nan(float v) {
+    float r;
+    asm("min.NaN.f32 %0, %1, 0f3F800000;\n\tmax.NaN.f32 %0, %0, 0fBF800000;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// CT: compile-time channel count (1, 2) or 0 = runtime
+template <int MODE, int CT>
+__global__ void __launch_bounds__(256) planar_resample_kernel(prs_args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C = CT ? CT : a.channels;
+    float *bufs = reinterpret_cast<float *>(smem_raw);                               // [2][C][pitch]
+    unsigned char *hit_tab = smem_raw + (size_t)2 * C * a.pitch * sizeof(float);     // [2][K*m]
+    __shared__ __align__(8) uint64_t bars[2];
+    const int t = threadIdx.x;
+    const bool active = t < a.Sp;
+    const long long tm = (long long)t * a.M;
+    const int off_t = (int)(tm / a.L), j_t = (int)(tm % a.L);
+    const bool is_j0 = (j_t == 0);
+    float w0 = 0.f, w1 = 1.f, w2 = 0.f, w3 = 0.f, fx = 0.f;
+    {
+        const double x = (double)j_t / (double)a.L;
+        fx = (float)x;
+        if (MODE == AUKIT_INTERP_CUBIC) {                               // Catmull-Rom weights of A:265, fp64 then narrowed
+            const double x2 = x * x, x3 = x2 * x;
+            w0 = (float)(-0.5 * x3 + x2 - 0.5 * x);
+            w1 = (float)(1.5 * x3 - 2.5 * x2 + 1.0);
+            w2 = (float)(-1.5 * x3 + 2.0 * x2 + 0.5 * x);
+            w3 = (float)(0.5 * x3 - 0.5 * x2);
+        }
+    }
+    const unsigned long long tile_out = (unsigned long long)a.Sp * a.K;
+    const int ntab = a.K * a.m;
+    const int K = a.K, Q = a.Q, Sp = a.Sp, pitch = a.pitch;
+    const int jrow = t / a.L;                                           // which of the m periods of an iteration this thread is in
+
+    // thread 0: bulk copies of one tile's rows, from a 16-byte aligned start
+    auto issue = [&](unsigned long long tile, int buf) {
+        const long long gA = (long long)(tile * (unsigned long long)a.K * (unsigned long long)a.Q) - 1;   // first frame the tile needs
+        const size_t foff = (size_t)(gA - (long long)a.in_first);
+        const size_t a0 = foff & ~(size_t)3;
+        const uint32_t bytes = (uint32_t)((a.nfr + (int)(foff - a0) + 3) / 4) * 16u;
+        mbar_expect_tx(&bars[buf], bytes * (uint32_t)C);
+        for (int c = 0; c < C; c++)
+            bulk_load(bufs + ((size_t)buf * C + c) * a.pitch, a.in + (size_t)c * a.in_stride + a0, bytes, &bars[buf]);
+    };
+    // exact hit / near-hit decision for a tile's j == 0 outputs with the reference's own fp64 expression (A:666-667)
+    auto decide = [&](unsigned long long tile, int buf) {
+        const unsigned long long base_out = tile * tile_out;
+        const long long F0 = (long long)(tile * (unsigned long long)a.K * (unsigned long long)a.Q);
+        for (int e = t; e < ntab; e += blockDim.x) {
+            const unsigned long long n = base_out + (unsigned long long)(e / a.m) * a.Sp + (unsigned long long)(e % a.m) * a.L;
+            const double xt = (double)(F0 + (long long)(e / a.m) * a.Q + (long long)(e % a.m) * a.M + 1);
+            const double x = __dadd_rn(__ddiv_rn((double)n, a.ratio), 1.0);
+            hit_tab[buf * ntab + e] = (x == xt) ? HIT : (x < xt ? NEAR_BELOW : NEAR_ABOVE);
+        }
+    };
+    // one channel of one output: taps at f[0..3] (p1 = f[1]), st = decision for a j == 0 output
+    auto value = [&](const float *f, int st) -> float {
+        const float p1 = f[1];
+        float v;
+        if (MODE == AUKIT_INTERP_CUBIC) v = __fmaf_rn(w3, f[3], __fmaf_rn(w2, f[2], __fmaf_rn(w1, p1, w0 * f[0])));
+        else if (MODE == AUKIT_INTERP_LINEAR) v = __fmaf_rn(f[2] - p1, fx, p1);
+        else v = p1;
+        float r = clamp_nan(v);
+        if (is_j0) {
+            // one output per period sits on (or one ulp beside) an input frame: decided exactly
+            if (st == HIT) r = p1;                                                       // copied unclamped, A:667
+            else if (MODE == AUKIT_INTERP_NONE && st == NEAR_BELOW) r = clamp_nan(f[0]); // floor(x) is one lower
+            else r = clamp_nan(p1);                                                      // weights at j == 0 are (0, 1, 0, 0)
+        }
+        return r;
+    };
+
+    unsigned long long tile = a.tile0 + blockIdx.x;
+    if (tile >= a.tile0 + a.ntiles) return;
+    if (t == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue(tile, 0);
+    }
+    decide(tile, 0);
+    __syncthreads();
+    uint32_t ph0 = 0u, ph1 = 0u;
+    for (int it = 0; tile < a.tile0 + a.ntiles; it++, tile += gridDim.x) {
+        const int buf = it & 1;
+        const unsigned long long next = tile + gridDim.x;
+        const bool has_next = next < a.tile0 + a.ntiles;
+        // the other buffer (tile it - 1) and its table are free: every thread passed the barrier that ended that tile
+        if (has_next) {
+            if (t == 0) issue(next, buf ^ 1);
+            decide(next, buf ^ 1);
+        }
+        mbar_wait(&bars[buf], buf ? ph1 : ph0);
+        if (buf) ph1 ^= 1u; else ph0 ^= 1u;
+        if (active) {
+            const long long gA = (long long)(tile * (unsigned long long)a.K * (unsigned long long)a.Q) - 1;
+            const int sh = (int)((size_t)(gA - (long long)a.in_first) & 3);          // staged index of frame gA
+            const float *f = bufs + (size_t)buf * C * pitch + off_t + sh;            // taps of output k = 0, channel 0
+            const unsigned char *ht = hit_tab + buf * ntab + jrow;
+            float *outp = a.out + (size_t)(tile * tile_out - a.out_first) + t;
+#pragma unroll 4
+            for (int k = 0; k < K; k++) {
+                int st = NEAR_ABOVE;
+                if (is_j0) st = ht[k * a.m];
+                if (CT == 1) {
+                    outp[0] = value(f, st);
+                } else if (CT == 2) {
+                    const float vl = value(f, st), vr = value(f + pitch, st);
+                    outp[0] = vl;
+                    outp[a.out_stride] = vr;
+                } else {
+                    for (int c = 0; c < C; c++) outp[(size_t)c * a.out_stride] = value(f + c * pitch, st);
+                }
+                f += Q;
+                outp += Sp;
+            }
+        }
+        __syncthreads();                                                // tile done: its buffer and table may be refilled
+    }
+}
+
+long long gcd_ll(long long x, long long y) { while (y) { long long r = x % y; x = y; y = r; } return x; }
+
+}  // namespace
+
+// Returns 1 when the whole range was produced (interior tiles here, the remainders through aukit_poly_resample_try),
+// 0 when this path does not apply, -1 on error.
+int aukit_planar_resample_try(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels, unsigned long long n_in_total,
+                              unsigned long long in_first, size_t in_avail, double srcRate, double dstRate, int interpolation,
+                              unsigned long long out_first, size_t n_out, float *d_out, size_t out_stride) {
+    // AUKIT_DISABLE_PLANAR=1 (diagnostic, tests): everything through the polyphase / per-frame kernels
+    const char *dis = getenv("AUKIT_DISABLE_PLANAR");
+    const bool disabled = dis && dis[0] == '1';
+    if (disabled || interpolation < AUKIT_INTERP_NONE || interpolation > AUKIT_INTERP_CUBIC) return 0;
+    if (channels < 1 || channels > 8 || ((uintptr_t)d_in & 15) || (channels > 1 && (in_stride & 3))) return 0;
+    const double sr = srcRate, dr = dstRate;
+    if (!(sr >= 1 && dr >= 1 && sr < 2147483648.0 && dr < 2147483648.0) || sr != floor(sr) || dr != floor(dr)) return 0;
+    const long long g = gcd_ll((long long)sr, (long long)dr);
+    const long long L = (long long)dr / g, M = (long long)sr / g;
+    if (L < 2 || L > 256 || M > 4096) return 0;                         // L == 1: the strided-gather kernels (pipeline_decim.cu)
+    const double ratio = dstRate / srcRate;
+    if ((double)(out_first + n_out) * (double)M / (double)L >= 268435456.0) return 0;   // rational-position regime only
+    prs_args a{};
+    a.L = (int)L; a.M = (int)M;
+    a.m = (int)(256 / L);
+    if ((long long)a.m * M > 4096) a.m = (int)(4096 / M);
+    if (a.m < 1) a.m = 1;
+    a.Sp = a.L * a.m;
+    a.Q = a.M * a.m;
+    const int threads = (a.Sp + 31) / 32 * 32;
+    const size_t budget = 32 * 1024;                                    // per buffer: small tiles, many resident CTAs
+    long long K = ((long long)(budget / (sizeof(float) * (size_t)channels)) - 12) / a.Q;
+    if (K < 1) K = 1;
+    if (K > 64) K = 64;
+    a.K = (int)K;
+    a.nfr = a.K * a.Q + 3;
+    a.pitch = (a.nfr + 3 + 3) / 4 * 4 + 4;
+    const size_t smem = (size_t)2 * channels * a.pitch * sizeof(float) + (size_t)2 * a.K * a.m + 16;
+    if (smem > 100 * 1024) return 0;
+    const unsigned long long tile_out = (unsigned long long)a.Sp * a.K;
+    // interior tiles: all outputs inside the range, all staged frames (from the aligned start to the rounded-up end)
+    // inside the signal and inside the window the caller holds
+    auto fits = [&](unsigned long long T) {
+        if (T * tile_out < out_first || (T + 1) * tile_out > out_first + n_out) return false;
+        const long long gA = (long long)(T * (unsigned long long)a.K * (unsigned long long)a.Q) - 1;
+        if (gA < (long long)in_first) return false;
+        const unsigned long long foff = (unsigned long long)gA - in_first, a0 = foff & ~3ull;
+        const unsigned long long last = in_first + a0 + (unsigned long long)((a.nfr + (int)(foff - a0) + 3) / 4) * 4;   // one past the last frame read
+        return last <= in_first + in_avail && last <= n_in_total;
+    };
+    unsigned long long T_lo = (out_first + tile_out - 1) / tile_out, T_hi = (out_first + n_out) / tile_out;   // [T_lo, T_hi)
+    while (T_lo < T_hi && !fits(T_lo)) T_lo++;
+    while (T_hi > T_lo && !fits(T_hi - 1)) T_hi--;
+    if (T_hi <= T_lo + 1) return 0;                                     // nothing worth a launch of its own
+    const unsigned long long o_lo = T_lo * tile_out, o_hi = T_hi * tile_out;
+    // The first and last tiles go through the polyphase kernel on the context's side stream, beside the interior kernel
+    // (disjoint output ranges; two ~11 us launches in series were a third of a 20 M-frame call).
+    cudaStream_t main_stream = ctx->stream;
+    if (aukit_cuda_check(cudaEventRecord(ctx->ev_fork, main_stream), "fork event")) return -1;
+    if (aukit_cuda_check(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0), "fork wait")) return -1;
+    ctx->stream = ctx->side_stream;
+    int edge_rc = 1;
+    if (o_lo > out_first)
+        edge_rc = aukit_poly_resample_try(ctx, d_in, in_stride, channels, n_in_total, in_first, in_avail, srcRate, dstRate, interpolation,
+                                          out_first, (size_t)(o_lo - out_first), d_out, out_stride);
+    if (edge_rc == 1 && o_hi < out_first + n_out)
+        edge_rc = aukit_poly_resample_try(ctx, d_in, in_stride, channels, n_in_total, in_first, in_avail, srcRate, dstRate, interpolation,
+                                          o_hi, (size_t)(out_first + n_out - o_hi), d_out + (size_t)(o_hi - out_first), out_stride);
+    ctx->stream = main_stream;
+    if (aukit_cuda_check(cudaEventRecord(ctx->ev_join, ctx->side_stream), "join event")) return -1;
+    if (aukit_cuda_check(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0), "join wait")) return -1;
+    if (edge_rc != 1) {
+        if (edge_rc == 0) aukit_fail("aukit_cuda: no polyphase kernel for the edge tiles of the range");
+        return -1;
+    }
+    a.in = d_in; a.in_stride = in_stride; a.in_first = in_first; a.channels = channels; a.ratio = ratio;
+    a.out = d_out; a.out_stride = out_stride; a.out_first = out_first;
+    a.tile0 = T_lo; a.ntiles = T_hi - T_lo;
+    auto go = [&](auto kern) -> int {
+        if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
+        int occ = 0;
+        if (aukit_cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem), "occupancy")) return -1;
+        if (occ < 1) return aukit_fail("aukit_cuda: planar resample kernel does not fit on an SM");
+        unsigned long long grid = (unsigned long long)ctx->num_sms * occ;
+        if (grid > a.ntiles) grid = a.ntiles;
+        kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
+        ctx->launches++;
+        return aukit_cuda_check(cudaGetLastError(), "planar_resample_kernel launch");
+    };
+    int rc;
+#define AUKIT_PRS(MODE) (channels == 1 ? go(planar_resample_kernel<MODE, 1>) : channels == 2 ? go(planar_resample_kernel<MODE, 2>) \
+                                                                                              : go(planar_resample_kernel<MODE, 0>))
+    if (interpolation == AUKIT_INTERP_NONE) rc = AUKIT_PRS(AUKIT_INTERP_NONE);
+    else if (interpolation == AUKIT_INTERP_LINEAR) rc = AUKIT_PRS(AUKIT_INTERP_LINEAR);
+    else rc = AUKIT_PRS(AUKIT_INTERP_CUBIC);
+#undef AUKIT_PRS
+    return rc ? -1 : 1;
+}

@@ -594,3 +594,31 @@ def test_far_shards_do_not_depend_on_the_sharding(ak):
             assert f32_equal_bits(two, whole) and f32_equal_bits(longer, whole), pos
     finally:
         ctx.set_stream(None)
+
+
+@pytest.mark.parametrize("src,dst", [(44100, 48000), (48000, 44100), (22050, 48000), (8000, 48000), (32000, 48000), (44100, 22050 * 3)])
+@pytest.mark.parametrize("interp", ["none", "linear", "cubic"])
+def test_planar_tma_resample_equals_polyphase_kernel(ak, O, monkeypatch, src, dst, interp):
+    """Audio:resample's interior tiles (resample_planar.cu: TMA-staged, double-buffered) against the polyphase kernel
+    that still does the first / last tiles, bit for bit, on data that leaves [-1, 1] and holds NaN / Inf (the exact-hit
+    copy of A:667 is unclamped, the clamp of A:668 lets NaN through), and against the oracle."""
+    rng = np.random.default_rng(src + dst)
+    for ch, n in ((1, 150_001), (2, 260_003), (3, 90_000)):
+        x = rng.uniform(-1.6, 1.6, (ch, n)).astype(np.float32)
+        x[0, 5000] = np.nan
+        if ch != 2:                 # (the reference's polynomial form A:265 turns an infinite tap into NaN, the weight form
+            x[ch - 1, 70_000] = np.inf      # into +-1 after the clamp: infinities are checked between the kernels only)
+            x[0, 12_345] = -np.inf
+        a = ak.Audio.from_numpy(x, src)
+        got = a.resample(dst, interp).numpy()
+        monkeypatch.setenv("AUKIT_DISABLE_PLANAR", "1")
+        other = a.resample(dst, interp).numpy()
+        monkeypatch.delenv("AUKIT_DISABLE_PLANAR")
+        assert got.shape == other.shape and f32_equal_bits(got, other), (ch, n)
+        if ch == 2:
+            ref = O.resample(x.astype(np.float64), src, dst, interp)
+            # (an output one ulp beside an input frame takes that frame: a non-finite NEIGHBOUR does not reach it as it
+            # does through the reference's ~1e-12 weights -- DESIGN.md "known deviations"; everything else must agree)
+            fin = np.isfinite(ref) & np.isfinite(got)
+            assert np.count_nonzero(np.isnan(ref) != np.isnan(got)) <= 12
+            assert np.max(np.abs(got[fin] - ref[fin])) <= 2 * TOL          # |values| reach 1.6 before the clamp
