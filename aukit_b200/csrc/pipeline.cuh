@@ -39,5 +39,9 @@ int aukit_poly_resample_try(aukit_ctx *ctx, const float *d_in, size_t in_stride,
 int aukit_planar_resample_try(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels, unsigned long long n_in_total,
                               unsigned long long in_first, size_t in_avail, double srcRate, double dstRate, int interpolation,
                               unsigned long long out_first, size_t n_out, float *d_out, size_t out_stride);
+// interpolate.sinc (A:267-281) on planar float32, whole range (resample_planar.cu); same return convention
+int aukit_planar_sinc_try(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels, unsigned long long n_in_total,
+                          unsigned long long in_first, size_t in_avail, double srcRate, double dstRate,
+                          unsigned long long out_first, size_t n_out, float *d_out, size_t out_stride);
 // ratio 2^-k (L == 1): every output is a copied sample -- pipeline_decim.cu; same return convention
 int aukit_pipeline_decim_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p, bool apply, long long M);

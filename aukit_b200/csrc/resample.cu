@@ -254,6 +254,11 @@ extern "C" int aukit_cuda_dev_resample(aukit_ctx *ctx, const float *d_in, size_t
                                               interpolation, out_first, n_out, d_out, out_stride);
         if (r != 0) return r < 0 ? -1 : 0;
     }
+    if (interpolation == AUKIT_INTERP_SINC) {
+        const int rs = aukit_planar_sinc_try(ctx, d_in, in_stride, channels, n_in_total, in_first, in_avail, srcRate, dstRate, out_first, n_out,
+                                             d_out, out_stride);
+        if (rs != 0) return rs < 0 ? -1 : 0;
+    }
     resample_args a{d_in, in_stride, channels, n_in_total, in_first, dstRate / srcRate, out_first, n_out, d_out, out_stride};
     a.y = 1.0 / a.ratio;
     a.quotient_fma_ok = aukit_quotient_fma_is_exact(a.ratio, 44) ? 1 : 0;

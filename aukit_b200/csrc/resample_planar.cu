@@ -181,6 +181,154 @@ __global__ void __launch_bounds__(256) planar_resample_kernel(prs_args a) {
     }
 }
 
+// ---- sinc (A:267-281): 21 taps per output.  Same tile geometry and TMA ring; a thread's 21 weights and their derivatives
+// (fp64 sinc at its rational phase j_t / L, narrowed) are loop invariants, corrected per output to first order for the
+// drift of the reference's fp64 position (x_ref - n*M/L = x * eps_r) -- the same table-plus-correction the
+// one-thread-per-frame kernel uses, minus its per-output table loads and global taps (45 G samples/s).  This kernel takes
+// the WHOLE output range of a call, edge tiles included (frames outside the signal are staged as zeros: the reference
+// skips those taps, A:271; a zero tap adds exactly nothing), so a range gives the same bits however it is sharded.
+struct sinc_args {
+    prs_args g;
+    unsigned long long n_total;
+    size_t in_avail;
+    size_t n_out;
+    float eps_r;
+};
+
+template <int CT>
+__global__ void __launch_bounds__(256) planar_sinc_kernel(sinc_args sa) {
+    const prs_args &a = sa.g;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C = CT ? CT : a.channels;
+    float *bufs = reinterpret_cast<float *>(smem_raw);                               // [2][C][pitch]
+    unsigned char *hit_tab = smem_raw + (size_t)2 * C * a.pitch * sizeof(float);     // [2][K*m]
+    __shared__ __align__(8) uint64_t bars[2];
+    const int t = threadIdx.x;
+    const bool active = t < a.Sp;
+    const long long tm = (long long)t * a.M;
+    const int off_t = (int)(tm / a.L), j_t = (int)(tm % a.L);
+    const bool is_j0 = (j_t == 0);
+    float w[21], wd[21];
+    const double fxd = (double)j_t / (double)a.L;
+#pragma unroll
+    for (int k = 0; k < 21; k++) {                                      // A:273-276 at fx = j / L, and d/dfx
+        const double px = 3.14159265358979323846 * (fxd - (double)(k - 10));
+        if (px == 0.0) { w[k] = 1.0f; wd[k] = 0.0f; }
+        else {
+            const double sn = sin(px), cs = cos(px);
+            w[k] = (float)(sn / px);
+            wd[k] = (float)(3.14159265358979323846 * (cs * px - sn) / (px * px));
+        }
+    }
+    const float fx = (float)fxd;
+    const unsigned long long tile_out = (unsigned long long)a.Sp * a.K;
+    const int ntab = a.K * a.m;
+    const int K = a.K, Q = a.Q, Sp = a.Sp, pitch = a.pitch;
+    const int jrow = t / a.L;
+    const long long n_total = (long long)sa.n_total, in_lo = (long long)a.in_first, in_hi = in_lo + (long long)sa.in_avail;
+    const unsigned long long out_lo = a.out_first, out_hi = a.out_first + sa.n_out;
+
+    auto first_frame = [&](unsigned long long tile) { return (long long)(tile * (unsigned long long)a.K * (unsigned long long)a.Q) - 10; };
+    // a tile whose staged frames (aligned start to rounded-up end) all exist in the window travels by bulk copy
+    auto interior = [&](unsigned long long tile) {
+        const long long gA = first_frame(tile);
+        if (gA < in_lo) return false;
+        const long long a0 = (gA - in_lo) & ~3ll;
+        const long long last = in_lo + a0 + (long long)((a.nfr + (int)((gA - in_lo) - a0) + 3) / 4) * 4;
+        return last <= in_hi && last <= n_total;
+    };
+    auto issue = [&](unsigned long long tile, int buf) {
+        const size_t foff = (size_t)(first_frame(tile) - in_lo);
+        const size_t a0 = foff & ~(size_t)3;
+        const uint32_t bytes = (uint32_t)((a.nfr + (int)(foff - a0) + 3) / 4) * 16u;
+        mbar_expect_tx(&bars[buf], bytes * (uint32_t)C);
+        for (int c = 0; c < C; c++)
+            bulk_load(bufs + ((size_t)buf * C + c) * a.pitch, a.in + (size_t)c * a.in_stride + a0, bytes, &bars[buf]);
+    };
+    auto decide = [&](unsigned long long tile, int buf) {
+        const unsigned long long base_out = tile * tile_out;
+        const long long F0 = (long long)(tile * (unsigned long long)a.K * (unsigned long long)a.Q);
+        for (int e = t; e < ntab; e += blockDim.x) {
+            const unsigned long long n = base_out + (unsigned long long)(e / a.m) * a.Sp + (unsigned long long)(e % a.m) * a.L;
+            const double xt = (double)(F0 + (long long)(e / a.m) * a.Q + (long long)(e % a.m) * a.M + 1);
+            const double x = __dadd_rn(__ddiv_rn((double)n, a.ratio), 1.0);
+            hit_tab[buf * ntab + e] = (x == xt) ? HIT : (x < xt ? NEAR_BELOW : NEAR_ABOVE);
+        }
+    };
+
+    unsigned long long tile = a.tile0 + blockIdx.x;
+    if (tile >= a.tile0 + a.ntiles) return;
+    if (t == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (interior(tile)) issue(tile, 0);
+    }
+    decide(tile, 0);
+    __syncthreads();
+    uint32_t ph0 = 0u, ph1 = 0u;
+    for (int it = 0; tile < a.tile0 + a.ntiles; it++, tile += gridDim.x) {
+        const int buf = it & 1;
+        const unsigned long long next = tile + gridDim.x;
+        if (next < a.tile0 + a.ntiles) {
+            if (t == 0 && interior(next)) issue(next, buf ^ 1);
+            decide(next, buf ^ 1);
+        }
+        const long long gA = first_frame(tile);
+        int sh;
+        if (interior(tile)) {
+            mbar_wait(&bars[buf], buf ? ph1 : ph0);
+            if (buf) ph1 ^= 1u; else ph0 ^= 1u;
+            sh = (int)((size_t)(gA - in_lo) & 3);
+        } else {
+            // edge tile: plain loads; frames outside the signal are zeros (taps the reference skips, A:271)
+            sh = 0;
+            for (int c = 0; c < C; c++) {
+                float *dst = bufs + ((size_t)buf * C + c) * pitch;
+                const float *row = a.in + (size_t)c * a.in_stride;
+                for (int f = t; f < a.nfr; f += blockDim.x) {
+                    const long long gi = gA + f;
+                    dst[f] = (gi >= 0 && gi < n_total && gi >= in_lo && gi < in_hi) ? row[gi - in_lo] : 0.0f;
+                }
+            }
+            __syncthreads();
+        }
+        if (active) {
+            const float *f = bufs + (size_t)buf * C * pitch + off_t + sh;            // tap k = -10 of output k = 0, channel 0
+            const unsigned char *ht = hit_tab + buf * ntab + jrow;
+            const unsigned long long o0 = tile * tile_out + t;                        // global index of this thread's output k = 0
+            float *outp = a.out + (size_t)((long long)o0 - (long long)a.out_first);
+            float xf = (float)((long long)(tile * (unsigned long long)a.K * (unsigned long long)a.Q) + off_t) + fx;   // rational position
+            const float qf = (float)Q;
+            for (int k = 0; k < K; k++, f += Q, outp += Sp, xf += qf) {
+                const unsigned long long o = o0 + (unsigned long long)k * Sp;
+                if (o < out_lo || o >= out_hi) continue;                              // first / last tile of a range
+                const float dl = xf * sa.eps_r;                                       // x_ref - x_rational
+                float cw[21];
+#pragma unroll
+                for (int q = 0; q < 21; q++) cw[q] = __fmaf_rn(wd[q], dl, w[q]);
+                const bool hit = is_j0 && ht[k * a.m] == HIT;
+                if (CT == 2) {
+                    float sl = 0.f, sr = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 21; q++) { sl = __fmaf_rn(f[q], cw[q], sl); sr = __fmaf_rn(f[pitch + q], cw[q], sr); }
+                    outp[0] = hit ? f[10] : clamp_nan(sl);                            // exact hit: copied unclamped, A:667
+                    outp[a.out_stride] = hit ? f[pitch + 10] : clamp_nan(sr);
+                } else {
+                    for (int c = 0; c < C; c++) {
+                        const float *fc = f + c * pitch;
+                        float sum = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 21; q++) sum = __fmaf_rn(fc[q], cw[q], sum);
+                        outp[(size_t)c * a.out_stride] = hit ? fc[10] : clamp_nan(sum);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 long long gcd_ll(long long x, long long y) { while (y) { long long r = x % y; x = y; y = r; } return x; }
 
 }  // namespace
@@ -276,5 +424,62 @@ int aukit_planar_resample_try(aukit_ctx *ctx, const float *d_in, size_t in_strid
     else if (interpolation == AUKIT_INTERP_LINEAR) rc = AUKIT_PRS(AUKIT_INTERP_LINEAR);
     else rc = AUKIT_PRS(AUKIT_INTERP_CUBIC);
 #undef AUKIT_PRS
+    return rc ? -1 : 1;
+}
+
+// interpolate.sinc on planar float32, the whole range of a call.  Returns 1 handled, 0 not applicable, -1 error.
+int aukit_planar_sinc_try(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels, unsigned long long n_in_total,
+                          unsigned long long in_first, size_t in_avail, double srcRate, double dstRate,
+                          unsigned long long out_first, size_t n_out, float *d_out, size_t out_stride) {
+    const char *dis = getenv("AUKIT_DISABLE_PLANAR");
+    if (dis && dis[0] == '1') return 0;
+    if (channels < 1 || channels > 8 || ((uintptr_t)d_in & 15) || (channels > 1 && (in_stride & 3))) return 0;
+    const double sr = srcRate, dr = dstRate;
+    if (!(sr >= 1 && dr >= 1 && sr < 2147483648.0 && dr < 2147483648.0) || sr != floor(sr) || dr != floor(dr)) return 0;
+    const long long g = gcd_ll((long long)sr, (long long)dr);
+    const long long L = (long long)dr / g, M = (long long)sr / g;
+    if (L > 256 || M > 4096) return 0;
+    const double ratio = dstRate / srcRate;
+    // the first-order correction covers the systematic drift; what is left (the quotient's rounding, <= x * 2^-53) must stay
+    // negligible against 2^-20 over 21 taps: positions below 2^27 frames
+    if ((double)(out_first + n_out) * (double)M / (double)L >= 134217728.0) return 0;
+    sinc_args sa{};
+    prs_args &a = sa.g;
+    a.L = (int)L; a.M = (int)M;
+    a.m = (int)(128 / L);
+    if (a.m < 1) a.m = 1;
+    if ((long long)a.m * M > 4096) a.m = (int)(4096 / M) > 0 ? (int)(4096 / M) : 1;
+    a.Sp = a.L * a.m;
+    a.Q = a.M * a.m;
+    const int threads = (a.Sp + 31) / 32 * 32;
+    if (threads > 256) return 0;
+    const size_t budget = 24 * 1024;
+    long long K = ((long long)(budget / (sizeof(float) * (size_t)channels)) - 32) / a.Q;
+    if (K < 1) K = 1;
+    if (K > 64) K = 64;
+    a.K = (int)K;
+    a.nfr = a.K * a.Q + 21;
+    a.pitch = (a.nfr + 3 + 3) / 4 * 4 + 4;
+    const size_t smem = (size_t)2 * channels * a.pitch * sizeof(float) + (size_t)2 * a.K * a.m + 16;
+    if (smem > 160 * 1024) return 0;
+    const unsigned long long tile_out = (unsigned long long)a.Sp * a.K;
+    a.in = d_in; a.in_stride = in_stride; a.in_first = in_first; a.channels = channels; a.ratio = ratio;
+    a.out = d_out; a.out_stride = out_stride; a.out_first = out_first;
+    a.tile0 = out_first / tile_out;
+    a.ntiles = (out_first + n_out - 1) / tile_out - a.tile0 + 1;
+    sa.n_total = n_in_total; sa.in_avail = in_avail; sa.n_out = n_out;
+    sa.eps_r = (float)(fma(-(double)M, ratio, (double)L) / ((double)M * ratio));
+    auto go = [&](auto kern) -> int {
+        if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
+        int occ = 0;
+        if (aukit_cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem), "occupancy")) return -1;
+        if (occ < 1) return aukit_fail("aukit_cuda: planar sinc kernel does not fit on an SM");
+        unsigned long long grid = (unsigned long long)ctx->num_sms * occ;
+        if (grid > a.ntiles) grid = a.ntiles;
+        kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(sa);
+        ctx->launches++;
+        return aukit_cuda_check(cudaGetLastError(), "planar_sinc_kernel launch");
+    };
+    const int rc = channels == 1 ? go(planar_sinc_kernel<1>) : channels == 2 ? go(planar_sinc_kernel<2>) : go(planar_sinc_kernel<0>);
     return rc ? -1 : 1;
 }

@@ -115,7 +115,8 @@ def table(sampler_cls, gpu_index=0, scale=1.0, iters=10, warm=3):
             f = lambda: ak._lib.check(lib.aukit_cuda_dev_msadpcm(ctx.handle, d_in.data_ptr(), nb, 8192, 8, None, None, 0, 1, d_out.data_ptr(), stride))
         ms = timed(f)
         report("K%d %s_adpcm 8ch blockAlign 8192" % (3 if kind == "ima" else 4, kind), ms, nb + fr * 8 * 4, fr * 8, "samples",
-               "serial chain per (block, channel), 32 chains per warp, 256-byte row flushes")
+               "serial chain per (block, channel), 32 chains per warp, 256-byte flushes aligned in absolute address"
+               + ("" if kind == "ima" else "; records staged through shared memory, speculated straight-line periods"))
         del d_in, d_out
     # ---- K5 resample f32 stereo 44.1 -> 48 kHz
     n = frames // 2
@@ -126,7 +127,16 @@ def table(sampler_cls, gpu_index=0, scale=1.0, iters=10, warm=3):
         y = torch.empty((2, stride), dtype=torch.float32, device="cuda")
         ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_resample(ctx.handle, x.data_ptr(), n, 2, n, 0, n, 44100.0, 48000.0, mode, 0, n_out,
                                                                      y.data_ptr(), stride)))
-        report("K5 resample %s f32 stereo 44.1->48k" % name, ms, (n + n_out) * 2 * 4, n_out * 2, "samples", "fp64 position per output frame (IEEE division)")
+        report("K5 resample %s f32 stereo 44.1->48k" % name, ms, (n + n_out) * 2 * 4, n_out * 2, "samples",
+               "polyphase weights per thread, TMA-staged double-buffered tiles (resample_planar.cu); exact fp64 decision for the one output per period that sits on an input frame")
+    # sinc (8f rank 4): 21 taps per output; a quarter of the buffer is enough for a stable figure
+    ns = n // 4
+    ns_out = int(lib.aukit_resample_out_len(ns, 44100.0, 48000.0))
+    ys = torch.empty((2, (ns_out + 31) // 32 * 32), dtype=torch.float32, device="cuda")
+    ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_resample(ctx.handle, x.data_ptr(), n, 2, ns, 0, ns, 44100.0, 48000.0, 3, 0, ns_out,
+                                                                 ys.data_ptr(), ys.shape[1])))
+    report("K5 resample sinc f32 stereo 44.1->48k", ms, (ns + ns_out) * 2 * 4, ns_out * 2, "samples", "21 taps per output (A:267-281), weight table per phase + first-order correction")
+    del ys
     # ---- K6 mono, K7 amplify, K8 absmax, K9 scale_clamp
     m = torch.empty(n, dtype=torch.float32, device="cuda")
     ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_mono(ctx.handle, x.data_ptr(), n, 2, n, m.data_ptr())))

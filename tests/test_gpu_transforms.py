@@ -622,3 +622,33 @@ def test_planar_tma_resample_equals_polyphase_kernel(ak, O, monkeypatch, src, ds
             fin = np.isfinite(ref) & np.isfinite(got)
             assert np.count_nonzero(np.isnan(ref) != np.isnan(got)) <= 12
             assert np.max(np.abs(got[fin] - ref[fin])) <= 2 * TOL          # |values| reach 1.6 before the clamp
+
+
+@pytest.mark.parametrize("src,dst,ch", [(44100, 48000, 2), (48000, 44100, 1), (22050, 44100, 3), (8000, 48000, 2)])
+def test_planar_sinc_kernel_at_size(ak, O, monkeypatch, src, dst, ch):
+    """interpolate.sinc through the polyphase TMA kernel over many tiles: against the oracle, against the one-thread-per-
+    frame kernel (same table-plus-correction weights: a few ulps apart), and sharded at an arbitrary output index with
+    the shards holding only their +-10 frame windows -- bit-identical to the unsharded call."""
+    lib, ctx = ak._lib.load(), ak.context()
+    n = 180_017
+    x = np.random.default_rng(src + dst + ch).uniform(-1, 1, (ch, n)).astype(np.float32)
+    a = ak.Audio.from_numpy(x, src)
+    got = a.resample(dst, "sinc").numpy()
+    ref = O.resample(x.astype(np.float64), src, dst, "sinc")
+    assert got.shape == ref.shape and float(np.max(np.abs(got - ref))) <= 2 * TOL
+    monkeypatch.setenv("AUKIT_DISABLE_PLANAR", "1")
+    other = a.resample(dst, "sinc").numpy()
+    monkeypatch.delenv("AUKIT_DISABLE_PLANAR")
+    assert float(np.max(np.abs(got - other))) <= 2.0 ** -21
+    n_out = got.shape[1]
+    cut = n_out // 3 + 7
+    parts = []
+    for o0, o1 in ((0, cut), (cut, n_out)):
+        f, c = C.c_uint64(), C.c_uint64()
+        assert lib.aukit_resample_window(n, float(src), float(dst), 3, o0, o1 - o0, C.byref(f), C.byref(c)) == 0
+        shard_in = ak.Audio.from_numpy(np.ascontiguousarray(x[:, f.value: f.value + c.value]), src)
+        out = ak.Audio.from_numpy(np.zeros((ch, o1 - o0), dtype=np.float32), dst)
+        ak._lib.check(lib.aukit_cuda_dev_resample(ctx.handle, shard_in.data_ptr, shard_in.stride, ch, n, f.value, c.value,
+                                                  float(src), float(dst), 3, o0, o1 - o0, out.data_ptr, out.stride))
+        parts.append(out.numpy())
+    assert f32_equal_bits(np.concatenate(parts, axis=1), got)
