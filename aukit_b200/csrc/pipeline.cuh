@@ -34,8 +34,7 @@ int aukit_pipeline_poly_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipe
 int aukit_poly_resample_try(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels, unsigned long long n_in_total,
                             unsigned long long in_first, size_t in_avail, double srcRate, double dstRate, int interpolation,
                             unsigned long long out_first, size_t n_out, float *d_out, size_t out_stride);
-// the interior tiles of the same call with TMA-staged, double-buffered tiles (resample_planar.cu), head and tail through the
-// function above; same return convention
+// the same call with TMA-staged, double-buffered tiles (resample_planar.cu: L <= 256, positions < 2^28); same return convention
 int aukit_planar_resample_try(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels, unsigned long long n_in_total,
                               unsigned long long in_first, size_t in_avail, double srcRate, double dstRate, int interpolation,
                               unsigned long long out_first, size_t n_out, float *d_out, size_t out_stride);

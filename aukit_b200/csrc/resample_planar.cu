@@ -1,4 +1,4 @@
-// resample_planar.cu -- K5 interior: Audio:resample (A:653-673) on planar float32 with TMA-staged, double-buffered tiles.
+// resample_planar.cu -- K5: Audio:resample (A:653-673) on planar float32 with TMA-staged, double-buffered tiles.
 //
 // The polyphase kernel of pipeline_poly.cu stages a tile, barriers, blends, barriers: ncu (profiles/r2_k5_ncu.txt)
 // showed its warps waiting at the barrier and on the staging loads (5.8 + 5.4 stalled warps per issue), 0.62 - 0.69 of
@@ -9,9 +9,10 @@
 //   * there is ONE __syncthreads per tile (the j == 0 decision table of the next tile is written before it);
 //   * CTAs are small (one period group, <= 256 threads) so that many are resident and their phases interleave.
 // Arithmetic, weights, the exact-hit / near-hit decisions (A:666-667) and the NaN-transparent clamp (A:228, A:668) are
-// those of poly_kernel's PX_TABLE mode, bit for bit: only tiles that lie inside the output range, inside the signal
-// and inside the window held in memory take this path; the first and last tiles of a call, positions >= 2^28 frames
-// and non-integer rates stay with pipeline_poly.cu / resample.cu (tests: interior == edges == one-thread-per-frame kernel).
+// those of poly_kernel's PX_TABLE mode, bit for bit.  One launch covers the whole range of a call: the first / last tiles
+// of the signal or of the caller's window are staged with plain loads and a clamped index (the nil substitutions of
+// A:259 / A:264) and masked to the requested outputs.  Positions >= 2^28 frames, L > 256 and non-integer rates stay
+// with pipeline_poly.cu / resample.cu (tests: this kernel == polyphase kernel == one-thread-per-frame kernel).
 #include "common.cuh"
 #include "pipeline.cuh"
 
@@ -54,6 +55,8 @@ struct prs_args {
     int L, M, m, Sp, Q, K, nfr;
     int pitch;                    // floats between the channel rows of a staged tile (multiple of 4)
     unsigned long long tile0, ntiles;
+    unsigned long long n_total;   // frames of the whole signal
+    size_t in_avail, n_out;       // frames held in `in`; outputs of this call
 };
 
 // clamp of A:228-232 in two instructions: min.NaN / max.NaN return NaN when an operand is NaN, so NaN passes through
@@ -94,6 +97,18 @@ __global__ void __launch_bounds__(256) planar_resample_kernel(prs_args a) {
     const int K = a.K, Q = a.Q, Sp = a.Sp, pitch = a.pitch;
     const int jrow = t / a.L;                                           // which of the m periods of an iteration this thread is in
 
+    const long long n_total = (long long)a.n_total, in_lo = (long long)a.in_first, in_hi = in_lo + (long long)a.in_avail;
+    const unsigned long long out_lo = a.out_first, out_hi = a.out_first + a.n_out;
+    // a tile whose staged frames (aligned start to rounded-up end) all exist in the window travels by bulk copy; the
+    // first / last tiles of the signal or of the caller's window are staged with plain loads and a clamped index
+    // (= the nil substitutions of A:259 / A:264)
+    auto interior = [&](unsigned long long tile) {
+        const long long gA = (long long)(tile * (unsigned long long)a.K * (unsigned long long)a.Q) - 1;
+        if (gA < in_lo) return false;
+        const long long a0 = (gA - in_lo) & ~3ll;
+        const long long last = in_lo + a0 + (long long)((a.nfr + (int)((gA - in_lo) - a0) + 3) / 4) * 4;
+        return last <= in_hi && last <= n_total;
+    };
     // thread 0: bulk copies of one tile's rows, from a 16-byte aligned start
     auto issue = [&](unsigned long long tile, int buf) {
         const long long gA = (long long)(tile * (unsigned long long)a.K * (unsigned long long)a.Q) - 1;   // first frame the tile needs
@@ -138,7 +153,7 @@ __global__ void __launch_bounds__(256) planar_resample_kernel(prs_args a) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        issue(tile, 0);
+        if (interior(tile)) issue(tile, 0);
     }
     decide(tile, 0);
     __syncthreads();
@@ -149,19 +164,40 @@ __global__ void __launch_bounds__(256) planar_resample_kernel(prs_args a) {
         const bool has_next = next < a.tile0 + a.ntiles;
         // the other buffer (tile it - 1) and its table are free: every thread passed the barrier that ended that tile
         if (has_next) {
-            if (t == 0) issue(next, buf ^ 1);
+            if (t == 0 && interior(next)) issue(next, buf ^ 1);
             decide(next, buf ^ 1);
         }
-        mbar_wait(&bars[buf], buf ? ph1 : ph0);
-        if (buf) ph1 ^= 1u; else ph0 ^= 1u;
+        const long long gA = (long long)(tile * (unsigned long long)a.K * (unsigned long long)a.Q) - 1;
+        int sh;                                                                       // staged index of frame gA
+        const bool whole = tile * tile_out >= out_lo && (tile + 1) * tile_out <= out_hi;
+        if (interior(tile)) {
+            mbar_wait(&bars[buf], buf ? ph1 : ph0);
+            if (buf) ph1 ^= 1u; else ph0 ^= 1u;
+            sh = (int)((size_t)(gA - in_lo) & 3);
+        } else {
+            sh = 0;
+            for (int c = 0; c < C; c++) {
+                float *dst = bufs + ((size_t)buf * C + c) * pitch;
+                const float *rowp = a.in + (size_t)c * a.in_stride;
+                for (int f = t; f < a.nfr; f += blockDim.x) {
+                    long long gi = gA + f;
+                    gi = gi < 0 ? 0 : (gi >= n_total ? n_total - 1 : gi);
+                    dst[f] = (gi >= in_lo && gi < in_hi) ? rowp[gi - in_lo] : 0.0f;   // outside the window: not needed by any output of this call
+                }
+            }
+            __syncthreads();
+        }
         if (active) {
-            const long long gA = (long long)(tile * (unsigned long long)a.K * (unsigned long long)a.Q) - 1;
-            const int sh = (int)((size_t)(gA - (long long)a.in_first) & 3);          // staged index of frame gA
             const float *f = bufs + (size_t)buf * C * pitch + off_t + sh;            // taps of output k = 0, channel 0
             const unsigned char *ht = hit_tab + buf * ntab + jrow;
-            float *outp = a.out + (size_t)(tile * tile_out - a.out_first) + t;
+            const unsigned long long o0 = tile * tile_out + t;                        // global index of this thread's output k = 0
+            float *outp = a.out + (size_t)((long long)o0 - (long long)a.out_first);
 #pragma unroll 4
             for (int k = 0; k < K; k++) {
+                if (!whole) {                                                         // first / last tile of a range
+                    const unsigned long long o = o0 + (unsigned long long)k * Sp;
+                    if (o < out_lo || o >= out_hi) { f += Q; outp += Sp; continue; }
+                }
                 int st = NEAR_ABOVE;
                 if (is_j0) st = ht[k * a.m];
                 if (CT == 1) {
@@ -189,9 +225,6 @@ __global__ void __launch_bounds__(256) planar_resample_kernel(prs_args a) {
 // skips those taps, A:271; a zero tap adds exactly nothing), so a range gives the same bits however it is sharded.
 struct sinc_args {
     prs_args g;
-    unsigned long long n_total;
-    size_t in_avail;
-    size_t n_out;
     float eps_r;
 };
 
@@ -225,8 +258,8 @@ __global__ void __launch_bounds__(256) planar_sinc_kernel(sinc_args sa) {
     const int ntab = a.K * a.m;
     const int K = a.K, Q = a.Q, Sp = a.Sp, pitch = a.pitch;
     const int jrow = t / a.L;
-    const long long n_total = (long long)sa.n_total, in_lo = (long long)a.in_first, in_hi = in_lo + (long long)sa.in_avail;
-    const unsigned long long out_lo = a.out_first, out_hi = a.out_first + sa.n_out;
+    const long long n_total = (long long)a.n_total, in_lo = (long long)a.in_first, in_hi = in_lo + (long long)a.in_avail;
+    const unsigned long long out_lo = a.out_first, out_hi = a.out_first + a.n_out;
 
     auto first_frame = [&](unsigned long long tile) { return (long long)(tile * (unsigned long long)a.K * (unsigned long long)a.Q) - 10; };
     // a tile whose staged frames (aligned start to rounded-up end) all exist in the window travels by bulk copy
@@ -333,8 +366,7 @@ long long gcd_ll(long long x, long long y) { while (y) { long long r = x % y; x 
 
 }  // namespace
 
-// Returns 1 when the whole range was produced (interior tiles here, the remainders through aukit_poly_resample_try),
-// 0 when this path does not apply, -1 on error.
+// Returns 1 when the range was produced, 0 when this path does not apply, -1 on error.
 int aukit_planar_resample_try(aukit_ctx *ctx, const float *d_in, size_t in_stride, int channels, unsigned long long n_in_total,
                               unsigned long long in_first, size_t in_avail, double srcRate, double dstRate, int interpolation,
                               unsigned long long out_first, size_t n_out, float *d_out, size_t out_stride) {
@@ -358,7 +390,7 @@ int aukit_planar_resample_try(aukit_ctx *ctx, const float *d_in, size_t in_strid
     a.Sp = a.L * a.m;
     a.Q = a.M * a.m;
     const int threads = (a.Sp + 31) / 32 * 32;
-    const size_t budget = 32 * 1024;                                    // per buffer: small tiles, many resident CTAs
+    const size_t budget = 16 * 1024;                                    // per buffer: small tiles, many resident CTAs, short tail
     long long K = ((long long)(budget / (sizeof(float) * (size_t)channels)) - 12) / a.Q;
     if (K < 1) K = 1;
     if (K > 64) K = 64;
@@ -368,44 +400,13 @@ int aukit_planar_resample_try(aukit_ctx *ctx, const float *d_in, size_t in_strid
     const size_t smem = (size_t)2 * channels * a.pitch * sizeof(float) + (size_t)2 * a.K * a.m + 16;
     if (smem > 100 * 1024) return 0;
     const unsigned long long tile_out = (unsigned long long)a.Sp * a.K;
-    // interior tiles: all outputs inside the range, all staged frames (from the aligned start to the rounded-up end)
-    // inside the signal and inside the window the caller holds
-    auto fits = [&](unsigned long long T) {
-        if (T * tile_out < out_first || (T + 1) * tile_out > out_first + n_out) return false;
-        const long long gA = (long long)(T * (unsigned long long)a.K * (unsigned long long)a.Q) - 1;
-        if (gA < (long long)in_first) return false;
-        const unsigned long long foff = (unsigned long long)gA - in_first, a0 = foff & ~3ull;
-        const unsigned long long last = in_first + a0 + (unsigned long long)((a.nfr + (int)(foff - a0) + 3) / 4) * 4;   // one past the last frame read
-        return last <= in_first + in_avail && last <= n_in_total;
-    };
-    unsigned long long T_lo = (out_first + tile_out - 1) / tile_out, T_hi = (out_first + n_out) / tile_out;   // [T_lo, T_hi)
-    while (T_lo < T_hi && !fits(T_lo)) T_lo++;
-    while (T_hi > T_lo && !fits(T_hi - 1)) T_hi--;
-    if (T_hi <= T_lo + 1) return 0;                                     // nothing worth a launch of its own
-    const unsigned long long o_lo = T_lo * tile_out, o_hi = T_hi * tile_out;
-    // The first and last tiles go through the polyphase kernel on the context's side stream, beside the interior kernel
-    // (disjoint output ranges; two ~11 us launches in series were a third of a 20 M-frame call).
-    cudaStream_t main_stream = ctx->stream;
-    if (aukit_cuda_check(cudaEventRecord(ctx->ev_fork, main_stream), "fork event")) return -1;
-    if (aukit_cuda_check(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0), "fork wait")) return -1;
-    ctx->stream = ctx->side_stream;
-    int edge_rc = 1;
-    if (o_lo > out_first)
-        edge_rc = aukit_poly_resample_try(ctx, d_in, in_stride, channels, n_in_total, in_first, in_avail, srcRate, dstRate, interpolation,
-                                          out_first, (size_t)(o_lo - out_first), d_out, out_stride);
-    if (edge_rc == 1 && o_hi < out_first + n_out)
-        edge_rc = aukit_poly_resample_try(ctx, d_in, in_stride, channels, n_in_total, in_first, in_avail, srcRate, dstRate, interpolation,
-                                          o_hi, (size_t)(out_first + n_out - o_hi), d_out + (size_t)(o_hi - out_first), out_stride);
-    ctx->stream = main_stream;
-    if (aukit_cuda_check(cudaEventRecord(ctx->ev_join, ctx->side_stream), "join event")) return -1;
-    if (aukit_cuda_check(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0), "join wait")) return -1;
-    if (edge_rc != 1) {
-        if (edge_rc == 0) aukit_fail("aukit_cuda: no polyphase kernel for the edge tiles of the range");
-        return -1;
-    }
+    // positions past the end of the signal (absurd ratios) are the caller's / the per-frame kernel's business
+    if (n_out < 4 * tile_out) return 0;                                 // short ranges: the polyphase kernel's tiles are as good
     a.in = d_in; a.in_stride = in_stride; a.in_first = in_first; a.channels = channels; a.ratio = ratio;
     a.out = d_out; a.out_stride = out_stride; a.out_first = out_first;
-    a.tile0 = T_lo; a.ntiles = T_hi - T_lo;
+    a.tile0 = out_first / tile_out;
+    a.ntiles = (out_first + n_out - 1) / tile_out - a.tile0 + 1;
+    a.n_total = n_in_total; a.in_avail = in_avail; a.n_out = n_out;
     auto go = [&](auto kern) -> int {
         if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
         int occ = 0;
@@ -467,7 +468,7 @@ int aukit_planar_sinc_try(aukit_ctx *ctx, const float *d_in, size_t in_stride, i
     a.out = d_out; a.out_stride = out_stride; a.out_first = out_first;
     a.tile0 = out_first / tile_out;
     a.ntiles = (out_first + n_out - 1) / tile_out - a.tile0 + 1;
-    sa.n_total = n_in_total; sa.in_avail = in_avail; sa.n_out = n_out;
+    a.n_total = n_in_total; a.in_avail = in_avail; a.n_out = n_out;
     sa.eps_r = (float)(fma(-(double)M, ratio, (double)L) / ((double)M * ratio));
     auto go = [&](auto kern) -> int {
         if (aukit_cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return -1;
