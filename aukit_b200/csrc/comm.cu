@@ -311,7 +311,7 @@ extern "C" int aukit_cuda_group_normalize(aukit_group *g, aukit_audio *const *sh
 // n_out = floor(n_in_total * ratio)).  Bit-identical to the same call on one GPU.
 // dst[c * dst_pitch + i]: host memory (kind = DeviceToHost) or device memory of any device (kind = Default: peer copies)
 static int group_preload_into(aukit_group *g, const aukit_pipeline_desc *whole, const void *h_in, size_t nbytes,
-                              double peakAmplitude, float *dst, size_t dst_pitch, cudaMemcpyKind kind) {
+                              double peakAmplitude, float *dst, size_t dst_pitch, cudaMemcpyKind kind, int dst_device) {
     if (!g || !whole || !dst) return aukit_fail("aukit_cuda: null argument");
     device_guard guard;
     const size_t FB = (size_t)whole->channels * (size_t)(whole->bitDepth / 8);
@@ -369,9 +369,15 @@ static int group_preload_into(aukit_group *g, const aukit_pipeline_desc *whole, 
         part &p = parts[i];
         if ((rc = aukit_cuda_check(cudaSetDevice(ctx->device), "cudaSetDevice"))) break;
         if ((rc = aukit_cuda_dev_pipeline_apply(ctx, &p.d, p.d_in, peakAmplitude, aukit_cuda_comm_values(g->comm[i]), p.d_out, p.stride))) break;
-        if (p.d.n_out)
+        if (p.d.n_out && kind == cudaMemcpyDeviceToHost) {
             rc = aukit_cuda_check(cudaMemcpy2DAsync(dst + p.d.out_first, dst_pitch * sizeof(float), p.d_out, p.stride * sizeof(float),
                                                     p.d.n_out * sizeof(float), (size_t)out_ch, kind, ctx->stream), "gather");
+        } else if (p.d.n_out) {
+            // device to device, possibly across devices: row by row (a 2-D copy between two devices is not accepted)
+            for (int c = 0; c < out_ch && !rc; c++)
+                rc = aukit_cuda_check(cudaMemcpyPeerAsync(dst + (size_t)c * dst_pitch + p.d.out_first, dst_device, p.d_out + (size_t)c * p.stride,
+                                                          ctx->device, p.d.n_out * sizeof(float), ctx->stream), "gather");
+        }
     }
     for (int i = 0; i < W; i++) {
         cudaSetDevice(g->ctx[i]->device);
@@ -387,7 +393,7 @@ extern "C" int aukit_cuda_group_preload(aukit_group *g, const aukit_pipeline_des
                                         double peakAmplitude, float *h_out) {
     if (!whole) return aukit_fail("aukit_cuda: null argument");
     return group_preload_into(g, whole, h_in, nbytes, peakAmplitude, h_out,
-                              (size_t)aukit_resample_out_len(whole->n_in_total, whole->srcRate, whole->dstRate), cudaMemcpyDeviceToHost);
+                              (size_t)aukit_resample_out_len(whole->n_in_total, whole->srcRate, whole->dstRate), cudaMemcpyDeviceToHost, -1);
 }
 
 // The same, gathered into ONE device-resident Audio that belongs to `owner` (any context, normally the caller's own on
@@ -403,7 +409,22 @@ extern "C" int aukit_cuda_group_preload_audio(aukit_group *g, aukit_ctx *owner, 
         if (aukit_audio_alloc(owner, whole->mono ? 1 : whole->channels, (size_t)n_out, whole->dstRate, &a)) return -1;
         if (aukit_cuda_synchronize(owner)) { aukit_cuda_audio_free(owner, a); return -1; }   // the allocation is stream-ordered on owner's stream
     }
-    const int rc = group_preload_into(g, whole, h_in, nbytes, peakAmplitude, a->data, a->stride, cudaMemcpyDefault);
+    // Audio buffers come from the devices' stream-ordered pools, which peers cannot touch by default: open the owner's pool
+    // to every member device (and the members' pools to the owner) once per call; the copies themselves are peer copies
+    for (int i = 0; i < g->n; i++) {
+        const int d = g->ctx[i]->device;
+        if (d == owner->device) continue;
+        cudaMemPool_t po, pm;
+        if (cudaDeviceGetDefaultMemPool(&po, owner->device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pm, d) == cudaSuccess) {
+            cudaMemAccessDesc to_member{}, to_owner{};
+            to_member.location.type = cudaMemLocationTypeDevice; to_member.location.id = d; to_member.flags = cudaMemAccessFlagsProtReadWrite;
+            to_owner.location.type = cudaMemLocationTypeDevice; to_owner.location.id = owner->device; to_owner.flags = cudaMemAccessFlagsProtReadWrite;
+            cudaMemPoolSetAccess(po, &to_member, 1);
+            cudaMemPoolSetAccess(pm, &to_owner, 1);
+        }
+        cudaGetLastError();                                             // without peer capability the peer copy below stages through the host
+    }
+    const int rc = group_preload_into(g, whole, h_in, nbytes, peakAmplitude, a->data, a->stride, cudaMemcpyDefault, owner->device);
     if (rc) { device_guard guard; cudaSetDevice(owner->device); aukit_cuda_audio_free(owner, a); return rc; }
     *out = a;
     return 0;

@@ -294,7 +294,7 @@ def run_b200(args):
                  "(own input window from the global frame index, exchanged max) and compared bits" % CHK,
                  "strong": {"workload": "%g h total split over %d GPUs" % (args.seconds / 3600.0, world), "ms_per_step": ms_strong,
                             "value": n_out_1h / (ms_strong * 1e-3) / 1e6, "scaling": "strong"},
-                 "exchange": "aukit_comm: peer-mapped atomicMax + arrival counter over NVLink, one kernel per rank (csrc/comm.cu)"
+                 "exchange": "aukit_comm: one tagged 8-byte posted write per peer into peer-mapped exchange blocks (CUDA IPC) + a poll on the own block, one kernel per rank in stream order between the passes (csrc/comm.cu)"
                              if sp.comm is not None else "torch.distributed all_reduce(MAX)"}
 
     # ---- per-kernel timing for the roofline (same stream, events around each launch batch)

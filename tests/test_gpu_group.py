@@ -80,6 +80,7 @@ def test_group_normalize_on_sharded_audio(ak, O, independent):
                 parts.append(a.numpy())
             got = np.concatenate(parts, axis=1)
             assert np.max(np.abs(got - ref)) <= TOL
+            ak.context().make_current()          # several devices in one process: the context in use is made current (include/aukit_cuda.h)
             one = ak.effects.normalize(ak.Audio.from_numpy(x, 48000), 0.9, independent).numpy()
             assert f32_equal_bits(got, one)
             del shards
