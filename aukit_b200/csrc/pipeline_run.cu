@@ -45,6 +45,7 @@ struct run_plan {
     unsigned long long tile0;     // first warp tile (32*L outputs each) of this launch
     unsigned long long ntiles;
     int nbuf;                     // static kernel: frame buffers in the CTA's ring
+    int nbuf2;                    // ... of a CTA whose tiles span two drift segments (a second weight table is resident)
     // static kernel: the launch's tile range as up to RUN_MAXSEG segments of constant drift (the weight table of a
     // segment is rebuilt in place by the first warp that reaches it -- one launch per pass instead of one per segment,
     // which cost a drain + refill of the persistent kernel each, ~8 us)
@@ -565,13 +566,23 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
     // nobody waits for DRAM unless DRAM is the bottleneck.
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pair = warp >> 1, cls = warp & 1, npairs = rp.nwarps >> 1;
-        const int nbuf = rp.nbuf;
-        // layout: weights[nW][L] float4 (nW = 2 when the launch spans several drift segments) | nbuf frame buffers | staging
-        float4 *W = reinterpret_cast<float4 *>(smem);
-        const int nW = rp.nseg > 1 ? 2 : 1;
-        const uint32_t bufs_off = (uint32_t)(nW * L) * 16, buf_bytes = (uint32_t)rp.raw_words * 4;
+        // Tiles of this CTA.  One drift segment in the launch: tile0 + blockIdx.x + i * gridDim.x (neighbouring CTAs stream
+        // neighbouring tiles).  Several segments: a contiguous chunk per CTA, so that only the CTA whose chunk holds a
+        // segment boundary needs two weight tables -- every other CTA keeps the frame buffer a second table would cost
+        // (the peak pass lost 5 % to that on far time shards).
+        const bool blocked = rp.nseg > 1;
+        const unsigned long long c0 = blocked ? rp.ntiles * blockIdx.x / gridDim.x : blockIdx.x;
+        const unsigned long long c1 = blocked ? rp.ntiles * (blockIdx.x + 1) / gridDim.x : rp.ntiles;
+        const unsigned long long cta_first = rp.tile0 + c0, cta_step = blocked ? 1ull : (unsigned long long)gridDim.x;
+        const int cta_n = blocked ? (int)(c1 - c0) : (c0 < rp.ntiles ? (int)((rp.ntiles - c0 + gridDim.x - 1) / gridDim.x) : 0);
         int seg0 = 0;
-        while (seg0 + 1 < rp.nseg && rp.tile0 + blockIdx.x >= rp.seg_end[seg0]) seg0++;
+        while (seg0 + 1 < rp.nseg && cta_first >= rp.seg_end[seg0]) seg0++;
+        const bool spans = blocked && cta_n > 0 && cta_first + (unsigned long long)(cta_n - 1) >= rp.seg_end[seg0];
+        // layout: weights[nW][L] float4 (nW = 2 when this CTA's tiles span drift segments) | nbuf frame buffers | staging
+        float4 *W = reinterpret_cast<float4 *>(smem);
+        const int nW = spans ? 2 : 1;
+        const int nbuf = spans ? rp.nbuf2 : rp.nbuf;
+        const uint32_t bufs_off = (uint32_t)(nW * L) * 16, buf_bytes = (uint32_t)rp.raw_words * 4;
         for (int e = threadIdx.x; e < L; e += blockDim.x) {     // fp64 weights of A:265 at fraction j/L + delta, narrowed
             const int j = (int)(((long long)e * M) % L);
             const double x = (double)j / (double)L + (double)rp.seg_delta[seg0];
@@ -587,19 +598,19 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
         if (threadIdx.x == 0) {
             // the byte offset of a tile inside its 16-byte aligned bulk copy (sh) is the same for every tile: the tile
             // pitch is a multiple of 16 bytes
-            const unsigned long long first = rp.tile0 + blockIdx.x, t_end = rp.tile0 + rp.ntiles;
+            const unsigned long long first = cta_first;
             const size_t boff = (size_t)((long long)(first * (unsigned long long)(SPERIODS * M)) - 1 - (long long)a.in_first) * 4;
             const int sh = (int)((boff & 15) >> 2);
-            const int n = first < t_end ? (int)((t_end - first + gridDim.x - 1) / gridDim.x) : 0;
+            const int n = cta_n;
             const uint32_t bytes = (uint32_t)(((size_t)(SPERIODS * M + 3 + sh) * 4 + 15) & ~(size_t)15);
             cst.src0 = (unsigned long long)(uintptr_t)(a.in + (boff & ~(size_t)15));
-            cst.src_step = (unsigned long long)gridDim.x * (SPERIODS * M * 4);
+            cst.src_step = cta_step * (SPERIODS * M * 4);
             cst.dst0 = APPLY ? (unsigned long long)(uintptr_t)(a.out + (size_t)(first * (unsigned long long)(SPERIODS * L) - a.out_first)) : 0ull;
-            cst.dst_step = (unsigned long long)gridDim.x * (SPERIODS * L * 4);
+            cst.dst_step = cta_step * (SPERIODS * L * 4);
             cst.bytes = bytes; cst.sh = sh; cst.n = n; cst.nbuf = nbuf; cst.npairs = npairs;
             cst.bufs_off = bufs_off; cst.buf_bytes = buf_bytes;
-            cst.tile_first = first; cst.tile_step = gridDim.x;
-            cst.nseg = rp.nseg;
+            cst.tile_first = first; cst.tile_step = cta_step;
+            cst.nseg = spans ? rp.nseg : 1;                    // one resident table: the segment logic of fetch() is off
             cst.wclaim[0] = cst.wclaim[1] = cst.wtag[0] = cst.wtag[1] = -1;
             cst.wclaim[seg0 & 1] = cst.wtag[seg0 & 1] = seg0;
             float mult = 0.f, one_hi = 1.0f;
@@ -774,13 +785,13 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
 template <bool APPLY, int L, int M>
 int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     rp.raw_words = ((SPERIODS * M + 3 + 3) + 31) / 32 * 32;       // tile + halo + alignment shift; 128-byte pitch
-    const size_t fixed = (size_t)(rp.nseg > 1 ? 2 : 1) * L * 16 + 128;
+    const size_t fixed = (size_t)L * 16 + 128;                     // one weight table; a CTA that spans segments trades a buffer for a second one
     const size_t buf = (size_t)rp.raw_words * 4, stage = APPLY ? 2 * SSTAGE_WORDS * 4 : 0;   // per buffer; per pair
     const size_t budget = 227 * 1024 - 2048;                       // opt-in maximum minus this kernel's static shared memory
     // buffers beyond one per pair = tiles in flight while every pair computes.  Measured: the peak pass (no staging, no
     // output stream) gains 9 % from 8 pairs + 4 over 9 + 2 (0.152 -> 0.139 ms); the apply pass is flat from 8 + 2 to 6 + 4
     // Warp pairs first (they are what issues instructions), spare buffers with what is left: 8 pairs + 2 (apply) or
-    // + 4 (peak; + 3 when a second weight table is resident).
+    // + 4 (peak).
     const int want_spare = APPLY ? 2 : 4, cap = APPLY ? 8 : 9;     // cap = launch bounds
     int np = 0, spare = want_spare;
     for (; spare >= 0; spare--) {
@@ -795,7 +806,10 @@ int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     if (nbuf < np) return 0;
     rp.nwarps = 2 * np;
     rp.nbuf = nbuf;
+    rp.nbuf2 = nbuf;
     const size_t smem = fixed + (size_t)nbuf * buf + (size_t)np * stage;
+    while (rp.nbuf2 > np && fixed + (size_t)L * 16 + (size_t)rp.nbuf2 * buf + (size_t)np * stage > smem) rp.nbuf2--;
+    if (fixed + (size_t)L * 16 + (size_t)rp.nbuf2 * buf + (size_t)np * stage > smem) return 0;
     // the final clamp to +-1 can only act when |peakAmplitude| is (about) 1 or more (negative peaks included: normalize(a, -2))
     const bool clamp1 = APPLY && !(fabs(a.peak) < 1.0 - 9.5367431640625e-07);
     // max(u, 0) of the sample conversion rides on the ALU pipe (CVTA): the FMA pipe is the busier one here
