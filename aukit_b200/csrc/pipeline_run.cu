@@ -570,18 +570,20 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
         // neighbouring tiles).  Several segments: a contiguous chunk per CTA, so that only the CTA whose chunk holds a
         // segment boundary needs two weight tables -- every other CTA keeps the frame buffer a second table would cost
         // (the peak pass lost 5 % to that on far time shards).
-        const bool blocked = rp.nseg > 1;
+        // (peak pass only: in the apply pass 146 distant output streams cost more than the buffer gains, 0.224 -> 0.234 ms)
+        const bool blocked = rp.nseg > 1 && !APPLY;
         const unsigned long long c0 = blocked ? rp.ntiles * blockIdx.x / gridDim.x : blockIdx.x;
         const unsigned long long c1 = blocked ? rp.ntiles * (blockIdx.x + 1) / gridDim.x : rp.ntiles;
         const unsigned long long cta_first = rp.tile0 + c0, cta_step = blocked ? 1ull : (unsigned long long)gridDim.x;
         const int cta_n = blocked ? (int)(c1 - c0) : (c0 < rp.ntiles ? (int)((rp.ntiles - c0 + gridDim.x - 1) / gridDim.x) : 0);
         int seg0 = 0;
         while (seg0 + 1 < rp.nseg && cta_first >= rp.seg_end[seg0]) seg0++;
-        const bool spans = blocked && cta_n > 0 && cta_first + (unsigned long long)(cta_n - 1) >= rp.seg_end[seg0];
+        const bool spans = rp.nseg > 1 && cta_n > 0 && seg0 + 1 < rp.nseg &&
+                           cta_first + (unsigned long long)(cta_n - 1) * cta_step >= rp.seg_end[seg0];
         // layout: weights[nW][L] float4 (nW = 2 when this CTA's tiles span drift segments) | nbuf frame buffers | staging
         float4 *W = reinterpret_cast<float4 *>(smem);
-        const int nW = spans ? 2 : 1;
-        const int nbuf = spans ? rp.nbuf2 : rp.nbuf;
+        const int nW = (APPLY ? rp.nseg > 1 : spans) ? 2 : 1;          // apply pass: strided tiles, every CTA meets every segment
+        const int nbuf = (!APPLY && spans) ? rp.nbuf2 : rp.nbuf;
         const uint32_t bufs_off = (uint32_t)(nW * L) * 16, buf_bytes = (uint32_t)rp.raw_words * 4;
         for (int e = threadIdx.x; e < L; e += blockDim.x) {     // fp64 weights of A:265 at fraction j/L + delta, narrowed
             const int j = (int)(((long long)e * M) % L);
@@ -610,7 +612,7 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
             cst.bytes = bytes; cst.sh = sh; cst.n = n; cst.nbuf = nbuf; cst.npairs = npairs;
             cst.bufs_off = bufs_off; cst.buf_bytes = buf_bytes;
             cst.tile_first = first; cst.tile_step = cta_step;
-            cst.nseg = spans ? rp.nseg : 1;                    // one resident table: the segment logic of fetch() is off
+            cst.nseg = nW == 2 ? rp.nseg : 1;                  // one resident table: the segment logic of fetch() is off
             cst.wclaim[0] = cst.wclaim[1] = cst.wtag[0] = cst.wtag[1] = -1;
             cst.wclaim[seg0 & 1] = cst.wtag[seg0 & 1] = seg0;
             float mult = 0.f, one_hi = 1.0f;
@@ -785,7 +787,9 @@ __global__ void __launch_bounds__(APPLY ? 512 : 576, 1) run_static_kernel(pipe_a
 template <bool APPLY, int L, int M>
 int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     rp.raw_words = ((SPERIODS * M + 3 + 3) + 31) / 32 * 32;       // tile + halo + alignment shift; 128-byte pitch
-    const size_t fixed = (size_t)L * 16 + 128;                     // one weight table; a CTA that spans segments trades a buffer for a second one
+    // peak pass: one weight table, a CTA whose chunk spans two segments trades a buffer for the second (nbuf2);
+    // apply pass: two tables in every CTA of a multi-segment launch
+    const size_t fixed = (size_t)((APPLY && rp.nseg > 1) ? 2 : 1) * L * 16 + 128;
     const size_t buf = (size_t)rp.raw_words * 4, stage = APPLY ? 2 * SSTAGE_WORDS * 4 : 0;   // per buffer; per pair
     const size_t budget = 227 * 1024 - 2048;                       // opt-in maximum minus this kernel's static shared memory
     // buffers beyond one per pair = tiles in flight while every pair computes.  Measured: the peak pass (no staging, no
@@ -808,8 +812,10 @@ int launch_run_static(aukit_ctx *ctx, const pipe_args &a, run_plan rp) {
     rp.nbuf = nbuf;
     rp.nbuf2 = nbuf;
     const size_t smem = fixed + (size_t)nbuf * buf + (size_t)np * stage;
-    while (rp.nbuf2 > np && fixed + (size_t)L * 16 + (size_t)rp.nbuf2 * buf + (size_t)np * stage > smem) rp.nbuf2--;
-    if (fixed + (size_t)L * 16 + (size_t)rp.nbuf2 * buf + (size_t)np * stage > smem) return 0;
+    if (!APPLY && rp.nseg > 1) {
+        while (rp.nbuf2 > np && fixed + (size_t)L * 16 + (size_t)rp.nbuf2 * buf + (size_t)np * stage > smem) rp.nbuf2--;
+        if (fixed + (size_t)L * 16 + (size_t)rp.nbuf2 * buf + (size_t)np * stage > smem) return 0;
+    }
     // the final clamp to +-1 can only act when |peakAmplitude| is (about) 1 or more (negative peaks included: normalize(a, -2))
     const bool clamp1 = APPLY && !(fabs(a.peak) < 1.0 - 9.5367431640625e-07);
     // max(u, 0) of the sample conversion rides on the ALU pipe (CVTA): the FMA pipe is the busier one here
