@@ -314,7 +314,7 @@ def run_b200(args):
     # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of this same workload (per launch)
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_apply_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_apply_traffic.json")))
         if world == 1 and not args.emulate_shard and abs(args.seconds - 3600.0) < 1e-6:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except (OSError, ValueError, KeyError):
@@ -461,7 +461,7 @@ def run_b200(args):
             "roofline": {
                 "bound": "hbm", "kernel": "fused apply pass: run_static_kernel<APPLY=true> (interior) + poly_kernel edges", "achieved": achieved, "peak": peak_gbs,
                 "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
-                "traffic_source": "profiles/r1_apply_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)" if traffic else None,
+                "traffic_source": "profiles/r2_apply_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed --set full capture of this build (profiles/r2_final_ncu_run_kernel.txt), not measured in this run" if traffic else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": apply_bytes, "ms_per_launch": ms_apply,
                 "peak_pass": {"algorithmic_bytes_per_launch": peak_bytes, "ms_per_launch": ms_peak,
