@@ -138,16 +138,16 @@ __global__ void __launch_bounds__(256) planar_resample_kernel(prs_args a) {
     // one channel of one output: taps at f[0..3] (p1 = f[1]), st = decision for a j == 0 output
     auto value = [&](const float *f, int st) -> float {
         const float p1 = f[1];
+        const float p0 = (MODE == AUKIT_INTERP_LINEAR) ? 0.f : f[0];    // `none` loads it unconditionally: selects, not branches, below
         float v;
-        if (MODE == AUKIT_INTERP_CUBIC) v = __fmaf_rn(w3, f[3], __fmaf_rn(w2, f[2], __fmaf_rn(w1, p1, w0 * f[0])));
+        if (MODE == AUKIT_INTERP_CUBIC) v = __fmaf_rn(w3, f[3], __fmaf_rn(w2, f[2], __fmaf_rn(w1, p1, w0 * p0)));
         else if (MODE == AUKIT_INTERP_LINEAR) v = __fmaf_rn(f[2] - p1, fx, p1);
         else v = p1;
         float r = clamp_nan(v);
         if (is_j0) {
             // one output per period sits on (or one ulp beside) an input frame: decided exactly
-            if (st == HIT) r = p1;                                                       // copied unclamped, A:667
-            else if (MODE == AUKIT_INTERP_NONE && st == NEAR_BELOW) r = clamp_nan(f[0]); // floor(x) is one lower
-            else r = clamp_nan(p1);                                                      // weights at j == 0 are (0, 1, 0, 0)
+            const float below = (MODE == AUKIT_INTERP_NONE && st == NEAR_BELOW) ? p0 : p1;   // `none`: floor(x) is one lower
+            r = st == HIT ? p1 : clamp_nan(below);               // HIT: copied unclamped, A:667; else weights (0, 1, 0, 0)
         }
         return r;
     };
@@ -201,8 +201,7 @@ __global__ void __launch_bounds__(256) planar_resample_kernel(prs_args a) {
             const unsigned char *ht = hit_tab + buf * ntab + jrow;
 #pragma unroll 4
             for (int k = 0; k < K; k++) {
-                int st = NEAR_ABOVE;
-                if (is_j0) st = ht[k * a.m];
+                const int st = ht[k * a.m];                          // read by every thread (one byte, no branch); only j == 0 threads use it
                 if (CT == 1) {
                     os[0] = value(f, st);
                 } else if (CT == 2) {
@@ -227,8 +226,7 @@ __global__ void __launch_bounds__(256) planar_resample_kernel(prs_args a) {
                     const unsigned long long o = o0 + (unsigned long long)k * Sp;
                     if (o < out_lo || o >= out_hi) { f += Q; outp += Sp; continue; }
                 }
-                int st = NEAR_ABOVE;
-                if (is_j0) st = ht[k * a.m];
+                const int st = ht[k * a.m];                          // read by every thread (one byte, no branch); only j == 0 threads use it
                 if (CT == 1) {
                     outp[0] = value(f, st);
                 } else if (CT == 2) {
