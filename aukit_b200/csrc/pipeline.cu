@@ -115,7 +115,17 @@ __global__ void __launch_bounds__(256) wide_f32_kernel(pipe_args a) {
         const bool staged = bulk_ok && ob + 256 <= a.n_out;            // a whole group of 256 frames (uniform over the CTA)
         if (o < a.n_out) {
         const unsigned long long i0 = a.out_first + o;
-        const double x = __dadd_rn(__ddiv_rn((double)i0, a.ratio), 1.0);   // A:666
+        // A:666: (i - 1) / ratio + 1 with the correctly rounded quotient -- by the IEEE division, or by the 3-operation FMA
+        // sequence where the host proved it equal for every index of the call (a third of this kernel's instructions)
+        const double nd = (double)i0;
+        double qd;
+        if (a.qfma_ok) {
+            const double q0 = __dmul_rn(nd, a.y);
+            qd = __fma_rn(__fma_rn(-q0, a.ratio, nd), a.y, q0);
+        } else {
+            qd = __ddiv_rn(nd, a.ratio);
+        }
+        const double x = __dadd_rn(qd, 1.0);
         const double fl = floor(x);
         const bool hit = (x == fl);
         const long long f = (long long)fl;                             // 1-based index of p1
@@ -217,7 +227,13 @@ int wide_try(aukit_ctx *ctx, const pipe_args &a, const aukit_pipeline_desc *p) {
     if (((uintptr_t)a.in & 15) != 0) return 0;
     int e2 = 0;
     if (frexp(a.ratio, &e2) == 0.5 && a.ratio <= 1.0) return 0;        // 1 / 2^k: the strided gather (K15) is the better kernel
-    const int rc = p->channels == 8 ? launch_wide_c<8, APPLY>(ctx, a, p->interpolation) : launch_wide_c<4, APPLY>(ctx, a, p->interpolation);
+    pipe_args b = a;
+    b.y = 1.0 / a.ratio;
+    // quotients up to the largest position of the WHOLE signal (not of this shard): every shard then takes the same arithmetic
+    int kmax = 0;
+    frexp((double)a.n_total + 4.0, &kmax);
+    b.qfma_ok = aukit_quotient_fma_is_exact(a.ratio, kmax + 1) ? 1 : 0;
+    const int rc = p->channels == 8 ? launch_wide_c<8, APPLY>(ctx, b, p->interpolation) : launch_wide_c<4, APPLY>(ctx, b, p->interpolation);
     return rc ? -1 : 1;
 }
 

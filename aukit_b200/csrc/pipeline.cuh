@@ -25,6 +25,10 @@ struct pipe_args {
     // that the per-channel clamp of A:668 acts on this signal, so run_static_kernel starts on its clamping twin.
     int *hint;
     int epoch;
+    // wide-frame kernel (K16): y = RN(1 / ratio) and whether the three-operation quotient fma(fma(-q0, ratio, n), y, q0),
+    // q0 = RN(n * y), is proved to equal the IEEE division n / ratio over the call's index range (aukit_quotient_fma_is_exact)
+    double y;
+    int qfma_ok;
 };
 
 // implemented in pipeline_poly.cu; returns 1 when it handled the launch, 0 when the generic
