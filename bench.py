@@ -521,7 +521,7 @@ def main():
     ap.add_argument("--configs", default="c3,c4,c5", help="which BASELINE configs to run beside the headline")
     ap.add_argument("--c3-clips", type=int, default=1024, help="clips in config 3 (1024 = BASELINE; fewer for profiler captures)")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel table (N = 1 only)")
-    ap.add_argument("--kernel-scale", type=float, default=0.5, help="size of the per-kernel table's buffers relative to config 2")
+    ap.add_argument("--kernel-scale", type=float, default=1.0, help="size of the per-kernel table's buffers relative to config 2")
     ap.add_argument("--sustained-steps", type=int, default=6000, help="extra back-to-back steps for the sustained figure (0 = skip)")
     ap.add_argument("--emulate-shard", default="", help="diagnostics: 'r/w' = run shard r of a w-GPU time-sharded buffer on one GPU")
     args = ap.parse_args()
