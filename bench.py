@@ -290,12 +290,24 @@ def run_b200(args):
         n_out_1h = int(lib.aukit_resample_out_len(n_in_1h, float(SRC_RATE), float(DST_RATE)))
         sp1.close()
         del d_in1, sp1
+        # the same weak-scaling step with the exchange done by NCCL (torch.distributed.all_reduce(MAX) between the passes):
+        # what north_star names and what round 1 shipped -- the baseline the in-library exchange is measured against
+        ms_nccl = None
+        if dist.get_backend() == "nccl":
+            spn = ShardedPreload(ctx, shard, n_in_total, BITS, "signed", CHANNELS, SRC_RATE, DST_RATE, INTERP, True, PEAK, exchange="torch")
+            ms_nccl, _ = timed(lambda: spn.run_device(d_in), args.steps, args.warmup)
+            nccl_same = bool(torch.equal(spn.d_out[0, :4096], sp.d_out[0, :4096]))
+            spn.close()
+            del spn
         multi = {"shard_bits_equal_single_gpu": bits_ok, "shard_check": "rank 0 recomputed the first %d outputs of every other rank's shard "
                  "(own input window from the global frame index, exchanged max) and compared bits" % CHK,
                  "strong": {"workload": "%g h total split over %d GPUs" % (args.seconds / 3600.0, world), "ms_per_step": ms_strong,
                             "value": n_out_1h / (ms_strong * 1e-3) / 1e6, "scaling": "strong"},
                  "exchange": "aukit_comm: one tagged 8-byte posted write per peer into peer-mapped exchange blocks (CUDA IPC) + a poll on the own block, one kernel per rank in stream order between the passes (csrc/comm.cu)"
                              if sp.comm is not None else "torch.distributed all_reduce(MAX)"}
+        if ms_nccl is not None:
+            multi["nccl_exchange"] = {"ms_per_step": ms_nccl, "value": n_out_total / (ms_nccl * 1e-3) / 1e6, "same_bits": nccl_same,
+                                      "what": "the same step with torch.distributed.all_reduce(MAX) over NCCL between the passes"}
 
     # ---- per-kernel timing for the roofline (same stream, events around each launch batch)
     desc = sp.desc
