@@ -168,6 +168,8 @@ static int l_wav(lua_State *L) {
     aukit_wav_info *info = (aukit_wav_info *)malloc(sizeof *info);
     aukit_audio *a = NULL;
     if (!info) return luaL_error(L, "out of memory");
+    /* the RIFF walk is host work: malformed files raise the reference's errors (A:1460-1507) before the device is touched */
+    if (aukit_cuda_wav_parse(d, n, info)) { free(info); return fail(L); }
     if (aukit_cuda_wav(ctx(L), d, n, optbool(L, 2, 0), (int)luaL_optinteger(L, 3, 0), info, &a)) { free(info); return fail(L); }
     push_audio(L, a);
     lua_createtable(L, 0, 8);
@@ -213,6 +215,7 @@ static int l_au(lua_State *L) {
     const char *d = luaL_checklstring(L, 1, &n);
     aukit_container_info ci;
     aukit_audio *a = NULL;
+    if (aukit_cuda_au_parse(d, n, &ci)) return fail(L);           /* header errors before the device is touched */
     if (aukit_cuda_au(ctx(L), d, n, &ci, &a)) return fail(L);
     return push_container(L, a, &ci, d);
 }
@@ -222,6 +225,7 @@ static int l_aiff(lua_State *L) {
     const char *d = luaL_checklstring(L, 1, &n);
     aukit_container_info ci;
     aukit_audio *a = NULL;
+    if (aukit_cuda_aiff_parse(d, n, &ci)) return fail(L);
     if (aukit_cuda_aiff(ctx(L), d, n, optbool(L, 2, 0), &ci, &a)) return fail(L);
     return push_container(L, a, &ci, d);
 }
