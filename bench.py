@@ -367,6 +367,7 @@ def run_b200(args):
     e2e_value = n_out_total / (ms_e2e * 1e-3) / 1e6
     checksum = float(h_out.abs().max())
     same = bool(torch.equal(h_out, h_out2))
+    e2e_slots = sp.slots
 
     # ---- raw PCIe ceiling of the same byte counts: concurrent pinned H2D + D2H on two streams, no kernels
     s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
@@ -486,7 +487,7 @@ def run_b200(args):
             },
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
                     "ms_per_step": ms_e2e, "steps": e2e_steps,
-                    "mode": "pipelined preloader (C-ABI aukit_cuda_preloader_*): clip i's D2H overlaps clip i+1's H2D, 2 device slots",
+                    "mode": "pipelined preloader (C-ABI aukit_cuda_preloader_*): clip i's D2H overlaps clip i+1's H2D, %d device slots" % e2e_slots,
                     "single_clip_ms": ms_single, "single_clip_value": n_out_total / (ms_single * 1e-3) / 1e6,
                     "outputs_identical_across_slots": same,
                     "pcie_ceiling": {"ms_per_step": ms_ceiling, "value": n_out_total / (ms_ceiling * 1e-3) / 1e6,
