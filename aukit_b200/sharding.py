@@ -136,8 +136,15 @@ class PeerExchange:
         dist.all_gather(allh, t, group=group)
         blob = b"".join(bytes(x.cpu().tolist()) for x in allh)
         buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
-        _lib.check(self.lib.aukit_cuda_comm_connect(h, buf))
-        dist.barrier(group)                                  # every rank has mapped every block before the first exchange
+        # every rank has mapped every block before the first exchange -- or none keeps its communicator: the MIN over
+        # ranks of "my mapping worked" doubles as the barrier, so a failure anywhere raises on ALL ranks together
+        rc = self.lib.aukit_cuda_comm_connect(h, buf)
+        err = "" if rc == 0 else self.lib.aukit_cuda_last_error().decode("latin-1")
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise _lib.AukitError(err or "aukit_cuda: another rank could not map its peers' exchange blocks")
 
     def allreduce_max_(self, t):
         _lib.check(self.lib.aukit_cuda_comm_allreduce_max(self.handle, t.data_ptr(), t.numel()))
@@ -164,7 +171,13 @@ class ShardedPreload:
         self.torch = torch
         self.comm = None
         if exchange == "peer" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            self.comm = PeerExchange(ctx)
+            # every rank must end up on the same exchange: if the peer mapping fails anywhere (e.g. ranks that cannot see
+            # each other's device: CUDA IPC needs the peer visible), ALL ranks fall back to torch.distributed -- loudly
+            try:
+                self.comm = PeerExchange(ctx)                # raises on every rank together (see there)
+            except _lib.AukitError as e:
+                import warnings
+                warnings.warn("aukit_b200: peer-memory exchange unavailable (%s); the normalize MAX goes through torch.distributed" % e)
         self.ctx = ctx
         self.lib = ctx.lib
         self.shard = shard
