@@ -17,6 +17,13 @@
 // Arithmetic is fp64 like the reference's (Lua numbers): in fp32 the rounding error of a low cut-off is
 // amplified by 1/a and would leave the 2^-20 tolerance; the kernel stays HBM-bound either way (6 fp64 ops
 // per sample).  Samples are narrowed to f32 only when stored.
+//
+// Large buffers with an ordinary cut-off take the BLOCKED variant of the same kernel instead of the look-back: when
+// (1-a)^8192 < 2^-80 (any cut-off above ~50 Hz at 48 kHz) the state entering a tile is, to fp64 precision, a function of
+// the previous tile alone -- the very truncation the look-back applies.  Each CTA then owns one contiguous chunk of tiles
+// and carries the state from tile to tile in a register; the state entering a chunk is the zero-start aggregate of the
+// tile before it, computed by a small pre-pass (one tile per chunk, read before anything is overwritten).  No tickets, no
+// slots to clear, no polling: the CTAs never talk to each other.
 #include "common.cuh"
 
 #include <math.h>
@@ -67,14 +74,110 @@ __device__ __forceinline__ void lp_fetch_tile(float *tile, const float *base, in
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// x^e for a small non-negative integer e by binary exponentiation: a handful of DMULs where pow() is a ~250-instruction
+// call (six of them per thread made the prologue a few per cent of the kernel).  The few-ulp difference from pow() is
+// far below the f32 rounding of the stored samples.
+__device__ __forceinline__ double lp_ipow(double x, unsigned e) {
+    double r = 1.0;
+    while (e) {
+        if (e & 1u) r *= x;
+        x *= x;
+        e >>= 1;
+    }
+    return r;
+}
+
+// one step of the reference's loop (A:3593-3594 / A:3613-3615); `first` = the channel's first sample, which both
+// effects leave as it is
+template <bool HIGH>
+__device__ __forceinline__ double lp_step(double y, float x, double &xp, bool first, double a) {
+    if (!HIGH) return y + a * ((double)x - y);
+    const double xd = (double)x;
+    const double r = first ? xd : a * ((y + xd) - xp);
+    xp = xd;
+    return r;
+}
+
+// Zero-start run of thread t's LP_PER samples, then the block-wide combine with the constant ratio pt per thread.
+// Returns the state entering thread t when nothing enters the tile; warp_tot[] holds the warps' inclusive totals
+// (valid after the barrier inside).  Samples past the end of the channel are zeros: they only decay the state, which
+// nothing reads afterwards.
+template <bool HIGH>
+__device__ __forceinline__ double lp_zero_scan(const float *tile, int t, double a, double xprev0, bool chan_first, double pt,
+                                               double p_warp, const double *pt_pow, double *warp_tot) {
+    const int lane = t & 31, warp = t >> 5;
+    double s = 0.0, xp = xprev0;
+#pragma unroll
+    for (int k = 0; k < LP_PER / 4; k++) {
+        const float4 v = *reinterpret_cast<const float4 *>(&tile[t * LP_ROW + 4 * k]);
+        s = lp_step<HIGH>(s, v.x, xp, chan_first && k == 0, a);
+        s = lp_step<HIGH>(s, v.y, xp, false, a);
+        s = lp_step<HIGH>(s, v.z, xp, false, a);
+        s = lp_step<HIGH>(s, v.w, xp, false, a);
+    }
+    double inc = s;
+    double r = pt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double up = shfl_up_d(inc, d);
+        if (lane >= d) inc = fma(r, up, inc);
+        r *= r;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    double wprev = 0.0;                                            // state entering this warp (zero tile carry)
+    for (int w = 0; w < warp; w++) wprev = fma(p_warp, wprev, warp_tot[w]);
+    double exc = shfl_up_d(inc, 1);                                // inclusive prefix of thread t-1
+    if (lane == 0) exc = 0.0;
+    return fma(pt_pow[lane], wprev, exc);
+}
+
+__device__ __forceinline__ double lp_tile_aggregate(const double *warp_tot, double p_warp) {
+    double agg = 0.0;
+    for (int w = 0; w < LP_THREADS / 32; w++) agg = fma(p_warp, agg, warp_tot[w]);
+    return agg;
+}
+
+// Pre-pass of the blocked variant: chunk_in[q] = state entering chunk q's first tile = zero-start aggregate of the tile
+// before it (0 where a chunk starts a channel: the kernel applies the channel-start rule itself).  Reads the untouched
+// input; that tile is always a full one of the same channel.
+template <bool HIGH>
+__global__ void __launch_bounds__(LP_THREADS)
+lp_chunk_states(const float *__restrict__ data, size_t stride, double a, double b, unsigned long long tiles_per_ch,
+                unsigned long long total, unsigned long long chunk, double *__restrict__ chunk_in) {
+    __shared__ __align__(16) float tile[LP_THREADS * LP_ROW];
+    __shared__ double pt_pow[LP_THREADS];
+    __shared__ double warp_tot[LP_THREADS / 32];
+    const int t = threadIdx.x;
+    const unsigned long long first = (unsigned long long)blockIdx.x * chunk;
+    if (first >= total || first % tiles_per_ch == 0) {
+        if (t == 0) chunk_in[blockIdx.x] = 0.0;
+        return;
+    }
+    const unsigned long long id = first - 1, ch = id / tiles_per_ch, tl = id % tiles_per_ch;
+    const float *base = data + (size_t)ch * stride + (size_t)tl * LP_TILE;
+    lp_fetch_tile(tile, base, LP_TILE, t);
+    const double pt = lp_ipow(b, LP_PER);
+    pt_pow[t] = lp_ipow(pt, (unsigned)t);
+    const double p_warp = lp_ipow(pt, 32);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    double xprev0 = 0.0;
+    if (HIGH) xprev0 = t > 0 ? (double)tile[(t - 1) * LP_ROW + LP_PER - 1] : (tl > 0 ? (double)base[-1] : 0.0);
+    lp_zero_scan<HIGH>(tile, t, a, xprev0, HIGH && tl == 0 && t == 0, pt, p_warp, pt_pow, warp_tot);
+    if (t == 0) chunk_in[blockIdx.x] = lp_tile_aggregate(warp_tot, p_warp);
+}
+
 // HIGH = false: effects.lowpass, y = y + a (x - y), per-step ratio b = 1 - a.
 // HIGH = true:  effects.highpass (A:3605-3618), y = a ((y + x) - x_prev), per-step ratio b = a, y[1] = x[1]; the
 //               previous INPUT sample across a tile boundary comes from `xb` (saved before anything is overwritten).
-template <bool HIGH>
+// BLOCKED:      CTA q owns tiles [q * chunk, (q + 1) * chunk) and carries the state itself (chunk_in[q] enters its
+//               first tile); otherwise tiles are claimed by ticket and chained by the look-back.
+template <bool HIGH, bool BLOCKED>
 __global__ void __launch_bounds__(LP_THREADS, LP_CTAS_PER_SM)
 lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, double a, double b,
                lp_slot *slots, unsigned long long *ticket, unsigned long long tiles_per_ch, const float *__restrict__ xb,
-               unsigned long long *poison) {
+               unsigned long long *poison, const double *__restrict__ chunk_in, unsigned long long chunk) {
     extern __shared__ __align__(16) float lp_dyn[];                     // two tile buffers (double buffered: see the loop)
     float *const tiles[2] = {lp_dyn, lp_dyn + LP_THREADS * LP_ROW};
     __shared__ double pt_pow[LP_THREADS];        // (ratio^LP_PER)^t
@@ -82,11 +185,11 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
     __shared__ double s_carry;
     __shared__ unsigned long long s_ticket[2];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const double pt = pow(b, (double)LP_PER);
-    pt_pow[t] = pow(pt, (double)t);
-    const double p_warp = pow(pt, 32.0), p_tile = pow(pt, (double)LP_THREADS);
-    const double pl = pow(p_tile, (double)lane); // look-back weight of the lane-th predecessor
-    const double p_tile32 = pow(p_tile, 32.0);
+    const double pt = lp_ipow(b, LP_PER);
+    pt_pow[t] = lp_ipow(pt, (unsigned)t);
+    const double p_warp = lp_ipow(pt, 32), p_tile = lp_ipow(pt, LP_THREADS);
+    const double pl = lp_ipow(p_tile, (unsigned)lane); // look-back weight of the lane-th predecessor
+    const double p_tile32 = lp_ipow(p_tile, 32);
     const unsigned long long total = tiles_per_ch * (unsigned long long)channels;
     auto tile_base = [&](unsigned long long id, int &cnt) -> float * {
         const unsigned long long ch = id / tiles_per_ch, tl = id % tiles_per_ch;
@@ -94,76 +197,51 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
         cnt = left < (size_t)LP_TILE ? (int)left : LP_TILE;
         return data + (size_t)ch * stride + (size_t)tl * LP_TILE;
     };
-    // prologue: claim the first tile and start loading it
-    if (t == 0) s_ticket[0] = atomicAdd(ticket, 1ull);
-    __syncthreads();
-    unsigned long long id = s_ticket[0];
+    // prologue: the first tile (BLOCKED: of this CTA's chunk; otherwise claimed by ticket) and its loads
+    unsigned long long id, end_id = total;
+    double state = 0.0;                              // BLOCKED, thread 0 only: state entering the current tile
+    if (BLOCKED) {
+        id = (unsigned long long)blockIdx.x * chunk;
+        if (id + chunk < total) end_id = id + chunk;
+        if (t == 0 && id < total) state = chunk_in[blockIdx.x];
+    } else {
+        if (t == 0) s_ticket[0] = atomicAdd(ticket, 1ull);
+        __syncthreads();
+        id = s_ticket[0];
+    }
     int cnt = 0;
     float *base = nullptr;
-    if (id < total) { base = tile_base(id, cnt); lp_fetch_tile(tiles[0], base, cnt, t); }
-    for (int it = 0; id < total; it++) {
+    if (id < end_id) { base = tile_base(id, cnt); lp_fetch_tile(tiles[0], base, cnt, t); }
+    for (int it = 0; id < end_id; it++) {
         float *tile = tiles[it & 1];
         // ---- this tile was fetched during the previous iteration; claim the next one
-        if (t == 0) s_ticket[(it + 1) & 1] = atomicAdd(ticket, 1ull);
+        if (!BLOCKED && t == 0) s_ticket[(it + 1) & 1] = atomicAdd(ticket, 1ull);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         // ---- next tile's loads are in flight while this one is processed (the other buffer was last read
         // before the barrier above)
-        const unsigned long long next_id = s_ticket[(it + 1) & 1];
+        const unsigned long long next_id = BLOCKED ? id + 1 : s_ticket[(it + 1) & 1];
         int next_cnt = 0;
         float *next_base = nullptr;
-        if (next_id < total) { next_base = tile_base(next_id, next_cnt); lp_fetch_tile(tiles[(it + 1) & 1], next_base, next_cnt, t); }
+        if (next_id < end_id) { next_base = tile_base(next_id, next_cnt); lp_fetch_tile(tiles[(it + 1) & 1], next_base, next_cnt, t); }
         const int ch = (int)(id / tiles_per_ch);
         const unsigned long long tl = id % tiles_per_ch;
-        // one step of the reference's loop (A:3593-3594 / A:3613-3615); `first` = the channel's first sample,
-        // which both effects leave as it is
-        auto step = [&](double y, float x, double &xp, bool first) -> double {
-            if (!HIGH) return y + a * ((double)x - y);
-            const double xd = (double)x;
-            const double r = first ? xd : a * ((y + xd) - xp);
-            xp = xd;
-            return r;
-        };
         // input sample just before this thread's first one (highpass only); read now, the rows are overwritten later
         double xprev0 = 0.0;
         if (HIGH) xprev0 = t > 0 ? (double)tile[(t - 1) * LP_ROW + LP_PER - 1] : (tl > 0 ? (double)xb[id] : 0.0);
         const bool chan_first = HIGH && tl == 0 && t == 0;
-        // ---- zero-start run of this thread's samples.  Samples past the end of the channel are zeros: they
-        // only decay the state, which nothing reads afterwards.
-        double s = 0.0, xp = xprev0;
-#pragma unroll
-        for (int k = 0; k < LP_PER / 4; k++) {
-            const float4 v = *reinterpret_cast<const float4 *>(&tile[t * LP_ROW + 4 * k]);
-            s = step(s, v.x, xp, chan_first && k == 0);
-            s = step(s, v.y, xp, false);
-            s = step(s, v.z, xp, false);
-            s = step(s, v.w, xp, false);
-        }
-        // ---- inclusive scan over the block with ratio pt per thread
-        double inc = s;
-        double r = pt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double up = shfl_up_d(inc, d);
-            if (lane >= d) inc = fma(r, up, inc);
-            r *= r;
-        }
-        if (lane == 31) warp_tot[warp] = inc;
-        __syncthreads();
-        double wprev = 0.0;                                            // state entering this warp (zero tile carry)
-        for (int w = 0; w < warp; w++) wprev = fma(p_warp, wprev, warp_tot[w]);
-        double exc = shfl_up_d(inc, 1);                                // inclusive prefix of thread t-1
-        if (lane == 0) exc = 0.0;
-        const double enter0 = fma(pt_pow[lane], wprev, exc);           // state entering thread t with a zero tile carry
-        // ---- tile aggregate + look-back (warp 0)
+        // ---- zero-start run of this thread's samples + inclusive scan over the block
+        const double enter0 = lp_zero_scan<HIGH>(tile, t, a, xprev0, chan_first, pt, p_warp, pt_pow, warp_tot);
+        // ---- tile aggregate + the state entering the tile (warp 0)
         if (warp == 0) {
-            double agg = 0.0;
-            for (int w = 0; w < LP_THREADS / 32; w++) agg = fma(p_warp, agg, warp_tot[w]);
+            const double agg = lp_tile_aggregate(warp_tot, p_warp);
             double carry;
             if (tl == 0) {
                 // A:3591: d[1] is untouched, which is what a state equal to d[1] gives (l + a*(l - l) = l);
-                // highpass handles its first sample inside step(), so nothing enters the first tile
+                // highpass handles its first sample inside lp_step(), so nothing enters the first tile
                 carry = HIGH ? 0.0 : (double)tile[0];
+            } else if (BLOCKED) {
+                carry = state;
             } else {
                 if (lane == 0) st_slot(&slots[id], agg, 1);
                 double acc = 0.0, scale = 1.0;
@@ -196,24 +274,29 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
             }
             if (lane == 0) {
                 const double incl = fma(p_tile, carry, agg);
-                st_slot(&slots[id], incl, 2);
+                if (BLOCKED) state = incl;
+                else st_slot(&slots[id], incl, 2);
                 // a non-finite state never leaves the reference's recurrence (A:3592-3595); the bounded look-back
-                // above can miss it, so the first such tile of a channel is recorded for lp_poison_fix
-                if (!isfinite(incl)) atomicMin(&poison[ch], tl);
+                // above (and the one-tile memory of a chunk start) can miss it, so the first such tile of a channel is
+                // recorded for lp_poison_fix, which reads the state from the tile's slot
+                if (!isfinite(incl)) {
+                    atomicMin(&poison[ch], tl);
+                    if (BLOCKED) st_slot(&slots[id], incl, 2);
+                }
                 s_carry = carry;
             }
         }
         __syncthreads();
         // ---- true run: state entering thread t = pt^t * (tile carry) + (state entering t with a zero tile carry)
         double y = fma(pt_pow[t], s_carry, enter0);
-        xp = xprev0;
+        double xp = xprev0;
 #pragma unroll
         for (int k = 0; k < LP_PER / 4; k++) {
             float4 v = *reinterpret_cast<const float4 *>(&tile[t * LP_ROW + 4 * k]);
-            y = step(y, v.x, xp, chan_first && k == 0); v.x = (float)y;
-            y = step(y, v.y, xp, false); v.y = (float)y;
-            y = step(y, v.z, xp, false); v.z = (float)y;
-            y = step(y, v.w, xp, false); v.w = (float)y;
+            y = lp_step<HIGH>(y, v.x, xp, chan_first && k == 0, a); v.x = (float)y;
+            y = lp_step<HIGH>(y, v.y, xp, false, a); v.y = (float)y;
+            y = lp_step<HIGH>(y, v.z, xp, false, a); v.z = (float)y;
+            y = lp_step<HIGH>(y, v.w, xp, false, a); v.w = (float)y;
             *reinterpret_cast<float4 *>(&tile[t * LP_ROW + 4 * k]) = v;
         }
         __syncthreads();
@@ -251,12 +334,15 @@ __global__ void lp_save_boundaries(const float *__restrict__ data, size_t stride
 // 8-byte read per CTA) for finite audio.
 template <bool HIGH>
 __global__ void lp_poison_fix(float *__restrict__ data, size_t stride, int channels, size_t n, const lp_slot *slots,
-                              unsigned long long tiles_per_ch, const unsigned long long *poison) {
+                              unsigned long long tiles_per_ch, const unsigned long long *poison, const float *__restrict__ xb) {
     for (int ch = 0; ch < channels; ch++) {
         const unsigned long long T = poison[ch];
-        if (T >= tiles_per_ch) continue;
+        if (T >= tiles_per_ch || T + 1 >= tiles_per_ch) continue;          // none (all ones), or nothing after it
         const double st = slots[(unsigned long long)ch * tiles_per_ch + T].v;
-        const float fill = (HIGH && isinf(st)) ? (float)st : __int_as_float(0x7FC00000);
+        // an infinite high-pass state stays infinite only while the inputs are finite: if it came from an infinite LAST
+        // input sample of tile T, the next step is a ((Inf + x) - Inf) = NaN
+        const bool keep_inf = HIGH && isinf(st) && isfinite(xb[(unsigned long long)ch * tiles_per_ch + T + 1]);
+        const float fill = keep_inf ? (float)st : __int_as_float(0x7FC00000);
         float *row = data + (size_t)ch * stride;
         for (size_t i = (size_t)(T + 1) * LP_TILE + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
              i += (size_t)gridDim.x * blockDim.x)
@@ -264,40 +350,61 @@ __global__ void lp_poison_fix(float *__restrict__ data, size_t stride, int chann
     }
 }
 
+template <bool HIGH, bool BLOCKED>
+static void lp_launch(aukit_ctx *ctx, unsigned grid, float *d, size_t stride, int channels, size_t n, double a, double ratio,
+                      lp_slot *slots, unsigned long long *ticket, unsigned long long tiles, const float *xb,
+                      unsigned long long *poison, const double *chunk_in, unsigned long long chunk) {
+    cudaFuncSetAttribute(lowpass_kernel<HIGH, BLOCKED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(lowpass_kernel<HIGH, BLOCKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP_SMEM);
+    lowpass_kernel<HIGH, BLOCKED><<<grid, LP_THREADS, LP_SMEM, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb,
+                                                                              poison, chunk_in, chunk);
+    lp_poison_fix<HIGH><<<ctx->num_sms, 256, 0, ctx->stream>>>(d, stride, channels, n, slots, tiles, poison, xb);
+    ctx->launches += 2;
+}
+
 static int lp_run(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n, double a, double ratio, bool high) {
     const unsigned long long tiles = (n + LP_TILE - 1) / LP_TILE, total = tiles * (unsigned long long)channels;
-    // scratch: one 16-byte slot per (channel, tile) + the ticket counter (+ the boundary samples for highpass)
+    const unsigned long long cap = (unsigned long long)ctx->num_sms * LP_CTAS_PER_SM;
+    // blocked chunks (see the top of the file): the state entering a tile must be the previous tile's business alone (the
+    // look-back's own 2^-80 cut), and the chunks long enough for the one extra tile per chunk of the pre-pass not to matter
+    const bool blocked = total >= 8 * cap && pow(ratio, (double)LP_TILE) < 8.3e-25 && pow(ratio, (double)LP_TILE) > -8.3e-25;
+    const unsigned long long chunk = blocked ? (total + cap - 1) / cap : 0;
+    const unsigned long long nchunks = blocked ? (total + chunk - 1) / chunk : 0;
+    // scratch: one 16-byte slot per (channel, tile) + the ticket counter (+ the boundary samples for highpass, + the
+    // states entering the chunks)
     void *scratch = nullptr;
     const size_t slot_bytes = (size_t)total * sizeof(lp_slot);
     const size_t xb_bytes = high ? (((size_t)total * sizeof(float) + 15) & ~(size_t)15) : 0;
     const size_t poison_bytes = (((size_t)channels * sizeof(unsigned long long)) + 15) & ~(size_t)15;
-    if (aukit_dev_alloc(ctx, slot_bytes + 16 + poison_bytes + xb_bytes, &scratch)) return -1;
+    const size_t chunk_bytes = (((size_t)nchunks * sizeof(double)) + 15) & ~(size_t)15;
+    if (aukit_dev_alloc(ctx, slot_bytes + 16 + poison_bytes + xb_bytes + chunk_bytes, &scratch)) return -1;
     lp_slot *slots = static_cast<lp_slot *>(scratch);
     unsigned long long *ticket = reinterpret_cast<unsigned long long *>(static_cast<char *>(scratch) + slot_bytes);
     unsigned long long *poison = ticket + 2;
     float *xb = high ? reinterpret_cast<float *>(static_cast<char *>(scratch) + slot_bytes + 16 + poison_bytes) : nullptr;
-    int rc = aukit_cuda_check(cudaMemsetAsync(scratch, 0, slot_bytes + 16, ctx->stream), "memset");
+    double *chunk_in = reinterpret_cast<double *>(static_cast<char *>(scratch) + slot_bytes + 16 + poison_bytes + xb_bytes);
+    // the slots are flags only for the look-back; the blocked variant writes (and lp_poison_fix reads) a slot only where
+    // the state went non-finite
+    int rc = blocked ? 0 : aukit_cuda_check(cudaMemsetAsync(scratch, 0, slot_bytes + 16, ctx->stream), "memset");
     if (!rc) rc = aukit_cuda_check(cudaMemsetAsync(poison, 0xFF, poison_bytes, ctx->stream), "memset");
     if (!rc && high) {
         lp_save_boundaries<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d, stride, tiles, total, xb);
         ctx->launches++;
     }
+    if (!rc && blocked) {
+        if (high) lp_chunk_states<true><<<(unsigned)nchunks, LP_THREADS, 0, ctx->stream>>>(d, stride, a, ratio, tiles, total, chunk, chunk_in);
+        else lp_chunk_states<false><<<(unsigned)nchunks, LP_THREADS, 0, ctx->stream>>>(d, stride, a, ratio, tiles, total, chunk, chunk_in);
+        ctx->launches++;
+    }
     if (!rc) {
-        unsigned long long g = total;
-        const unsigned long long cap = (unsigned long long)ctx->num_sms * LP_CTAS_PER_SM;
-        if (g > cap) g = cap;
+        const unsigned g = (unsigned)(blocked ? nchunks : (total < cap ? total : cap));
         if (high) {
-            cudaFuncSetAttribute(lowpass_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(lowpass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP_SMEM);
-            lowpass_kernel<true><<<(unsigned)g, LP_THREADS, LP_SMEM, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb, poison);
-            lp_poison_fix<true><<<ctx->num_sms, 256, 0, ctx->stream>>>(d, stride, channels, n, slots, tiles, poison);
+            if (blocked) lp_launch<true, true>(ctx, g, d, stride, channels, n, a, ratio, slots, ticket, tiles, xb, poison, chunk_in, chunk);
+            else lp_launch<true, false>(ctx, g, d, stride, channels, n, a, ratio, slots, ticket, tiles, xb, poison, chunk_in, chunk);
         } else {
-            cudaFuncSetAttribute(lowpass_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(lowpass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP_SMEM);
-            lowpass_kernel<false><<<(unsigned)g, LP_THREADS, LP_SMEM, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb, poison);
-            lp_poison_fix<false><<<ctx->num_sms, 256, 0, ctx->stream>>>(d, stride, channels, n, slots, tiles, poison);
+            if (blocked) lp_launch<false, true>(ctx, g, d, stride, channels, n, a, ratio, slots, ticket, tiles, xb, poison, chunk_in, chunk);
+            else lp_launch<false, false>(ctx, g, d, stride, channels, n, a, ratio, slots, ticket, tiles, xb, poison, chunk_in, chunk);
         }
-        ctx->launches += 2;
         rc = aukit_cuda_check(cudaGetLastError(), "lowpass_kernel launch");
     }
     aukit_dev_free(ctx, scratch);

@@ -522,6 +522,50 @@ def test_highpass_matches_oracle(ak, O, n, ch, freq, rate):
     assert float(np.max(np.abs(got - ref))) <= 2 * TOL
 
 
+@pytest.mark.parametrize("kind,n,ch,freq,rate", [("low", 10_100_003, 3, 200.0, 44100), ("low", 30_000_001, 1, 24000.0, 48000),
+                                                  ("high", 10_100_003, 3, 200.0, 48000), ("high", 15_000_000, 2, 8000.0, 44100)])
+def test_lowpass_highpass_blocked_chunks_at_size(ak, O, kind, n, ch, freq, rate):
+    """Buffers of thousands of tiles with an ordinary cut-off take the blocked variant (csrc/lowpass.cu: one contiguous
+    chunk of tiles per CTA, state carried in a register, chunk-start states from the pre-pass): chunks that straddle
+    channel boundaries, a ragged last tile, both effects -- against the sequential reference recurrence."""
+    x = (np.random.default_rng(n + ch).uniform(-1, 1, (ch, n)) + 0.3).astype(np.float32)
+    a = ak.Audio.from_numpy(x, rate)
+    fx = ak.effects.lowpass if kind == "low" else ak.effects.highpass
+    assert fx(a, freq) is a
+    got = a.numpy()
+    ref = (O.lowpass if kind == "low" else O.highpass)(x.astype(np.float64), freq, rate)
+    assert got.shape == ref.shape
+    assert np.array_equal(got[:, 0], x[:, 0])
+    assert float(np.max(np.abs(got - ref))) <= (TOL if kind == "low" else 2 * TOL)
+
+
+@pytest.mark.parametrize("n,at", [(300_001, 101_234), (300_001, 8192 * 5 - 1), (10_100_003, 3_367_901), (10_100_003, 8192 * 700 - 1)])
+def test_lowpass_highpass_non_finite_input_poisons_the_rest_of_the_channel(ak, O, n, at):
+    """A:3592-3595 / A:3613-3615: once the state is non-finite it stays so -- every later sample of THAT channel, however
+    many tiles (or chunks) away; the other channels are untouched.  Small buffers take the look-back, large ones the
+    blocked chunks; both rely on lp_poison_fix beyond their one-tile / 2^-80 memory.  An infinite input as the LAST sample
+    of a tile leaves an infinite state behind that must not be taken for a lasting one."""
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-0.9, 0.9, (3, n)).astype(np.float32)
+    x[1, at] = np.nan                                   # mid-tile, or the last sample of a tile
+    a = ak.Audio.from_numpy(x, 48000)
+    ak.effects.lowpass(a, 2000.0)
+    got = a.numpy()
+    ref = O.lowpass(x.astype(np.float64), 2000.0, 48000)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.isnan(got[1, at:]).all() and np.isfinite(got[1, :at]).all() and np.isfinite(got[[0, 2]]).all()
+    fin = np.isfinite(ref)
+    assert float(np.max(np.abs(got[fin] - ref[fin]))) <= TOL
+    x[1, at] = np.inf                                   # highpass: +Inf once, then (Inf + x) - Inf = NaN for good
+    a = ak.Audio.from_numpy(x, 48000)
+    ak.effects.highpass(a, 300.0)
+    got = a.numpy()
+    ref = O.highpass(x.astype(np.float64), 300.0, 48000)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(np.isinf(got), np.isinf(ref))
+    fin = np.isfinite(ref)
+    assert float(np.max(np.abs(got[fin] - ref[fin]))) <= 2 * TOL
+
+
 def _quiet_with_bursts(n, bursts, seed=77, base=12000):
     """Moderate-level stereo noise (no cubic overshoot can reach +-1) with full-scale noise in `bursts`."""
     rng = np.random.default_rng(seed)
