@@ -366,8 +366,10 @@ static int lp_run(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t 
     const unsigned long long tiles = (n + LP_TILE - 1) / LP_TILE, total = tiles * (unsigned long long)channels;
     const unsigned long long cap = (unsigned long long)ctx->num_sms * LP_CTAS_PER_SM;
     // blocked chunks (see the top of the file): the state entering a tile must be the previous tile's business alone (the
-    // look-back's own 2^-80 cut), and the chunks long enough for the one extra tile per chunk of the pre-pass not to matter
-    const bool blocked = total >= 8 * cap && pow(ratio, (double)LP_TILE) < 8.3e-25 && pow(ratio, (double)LP_TILE) > -8.3e-25;
+    // look-back's own 2^-80 cut), and the chunks long enough for the one extra tile read per chunk of the pre-pass to cost
+    // less than the look-back does (measured: chunks of 4 - 5 tiles are 4 % SLOWER than the look-back, 44 tiles 18 % faster)
+    const double p_tile = pow(ratio, (double)LP_TILE);
+    const bool blocked = total >= 8 * cap && p_tile < 8.3e-25 && p_tile > -8.3e-25;
     const unsigned long long chunk = blocked ? (total + cap - 1) / cap : 0;
     const unsigned long long nchunks = blocked ? (total + chunk - 1) / chunk : 0;
     // scratch: one 16-byte slot per (channel, tile) + the ticket counter (+ the boundary samples for highpass, + the
