@@ -138,20 +138,27 @@ __device__ __forceinline__ double lp_tile_aggregate(const double *warp_tot, doub
     return agg;
 }
 
-// Pre-pass of the blocked variant: chunk_in[q] = state entering chunk q's first tile = zero-start aggregate of the tile
-// before it (0 where a chunk starts a channel: the kernel applies the channel-start rule itself).  Reads the untouched
-// input; that tile is always a full one of the same channel.
+// What enters chunk q's first tile: the state (zero-start aggregate of the tile before it) and, for the high-pass, that
+// tile's last INPUT sample.
+struct __align__(16) lp_chunk_in { double state, xlast; };
+
+// Pre-pass of the blocked variant: fills chunk_in[q] (zeros where a chunk starts a channel: the kernel applies the
+// channel-start rule itself) and resets the per-channel poison marks.  Reads the untouched input; the tile before a chunk
+// is always a full one of the same channel.
 template <bool HIGH>
 __global__ void __launch_bounds__(LP_THREADS)
-lp_chunk_states(const float *__restrict__ data, size_t stride, double a, double b, unsigned long long tiles_per_ch,
-                unsigned long long total, unsigned long long chunk, double *__restrict__ chunk_in) {
+lp_chunk_states(const float *__restrict__ data, size_t stride, int channels, double a, double b, unsigned long long tiles_per_ch,
+                unsigned long long total, unsigned long long chunk, lp_chunk_in *__restrict__ chunk_in,
+                unsigned long long *__restrict__ poison) {
     __shared__ __align__(16) float tile[LP_THREADS * LP_ROW];
     __shared__ double pt_pow[LP_THREADS];
     __shared__ double warp_tot[LP_THREADS / 32];
     const int t = threadIdx.x;
+    if (blockIdx.x == 0)
+        for (int c = t; c < channels; c += LP_THREADS) poison[c] = ~0ull;
     const unsigned long long first = (unsigned long long)blockIdx.x * chunk;
     if (first >= total || first % tiles_per_ch == 0) {
-        if (t == 0) chunk_in[blockIdx.x] = 0.0;
+        if (t == 0) chunk_in[blockIdx.x] = lp_chunk_in{0.0, 0.0};
         return;
     }
     const unsigned long long id = first - 1, ch = id / tiles_per_ch, tl = id % tiles_per_ch;
@@ -165,24 +172,26 @@ lp_chunk_states(const float *__restrict__ data, size_t stride, double a, double 
     double xprev0 = 0.0;
     if (HIGH) xprev0 = t > 0 ? (double)tile[(t - 1) * LP_ROW + LP_PER - 1] : (tl > 0 ? (double)base[-1] : 0.0);
     lp_zero_scan<HIGH>(tile, t, a, xprev0, HIGH && tl == 0 && t == 0, pt, p_warp, pt_pow, warp_tot);
-    if (t == 0) chunk_in[blockIdx.x] = lp_tile_aggregate(warp_tot, p_warp);
+    if (t == 0) chunk_in[blockIdx.x] = lp_chunk_in{lp_tile_aggregate(warp_tot, p_warp), (double)tile[(LP_THREADS - 1) * LP_ROW + LP_PER - 1]};
 }
 
 // HIGH = false: effects.lowpass, y = y + a (x - y), per-step ratio b = 1 - a.
 // HIGH = true:  effects.highpass (A:3605-3618), y = a ((y + x) - x_prev), per-step ratio b = a, y[1] = x[1]; the
 //               previous INPUT sample across a tile boundary comes from `xb` (saved before anything is overwritten).
 // BLOCKED:      CTA q owns tiles [q * chunk, (q + 1) * chunk) and carries the state itself (chunk_in[q] enters its
-//               first tile); otherwise tiles are claimed by ticket and chained by the look-back.
+//               first tile; the high-pass keeps each tile's last input sample for the next one in shared memory, no
+//               `xb`); otherwise tiles are claimed by ticket and chained by the look-back.
 template <bool HIGH, bool BLOCKED>
 __global__ void __launch_bounds__(LP_THREADS, LP_CTAS_PER_SM)
 lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, double a, double b,
                lp_slot *slots, unsigned long long *ticket, unsigned long long tiles_per_ch, const float *__restrict__ xb,
-               unsigned long long *poison, const double *__restrict__ chunk_in, unsigned long long chunk) {
+               unsigned long long *poison, const lp_chunk_in *__restrict__ chunk_in, unsigned long long chunk) {
     extern __shared__ __align__(16) float lp_dyn[];                     // two tile buffers (double buffered: see the loop)
     float *const tiles[2] = {lp_dyn, lp_dyn + LP_THREADS * LP_ROW};
     __shared__ double pt_pow[LP_THREADS];        // (ratio^LP_PER)^t
     __shared__ double warp_tot[LP_THREADS / 32];
     __shared__ double s_carry;
+    __shared__ double s_xlast[2];                // BLOCKED high-pass: last input sample of the previous tile (slot it & 1)
     __shared__ unsigned long long s_ticket[2];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const double pt = lp_ipow(b, LP_PER);
@@ -203,7 +212,11 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
     if (BLOCKED) {
         id = (unsigned long long)blockIdx.x * chunk;
         if (id + chunk < total) end_id = id + chunk;
-        if (t == 0 && id < total) state = chunk_in[blockIdx.x];
+        if (t == 0 && id < total) {
+            const lp_chunk_in ci = chunk_in[blockIdx.x];
+            state = ci.state;
+            s_xlast[0] = ci.xlast;               // read by this thread only before the next write to the slot
+        }
     } else {
         if (t == 0) s_ticket[0] = atomicAdd(ticket, 1ull);
         __syncthreads();
@@ -228,7 +241,8 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
         const unsigned long long tl = id % tiles_per_ch;
         // input sample just before this thread's first one (highpass only); read now, the rows are overwritten later
         double xprev0 = 0.0;
-        if (HIGH) xprev0 = t > 0 ? (double)tile[(t - 1) * LP_ROW + LP_PER - 1] : (tl > 0 ? (double)xb[id] : 0.0);
+        if (HIGH) xprev0 = t > 0 ? (double)tile[(t - 1) * LP_ROW + LP_PER - 1] : (tl > 0 ? (BLOCKED ? s_xlast[it & 1] : (double)xb[id]) : 0.0);
+        if (HIGH && BLOCKED && t == LP_THREADS - 1) s_xlast[(it + 1) & 1] = (double)tile[t * LP_ROW + LP_PER - 1];
         const bool chan_first = HIGH && tl == 0 && t == 0;
         // ---- zero-start run of this thread's samples + inclusive scan over the block
         const double enter0 = lp_zero_scan<HIGH>(tile, t, a, xprev0, chan_first, pt, p_warp, pt_pow, warp_tot);
@@ -281,7 +295,9 @@ lowpass_kernel(float *__restrict__ data, size_t stride, int channels, size_t n, 
                 // recorded for lp_poison_fix, which reads the state from the tile's slot
                 if (!isfinite(incl)) {
                     atomicMin(&poison[ch], tl);
-                    if (BLOCKED) st_slot(&slots[id], incl, 2);
+                    // flag 3: the tile's last input sample is not finite either (still unmodified here); lp_poison_fix
+                    // needs to know for the high-pass, and the blocked variant has no `xb` to look it up in
+                    if (BLOCKED) st_slot(&slots[id], incl, (HIGH && !isfinite(tile[(LP_THREADS - 1) * LP_ROW + LP_PER - 1])) ? 3 : 2);
                 }
                 s_carry = carry;
             }
@@ -335,13 +351,15 @@ __global__ void lp_save_boundaries(const float *__restrict__ data, size_t stride
 template <bool HIGH>
 __global__ void lp_poison_fix(float *__restrict__ data, size_t stride, int channels, size_t n, const lp_slot *slots,
                               unsigned long long tiles_per_ch, const unsigned long long *poison, const float *__restrict__ xb) {
+    // xb == nullptr: blocked variant, the slot's flag says whether tile T's last input sample was finite
     for (int ch = 0; ch < channels; ch++) {
         const unsigned long long T = poison[ch];
         if (T >= tiles_per_ch || T + 1 >= tiles_per_ch) continue;          // none (all ones), or nothing after it
-        const double st = slots[(unsigned long long)ch * tiles_per_ch + T].v;
+        const lp_slot sl = slots[(unsigned long long)ch * tiles_per_ch + T];
+        const double st = sl.v;
         // an infinite high-pass state stays infinite only while the inputs are finite: if it came from an infinite LAST
         // input sample of tile T, the next step is a ((Inf + x) - Inf) = NaN
-        const bool keep_inf = HIGH && isinf(st) && isfinite(xb[(unsigned long long)ch * tiles_per_ch + T + 1]);
+        const bool keep_inf = HIGH && isinf(st) && (xb ? isfinite(xb[(unsigned long long)ch * tiles_per_ch + T + 1]) : sl.flag == 2);
         const float fill = keep_inf ? (float)st : __int_as_float(0x7FC00000);
         float *row = data + (size_t)ch * stride;
         for (size_t i = (size_t)(T + 1) * LP_TILE + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -353,7 +371,7 @@ __global__ void lp_poison_fix(float *__restrict__ data, size_t stride, int chann
 template <bool HIGH, bool BLOCKED>
 static void lp_launch(aukit_ctx *ctx, unsigned grid, float *d, size_t stride, int channels, size_t n, double a, double ratio,
                       lp_slot *slots, unsigned long long *ticket, unsigned long long tiles, const float *xb,
-                      unsigned long long *poison, const double *chunk_in, unsigned long long chunk) {
+                      unsigned long long *poison, const lp_chunk_in *chunk_in, unsigned long long chunk) {
     cudaFuncSetAttribute(lowpass_kernel<HIGH, BLOCKED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(lowpass_kernel<HIGH, BLOCKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP_SMEM);
     lowpass_kernel<HIGH, BLOCKED><<<grid, LP_THREADS, LP_SMEM, ctx->stream>>>(d, stride, channels, n, a, ratio, slots, ticket, tiles, xb,
@@ -376,26 +394,26 @@ static int lp_run(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t 
     // states entering the chunks)
     void *scratch = nullptr;
     const size_t slot_bytes = (size_t)total * sizeof(lp_slot);
-    const size_t xb_bytes = high ? (((size_t)total * sizeof(float) + 15) & ~(size_t)15) : 0;
+    const size_t xb_bytes = (high && !blocked) ? (((size_t)total * sizeof(float) + 15) & ~(size_t)15) : 0;
     const size_t poison_bytes = (((size_t)channels * sizeof(unsigned long long)) + 15) & ~(size_t)15;
-    const size_t chunk_bytes = (((size_t)nchunks * sizeof(double)) + 15) & ~(size_t)15;
+    const size_t chunk_bytes = (size_t)nchunks * sizeof(lp_chunk_in);
     if (aukit_dev_alloc(ctx, slot_bytes + 16 + poison_bytes + xb_bytes + chunk_bytes, &scratch)) return -1;
     lp_slot *slots = static_cast<lp_slot *>(scratch);
     unsigned long long *ticket = reinterpret_cast<unsigned long long *>(static_cast<char *>(scratch) + slot_bytes);
     unsigned long long *poison = ticket + 2;
-    float *xb = high ? reinterpret_cast<float *>(static_cast<char *>(scratch) + slot_bytes + 16 + poison_bytes) : nullptr;
-    double *chunk_in = reinterpret_cast<double *>(static_cast<char *>(scratch) + slot_bytes + 16 + poison_bytes + xb_bytes);
+    float *xb = xb_bytes ? reinterpret_cast<float *>(static_cast<char *>(scratch) + slot_bytes + 16 + poison_bytes) : nullptr;
+    lp_chunk_in *chunk_in = reinterpret_cast<lp_chunk_in *>(static_cast<char *>(scratch) + slot_bytes + 16 + poison_bytes + xb_bytes);
     // the slots are flags only for the look-back; the blocked variant writes (and lp_poison_fix reads) a slot only where
-    // the state went non-finite
+    // the state went non-finite, and its pre-pass also resets the poison marks
     int rc = blocked ? 0 : aukit_cuda_check(cudaMemsetAsync(scratch, 0, slot_bytes + 16, ctx->stream), "memset");
-    if (!rc) rc = aukit_cuda_check(cudaMemsetAsync(poison, 0xFF, poison_bytes, ctx->stream), "memset");
-    if (!rc && high) {
+    if (!rc && !blocked) rc = aukit_cuda_check(cudaMemsetAsync(poison, 0xFF, poison_bytes, ctx->stream), "memset");
+    if (!rc && xb) {
         lp_save_boundaries<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d, stride, tiles, total, xb);
         ctx->launches++;
     }
     if (!rc && blocked) {
-        if (high) lp_chunk_states<true><<<(unsigned)nchunks, LP_THREADS, 0, ctx->stream>>>(d, stride, a, ratio, tiles, total, chunk, chunk_in);
-        else lp_chunk_states<false><<<(unsigned)nchunks, LP_THREADS, 0, ctx->stream>>>(d, stride, a, ratio, tiles, total, chunk, chunk_in);
+        if (high) lp_chunk_states<true><<<(unsigned)nchunks, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, a, ratio, tiles, total, chunk, chunk_in, poison);
+        else lp_chunk_states<false><<<(unsigned)nchunks, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, a, ratio, tiles, total, chunk, chunk_in, poison);
         ctx->launches++;
     }
     if (!rc) {
