@@ -107,3 +107,41 @@ def test_ima_aligned_word_schedule_visits_every_word_once():
             assert seen == list(range(groups)), (groups, G0)
             if M > 1:                                                          # words loaded before the loop for iteration 1
                 assert 8 - G0 + 7 < groups
+
+
+def test_blocked_lowpass_chunk_start_state_is_exact_to_fp64():
+    """csrc/lowpass.cu, BLOCKED variant: where (1-a)^8192 < 8.3e-25 (2^-80) the state entering a chunk is taken to be the
+    zero-start end state of the ONE tile before it.  Restated serially in fp64: against the full recurrence (A:3592-3595,
+    A:3613-3615) the chunk-start state differs by at most (1-a)^8192 * |state|, far below an fp64 ulp of a sample-sized
+    value, at the lowest cut-off `lp_run` lets through (and its threshold is where this test says it is)."""
+    import math
+    T = 8192
+    rng = np.random.default_rng(11)
+    x = (rng.uniform(-1, 1, 3 * T) + 0.3).astype(np.float32).astype(np.float64)
+
+    def low(a, xs, y):
+        for v in xs:
+            y = y + a * (v - y)
+        return y
+
+    def high(a, xs, y, xp):
+        for v in xs:
+            y = a * ((y + v) - xp)
+            xp = v
+        return y
+
+    for rate in (48000.0, 44100.0, 8000.0):
+        # the lowest low-pass cut-off that passes the host test: (1 - a)^T < 8.3e-25 with a = 1 - exp(-2 pi f / rate)
+        f_min = -math.log(8.3e-25) / T * rate / (2 * math.pi)
+        assert 40.0 < f_min * 48000.0 / rate < 53.0
+        a = 1.0 - math.exp(-(f_min * 1.001 / rate) * 2 * math.pi)
+        assert (1.0 - a) ** T < 8.3e-25
+        full = low(a, x[: 2 * T], x[0])                       # true state after two tiles (d[1] untouched: state = d[1])
+        trunc = low(a, x[T: 2 * T], 0.0)                      # what lp_chunk_states computes for a chunk starting at tile 2
+        assert abs(full - trunc) <= 8.3e-25 * 1.5 and abs(full) > 1e-3
+        # high-pass: ratio a = 1 / (2 pi f / rate + 1); the same bound with a^T
+        ah = 8.3e-25 ** (1.0 / T) * 0.9999
+        assert ah ** T < 8.3e-25
+        full = high(ah, x[1: 2 * T], x[0], x[0])
+        trunc = high(ah, x[T: 2 * T], 0.0, x[T - 1])
+        assert abs(full - trunc) <= 8.3e-25 * 4.0
