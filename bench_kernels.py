@@ -170,9 +170,9 @@ def table(sampler_cls, gpu_index=0, scale=1.0, iters=10, warm=3):
     # ---- K11 lowpass (8f rank 1): in place, 4 B read + 4 B written per sample
     for f in (24000.0, 200.0):
         ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_lowpass(ctx.handle, x.data_ptr(), n, 2, n, f, 48000.0)))
-        report("K11 lowpass 2ch f=%g Hz" % f, ms, n * 2 * 8, n * 2, "samples", "chained-tile scan, fp64 state")
+        report("K11 lowpass 2ch f=%g Hz" % f, ms, n * 2 * 8, n * 2, "samples", "blocked chunks (state carried per CTA) at this size, fp64 state")
     ms = timed(lambda: ak._lib.check(lib.aukit_cuda_dev_highpass(ctx.handle, x.data_ptr(), n, 2, n, 200.0, 48000.0)))
-    report("K11 highpass 2ch f=200 Hz", ms, n * 2 * 8, n * 2, "samples", "same scan, ratio a, saved tile-boundary inputs")
+    report("K11 highpass 2ch f=200 Hz", ms, n * 2 * 8, n * 2, "samples", "same kernel, ratio a; last input sample handed from tile to tile in shared memory")
     sampler.__exit__(None, None, None)
     return {"clocks": sampler.summary(), "scale": scale, "iters": iters, "rows": records}
 
