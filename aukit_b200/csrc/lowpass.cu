@@ -23,7 +23,8 @@
 // the previous tile alone -- the very truncation the look-back applies.  Each CTA then owns one contiguous chunk of tiles
 // and carries the state from tile to tile in a register; the state entering a chunk is the zero-start aggregate of the
 // tile before it, computed by a small pre-pass (one tile per chunk, read before anything is overwritten).  No tickets, no
-// slots to clear, no polling: the CTAs never talk to each other.
+// slots to clear, no polling: the CTAs never talk to each other.  Lower cut-offs (down to ~10 Hz) work the same way with a
+// pre-pass over the 2 - 8 tiles whose combined weight is below 2^-80, while the chunks are long enough to amortise it.
 #include "common.cuh"
 
 #include <math.h>
@@ -138,17 +139,18 @@ __device__ __forceinline__ double lp_tile_aggregate(const double *warp_tot, doub
     return agg;
 }
 
-// What enters chunk q's first tile: the state (zero-start aggregate of the tile before it) and, for the high-pass, that
-// tile's last INPUT sample.
+// What enters chunk q's first tile: the state and, for the high-pass, the last INPUT sample of the tile before it.
 struct __align__(16) lp_chunk_in { double state, xlast; };
 
 // Pre-pass of the blocked variant: fills chunk_in[q] (zeros where a chunk starts a channel: the kernel applies the
-// channel-start rule itself) and resets the per-channel poison marks.  Reads the untouched input; the tile before a chunk
-// is always a full one of the same channel.
+// channel-start rule itself) and resets the per-channel poison marks.  The state entering a chunk is that of a run from
+// zero over the `warm` tiles before it -- `warm` chosen by the host so that ratio^(8192 warm) < 2^-80: whatever came
+// earlier weighs less than an fp64 ulp -- or from the channel's first tile if that is nearer, which is exact.  Reads the
+// untouched input; the tiles before a chunk are always full ones of the same channel.
 template <bool HIGH>
 __global__ void __launch_bounds__(LP_THREADS)
 lp_chunk_states(const float *__restrict__ data, size_t stride, int channels, double a, double b, unsigned long long tiles_per_ch,
-                unsigned long long total, unsigned long long chunk, lp_chunk_in *__restrict__ chunk_in,
+                unsigned long long total, unsigned long long chunk, int warm, lp_chunk_in *__restrict__ chunk_in,
                 unsigned long long *__restrict__ poison) {
     __shared__ __align__(16) float tile[LP_THREADS * LP_ROW];
     __shared__ double pt_pow[LP_THREADS];
@@ -157,22 +159,30 @@ lp_chunk_states(const float *__restrict__ data, size_t stride, int channels, dou
     if (blockIdx.x == 0)
         for (int c = t; c < channels; c += LP_THREADS) poison[c] = ~0ull;
     const unsigned long long first = (unsigned long long)blockIdx.x * chunk;
-    if (first >= total || first % tiles_per_ch == 0) {
+    const unsigned long long tl0 = first % tiles_per_ch, ch = first / tiles_per_ch;
+    if (first >= total || tl0 == 0) {
         if (t == 0) chunk_in[blockIdx.x] = lp_chunk_in{0.0, 0.0};
         return;
     }
-    const unsigned long long id = first - 1, ch = id / tiles_per_ch, tl = id % tiles_per_ch;
-    const float *base = data + (size_t)ch * stride + (size_t)tl * LP_TILE;
-    lp_fetch_tile(tile, base, LP_TILE, t);
     const double pt = lp_ipow(b, LP_PER);
     pt_pow[t] = lp_ipow(pt, (unsigned)t);
-    const double p_warp = lp_ipow(pt, 32);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    double xprev0 = 0.0;
-    if (HIGH) xprev0 = t > 0 ? (double)tile[(t - 1) * LP_ROW + LP_PER - 1] : (tl > 0 ? (double)base[-1] : 0.0);
-    lp_zero_scan<HIGH>(tile, t, a, xprev0, HIGH && tl == 0 && t == 0, pt, p_warp, pt_pow, warp_tot);
-    if (t == 0) chunk_in[blockIdx.x] = lp_chunk_in{lp_tile_aggregate(warp_tot, p_warp), (double)tile[(LP_THREADS - 1) * LP_ROW + LP_PER - 1]};
+    const double p_warp = lp_ipow(pt, 32), p_tile = lp_ipow(pt, LP_THREADS);
+    double state = 0.0;                                                 // thread 0
+    for (unsigned long long tl = tl0 < (unsigned long long)warm ? 0 : tl0 - (unsigned long long)warm; tl < tl0; tl++) {
+        const float *base = data + (size_t)ch * stride + (size_t)tl * LP_TILE;
+        __syncthreads();                                                // the previous tile (and warp_tot) has been read
+        lp_fetch_tile(tile, base, LP_TILE, t);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        double xprev0 = 0.0;
+        if (HIGH) xprev0 = t > 0 ? (double)tile[(t - 1) * LP_ROW + LP_PER - 1] : (tl > 0 ? (double)base[-1] : 0.0);
+        lp_zero_scan<HIGH>(tile, t, a, xprev0, HIGH && tl == 0 && t == 0, pt, p_warp, pt_pow, warp_tot);
+        if (t == 0) {
+            const double carry = tl == 0 ? (HIGH ? 0.0 : (double)tile[0]) : state;     // A:3591, as in the kernel below
+            state = fma(p_tile, carry, lp_tile_aggregate(warp_tot, p_warp));
+        }
+    }
+    if (t == 0) chunk_in[blockIdx.x] = lp_chunk_in{state, (double)tile[(LP_THREADS - 1) * LP_ROW + LP_PER - 1]};
 }
 
 // HIGH = false: effects.lowpass, y = y + a (x - y), per-step ratio b = 1 - a.
@@ -383,11 +393,15 @@ static void lp_launch(aukit_ctx *ctx, unsigned grid, float *d, size_t stride, in
 static int lp_run(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t n, double a, double ratio, bool high) {
     const unsigned long long tiles = (n + LP_TILE - 1) / LP_TILE, total = tiles * (unsigned long long)channels;
     const unsigned long long cap = (unsigned long long)ctx->num_sms * LP_CTAS_PER_SM;
-    // blocked chunks (see the top of the file): the state entering a tile must be the previous tile's business alone (the
-    // look-back's own 2^-80 cut), and the chunks long enough for the one extra tile read per chunk of the pre-pass to cost
-    // less than the look-back does (measured: chunks of 4 - 5 tiles are 4 % SLOWER than the look-back, 44 tiles 18 % faster)
-    const double p_tile = pow(ratio, (double)LP_TILE);
-    const bool blocked = total >= 8 * cap && p_tile < 8.3e-25 && p_tile > -8.3e-25;
+    // blocked chunks (see the top of the file).  `warm` = tiles of memory: the fewest whose combined weight
+    // |ratio|^(8192 warm) is below 2^-80, the look-back's own cut (1 for any cut-off above ~50 Hz at 48 kHz, 2 from ~26 Hz,
+    // 5 from ~10 Hz).  Each chunk's pre-pass reads that many extra tiles, so the chunks must be long enough for that to cost
+    // less than the look-back does (measured with warm = 1: chunks of 4 - 5 tiles are 4 % SLOWER than the look-back, 44 tiles
+    // 18 % faster): at least 8 tiles, and four times the warm-up.  NaN or |ratio| >= 1 never qualifies.
+    int warm = 0;
+    for (int w = 1; w <= 8 && !warm; w++)
+        if (pow(fabs(ratio), (double)LP_TILE * w) < 8.3e-25) warm = w;
+    const bool blocked = warm > 0 && total >= (unsigned long long)(warm > 2 ? 4 * warm : 8) * cap;
     const unsigned long long chunk = blocked ? (total + cap - 1) / cap : 0;
     const unsigned long long nchunks = blocked ? (total + chunk - 1) / chunk : 0;
     // scratch: one 16-byte slot per (channel, tile) + the ticket counter (+ the boundary samples for highpass, + the
@@ -412,8 +426,8 @@ static int lp_run(aukit_ctx *ctx, float *d, size_t stride, int channels, size_t 
         ctx->launches++;
     }
     if (!rc && blocked) {
-        if (high) lp_chunk_states<true><<<(unsigned)nchunks, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, a, ratio, tiles, total, chunk, chunk_in, poison);
-        else lp_chunk_states<false><<<(unsigned)nchunks, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, a, ratio, tiles, total, chunk, chunk_in, poison);
+        if (high) lp_chunk_states<true><<<(unsigned)nchunks, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, a, ratio, tiles, total, chunk, warm, chunk_in, poison);
+        else lp_chunk_states<false><<<(unsigned)nchunks, LP_THREADS, 0, ctx->stream>>>(d, stride, channels, a, ratio, tiles, total, chunk, warm, chunk_in, poison);
         ctx->launches++;
     }
     if (!rc) {

@@ -145,3 +145,11 @@ def test_blocked_lowpass_chunk_start_state_is_exact_to_fp64():
         full = high(ah, x[1: 2 * T], x[0], x[0])
         trunc = high(ah, x[T: 2 * T], 0.0, x[T - 1])
         assert abs(full - trunc) <= 8.3e-25 * 4.0
+    # lower cut-offs: the pre-pass runs from zero over `warm` tiles, the fewest with ratio^(T warm) < 8.3e-25 (lp_run)
+    for f, warm in ((30.0, 2), (12.0, 5)):
+        a = 1.0 - math.exp(-(f / 48000.0) * 2 * math.pi)
+        assert (1.0 - a) ** (T * warm) < 8.3e-25 <= (1.0 - a) ** (T * (warm - 1))
+        xs = (rng.uniform(-1, 1, (warm + 1) * T) + 0.3).astype(np.float32).astype(np.float64)
+        full = low(a, xs, xs[0])
+        trunc = low(a, xs[T:], 0.0)
+        assert abs(full - trunc) <= 8.3e-25 * 1.5 and abs(full) > 1e-3
